@@ -1,0 +1,189 @@
+// airice_core.cuh -- closed-form air->ice ray arithmetic shared by the three CUDA kernels.
+//
+// Everything here is FP64 scalar math on registers; the medium model and the per-launch plan arrive
+// as kernel parameters (constant bank), so a thread touches HBM only for its own inputs/outputs.
+//
+// Reference behaviour being reproduced (file:line under /root/reference):
+//   n(h) of air / ice ............ MultiRayAirIceRefraction.cc:150-263
+//   fDnfR / ftimeD / fpathD ...... MultiRayAirIceRefraction.cc:377-447
+//   layer walk ................... MultiRayAirIceRefraction.cc:661-804 (solver), 1796-1879 (table)
+//   ice leg ...................... MultiRayAirIceRefraction.cc:807-869, 1893-1922
+//   Fresnel Trans_S/Trans_P ...... MultiRayAirIceRefraction.cc:285-337
+//
+// Algebra used (exact identities of the reference formulas, n = A + B e^{C'x}, C' = -C_layer,
+// sA = sqrt(A^2-L^2), D = n^2-L^2, R = sqrt(D), T = A n - L^2 + sA R, G = C'x - ln T, H = ln(n+R)):
+//   fDnfR  = (L/C')(1/sA) G
+//   ftimeD = (1/(c C' R)) (D + G A^2 R / sA + A R H)
+//   fpathD = (H + (A/sA) G) / C'
+// so one layer end costs 1 sqrt + 1 log (distance only) or 1 sqrt + 2 log (distance, time, path), and
+// n at every layer end except the transmitter is ray-independent (host-computed into AirIcePlan).
+// The reference re-evaluates n(x) 9x in ftimeD and exp() 13x in fpathD; nothing of that survives.
+//
+// Code-size discipline: a ray is a list of at most 6 segments (<=5 air layers, then the ice leg) that all run
+// through ONE loop body (never unrolled), so the hot loop of each kernel is a few hundred instructions and
+// stays resident in the SM's instruction cache.  (The first version unrolled the layer loop and inlined every
+// evaluation: 230 KB of SASS, and ncu showed 10 "no instruction" stall cycles per issued instruction.)
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AIRICE_HD __host__ __device__ __forceinline__
+#define AIRICE_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define AIRICE_HD inline
+#define AIRICE_HD_NOINLINE
+#endif
+
+#define AIRICE_MAX_LAYERS 5
+
+// Per-context medium model (one Atmosphere.dat + ice model + which copy of the reference, i.e. which pi).
+struct AirIceMedium {
+  int nlayers;                        // MaxLayers (M.cc:142)
+  int variant;                        // 0 = MultiRayAirIceRefraction, 1 = pythonwrapper/AirIceRayTracing
+  double hlo[AIRICE_MAX_LAYERS + 1];  // ATMLAY[k]/100 in metres; hlo[nlayers] closes the top layer
+  double B[AIRICE_MAX_LAYERS];        // B_air
+  double C[AIRICE_MAX_LAYERS];        // C_air
+  double A_ice, B_ice, C_ice;
+  double pi;                          // 3.1415927 (M.h:29) or 4*atan(1) (P.h:25)
+  double deg2rad;                     // pi/180.0, rounded once like the reference expression
+  double rad2deg;                     // 180/pi
+  double c;                           // 299792458 (M.h:30)
+};
+
+// Per-(ice height, receiver depth) plan: every ray-independent number of the layer walk, computed on
+// the host with the same libm the reference uses.  Slot AIRICE_MAX_LAYERS of the per-segment arrays is the ice leg.
+#define AIRICE_ICE_SLOT AIRICE_MAX_LAYERS
+struct AirIcePlan {
+  int kb;          // layer that contains the ice surface (= SkipLayersBelow, M.cc:680-690)
+  int has_ice;     // receiver below the surface (depth != 0), M.cc:901
+  double ice_h;    // ice-surface height after the depth>=0 fold (M.cc:1472-1476)
+  double depth;    // receiver depth, positive, 0 when the receiver sits in air
+  double neg_c[AIRICE_MAX_LAYERS + 1];    // C' = -C of the segment's medium
+  double stop_x[AIRICE_MAX_LAYERS + 1];   // lower end: ice_h for k==kb else hlo[k] (M.cc:722-728); ice leg: depth
+  double stop_n[AIRICE_MAX_LAYERS + 1];
+  double start_x[AIRICE_MAX_LAYERS + 1];  // upper end when entered from above: hlo[k+1]-1e-5 (M.cc:715); ice leg: 0
+  double start_n[AIRICE_MAX_LAYERS + 1];
+  double relay[AIRICE_MAX_LAYERS + 1];    // n_start[k]/n_stop[k+1]: Snell hand-over of the table path (M.cc:1871)
+};
+
+AIRICE_HD double airice_n_air(const AirIceMedium& m, int k, double z) { return 1.0 + m.B[k] * exp(-m.C[k] * z); }
+
+// Top layer of a transmitter height for the walk (SkipLayersAbove, M.cc:666-676); -1 = in no layer.
+AIRICE_HD int airice_top_layer(const AirIceMedium& m, double h) {
+  int kt = -1;
+#pragma unroll
+  for (int k = 0; k < AIRICE_MAX_LAYERS; k++)
+    if (k < m.nlayers && h >= m.hlo[k] && h < m.hlo[k + 1]) kt = k;
+  return kt;
+}
+
+struct AirIceRay {   // everything the reference reports for one ray (metres, seconds, degrees)
+  double x_air, x_ice, t_air, t_ice, p_air, p_ice;
+  double inc_ice_deg, recv_deg, refr_deg;
+  double trans_s, trans_p;
+};
+
+// Horizontal distance only (the root function's X), with optional dX/dL for Newton.  The solver path carries L
+// unchanged through all layers and into the ice (M.cc:757-771, 894-902).
+template <bool DERIV>
+AIRICE_HD double airice_x_total(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
+                                double& dXdL) {
+  const double L2 = L * L;
+  const double sAir = sqrt(1.0 * 1.0 - L2), sIce = sqrt(m.A_ice * m.A_ice - L2);
+  const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
+  const int nseg = nair + (p.has_ice ? 1 : 0);
+  double X = 0.0, dX = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < nseg; j++) {
+    const bool air = j < nair;
+    const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
+    const double A = air ? 1.0 : m.A_ice;
+    const double sA = air ? sAir : sIce;
+    const double Cn = p.neg_c[k];
+    const bool top = (j == 0) && air;
+    const double xt = top ? h : p.start_x[k];
+    const double nt = top ? n_tx : p.start_n[k];
+    const double xb = p.stop_x[k], nb = p.stop_n[k];
+    const double Rb = sqrt(nb * nb - L2), Rt = sqrt(nt * nt - L2);
+    const double Tb = A * nb - L2 + sA * Rb, Tt = A * nt - L2 + sA * Rt;
+    const double Gb = Cn * xb - log(Tb), Gt = Cn * xt - log(Tt);
+    const double inv_sA = 1.0 / sA;
+    const double mult = (L / Cn) * inv_sA;
+    const double seg = mult * Gb - mult * Gt;   // F(stop) - F(start), as GetRayHorizontalPath forms it (M.cc:463)
+    X += air ? -seg : seg;
+    if (DERIV) {
+      const double qb = (sA + Rb) * (sA + Rb) / (Tb * Rb), qt = (sA + Rt) * (sA + Rt) / (Tt * Rt);
+      const double dseg = (1.0 / Cn) * inv_sA * (A * A * inv_sA * inv_sA * (Gb - Gt) + L2 * inv_sA * (qb - qt));
+      dX += air ? -dseg : dseg;
+    }
+  }
+  dXdL = dX;
+  return X;
+}
+
+// Full evaluation of one ray: distances, times, geometric paths, angles, Fresnel coefficients.
+// RELAY = true  -> forward tracer / table cell (GetRayTracingSolutions, M.cc:1796-2017): L is handed from layer to
+//                  layer through Snell at the boundary (L *= n_start[k]/n_stop[k+1]).
+// RELAY = false -> tail of a launch-angle solve (Air2IceRayTracing, M.cc:1524-1614): one L throughout.
+template <bool RELAY>
+AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
+                               bool in_ice, AirIceRay& r) {
+  const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
+  const int nseg = nair + (in_ice ? 1 : 0);
+  double xa = 0.0, ta = 0.0, ga = 0.0, xi = 0.0, ti = 0.0, gi = 0.0;
+  double Lk = L, Rsurf = 0.0;
+  r.recv_deg = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < nseg; j++) {
+    const bool air = j < nair;
+    const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
+    const bool top = (j == 0) && air;
+    if (RELAY && air && !top) Lk = Lk * p.relay[k];
+    const double A = air ? 1.0 : m.A_ice;
+    const double L2 = Lk * Lk;
+    const double sA = sqrt(A * A - L2), inv_sA = 1.0 / sA;
+    const double Cn = p.neg_c[k];
+    const double xt = top ? h : p.start_x[k];
+    const double nt = top ? n_tx : p.start_n[k];
+    const double xb = p.stop_x[k], nb = p.stop_n[k];
+    const double Db = nb * nb - L2, Dt = nt * nt - L2;
+    const double Rb = sqrt(Db), Rt = sqrt(Dt);
+    const double Gb = Cn * xb - log(A * nb - L2 + sA * Rb), Gt = Cn * xt - log(A * nt - L2 + sA * Rt);
+    const double Hb = log(nb + Rb), Ht = log(nt + Rt);
+    const double mult = (Lk / Cn) * inv_sA;
+    const double xs = mult * Gb - mult * Gt;
+    const double tb = (1.0 / ((m.c * Cn) * Rb)) * ((Db + (Gb * (A * A * Rb)) / sA) + (A * Rb) * Hb);
+    const double tt = (1.0 / ((m.c * Cn) * Rt)) * ((Dt + (Gt * (A * A * Rt)) / sA) + (A * Rt) * Ht);
+    const double ts = tb - tt;
+    const double gs = (Hb + (A * inv_sA) * Gb) / Cn - (Ht + (A * inv_sA) * Gt) / Cn;
+    if (air) {
+      xa += -xs; ta += -ts; ga += -gs;
+      Rsurf = Rb;  // after the last air segment: sqrt(n_air(surface)^2 - L^2) = n1 cos(incidence)
+    } else {
+      xi = xs; ti = ts; gi = gs;
+      r.recv_deg = asin(Lk / nb) * m.rad2deg;  // M.cc:824 / 583-589
+    }
+  }
+  r.x_air = xa; r.t_air = ta; r.p_air = ga;
+  r.x_ice = xi; r.t_ice = ti; r.p_ice = gi;
+  // incidence on the ice surface: receive angle of the bottom air segment, asin(L/n(surface)) (M.cc:760, 583-589).
+  // NB: with RELAY the ice leg re-derives L as n_air(surface) sin(incidence) (M.cc:1913, 565-589), which is Lk again.
+  const double n1 = p.stop_n[p.kb < AIRICE_MAX_LAYERS ? p.kb : 0];
+  const double n2 = p.start_n[AIRICE_ICE_SLOT];  // n_ice(0)
+  const double Lsurf = in_ice ? Lk : Lk;
+  const double si = Lsurf / n1;
+  r.inc_ice_deg = asin(si) * m.rad2deg;
+  // Fresnel field transmission, air->ice at the surface (M.cc:285-301, 321-337) without trig:
+  // sin(theta_i) = L/n1, n1 cos(theta_i) = sqrt(n1^2-L^2) = R of the bottom end.
+  const double u = (n1 / n2) * si;
+  const double sq = sqrt(1.0 - u * u);
+  const double c1 = Rsurf;
+  double trs = 1.0 + (c1 - n2 * sq) / (c1 + n2 * sq);
+  const double c2 = c1 / n1;  // cos(theta_i)
+  double trp = (1.0 - (n1 * sq - n2 * c2) / (n1 * sq + n2 * c2)) * (n1 / n2);
+  if (trs != trs) trs = 0.0;
+  if (trp != trp) trp = 0.0;
+  r.trans_s = trs; r.trans_p = trp;
+  r.refr_deg = asin(u) * m.rad2deg;  // refracted angle just below the surface (P.cc:1081)
+}

@@ -1,0 +1,427 @@
+// capi.cu -- extern "C" layer of libairice_b200.so (declarations + reference citations in include/airice_b200.h).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/airice_b200.h"
+#include "airice_host.hpp"
+#include "kernels.cuh"
+
+using namespace airice;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return -100 - (int)e;
+}
+#define CK(call)                                  \
+  do {                                            \
+    cudaError_t e__ = (call);                     \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+}  // namespace
+
+struct airice_ctx {
+  int device = 0;
+  AirIceMedium medium;
+  double n0 = 0;
+  int npoints = 0;
+  std::map<std::pair<double, double>, AirIcePlan> plans;
+  // host-API pipeline: 2 device staging slots on 2 streams (copies go straight from/to the caller's buffers;
+  // when those are pinned the H2D of chunk k+1, the kernel of chunk k and the D2H of chunk k-1 overlap)
+  static const int kSlots = 2;
+  cudaStream_t streams[kSlots] = {nullptr, nullptr};
+  void* dev[kSlots] = {nullptr, nullptr};
+  size_t slot_bytes = 0;
+
+  const AirIcePlan& plan(double ice_m, double depth_m) {
+    auto key = std::make_pair(ice_m, depth_m);
+    auto it = plans.find(key);
+    if (it == plans.end()) {
+      AirIcePlan p;
+      make_plan(medium, ice_m, depth_m, &p);
+      it = plans.emplace(key, p).first;
+    }
+    return it->second;
+  }
+};
+
+struct airice_table {
+  airice_ctx* ctx = nullptr;
+  bool owns = false;
+  float* cols[AIRICE_TABLE_NCOLS32] = {nullptr};
+  int* row_first = nullptr;
+  int* row_last = nullptr;
+  int64_t n_h = 0, n_th = 0, cells = 0;
+  double loop_stop_h = 0, h_step = 0;
+  LookupTable view() const {
+    LookupTable t;
+    for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t.col[k] = cols[k];
+    t.cells = cells; t.n_h = (int)n_h; t.n_th = (int)n_th;
+    t.loop_stop_h = loop_stop_h; t.h_step = h_step;
+    t.row_first = row_first; t.row_last = row_last;
+    return t;
+  }
+};
+
+namespace {
+
+int ensure_slots(airice_ctx* c, size_t bytes) {
+  if (c->slot_bytes >= bytes) return 0;
+  for (int s = 0; s < airice_ctx::kSlots; s++) {
+    if (c->dev[s]) cudaFree(c->dev[s]);
+    c->dev[s] = nullptr;
+  }
+  c->slot_bytes = 0;
+  for (int s = 0; s < airice_ctx::kSlots; s++) {
+    CK(cudaMalloc(&c->dev[s], bytes));
+    if (!c->streams[s]) CK(cudaStreamCreateWithFlags(&c->streams[s], cudaStreamNonBlocking));
+  }
+  c->slot_bytes = bytes;
+  return 0;
+}
+
+// Upload per-row transmitter data for rows [r0,r1) and launch kernel 1 on them.
+int build_rows(airice_ctx* ctx, const TableGrid& g, int64_t r0, int64_t r1, double* const* cols64, float* const* cols32,
+               cudaStream_t s) {
+  const int64_t rows_avail = g.first_skipped_row < g.n_h ? g.first_skipped_row : g.n_h;
+  if (r0 < 0 || r1 > rows_avail || r0 > r1) return fail(-3, "table rows out of range");
+  if (r1 == r0) return 0;
+  std::vector<double> h, ntx;
+  std::vector<int> kt;
+  grid_rows(ctx->medium, g, r0, r1, &h, &ntx, &kt);
+  const int64_t nr = r1 - r0;
+  double* d_rows = nullptr;
+  int* d_kt = nullptr;
+  CK(cudaMallocAsync((void**)&d_rows, sizeof(double) * 2 * nr, s));
+  CK(cudaMallocAsync((void**)&d_kt, sizeof(int) * nr, s));
+  // pageable sources: the runtime copies them to its own staging buffer before returning
+  CK(cudaMemcpyAsync(d_rows, h.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_rows + nr, ntx.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_kt, kt.data(), sizeof(int) * nr, cudaMemcpyHostToDevice, s));
+  TableArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.cell0 = r0 * g.n_th; a.ncells = nr * g.n_th; a.n_th = g.n_th; a.row0 = r0;
+  a.row_h = d_rows; a.row_ntx = d_rows + nr; a.row_kt = d_kt;
+  a.th_start = g.th_start; a.th_step = g.th_step; a.th_stop = g.th_stop;
+  a.in_ice = g.in_ice;
+  if (cols64) for (int k = 0; k < AIRICE_TABLE_NCOLS64; k++) a.c64[k] = cols64[k];
+  if (cols32) for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) a.c32[k] = cols32[k];
+  if (cols32) for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) if (!cols32[k]) return fail(-4, "all 11 float columns are required");
+  // the table path hands the surface height of the grid (ice, or ice+depth for a receiver in air) to the walk
+  const AirIcePlan& p = ctx->plan(g.ice_h, g.depth_signed);
+  cudaError_t e = launch_table(ctx->medium, p, a, s);
+  cudaFreeAsync(d_rows, s);
+  cudaFreeAsync(d_kt, s);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_table");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* airice_last_error(void) { return g_err.c_str(); }
+
+int airice_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int airice_create(const char* atmosphere_path, int variant, int device, airice_ctx** out) {
+  if (!out || !atmosphere_path) return fail(-1, "null argument");
+  if (variant != AIRICE_VARIANT_MULTIRAY && variant != AIRICE_VARIANT_PYWRAP) return fail(-1, "unknown variant");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(-2, std::string("no CUDA device available (this library has no CPU path): ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device < 0 || device >= ndev) return fail(-2, "device index out of range");
+  airice_ctx* c = new airice_ctx();
+  c->device = device;
+  std::string err;
+  int rc = load_medium(atmosphere_path, variant, &c->medium, &c->n0, &c->npoints, &err);
+  if (rc != 0) { delete c; return fail(rc, err); }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaSetDevice"); }
+  *out = c;
+  return 0;
+}
+
+void airice_destroy(airice_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (int s = 0; s < airice_ctx::kSlots; s++) {
+    if (c->dev[s]) cudaFree(c->dev[s]);
+    if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
+  }
+  delete c;
+}
+
+int airice_get_medium(const airice_ctx* c, double out[24]) {
+  if (!c || !out) return fail(-1, "null argument");
+  const AirIceMedium& m = c->medium;
+  out[0] = m.nlayers;
+  for (int i = 0; i < 5; i++) { out[1 + i] = m.hlo[i] * 100; out[6 + i] = m.B[i]; out[11 + i] = m.C[i]; }
+  out[1 + 4] = 150000 * 100;
+  out[16] = m.A_ice; out[17] = m.B_ice; out[18] = m.C_ice; out[19] = m.pi; out[20] = c->n0; out[21] = c->npoints;
+  out[22] = 0; out[23] = 0;
+  return 0;
+}
+
+int airice_set_ice_model(airice_ctx* c, double A, double B, double C) {
+  if (!c) return fail(-1, "null context");
+  c->medium.A_ice = A; c->medium.B_ice = B; c->medium.C_ice = C;
+  c->plans.clear();
+  return 0;
+}
+
+int airice_table_dims(const airice_ctx* c, double depth_m, double ice_m, double h_top, double h_step, double th_start,
+                      double th_step, double th_stop, int64_t* n_h, int64_t* n_th) {
+  if (!c) return fail(-1, "null context");
+  TableGrid g; std::string err;
+  int rc = make_grid(depth_m, ice_m, h_top, h_step, th_start, th_step, th_stop, &g, &err);
+  if (rc) return fail(rc, err);
+  if (n_h) *n_h = g.first_skipped_row < g.n_h ? g.first_skipped_row : g.n_h;
+  if (n_th) *n_th = g.n_th;
+  return 0;
+}
+
+int airice_table_build_device(airice_ctx* c, double depth_m, double ice_m, double h_top, double h_step,
+                              double th_start, double th_step, double th_stop, int64_t row_begin, int64_t row_end,
+                              double* const* cols64, float* const* cols32, void* stream) {
+  if (!c) return fail(-1, "null context");
+  if (!cols64 && !cols32) return fail(-1, "no output columns");
+  CK(cudaSetDevice(c->device));
+  TableGrid g; std::string err;
+  int rc = make_grid(depth_m, ice_m, h_top, h_step, th_start, th_step, th_stop, &g, &err);
+  if (rc) return fail(rc, err);
+  return build_rows(c, g, row_begin, row_end, cols64, cols32, (cudaStream_t)stream);
+}
+
+int airice_table_create(airice_ctx* c, double depth_m, double ice_m, double h_top, double h_step, double th_start,
+                        double th_step, double th_stop, airice_table** out) {
+  if (!c || !out) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  TableGrid g; std::string err;
+  int rc = make_grid(depth_m, ice_m, h_top, h_step, th_start, th_step, th_stop, &g, &err);
+  if (rc) return fail(rc, err);
+  airice_table* t = new airice_table();
+  t->ctx = c; t->owns = true;
+  t->n_h = g.first_skipped_row < g.n_h ? g.first_skipped_row : g.n_h;
+  t->n_th = g.n_th; t->cells = t->n_h * t->n_th;
+  t->loop_stop_h = g.loop_stop_h; t->h_step = g.h_step;
+  if (t->cells >= 2147483647LL) { delete t; return fail(-5, "lookup tables are limited to 2^31-1 cells (the reference indexes them with int)"); }
+  float* block = nullptr;
+  cudaError_t e = cudaMalloc((void**)&block, sizeof(float) * t->cells * AIRICE_TABLE_NCOLS32);
+  if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(table)"); }
+  for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t->cols[k] = block + (int64_t)k * t->cells;
+  e = cudaMalloc((void**)&t->row_first, sizeof(int) * 2 * t->n_h);
+  if (e != cudaSuccess) { cudaFree(block); delete t; return cuda_fail(e, "cudaMalloc(row ranges)"); }
+  t->row_last = t->row_first + t->n_h;
+  rc = build_rows(c, g, 0, t->n_h, nullptr, t->cols, nullptr);
+  if (rc == 0) {
+    e = launch_row_ranges(t->view(), t->row_first, t->row_last, nullptr);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) rc = cuda_fail(e, "row ranges");
+  }
+  if (rc) { airice_table_destroy(t); return rc; }
+  *out = t;
+  return 0;
+}
+
+int airice_table_wrap(airice_ctx* c, const float* const* d_cols32, int64_t n_h, int64_t n_th, double loop_stop_h,
+                      double h_step, airice_table** out) {
+  if (!c || !out || !d_cols32) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  if (n_h * n_th >= 2147483647LL) return fail(-5, "lookup tables are limited to 2^31-1 cells");
+  airice_table* t = new airice_table();
+  t->ctx = c; t->owns = false;
+  for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t->cols[k] = const_cast<float*>(d_cols32[k]);
+  t->n_h = n_h; t->n_th = n_th; t->cells = n_h * n_th; t->loop_stop_h = loop_stop_h; t->h_step = h_step;
+  cudaError_t e = cudaMalloc((void**)&t->row_first, sizeof(int) * 2 * n_h);
+  if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(row ranges)"); }
+  t->row_last = t->row_first + n_h;
+  e = launch_row_ranges(t->view(), t->row_first, t->row_last, nullptr);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+  if (e != cudaSuccess) { airice_table_destroy(t); return cuda_fail(e, "row ranges"); }
+  *out = t;
+  return 0;
+}
+
+void airice_table_destroy(airice_table* t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->device);
+  if (t->owns && t->cols[0]) cudaFree(t->cols[0]);
+  if (t->row_first) cudaFree(t->row_first);
+  delete t;
+}
+
+int airice_table_info(const airice_table* t, int64_t info[4]) {
+  if (!t) return fail(-1, "null table");
+  info[0] = t->n_h; info[1] = t->n_th; info[2] = t->cells; info[3] = AIRICE_TABLE_NCOLS32;
+  return 0;
+}
+
+int airice_table_copy_column(const airice_table* t, int col, float* host_out) {
+  if (!t || col < 0 || col >= AIRICE_TABLE_NCOLS32) return fail(-1, "bad table/column");
+  CK(cudaSetDevice(t->ctx->device));
+  CK(cudaMemcpy(host_out, t->cols[col], sizeof(float) * t->cells, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int airice_table_column_ptr(const airice_table* t, int col, const float** d_ptr) {
+  if (!t || col < 0 || col >= AIRICE_TABLE_NCOLS32) return fail(-1, "bad table/column");
+  *d_ptr = t->cols[col];
+  return 0;
+}
+
+int airice_table_copy_row_ranges(const airice_table* t, int32_t* host_first, int32_t* host_last) {
+  if (!t) return fail(-1, "null table");
+  CK(cudaSetDevice(t->ctx->device));
+  CK(cudaMemcpy(host_first, t->row_first, sizeof(int) * t->n_h, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(host_last, t->row_last, sizeof(int) * t->n_h, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int airice_forward_device(airice_ctx* c, int64_t n, const double* d_theta, const double* d_h, double depth_m,
+                          double ice_m, double* const* cols64, void* stream) {
+  if (!c || !cols64) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  // GetRayTracingSolutions takes the surface height as given (no depth fold); depth>=0 just means "no ice leg"
+  const int in_ice = depth_m < 0 ? 1 : 0;
+  const AirIcePlan& p = c->plan(ice_m, in_ice ? depth_m : 0.0);
+  ForwardArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n; a.theta = d_theta; a.h = d_h; a.in_ice = in_ice;
+  for (int k = 0; k < AIRICE_TABLE_NCOLS64; k++) a.c64[k] = cols64[k];
+  cudaError_t e = launch_forward(c->medium, p, a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_forward");
+  return 0;
+}
+
+int airice_solve_device(airice_ctx* c, int64_t n, const double* d_h, const double* d_dist, double depth, double ice,
+                        int units, double* const* d_out, uint8_t* d_ok, int32_t* d_nevals, void* stream) {
+  if (!c || !d_out) return fail(-1, "null argument");
+  if (units != AIRICE_UNITS_M_DEG && units != AIRICE_UNITS_CM_RAD) return fail(-1, "unknown units");
+  CK(cudaSetDevice(c->device));
+  const double sc = (units == AIRICE_UNITS_CM_RAD) ? 100.0 : 1.0;
+  const AirIcePlan& p = c->plan(ice / sc, depth / sc);  // same "/100" the reference applies (M.cc:949-950)
+  SolveArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n; a.h = d_h; a.d = d_dist; a.ice = ice; a.depth = depth; a.units = units;
+  const int nc = units == AIRICE_UNITS_CM_RAD ? AIRICE_SOLVE_COLS_CM_RAD : AIRICE_SOLVE_COLS;
+  for (int k = 0; k < nc; k++) a.out[k] = d_out[k];
+  a.ok = d_ok; a.nevals = d_nevals;
+  cudaError_t e = launch_solve(c->medium, p, a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_solve");
+  return 0;
+}
+
+// Host-buffer path: the batch is cut into chunks that alternate between two streams, each with its own device
+// staging slot.  Copies go directly from/to the caller's buffers (no extra host memcpy); with pinned caller memory
+// the H2D of chunk k+1, the kernel of chunk k and the D2H of chunk k-1 run concurrently.
+int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* dist, double depth, double ice,
+                      int units, double* out, uint8_t* ok) {
+  if (!c || !h || !dist || !out || !ok) return fail(-1, "null argument");
+  if (units != AIRICE_UNITS_M_DEG && units != AIRICE_UNITS_CM_RAD) return fail(-1, "unknown units");
+  CK(cudaSetDevice(c->device));
+  const int nc = units == AIRICE_UNITS_CM_RAD ? AIRICE_SOLVE_COLS_CM_RAD : AIRICE_SOLVE_COLS;
+  const int64_t chunk = n < (1 << 20) ? (n > 0 ? n : 1) : (1 << 20);
+  int rc = ensure_slots(c, (size_t)chunk * (sizeof(double) * (2 + nc) + 1) + 64);
+  if (rc) return rc;
+  const double sc = (units == AIRICE_UNITS_CM_RAD) ? 100.0 : 1.0;
+  const AirIcePlan& p = c->plan(ice / sc, depth / sc);
+  int slot = 0;
+  for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    double* dh = (double*)c->dev[slot];
+    cudaStream_t s = c->streams[slot];
+    CK(cudaMemcpyAsync(dh, h + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, dist + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    SolveArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = m; a.h = dh; a.d = dh + chunk; a.ice = ice; a.depth = depth; a.units = units;
+    for (int k = 0; k < nc; k++) a.out[k] = dh + (2 + k) * chunk;
+    a.ok = (uint8_t*)(dh + (2 + nc) * chunk);
+    cudaError_t e = launch_solve(c->medium, p, a, s);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_solve");
+    for (int k = 0; k < nc; k++)
+      CK(cudaMemcpyAsync(out + (int64_t)k * n + off, a.out[k], sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ok + off, a.ok, (size_t)m, cudaMemcpyDeviceToHost, s));
+  }
+  for (int s = 0; s < airice_ctx::kSlots; s++)
+    if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
+  return 0;
+}
+
+int airice_lookup_device(airice_ctx* c, const airice_table* t, int64_t n, const double* d_h_cm, const double* d_dist_cm,
+                         double* const* d_out, uint8_t* d_ok, void* stream) {
+  if (!c || !t || !d_out || !d_ok) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  LookupArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n; a.h_cm = d_h_cm; a.d_cm = d_dist_cm; a.ok = d_ok;
+  for (int k = 0; k < AIRICE_LOOKUP_NCOLS; k++) a.out[k] = d_out[k];
+  cudaError_t e = launch_lookup(c->medium, t->view(), a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_lookup");
+  return 0;
+}
+
+int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const double* h_cm, const double* dist_cm,
+                       double* out, uint8_t* ok) {
+  if (!c || !t || !h_cm || !dist_cm || !out || !ok) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int nc = AIRICE_LOOKUP_NCOLS;
+  const int64_t chunk = n < (1 << 20) ? (n > 0 ? n : 1) : (1 << 20);
+  int rc = ensure_slots(c, (size_t)chunk * (sizeof(double) * (2 + nc) + 1) + 64);
+  if (rc) return rc;
+  int slot = 0;
+  for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    double* dh = (double*)c->dev[slot];
+    cudaStream_t s = c->streams[slot];
+    CK(cudaMemcpyAsync(dh, h_cm + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, dist_cm + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    LookupArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = m; a.h_cm = dh; a.d_cm = dh + chunk; a.ok = (uint8_t*)(dh + (2 + nc) * chunk);
+    for (int k = 0; k < nc; k++) a.out[k] = dh + (2 + k) * chunk;
+    cudaError_t e = launch_lookup(c->medium, t->view(), a, s);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_lookup");
+    for (int k = 0; k < nc; k++)
+      CK(cudaMemcpyAsync(out + (int64_t)k * n + off, a.out[k], sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ok + off, a.ok, (size_t)m, cudaMemcpyDeviceToHost, s));
+  }
+  for (int s = 0; s < airice_ctx::kSlots; s++)
+    if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
+  return 0;
+}
+
+int airice_fp64_peak_tflops(airice_ctx* c, double* tflops) {
+  if (!c || !tflops) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  cudaError_t e = fp64_peak_probe(tflops, 4096, nullptr);
+  if (e != cudaSuccess) return cuda_fail(e, "fp64_peak_probe");
+  return 0;
+}
+
+int airice_sync(airice_ctx* c) {
+  if (!c) return fail(-1, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+}  // extern "C"

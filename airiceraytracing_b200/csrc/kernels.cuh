@@ -1,0 +1,89 @@
+// kernels.cuh -- launch-side declarations of the three sm_100a kernels (+ the FP64 FMA peak probe).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "airice_core.cuh"
+
+#define AIRICE_TABLE_NCOLS64 17
+#define AIRICE_TABLE_NCOLS32 11
+#define AIRICE_SOLVE_NCOLS 13
+#define AIRICE_LOOKUP_NCOLS 9
+
+namespace airice {
+
+// ---- kernel 1: forward table.  One thread per (Tx height, launch angle) cell, flat cell index
+// cell = ihei*n_th + iang exactly as MakeRayTracingTable orders its push_backs (M.cc:2079-2118).
+struct TableArgs {
+  int64_t cell0;      // first flat cell of this launch
+  int64_t ncells;     // cells in this launch
+  int64_t n_th;       // TotalAngleSteps
+  int64_t row0;       // row index of row_h[0]
+  const double* row_h;    // per-row Tx height (host-built: M.cc:2080,2089-2091)
+  const double* row_ntx;  // per-row n(h) (host libm)
+  const int* row_kt;      // per-row top layer (-1: outside every layer)
+  double th_start, th_step, th_stop;
+  int in_ice;
+  // f64 columns = dummy[1..17] of GetRayTracingSolutions (M.cc:1999-2016):
+  //  0 h, 1 X, 2 X_air, 3 X_ice, 4 opt, 5 opt_air, 6 opt_ice, 7 t[ns], 8 t_air[ns], 9 t_ice[ns],
+  //  10 launch, 11 incident, 12 received, 13 T_S, 14 T_P, 15 geo_air, 16 geo_ice.  nullptr = not wanted.
+  double* c64[AIRICE_TABLE_NCOLS64];
+  // float columns in the reference's AllTableAllAntData order (M.cc:2101-2111):
+  //  0 h, 1 X, 2 opt_ice, 3 opt_air, 4 launch, 5 X_air, 6 T_S, 7 T_P, 8 geo_air, 9 geo_ice, 10 received.
+  float* c32[AIRICE_TABLE_NCOLS32];
+};
+cudaError_t launch_table(const AirIceMedium& m, const AirIcePlan& p, const TableArgs& a, cudaStream_t s);
+
+// kernel 1b: the same forward tracer on arbitrary (theta, h) cells (batched GetRayTracingSolutions, M.cc:1796-2017);
+// n(h) of the transmitter is evaluated on the device here.
+struct ForwardArgs {
+  int64_t n;
+  const double* theta;
+  const double* h;
+  int in_ice;
+  double* c64[AIRICE_TABLE_NCOLS64];
+};
+cudaError_t launch_forward(const AirIceMedium& m, const AirIcePlan& p, const ForwardArgs& a, cudaStream_t s);
+
+// ---- kernel 2: batched launch-angle solve.  One thread per Tx->Rx pair.
+enum { AIRICE_UNITS_M_DEG = 0, AIRICE_UNITS_CM_RAD = 1 };
+struct SolveArgs {
+  int64_t n;
+  const double* h;  // Tx heights a.s.l.
+  const double* d;  // horizontal distances
+  double ice;       // ice-surface height (same units as h)
+  double depth;     // signed receiver depth (negative = in ice), same units
+  int units;        // AIRICE_UNITS_M_DEG: metres in, 13 columns out (m, s, deg);
+                    // AIRICE_UNITS_CM_RAD: cm in, the 9 outputs of GetHorizontalDistanceToIntersectionPoint (M.h:170)
+  // M_DEG columns: 0 X_total, 1 X_air, 2 X_ice, 3 t_air[s], 4 t_ice[s], 5 launch, 6 received(ice), 7 T_S, 8 T_P,
+  //                9 geo_air, 10 geo_ice, 11 incident on ice, 12 refracted angle below the surface (P.cc:1081)
+  // CM_RAD columns: 0 opt_ice, 1 opt_air, 2 geo_ice, 3 geo_air, 4 launch[rad], 5 X_air, 6 T_S, 7 T_P, 8 received[rad]
+  double* out[AIRICE_SOLVE_NCOLS];
+  uint8_t* ok;        // solution flag (M.cc:974-983)
+  int32_t* nevals;    // optional: distance evaluations spent (Newton + replay), diagnostics
+};
+cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const SolveArgs& a, cudaStream_t s);
+
+// ---- kernel 3: table lookup (GetHorizontalDistanceToIntersectionPoint_Table, M.cc:1305-1462)
+struct LookupTable {
+  const float* col[AIRICE_TABLE_NCOLS32];
+  int64_t cells;
+  int n_h, n_th;
+  double loop_stop_h, h_step;
+  const int* row_first;  // per row: first/last bin with a usable X (trim of M.cc:1050-1072), precomputed
+  const int* row_last;
+};
+struct LookupArgs {
+  int64_t n;
+  const double* h_cm;
+  const double* d_cm;
+  double* out[AIRICE_LOOKUP_NCOLS];  // same 9 slots as the CM_RAD solve
+  uint8_t* ok;                       // solution flag (M.cc:1356-1449)
+};
+cudaError_t launch_row_ranges(const LookupTable& t, int* row_first, int* row_last, cudaStream_t s);
+cudaError_t launch_lookup(const AirIceMedium& m, const LookupTable& t, const LookupArgs& a, cudaStream_t s);
+
+// ---- FP64 FMA peak probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
+cudaError_t fp64_peak_probe(double* tflops_out, int iters, cudaStream_t s);
+
+}  // namespace airice

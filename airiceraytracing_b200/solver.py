@@ -1,0 +1,224 @@
+"""Host-side handle on the C ABI: one AirIceSolver per GPU (mirrors the reference's per-process state:
+MakeAtmosphere() once, then tables / solves / lookups).  All arrays are torch CUDA tensors (device API) or
+numpy / pinned torch CPU tensors (host API); nothing is computed in Python."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import check, ptr_array
+
+# dummy[1..17] of GetRayTracingSolutions (MultiRayAirIceRefraction.cc:1999-2016)
+TABLE_COLUMNS64 = ["h", "x", "x_air", "x_ice", "opt", "opt_air", "opt_ice", "t_ns", "t_air_ns", "t_ice_ns", "launch",
+                   "incident", "received", "trans_s", "trans_p", "geo_air", "geo_ice"]
+# README.md:8 "13 columns": entry number (implicit cell index) + these twelve
+README_COLUMNS = ["h", "x", "x_air", "x_ice", "t_ns", "t_air_ns", "t_ice_ns", "launch", "incident", "received",
+                  "trans_s", "trans_p"]
+# AllTableAllAntData order (MultiRayAirIceRefraction.cc:2101-2111)
+TABLE_COLUMNS32 = ["h", "x", "opt_ice", "opt_air", "launch", "x_air", "trans_s", "trans_p", "geo_air", "geo_ice",
+                   "received"]
+SOLVE_COLUMNS_M_DEG = ["x", "x_air", "x_ice", "t_air", "t_ice", "launch", "received", "trans_s", "trans_p", "geo_air",
+                       "geo_ice", "incident", "refracted"]
+# by-reference arguments of GetHorizontalDistanceToIntersectionPoint (MultiRayAirIceRefraction.h:170)
+SOLVE_COLUMNS_CM_RAD = ["opt_ice", "opt_air", "geo_ice", "geo_air", "launch", "x_air", "trans_s", "trans_p", "received"]
+
+REFERENCE_GRID = dict(h_top=100000.0, h_step=10.0, th_start=90.1, th_step=0.1, th_stop=180.0)  # M.cc:12-18,2044
+README_GRID = dict(h_top=100000.0, h_step=20.0, th_start=92.0, th_step=0.5, th_stop=180.0)    # README.md:7-8
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Table:
+    """Device-resident float table (one entry of the reference's AllTableAllAntData) plus its row trim ranges."""
+
+    def __init__(self, solver, handle, keepalive=None):
+        self.solver, self.handle, self._keep = solver, handle, keepalive
+        info = (C.c_int64 * 4)()
+        check(solver.lib.airice_table_info(handle, info))
+        self.n_h, self.n_th, self.cells = int(info[0]), int(info[1]), int(info[2])
+
+    def columns(self):
+        out = np.empty((_capi.TABLE_COLS32, self.cells), dtype=np.float32)
+        for k in range(_capi.TABLE_COLS32):
+            check(self.solver.lib.airice_table_copy_column(self.handle, k, out[k].ctypes.data))
+        return out
+
+    def row_ranges(self):
+        first = np.empty(self.n_h, dtype=np.int32)
+        last = np.empty(self.n_h, dtype=np.int32)
+        check(self.solver.lib.airice_table_copy_row_ranges(self.handle, first.ctypes.data, last.ctypes.data))
+        return first, last
+
+    def close(self):
+        if self.handle:
+            self.solver.lib.airice_table_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class AirIceSolver:
+    def __init__(self, atmosphere="Atmosphere.dat", variant=_capi.VARIANT_MULTIRAY, device=0):
+        self.lib = _capi.load()
+        if not torch.cuda.is_available():
+            raise _capi.AirIceError("no CUDA device visible: airiceraytracing_b200 has no CPU path")
+        self.device = int(device)
+        self.torch_device = torch.device("cuda", self.device)
+        h = C.c_void_p()
+        check(self.lib.airice_create(str(atmosphere).encode(), int(variant), self.device, C.byref(h)))
+        self.handle = h
+        self.variant = variant
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.airice_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ medium
+    def medium(self):
+        out = (C.c_double * 24)()
+        check(self.lib.airice_get_medium(self.handle, out))
+        return dict(max_layers=int(out[0]), atmlay_cm=list(out[1:6]), B_air=list(out[6:11]), C_air=list(out[11:16]),
+                    A_ice=out[16], B_ice=out[17], C_ice=out[18], pi=out[19], n0=out[20], npoints=int(out[21]))
+
+    def set_ice_model(self, A, B, C_):
+        check(self.lib.airice_set_ice_model(self.handle, A, B, C_))
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        check(self.lib.airice_fp64_peak_tflops(self.handle, C.byref(v)))
+        return v.value
+
+    def sync(self):
+        check(self.lib.airice_sync(self.handle))
+
+    # ------------------------------------------------------------------ kernel 1
+    def table_dims(self, depth_m, ice_m, h_top=100000.0, h_step=10.0, th_start=90.1, th_step=0.1, th_stop=180.0):
+        nh, nth = C.c_int64(), C.c_int64()
+        check(self.lib.airice_table_dims(self.handle, depth_m, ice_m, h_top, h_step, th_start, th_step, th_stop,
+                                         C.byref(nh), C.byref(nth)))
+        return nh.value, nth.value
+
+    def table_build(self, depth_m, ice_m, h_top=100000.0, h_step=10.0, th_start=90.1, th_step=0.1, th_stop=180.0,
+                    rows=None, columns64=TABLE_COLUMNS64, want32=False, out64=None, out32=None):
+        """Build rows [rows[0], rows[1]) of the forward table into SoA device tensors.
+
+        Returns (f64 [len(columns64), cells] or None, f32 [11, cells] or None)."""
+        n_h, n_th = self.table_dims(depth_m, ice_m, h_top, h_step, th_start, th_step, th_stop)
+        r0, r1 = (0, n_h) if rows is None else rows
+        cells = (r1 - r0) * n_th
+        p64 = None
+        if columns64:
+            if out64 is None:
+                out64 = torch.empty((len(columns64), cells), dtype=torch.float64, device=self.torch_device)
+            ptrs = [None] * _capi.TABLE_COLS64
+            for k, name in enumerate(columns64):
+                ptrs[TABLE_COLUMNS64.index(name)] = out64[k].data_ptr()
+            p64 = ptr_array(ptrs)
+        p32 = None
+        if want32:
+            if out32 is None:
+                out32 = torch.empty((_capi.TABLE_COLS32, cells), dtype=torch.float32, device=self.torch_device)
+            p32 = ptr_array([out32[k].data_ptr() for k in range(_capi.TABLE_COLS32)])
+        check(self.lib.airice_table_build_device(self.handle, depth_m, ice_m, h_top, h_step, th_start, th_step, th_stop,
+                                                 r0, r1, p64, p32, _stream_ptr(self.torch_device)))
+        return (out64 if columns64 else None), (out32 if want32 else None)
+
+    def forward(self, theta, h, depth_m, ice_m):
+        """Batched GetRayTracingSolutions on arbitrary (theta, h) device tensors -> f64 [17, n]."""
+        theta = theta.to(self.torch_device, torch.float64).contiguous()
+        h = h.to(self.torch_device, torch.float64).contiguous()
+        n = theta.numel()
+        out = torch.empty((_capi.TABLE_COLS64, n), dtype=torch.float64, device=self.torch_device)
+        check(self.lib.airice_forward_device(self.handle, n, theta.data_ptr(), h.data_ptr(), depth_m, ice_m,
+                                             ptr_array([out[k].data_ptr() for k in range(_capi.TABLE_COLS64)]),
+                                             _stream_ptr(self.torch_device)))
+        return out
+
+    def table_create(self, depth_m, ice_m, h_top=100000.0, h_step=10.0, th_start=90.1, th_step=0.1, th_stop=180.0):
+        h = C.c_void_p()
+        check(self.lib.airice_table_create(self.handle, depth_m, ice_m, h_top, h_step, th_start, th_step, th_stop,
+                                           C.byref(h)))
+        return Table(self, h)
+
+    def table_wrap(self, cols32, n_h, n_th, loop_stop_h, h_step):
+        """Wrap an [11, n_h*n_th] float32 device tensor (kept alive by the returned Table)."""
+        cols32 = cols32.to(self.torch_device, torch.float32).contiguous()
+        h = C.c_void_p()
+        check(self.lib.airice_table_wrap(self.handle, ptr_array([cols32[k].data_ptr() for k in range(11)]), n_h, n_th,
+                                         loop_stop_h, h_step, C.byref(h)))
+        return Table(self, h, keepalive=cols32)
+
+    # ------------------------------------------------------------------ kernel 2
+    def solve(self, h, d, depth, ice, units=_capi.UNITS_CM_RAD, out=None, ok=None, nevals=False):
+        """Batched launch-angle solve on device tensors.  Returns (out [ncols, n] f64, ok [n] uint8[, nevals])."""
+        h = h.to(self.torch_device, torch.float64).contiguous()
+        d = d.to(self.torch_device, torch.float64).contiguous()
+        n = h.numel()
+        nc = _capi.SOLVE_COLS_CM_RAD if units == _capi.UNITS_CM_RAD else _capi.SOLVE_COLS
+        if out is None:
+            out = torch.empty((nc, n), dtype=torch.float64, device=self.torch_device)
+        if ok is None:
+            ok = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
+        nev = torch.empty(n, dtype=torch.int32, device=self.torch_device) if nevals else None
+        check(self.lib.airice_solve_device(self.handle, n, h.data_ptr(), d.data_ptr(), depth, ice, units,
+                                           ptr_array([out[k].data_ptr() for k in range(nc)]), ok.data_ptr(),
+                                           nev.data_ptr() if nevals else None, _stream_ptr(self.torch_device)))
+        return (out, ok, nev) if nevals else (out, ok)
+
+    def solve_host(self, h, d, depth, ice, units=_capi.UNITS_CM_RAD, out=None, ok=None):
+        """Same through host buffers (numpy arrays or pinned torch CPU tensors); copies happen inside the call."""
+        n = int(h.shape[0])
+        nc = _capi.SOLVE_COLS_CM_RAD if units == _capi.UNITS_CM_RAD else _capi.SOLVE_COLS
+        if out is None:
+            out = np.empty((nc, n), dtype=np.float64)
+        if ok is None:
+            ok = np.empty(n, dtype=np.uint8)
+        check(self.lib.airice_solve_host(self.handle, n, _host_ptr(h), _host_ptr(d), depth, ice, units, _host_ptr(out),
+                                         _host_ptr(ok)))
+        return out, ok
+
+    # ------------------------------------------------------------------ kernel 3
+    def lookup(self, table, h_cm, d_cm, out=None, ok=None):
+        h_cm = h_cm.to(self.torch_device, torch.float64).contiguous()
+        d_cm = d_cm.to(self.torch_device, torch.float64).contiguous()
+        n = h_cm.numel()
+        if out is None:
+            out = torch.empty((_capi.LOOKUP_COLS, n), dtype=torch.float64, device=self.torch_device)
+        if ok is None:
+            ok = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
+        check(self.lib.airice_lookup_device(self.handle, table.handle, n, h_cm.data_ptr(), d_cm.data_ptr(),
+                                            ptr_array([out[k].data_ptr() for k in range(_capi.LOOKUP_COLS)]),
+                                            ok.data_ptr(), _stream_ptr(self.torch_device)))
+        return out, ok
+
+    def lookup_host(self, table, h_cm, d_cm, out=None, ok=None):
+        n = int(h_cm.shape[0])
+        if out is None:
+            out = np.empty((_capi.LOOKUP_COLS, n), dtype=np.float64)
+        if ok is None:
+            ok = np.empty(n, dtype=np.uint8)
+        check(self.lib.airice_lookup_host(self.handle, table.handle, n, _host_ptr(h_cm), _host_ptr(d_cm), _host_ptr(out),
+                                          _host_ptr(ok)))
+        return out, ok
+
+
+def _host_ptr(a):
+    if isinstance(a, torch.Tensor):
+        assert a.device.type == "cpu" and a.is_contiguous()
+        return a.data_ptr()
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data

@@ -1,0 +1,104 @@
+/* airice_b200.h -- C ABI of the B200-native air->ice ray solver (libairice_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of uzairlatif90/AirIceRayTracing: plain pointers and sizes,
+ * no C++/torch types.  Each entry point names the reference interface it replaces (paths are relative to the
+ * reference repository root).  Device entry points take DEVICE pointers and a cudaStream_t passed as void*
+ * (NULL = default stream) and do not synchronise; host entry points take HOST pointers, stage through pinned
+ * memory on the context's own streams and return when the results are in the caller's buffers.
+ *
+ * All functions return 0 on success or a negative error code; airice_last_error() describes the last failure
+ * on the calling thread.  A context is bound to one GPU and may be used from one thread at a time.
+ */
+#ifndef AIRICE_B200_H
+#define AIRICE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct airice_ctx airice_ctx;
+typedef struct airice_table airice_table;
+
+enum { AIRICE_VARIANT_MULTIRAY = 0, /* MultiRayAirIceRefraction.{h,cc}: pi = 3.1415927 (MultiRayAirIceRefraction.h:29) */
+       AIRICE_VARIANT_PYWRAP = 1    /* pythonwrapper/AirIceRayTracing.{h,cc}: pi = 4*atan(1) (AirIceRayTracing.h:25) */ };
+enum { AIRICE_UNITS_M_DEG_C = 0, AIRICE_UNITS_CM_RAD_C = 1 };
+
+#define AIRICE_TABLE_COLS64 17
+#define AIRICE_TABLE_COLS32 11
+#define AIRICE_SOLVE_COLS 13
+#define AIRICE_SOLVE_COLS_CM_RAD 9
+#define AIRICE_LOOKUP_COLS 9
+
+/* ---- context: replaces MakeAtmosphere() (MultiRayAirIceRefraction.cc:920-942, .h:157) and
+ * AirIceRayTracing::MakeAtmosphere(file) (pythonwrapper/AirIceRayTracing.cc:860-882).  Parses the GDAS file once. */
+int airice_create(const char *atmosphere_path, int variant, int device, airice_ctx **out);
+void airice_destroy(airice_ctx *ctx);
+const char *airice_last_error(void);
+int airice_device_count(void);
+/* out[0]=MaxLayers, out[1..5]=ATMLAY[cm], out[6..10]=B_air, out[11..15]=C_air, out[16..18]=A,B,C of ice,
+ * out[19]=pi, out[20]=spline n(h=0), out[21]=#spline knots */
+int airice_get_medium(const airice_ctx *ctx, double out[24]);
+/* the reference's mutable ice-model globals A_ice/B_ice/C_ice (MultiRayAirIceRefraction.h:72-74) */
+int airice_set_ice_model(airice_ctx *ctx, double A, double B, double C);
+
+/* ---- kernel 1: forward table = MakeRayTracingTable (MultiRayAirIceRefraction.cc:2019-2158, .h:204) and its
+ * per-cell worker GetRayTracingSolutions (MultiRayAirIceRefraction.cc:1796-2017, .h:198).
+ * Grid: heights h_top, h_top-h_step, ... down to the surface (last row snapped), angles th_start, +th_step, ...
+ * (last bin snapped to th_stop); cell = row*n_th + bin.  All lengths in metres, angles in degrees, depth negative
+ * for a receiver in ice.  The reference's own grid is (100000, 10, 90.1, 0.1, 180)  (MultiRayAirIceRefraction.cc:12-18,2044). */
+int airice_table_dims(const airice_ctx *ctx, double depth_m, double ice_m, double h_top, double h_step,
+                      double th_start, double th_step, double th_stop, int64_t *n_h, int64_t *n_th);
+/* Builds rows [row_begin,row_end) into caller-owned DEVICE columns (SoA; each column holds (row_end-row_begin)*n_th
+ * entries).  cols64: 17 pointers = dummy[1..17] of GetRayTracingSolutions, cols32: 11 pointers in the reference's
+ * AllTableAllAntData float layout; either array may be NULL, individual f64 columns may be NULL. */
+int airice_table_build_device(airice_ctx *ctx, double depth_m, double ice_m, double h_top, double h_step,
+                              double th_start, double th_step, double th_stop, int64_t row_begin, int64_t row_end,
+                              double *const *cols64, float *const *cols32, void *stream);
+/* Forward-traces arbitrary (theta, h) cells (batched GetRayTracingSolutions): DEVICE inputs, 17 f64 SoA outputs. */
+int airice_forward_device(airice_ctx *ctx, int64_t n, const double *d_theta, const double *d_h, double depth_m,
+                          double ice_m, double *const *cols64, void *stream);
+
+/* Library-owned float table for lookups = one entry of AllTableAllAntData (MultiRayAirIceRefraction.cc:9,2136). */
+int airice_table_create(airice_ctx *ctx, double depth_m, double ice_m, double h_top, double h_step, double th_start,
+                        double th_step, double th_stop, airice_table **out);
+/* Wraps 11 caller-owned DEVICE float columns (e.g. a gathered multi-GPU table or a reference-built table). */
+int airice_table_wrap(airice_ctx *ctx, const float *const *d_cols32, int64_t n_h, int64_t n_th, double loop_stop_h,
+                      double h_step, airice_table **out);
+void airice_table_destroy(airice_table *t);
+/* info[0]=n_h, info[1]=n_th, info[2]=cells, info[3]=11 */
+int airice_table_info(const airice_table *t, int64_t info[4]);
+int airice_table_copy_column(const airice_table *t, int col, float *host_out);
+int airice_table_column_ptr(const airice_table *t, int col, const float **d_ptr);
+/* row trim ranges (FindClosestAirTxHeight's StartBin/EndBin scans, MultiRayAirIceRefraction.cc:1050-1072), per row */
+int airice_table_copy_row_ranges(const airice_table *t, int32_t *host_first, int32_t *host_last);
+
+/* ---- kernel 2: batched launch-angle solve = Air2IceRayTracing (MultiRayAirIceRefraction.cc:1464-1616, .h:191) under
+ * GetHorizontalDistanceToIntersectionPoint (MultiRayAirIceRefraction.cc:945-989, .h:170); variant 1 follows
+ * AirIceRayTracing::GetRayTracingSolution (pythonwrapper/AirIceRayTracing.cc:884-1086).
+ * units = CM_RAD: inputs in cm, 9 output columns in the order of the reference's by-reference arguments
+ *   (opt ice, opt air, geo ice, geo air, launch[rad], X_air, T_S, T_P, received[rad]);
+ * units = M_DEG: inputs in m, 13 columns (X, X_air, X_ice, t_air[s], t_ice[s], launch, received, T_S, T_P, geo air,
+ *   geo ice, incident on ice, refracted below surface).  out: array of column pointers, NULL entries are skipped.
+ * ok: the reference's bool (|X-d| test, MultiRayAirIceRefraction.cc:974-983).  nevals: optional diagnostics. */
+int airice_solve_device(airice_ctx *ctx, int64_t n, const double *d_h, const double *d_dist, double depth,
+                        double ice, int units, double *const *d_out, uint8_t *d_ok, int32_t *d_nevals, void *stream);
+/* Same through HOST buffers: out is a dense SoA block out[col*n + i] with 9 (CM_RAD) or 13 (M_DEG) columns. */
+int airice_solve_host(airice_ctx *ctx, int64_t n, const double *h, const double *dist, double depth, double ice,
+                      int units, double *out, uint8_t *ok);
+
+/* ---- kernel 3: table lookup = GetHorizontalDistanceToIntersectionPoint_Table
+ * (MultiRayAirIceRefraction.cc:1305-1462, .h:189) with FindClosestAirTxHeight / FindClosestTHD / GetParValues
+ * (MultiRayAirIceRefraction.cc:1033-1302).  cm/rad in and out, 9 columns as for CM_RAD solves. */
+int airice_lookup_device(airice_ctx *ctx, const airice_table *t, int64_t n, const double *d_h_cm,
+                         const double *d_dist_cm, double *const *d_out, uint8_t *d_ok, void *stream);
+int airice_lookup_host(airice_ctx *ctx, const airice_table *t, int64_t n, const double *h_cm, const double *dist_cm,
+                       double *out, uint8_t *ok);
+
+/* ---- measurement helpers */
+int airice_fp64_peak_tflops(airice_ctx *ctx, double *tflops); /* dependent-free DFMA probe, roofline denominator */
+int airice_sync(airice_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

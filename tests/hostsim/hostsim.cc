@@ -1,0 +1,74 @@
+// TEST INFRASTRUCTURE ONLY: compiles the product's device math headers (airice_core.cuh, airice_solve.cuh)
+// for the HOST so that `pytest -m "not gpu"` can check the kernel arithmetic against the oracle in a
+// container without a GPU.  It is never loaded by the product; the shipped path is CUDA only.
+#include <cstring>
+#include <string>
+
+#include "airice_host.hpp"
+#include "airice_solve.cuh"
+
+using namespace airice;
+
+static AirIceMedium g_m;
+
+extern "C" {
+int sim_load(const char* path, int variant) {
+  std::string err; double n0; int np;
+  return load_medium(path, variant, &g_m, &n0, &np, &err);
+}
+void sim_medium(double* out) {
+  out[0] = g_m.nlayers;
+  for (int i = 0; i < 5; i++) { out[1 + i] = g_m.hlo[i] * 100; out[6 + i] = g_m.B[i]; out[11 + i] = g_m.C[i]; }
+  out[16] = g_m.A_ice; out[17] = g_m.B_ice; out[18] = g_m.C_ice; out[19] = g_m.pi;
+}
+static int top_layer(double h) {
+  for (int i = 0; i < g_m.nlayers; i++) if (h >= g_m.hlo[i] && h < g_m.hlo[i + 1]) return i;
+  return -1;
+}
+// GetRayTracingSolutions layout: out[18]
+void sim_forward(double theta, double h, double ice, double depth, int inice, double* out) {
+  AirIcePlan p; make_plan(g_m, ice, depth, &p);
+  const int kt = top_layer(h);
+  const double ntx = n_air(g_m, h);
+  const double L = airice_L_of_theta(g_m, ntx, theta);
+  AirIceRay r;
+  airice_ray_full<true>(g_m, p, kt, h, ntx, L, inice != 0, r);
+  for (int i = 0; i < 18; i++) out[i] = 0;
+  out[1] = h; out[2] = r.x_air + r.x_ice; out[3] = r.x_air; out[4] = r.x_ice;
+  out[5] = (r.t_ice + r.t_air) * g_m.c; out[6] = r.t_air * g_m.c; out[7] = r.t_ice * g_m.c;
+  out[8] = (r.t_ice + r.t_air) * 1e9; out[9] = r.t_air * 1e9; out[10] = r.t_ice * 1e9;
+  out[11] = theta; out[12] = r.inc_ice_deg; out[13] = r.recv_deg; out[14] = r.trans_s; out[15] = r.trans_p;
+  out[16] = r.p_air; out[17] = r.p_ice;
+}
+// GetHorizontalDistanceToIntersectionPoint layout (cm/rad): out[9]; stats[0..2] = newton evals, replay evals, theta*
+int sim_solve_cm(double h_cm, double d_cm, double depth_cm, double ice_cm, double* out, double* stats) {
+  const double h = h_cm / 100, d = d_cm / 100, ice = ice_cm / 100, depth = depth_cm / 100;
+  AirIcePlan p; make_plan(g_m, ice, depth, &p);
+  const int kt = top_layer(h);
+  const double ntx = 1.0 + g_m.B[kt < 0 ? 0 : kt] * exp(-g_m.C[kt < 0 ? 0 : kt] * h);
+  double ta;
+  const double thR = airice_straight_angle(g_m, h, d, ice, depth, ta);
+  AirIceSolveStat st; double ths;
+  const double theta = airice_solve_theta(g_m, p, kt, h, ntx, d, thR, ta, ths, st);
+  const double L = airice_L_of_theta(g_m, ntx, theta);
+  AirIceRay r;
+  airice_ray_full<false>(g_m, p, kt, h, ntx, L, p.has_ice != 0, r);
+  out[0] = (r.t_ice * g_m.c) * 100; out[1] = (r.t_air * g_m.c) * 100; out[2] = r.p_ice * 100; out[3] = r.p_air * 100;
+  out[4] = theta * (g_m.pi / 180); out[5] = r.x_air * 100; out[6] = r.trans_s; out[7] = r.trans_p;
+  out[8] = r.recv_deg * (g_m.pi / 180);
+  if (stats) { stats[0] = st.n_newton; stats[1] = st.n_replay; stats[2] = ths; }
+  return airice_check_solution(r.x_ice + r.x_air, d) ? 1 : 0;
+}
+void sim_solve_cm_batch(long n, const double* h_cm, const double* d_cm, double depth_cm, double ice_cm, double* out,
+                        unsigned char* ok, double* stats) {
+  for (long i = 0; i < n; i++) ok[i] = (unsigned char)sim_solve_cm(h_cm[i], d_cm[i], depth_cm, ice_cm, out + 9 * i, stats ? stats + 3 * i : nullptr);
+}
+void sim_forward_batch(long n, const double* th, const double* h, double ice, double depth, int inice, double* out) {
+  for (long i = 0; i < n; i++) sim_forward(th[i], h[i], ice, depth, inice, out + 18 * i);
+}
+// d/dL check: returns X and analytic dX/dL
+double sim_x_total(double h, double ice, double depth, double L, double* dXdL) {
+  AirIcePlan p; make_plan(g_m, ice, depth, &p);
+  return airice_x_total<true>(g_m, p, top_layer(h), h, n_air(g_m, h), L, *dXdL);
+}
+}

@@ -1,0 +1,31 @@
+"""Short single-GPU workload for ncu captures: a few launches of each kernel on resident inputs."""
+import os, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from airiceraytracing_b200 import AirIceSolver, UNITS_CM_RAD
+ATM = os.path.join(ROOT, "tests", "golden", "Atmosphere.dat")
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 2_000_000
+S = AirIceSolver(ATM)
+rng = np.random.default_rng(20260418)
+h = rng.uniform(3001, 100000, n); ang = rng.uniform(90.2, 179.8, n)
+d = (h - 3000 + 200) * np.tan((180 - ang) * 3.1415927 / 180)
+dh, dd = torch.from_numpy(h * 100).cuda(), torch.from_numpy(d * 100).cuda()
+out = torch.empty((9, n), dtype=torch.float64, device="cuda"); ok = torch.empty(n, dtype=torch.uint8, device="cuda")
+if which in ("all", "solve"):
+    for _ in range(3):
+        S.solve(dh, dd, -20000., 300000., UNITS_CM_RAD, out=out, ok=ok)
+if which in ("all", "table"):
+    for _ in range(3):
+        S.table_build(-200., 3000., h_step=20., th_start=92., th_step=0.5)
+    for _ in range(2):
+        S.table_build(-200., 3000.)
+if which in ("all", "lookup"):
+    T = S.table_create(-200., 3000.)
+    o2 = torch.empty((9, n), dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        S.lookup(T, dh, dd, out=o2, ok=ok)
+torch.cuda.synchronize()
+print("done", which, n)
