@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the air->ice hot path (BASELINE.json metric: launch-angle solves/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P]
+
+One "step" = one pass of the batched launch-angle solve over a synthetic batch of `pairs` Tx->Rx pairs per GPU
+(BASELINE config 4: 1e7 random (Tx height, horizontal distance) pairs -> one Rx at -200 m, ice surface 3000 m,
+constructed like RunMultiRayCode_loop.C:85-96).  Prints ONE JSON line on rank 0.
+
+  value     whole-job solves/s with inputs resident in HBM (device C ABI, CUDA events on the launch stream,
+            barrier + synchronize on both sides, max over ranks)
+  e2e       the same metric through the host-buffer C ABI (airice_solve_host): pinned host inputs, H2D and D2H
+            copies inside the timed region
+  roofline  FP64-pipe roofline of the solve kernel: algorithmic flop (SURVEY.md 8d accounting) / kernel time,
+            against the FP64 FMA peak measured live by the library's DFMA probe (MEASURED_PEAKS.json has no FP64 figure)
+  cpu_baseline  the reference's own CPU code (oracle/_ref, unmodified sources + GSL stand-in) on a bounded sample of
+            the same batch, one process per host core
+
+`--impl reference` times that CPU path alone on the same workload definition (bounded sample per step).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+ATMOSPHERE = os.path.join(ROOT, "tests", "golden", "Atmosphere.dat")
+PI_M = 3.1415927            # MultiRayAirIceRefraction.h:29
+ICE_CM, DEPTH_CM = 300000.0, -20000.0
+METRIC = "air->ice launch-angle solves/sec"
+UNIT = "solves/s"
+
+
+def make_pairs(n, seed):
+    """BASELINE config 4 / SURVEY.md 8d: h ~ U(3001,100000) m, straight-line angle ~ U(90.2,179.8) deg,
+    d = (h - ice - depth) tan(180 - angle) with the reference's pi (RunMultiRayCode_loop.C:88-96); cm units."""
+    rng = np.random.default_rng(seed)
+    h = rng.uniform(3001.0, 100000.0, n)
+    ang = rng.uniform(90.2, 179.8, n)
+    d = (h - 3000.0 + 200.0) * np.tan((180.0 - ang) * PI_M / 180.0)
+    return h * 100.0, d * 100.0
+
+
+def workload_config(pairs, n_gpus):
+    return {"workload": "C4 batched Air2IceRayTracing direct solve: %d random (Tx height, horizontal distance) pairs "
+                        "per GPU -> one in-ice Rx (-200 m, ice 3000 m, ARA2 Atmosphere.dat)" % pairs,
+            "pairs_per_gpu": pairs, "global_pairs": pairs * n_gpus, "seed": 20260418,
+            "ordering": "unsorted (random)", "parallelism": "index-sharded x%d, no data-path collective" % n_gpus,
+            "cache": "inputs+outputs per step (89 B/pair = %.0f MB) exceed the 126 MB L2" % (pairs * 89 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_worker(args):
+    kind, h_cm, d_cm = args
+    from oracle.ref import Oracle, Reference
+    impl = Reference(ATMOSPHERE) if kind == "reference" else Oracle(ATMOSPHERE)
+    t0 = time.perf_counter()
+    ok, out = impl.solve_cm_batch(h_cm, d_cm, DEPTH_CM, ICE_CM)
+    return time.perf_counter() - t0, int(ok.sum())
+
+
+def cpu_reference_rate(h_cm, d_cm, per_core, cores=None):
+    """Times the reference CPU path on the first per_core*cores pairs, one forked process per core (the reference is
+    single-threaded with per-process static state).  Returns (solves/s, cores, kind, sample text)."""
+    from oracle.ref import reference_available
+    kind = "reference" if reference_available() else "port"
+    cores = cores or max(1, min(os.cpu_count() or 1, 64))
+    n = min(per_core * cores, h_cm.size)
+    per = n // cores
+    jobs = [(kind, h_cm[i * per:(i + 1) * per].copy(), d_cm[i * per:(i + 1) * per].copy()) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(kind, h_cm[:8].copy(), d_cm[:8].copy())] * cores)  # start-up: parse Atmosphere.dat
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, jobs)
+        wall = time.perf_counter() - t0
+    rate = per * cores / wall
+    sample = "first %d pairs of the same batch, %d per process x %d processes, %s at -O2, stdout muted" % (
+        per * cores, per, cores,
+        "unmodified reference MultiRayAirIceRefraction.cc (GetHorizontalDistanceToIntersectionPoint) + GSL stand-in"
+        if kind == "reference" else "oracle/airice_oracle.c restatement")
+    return rate, cores, kind, sample, wall, max(r[0] for r in res)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    h_cm, d_cm = make_pairs(min(args.pairs, 4_000_000), 20260418)
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    per_core = 2500
+    times = []
+    info = None
+    for it in range(args.warmup + args.steps):
+        info = cpu_reference_rate(h_cm, d_cm, per_core, cores)
+        if it >= args.warmup:
+            times.append(per_core * cores / info[0])
+    t = float(np.mean(times))
+    value = per_core * cores / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.pairs, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info[1], "kind": info[2], "sample": info[3]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "each step = a bounded sample (%d pairs) of the workload, all %d host cores" % (per_core * cores, cores)}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            p = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def algorithmic_flops(solver, h_cm, nev):
+    """SURVEY.md 8d accounting: F_solve = N_eval * F_f(s) + F_full(s), s = air segments traversed,
+    F_f(s) = 142 (s+1) + 90, F_full(s) = 272 (s+1) + 355 (add/mul 1, fma 2, div/sqrt 20, exp 30, log 40, sin 40,
+    asin 50).  N_eval is the measured per-pair count of distance evaluations of OUR solver."""
+    import torch
+    m = solver.medium()
+    edges = torch.tensor([x / 100.0 for x in m["atmlay_cm"][1:m["max_layers"]]], dtype=torch.float64, device=h_cm.device)
+    kt = torch.bucketize(h_cm / 100.0, edges, right=True)
+    kb = int(torch.bucketize(torch.tensor([ICE_CM / 100.0], dtype=torch.float64, device=h_cm.device), edges, right=True))
+    s = (kt - kb + 1).clamp_min(0).double()
+    flops = nev.double() * (142.0 * (s + 1) + 90.0) + (272.0 * (s + 1) + 355.0)
+    return float(flops.sum()), float(nev.double().mean()), float(s.mean())
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from airiceraytracing_b200 import UNITS_CM_RAD, AirIceSolver
+    from airiceraytracing_b200.solver import README_COLUMNS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: airiceraytracing_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    solver = AirIceSolver(ATMOSPHERE, device=local)
+    n = args.pairs
+    h_np, d_np = make_pairs(n, 20260418 + rank)       # weak scaling: every rank its own batch of the same shape
+    h = torch.from_numpy(h_np).to(dev)
+    d = torch.from_numpy(d_np).to(dev)
+    out = torch.empty((9, n), dtype=torch.float64, device=dev)
+    ok = torch.empty(n, dtype=torch.uint8, device=dev)
+
+    def step():
+        solver.solve(h, d, DEPTH_CM, ICE_CM, UNITS_CM_RAD, out=out, ok=ok)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_wall0 = time.perf_counter()
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
+    kernel_ms = float(np.mean([ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]))
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+    solved = float(ok.float().mean())
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory, copies inside the timed region)
+    ph, pd = torch.from_numpy(h_np).pin_memory(), torch.from_numpy(d_np).pin_memory()
+    po = torch.empty((9, n), dtype=torch.float64).pin_memory()
+    pk = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        solver.solve_host(ph, pd, DEPTH_CM, ICE_CM, UNITS_CM_RAD, out=po, ok=pk)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        solver.solve_host(ph, pd, DEPTH_CM, ICE_CM, UNITS_CM_RAD, out=po, ok=pk)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_value = world * n / e2e_s
+    e2e_matches = bool(torch.equal(po[:, :4096], out[:, :4096].cpu()) or
+                       np.array_equal(po[:, :4096].numpy(), out[:, :4096].cpu().numpy(), equal_nan=True))
+
+    # ---- roofline of the solve kernel (rank 0's batch)
+    _, _, nev = solver.solve(h, d, DEPTH_CM, ICE_CM, UNITS_CM_RAD, out=out, ok=ok, nevals=True)
+    torch.cuda.synchronize()
+    flops, mean_evals, mean_segs = algorithmic_flops(solver, h, nev)
+    peak_tf = max(solver.fp64_peak_tflops() for _ in range(2))
+    achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "solve_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj["dram_bytes_per_pair"] * n
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "kernel": "airice_solve_kernel", "achieved": achieved_tf, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "peak_source": "FP64 FMA rate measured live by airice_fp64_peak_tflops (dependent-free DFMA probe); "
+                               "MEASURED_PEAKS.json carries no FP64 figure",
+                "algorithmic_flop_per_solve": flops / n, "mean_distance_evals_per_solve": mean_evals,
+                "mean_air_segments": mean_segs, "kernel_ms": kernel_ms,
+                "hbm": {"algorithmic_bytes_per_solve": 89, "achieved_gbs": 89.0 * n / (kernel_ms * 1e-3) / 1e9}}
+
+    # ---- secondary workloads of the same hot path: table build (MakeRayTracingTable) and table lookup
+    extras = {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    def time_ms(fn, reps=3, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    if not args.skip_extras:
+        del po
+        # reference grid (MultiRayAirIceRefraction.cc:12-18): the whole table per GPU (as MakeRayTracingTable is called per antenna)
+        n_h, n_th = solver.table_dims(-200.0, 3000.0)
+        cells = n_h * n_th
+        o32 = torch.empty((11, cells), dtype=torch.float32, device=dev)
+        ms = time_ms(lambda: solver.table_build(-200.0, 3000.0, columns64=None, want32=True, out32=o32))
+        extras["table_reference_grid"] = {"grid": "%dx%d = %d cells, 11 float columns (reference layout)" % (n_h, n_th, cells),
+                                          "ms": ms, "cells_per_s": cells / ms * 1e3, "store_gbs": cells * 44 / ms / 1e6}
+        del o32
+        # fine grid (BASELINE config 3): 1 m x 0.005 deg from the top of the tabulated data, rows sharded over ranks
+        kw = dict(h_top=23141.03, h_step=1.0, th_start=92.0, th_step=0.005, th_stop=180.0)
+        n_h, n_th = solver.table_dims(-200.0, 3000.0, **kw)
+        r0, r1 = (n_h * rank) // world, (n_h * (rank + 1)) // world
+        cells = (r1 - r0) * n_th
+        o64 = torch.empty((len(README_COLUMNS), cells), dtype=torch.float64, device=dev)
+        barrier()
+        ms = max_over_ranks(time_ms(lambda: solver.table_build(-200.0, 3000.0, rows=(r0, r1), columns64=README_COLUMNS,
+                                                               out64=o64, **kw), reps=2, warm=1))
+        total_cells = n_h * n_th
+        gbs = cells * 8 * len(README_COLUMNS) / ms / 1e6
+        extras["table_fine_grid"] = {"grid": "%dx%d = %d cells (1 m x 0.005 deg), README's 13 columns (12 f64 + implicit "
+                                             "entry index), rows sharded over %d GPU(s)" % (n_h, n_th, total_cells, world),
+                                     "ms": ms, "cells_per_s": total_cells / ms * 1e3, "store_gbs_per_gpu": gbs,
+                                     "hbm_frac_of_measured_copy_peak": gbs / hbm_peak}
+        del o64
+        T = solver.table_create(-200.0, 3000.0)
+        ms = time_ms(lambda: solver.lookup(T, h, d, out=out, ok=ok))
+        extras["lookup"] = {"table": "reference grid 9701x900 float", "lookups": n, "ms": ms, "lookups_per_s": world * n / ms * 1e3,
+                            "algorithmic_gbs": n * (16 + 73 + 176) / ms / 1e6, "solved": float(ok.float().mean())}
+        T.close()
+        if world > 1:
+            # result reassembly: one all-gather of the 9 output columns
+            gathered = torch.empty((world, 9, n), dtype=torch.float64, device=dev)
+            ms = max_over_ranks(time_ms(lambda: dist.all_gather_into_tensor(gathered, out), reps=3, warm=1))
+            extras["gather"] = {"collective": "ncclAllGather of 9 f64 columns x %d pairs per rank" % n, "ms": ms,
+                                "bus_gbs": (world - 1) * 72.0 * n / ms / 1e6}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        rate, cores, kind, sample, wall, _ = cpu_reference_rate(h_np, d_np, 20000)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "wall_s": wall}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 73 * n,
+                        "api": "airice_solve_host (C ABI, pinned host buffers, 1M-pair chunks on 2 streams)",
+                        "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_matches},
+                "gpu_launches": args.steps, "kernels_per_step": ["airice_solve_kernel"],
+                "solved_fraction": solved, "roofline": roofline, "cpu_baseline": cpu}
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=10_000_000)
+    ap.add_argument("--skip-extras", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

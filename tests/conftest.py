@@ -1,0 +1,162 @@
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ATMOSPHERE = os.path.join(GOLDEN, "Atmosphere.dat")
+
+# tolerances of BASELINE.json:north_star
+RTOL_DIST = 1e-9     # distances, times, path lengths (relative)
+ATOL_ANGLE_DEG = 1e-7
+ATOL_COEFF = 1e-9
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+@pytest.fixture(scope="session")
+def oracle_built():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    return True
+
+
+@pytest.fixture(scope="session")
+def oracle(oracle_built):
+    from oracle.ref import Oracle
+    return Oracle(ATMOSPHERE, 0)
+
+
+@pytest.fixture(scope="session")
+def oracle_pywrap(oracle_built):
+    from oracle.ref import Oracle
+    return Oracle(ATMOSPHERE, 1)
+
+
+@pytest.fixture(scope="session")
+def reference(oracle_built):
+    """The unmodified reference build; skipped where oracle/_ref was not shipped/built."""
+    from oracle.ref import Reference, reference_available
+    if not reference_available():
+        pytest.skip("oracle/_ref/libmultiray_ref.so not present")
+    return Reference(ATMOSPHERE)
+
+
+class HostSim:
+    """Host build of the device math headers (tests/hostsim): test infrastructure for GPU-less checks."""
+
+    def __init__(self):
+        subprocess.check_call(["bash", os.path.join(ROOT, "tests", "hostsim", "build.sh")])
+        self.lib = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "_build", "libhostsim.so"))
+        dp = C.POINTER(C.c_double)
+        self.dp = dp
+        L = self.lib
+        L.sim_forward_batch.argtypes = [C.c_long, dp, dp, C.c_double, C.c_double, C.c_int, dp]
+        L.sim_solve_cm_batch.argtypes = [C.c_long, dp, dp, C.c_double, C.c_double, dp, C.POINTER(C.c_ubyte), dp]
+        L.sim_x_total.restype = C.c_double
+        L.sim_x_total.argtypes = [C.c_double] * 4 + [dp]
+        assert L.sim_load(ATMOSPHERE.encode(), 0) == 0
+
+    def medium(self):
+        out = np.zeros(20)
+        self.lib.sim_medium(out.ctypes.data_as(self.dp))
+        return dict(max_layers=int(out[0]), atmlay_cm=list(out[1:6]), B_air=list(out[6:11]), C_air=list(out[11:16]),
+                    pi=out[19])
+
+    def forward(self, theta, h, ice, depth, inice=True):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        out = np.zeros((theta.size, 18))
+        self.lib.sim_forward_batch(theta.size, theta.ctypes.data_as(self.dp), h.ctypes.data_as(self.dp), ice, depth,
+                                   int(inice), out.ctypes.data_as(self.dp))
+        return out
+
+    def solve_cm(self, h_cm, d_cm, depth_cm, ice_cm):
+        h_cm = np.ascontiguousarray(h_cm, dtype=np.float64)
+        d_cm = np.ascontiguousarray(d_cm, dtype=np.float64)
+        n = h_cm.size
+        out = np.zeros((n, 9))
+        ok = np.zeros(n, dtype=np.uint8)
+        st = np.zeros((n, 3))
+        self.lib.sim_solve_cm_batch(n, h_cm.ctypes.data_as(self.dp), d_cm.ctypes.data_as(self.dp), depth_cm, ice_cm,
+                                    out.ctypes.data_as(self.dp), ok.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                    st.ctypes.data_as(self.dp))
+        return ok.astype(bool), out, st
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    return HostSim()
+
+
+@pytest.fixture(scope="session")
+def solver():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from airiceraytracing_b200 import AirIceSolver
+    return AirIceSolver(ATMOSPHERE, device=0)
+
+
+@pytest.fixture(scope="session")
+def solver_pywrap():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from airiceraytracing_b200 import AirIceSolver, VARIANT_PYWRAP
+    return AirIceSolver(ATMOSPHERE, variant=VARIANT_PYWRAP, device=0)
+
+
+# ---------------------------------------------------------------- comparison helpers shared by CPU and GPU tests
+def assert_forward_close(got18, ref18, what=""):
+    """got/ref in the GetRayTracingSolutions dummy[0..17] layout (MultiRayAirIceRefraction.cc:1999-2016)."""
+    nan_ref = np.isnan(ref18[:, 2])
+    assert np.array_equal(np.isnan(got18[:, 2]), nan_ref), what + ": NaN cells differ"
+    m = ~nan_ref
+    for k in (2, 3, 4, 5, 6, 7, 8, 9, 10, 16, 17):  # distances, optical paths, times, geometric paths
+        den = np.maximum(np.abs(ref18[m, k]), 1e-300)
+        rel = np.abs(got18[m, k] - ref18[m, k]) / den
+        rel = np.where(ref18[m, k] == 0, np.abs(got18[m, k]), rel)
+        assert rel.max() <= RTOL_DIST, "%s: column %d rel err %.3e" % (what, k, rel.max())
+    for k in (11, 12, 13):
+        assert np.abs(got18[m, k] - ref18[m, k]).max() <= ATOL_ANGLE_DEG, "%s: angle column %d" % (what, k)
+    for k in (14, 15):
+        assert np.abs(got18[:, k] - ref18[:, k]).max() <= ATOL_COEFF, "%s: coefficient column %d" % (what, k)
+    assert np.array_equal(got18[:, 1], ref18[:, 1]), what + ": Tx heights differ"
+
+
+def assert_solve_close(ok, out9, ok_ref, ref9, pi, what="", max_tie_frac=0.0):
+    """cm/rad layout of GetHorizontalDistanceToIntersectionPoint (MultiRayAirIceRefraction.h:170).
+
+    Flags must be identical.  Numeric outputs are compared where the reference found a solution.  `max_tie_frac`
+    allows that fraction of solves to sit one final bisection cell (<=2e-7 deg) away from the reference: those are
+    the rounding ties of the reference's own loose bisection ('bisection replay')."""
+    assert np.array_equal(ok, ok_ref), "%s: %d solution flags differ" % (what, int((ok != ok_ref).sum()))
+    m = ok_ref
+    if not m.any():
+        return
+    dang = np.abs(out9[m, 4] - ref9[m, 4]) * 180 / pi
+    tie = dang > ATOL_ANGLE_DEG
+    assert tie.mean() <= max_tie_frac, "%s: %d launch angles off by more than 1e-7 deg (max %.3e)" % (
+        what, int(tie.sum()), dang.max())
+    assert dang.max() <= 2.5e-7, "%s: launch angle off by more than one bisection cell: %.3e deg" % (what, dang.max())
+    g = ~tie
+    for k in (0, 1, 2, 3, 5):
+        r, o = ref9[m, k][g], out9[m, k][g]
+        rel = np.where(r == 0, np.abs(o), np.abs(o - r) / np.maximum(np.abs(r), 1e-300))
+        assert rel.max() <= RTOL_DIST, "%s: column %d rel err %.3e" % (what, k, rel.max())
+    for k in (6, 7):
+        assert np.abs(out9[m, k][g] - ref9[m, k][g]).max() <= ATOL_COEFF, "%s: coefficient %d" % (what, k)
+    assert (np.abs(out9[m, 8][g] - ref9[m, 8][g]) * 180 / pi).max() <= ATOL_ANGLE_DEG, what + ": received angle"

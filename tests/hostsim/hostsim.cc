@@ -27,7 +27,8 @@ static int top_layer(double h) {
 }
 // GetRayTracingSolutions layout: out[18]
 void sim_forward(double theta, double h, double ice, double depth, int inice, double* out) {
-  AirIcePlan p; make_plan(g_m, ice, depth, &p);
+  // GetRayTracingSolutions takes the surface height as given; depth only matters for the ice leg
+  AirIcePlan p; make_plan(g_m, ice, inice ? depth : 0.0, &p);
   const int kt = top_layer(h);
   const double ntx = n_air(g_m, h);
   const double L = airice_L_of_theta(g_m, ntx, theta);
