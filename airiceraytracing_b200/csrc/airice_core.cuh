@@ -37,6 +37,15 @@
 
 #define AIRICE_MAX_LAYERS 5
 
+// Product rounded on its own (never contracted into an FMA with a following add).  Used where the reference forms
+// F(stop)-F(start) from two separately rounded products: for a zero-thickness segment (Tx exactly on the ice surface,
+// the last table row) the reference gets an exact 0, and a*b-c*d fused as fma(a,b,-(c*d)) would leave rounding dust.
+#if defined(__CUDA_ARCH__)
+#define AIRICE_MUL(a, b) __dmul_rn((a), (b))
+#else
+#define AIRICE_MUL(a, b) ((a) * (b))
+#endif
+
 // Per-context medium model (one Atmosphere.dat + ice model + which copy of the reference, i.e. which pi).
 struct AirIceMedium {
   int nlayers;                        // MaxLayers (M.cc:142)
@@ -110,7 +119,7 @@ AIRICE_HD double airice_x_total(const AirIceMedium& m, const AirIcePlan& p, int 
     const double Gb = Cn * xb - log(Tb), Gt = Cn * xt - log(Tt);
     const double inv_sA = 1.0 / sA;
     const double mult = (L / Cn) * inv_sA;
-    const double seg = mult * Gb - mult * Gt;   // F(stop) - F(start), as GetRayHorizontalPath forms it (M.cc:463)
+    const double seg = AIRICE_MUL(mult, Gb) - AIRICE_MUL(mult, Gt);   // F(stop) - F(start) as GetRayHorizontalPath forms it (M.cc:463)
     X += air ? -seg : seg;
     if (DERIV) {
       const double qb = (sA + Rb) * (sA + Rb) / (Tb * Rb), qt = (sA + Rt) * (sA + Rt) / (Tt * Rt);
@@ -152,9 +161,9 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
     const double Gb = Cn * xb - log(A * nb - L2 + sA * Rb), Gt = Cn * xt - log(A * nt - L2 + sA * Rt);
     const double Hb = log(nb + Rb), Ht = log(nt + Rt);
     const double mult = (Lk / Cn) * inv_sA;
-    const double xs = mult * Gb - mult * Gt;
-    const double tb = (1.0 / ((m.c * Cn) * Rb)) * ((Db + (Gb * (A * A * Rb)) / sA) + (A * Rb) * Hb);
-    const double tt = (1.0 / ((m.c * Cn) * Rt)) * ((Dt + (Gt * (A * A * Rt)) / sA) + (A * Rt) * Ht);
+    const double xs = AIRICE_MUL(mult, Gb) - AIRICE_MUL(mult, Gt);
+    const double tb = AIRICE_MUL(1.0 / ((m.c * Cn) * Rb), (Db + (Gb * (A * A * Rb)) / sA) + (A * Rb) * Hb);
+    const double tt = AIRICE_MUL(1.0 / ((m.c * Cn) * Rt), (Dt + (Gt * (A * A * Rt)) / sA) + (A * Rt) * Ht);
     const double ts = tb - tt;
     const double gs = (Hb + (A * inv_sA) * Gb) / Cn - (Ht + (A * inv_sA) * Gt) / Cn;
     if (air) {

@@ -315,6 +315,7 @@ int airice_solve_device(airice_ctx* c, int64_t n, const double* d_h, const doubl
                         int units, double* const* d_out, uint8_t* d_ok, int32_t* d_nevals, void* stream) {
   if (!c || !d_out) return fail(-1, "null argument");
   if (units != AIRICE_UNITS_M_DEG && units != AIRICE_UNITS_CM_RAD) return fail(-1, "unknown units");
+  if (n == 0) return 0;
   CK(cudaSetDevice(c->device));
   const double sc = (units == AIRICE_UNITS_CM_RAD) ? 100.0 : 1.0;
   const AirIcePlan& p = c->plan(ice / sc, depth / sc);  // same "/100" the reference applies (M.cc:949-950)
@@ -334,8 +335,10 @@ int airice_solve_device(airice_ctx* c, int64_t n, const double* d_h, const doubl
 // the H2D of chunk k+1, the kernel of chunk k and the D2H of chunk k-1 run concurrently.
 int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* dist, double depth, double ice,
                       int units, double* out, uint8_t* ok) {
-  if (!c || !h || !dist || !out || !ok) return fail(-1, "null argument");
+  if (!c) return fail(-1, "null context");
   if (units != AIRICE_UNITS_M_DEG && units != AIRICE_UNITS_CM_RAD) return fail(-1, "unknown units");
+  if (n == 0) return 0;
+  if (!h || !dist || !out || !ok) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));
   const int nc = units == AIRICE_UNITS_CM_RAD ? AIRICE_SOLVE_COLS_CM_RAD : AIRICE_SOLVE_COLS;
   const int64_t chunk = n < (1 << 20) ? (n > 0 ? n : 1) : (1 << 20);
@@ -368,7 +371,9 @@ int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* d
 
 int airice_lookup_device(airice_ctx* c, const airice_table* t, int64_t n, const double* d_h_cm, const double* d_dist_cm,
                          double* const* d_out, uint8_t* d_ok, void* stream) {
-  if (!c || !t || !d_out || !d_ok) return fail(-1, "null argument");
+  if (!c || !t) return fail(-1, "null argument");
+  if (n == 0) return 0;
+  if (!d_out || !d_ok) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));
   LookupArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -381,7 +386,9 @@ int airice_lookup_device(airice_ctx* c, const airice_table* t, int64_t n, const 
 
 int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const double* h_cm, const double* dist_cm,
                        double* out, uint8_t* ok) {
-  if (!c || !t || !h_cm || !dist_cm || !out || !ok) return fail(-1, "null argument");
+  if (!c || !t) return fail(-1, "null argument");
+  if (n == 0) return 0;
+  if (!h_cm || !dist_cm || !out || !ok) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));
   const int nc = AIRICE_LOOKUP_NCOLS;
   const int64_t chunk = n < (1 << 20) ? (n > 0 ? n : 1) : (1 << 20);
