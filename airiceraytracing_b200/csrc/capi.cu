@@ -43,6 +43,14 @@ struct airice_ctx {
   cudaStream_t streams[kSlots] = {nullptr, nullptr};
   void* dev[kSlots] = {nullptr, nullptr};
   size_t slot_bytes = 0;
+  // per-row transmitter data (height, n(h), top layer) of the last table grid built: uploaded once, reused by
+  // every rebuild of the same rows (MakeRayTracingTable is called once per antenna depth on the same grid)
+  struct RowCache {
+    double key[7] = {0, 0, 0, 0, 0, 0, 0};
+    int64_t r0 = -1, r1 = -1;
+    double* d_rows = nullptr;
+    int* d_kt = nullptr;
+  } rows;
 
   const AirIcePlan& plan(double ice_m, double depth_m) {
     auto key = std::make_pair(ice_m, depth_m);
@@ -97,18 +105,27 @@ int build_rows(airice_ctx* ctx, const TableGrid& g, int64_t r0, int64_t r1, doub
   const int64_t rows_avail = g.first_skipped_row < g.n_h ? g.first_skipped_row : g.n_h;
   if (r0 < 0 || r1 > rows_avail || r0 > r1) return fail(-3, "table rows out of range");
   if (r1 == r0) return 0;
-  std::vector<double> h, ntx;
-  std::vector<int> kt;
-  grid_rows(ctx->medium, g, r0, r1, &h, &ntx, &kt);
   const int64_t nr = r1 - r0;
-  double* d_rows = nullptr;
-  int* d_kt = nullptr;
-  CK(cudaMallocAsync((void**)&d_rows, sizeof(double) * 2 * nr, s));
-  CK(cudaMallocAsync((void**)&d_kt, sizeof(int) * nr, s));
-  // pageable sources: the runtime copies them to its own staging buffer before returning
-  CK(cudaMemcpyAsync(d_rows, h.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(d_rows + nr, ntx.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(d_kt, kt.data(), sizeof(int) * nr, cudaMemcpyHostToDevice, s));
+  const double key[7] = {g.h_top, g.h_step, g.loop_stop_h, (double)g.n_h, ctx->medium.B[0], ctx->medium.C[0], (double)ctx->medium.nlayers};
+  airice_ctx::RowCache& rc = ctx->rows;
+  if (!(rc.d_rows && rc.r0 == r0 && rc.r1 == r1 && std::memcmp(rc.key, key, sizeof(key)) == 0)) {
+    std::vector<double> h, ntx;
+    std::vector<int> kt;
+    grid_rows(ctx->medium, g, r0, r1, &h, &ntx, &kt);
+    CK(cudaStreamSynchronize(s));  // a previous launch on this stream may still read the old arrays
+    if (rc.d_rows) cudaFree(rc.d_rows);
+    if (rc.d_kt) cudaFree(rc.d_kt);
+    rc.d_rows = nullptr; rc.d_kt = nullptr; rc.r0 = rc.r1 = -1;
+    CK(cudaMalloc((void**)&rc.d_rows, sizeof(double) * 2 * nr));
+    CK(cudaMalloc((void**)&rc.d_kt, sizeof(int) * nr));
+    CK(cudaMemcpy(rc.d_rows, h.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(rc.d_rows + nr, ntx.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(rc.d_kt, kt.data(), sizeof(int) * nr, cudaMemcpyHostToDevice));
+    std::memcpy(rc.key, key, sizeof(key));
+    rc.r0 = r0; rc.r1 = r1;
+  }
+  double* d_rows = rc.d_rows;
+  int* d_kt = rc.d_kt;
   TableArgs a;
   std::memset(&a, 0, sizeof(a));
   a.cell0 = r0 * g.n_th; a.ncells = nr * g.n_th; a.n_th = g.n_th; a.row0 = r0;
@@ -121,8 +138,6 @@ int build_rows(airice_ctx* ctx, const TableGrid& g, int64_t r0, int64_t r1, doub
   // the table path hands the surface height of the grid (ice, or ice+depth for a receiver in air) to the walk
   const AirIcePlan& p = ctx->plan(g.ice_h, g.depth_signed);
   cudaError_t e = launch_table(ctx->medium, p, a, s);
-  cudaFreeAsync(d_rows, s);
-  cudaFreeAsync(d_kt, s);
   if (e != cudaSuccess) return cuda_fail(e, "launch_table");
   return 0;
 }
@@ -166,6 +181,8 @@ void airice_destroy(airice_ctx* c) {
     if (c->dev[s]) cudaFree(c->dev[s]);
     if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
   }
+  if (c->rows.d_rows) cudaFree(c->rows.d_rows);
+  if (c->rows.d_kt) cudaFree(c->rows.d_kt);
   delete c;
 }
 
@@ -311,8 +328,42 @@ int airice_forward_device(airice_ctx* c, int64_t n, const double* d_theta, const
   return 0;
 }
 
-int airice_solve_device(airice_ctx* c, int64_t n, const double* d_h, const double* d_dist, double depth, double ice,
-                        int units, double* const* d_out, uint8_t* d_ok, int32_t* d_nevals, void* stream) {
+int airice_forward_host(airice_ctx* c, int64_t n, const double* theta, const double* h, double depth_m, double ice_m,
+                        double* out) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!theta || !h || !out) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int nc = AIRICE_TABLE_NCOLS64;
+  const int64_t chunk = n < (1 << 20) ? n : (1 << 20);
+  int rc = ensure_slots(c, (size_t)chunk * sizeof(double) * (2 + nc) + 64);
+  if (rc) return rc;
+  const int in_ice = depth_m < 0 ? 1 : 0;
+  const AirIcePlan& p = c->plan(ice_m, in_ice ? depth_m : 0.0);
+  int slot = 0;
+  for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    double* dh = (double*)c->dev[slot];
+    cudaStream_t s = c->streams[slot];
+    CK(cudaMemcpyAsync(dh, theta + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, h + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    ForwardArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = m; a.theta = dh; a.h = dh + chunk; a.in_ice = in_ice;
+    for (int k = 0; k < nc; k++) a.c64[k] = dh + (2 + k) * chunk;
+    cudaError_t e = launch_forward(c->medium, p, a, s);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_forward");
+    for (int k = 0; k < nc; k++)
+      CK(cudaMemcpyAsync(out + (int64_t)k * n + off, a.c64[k], sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+  }
+  for (int s = 0; s < airice_ctx::kSlots; s++)
+    if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
+  return 0;
+}
+
+int airice_solve_device(airice_ctx* c, int64_t n, const double* d_h, const double* d_dist, const double* d_straight,
+                        double depth, double ice, int units, double* const* d_out, uint8_t* d_ok, int32_t* d_nevals,
+                        void* stream) {
   if (!c || !d_out) return fail(-1, "null argument");
   if (units != AIRICE_UNITS_M_DEG && units != AIRICE_UNITS_CM_RAD) return fail(-1, "unknown units");
   if (n == 0) return 0;
@@ -321,7 +372,7 @@ int airice_solve_device(airice_ctx* c, int64_t n, const double* d_h, const doubl
   const AirIcePlan& p = c->plan(ice / sc, depth / sc);  // same "/100" the reference applies (M.cc:949-950)
   SolveArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.n = n; a.h = d_h; a.d = d_dist; a.ice = ice; a.depth = depth; a.units = units;
+  a.n = n; a.h = d_h; a.d = d_dist; a.straight = d_straight; a.ice = ice; a.depth = depth; a.units = units;
   const int nc = units == AIRICE_UNITS_CM_RAD ? AIRICE_SOLVE_COLS_CM_RAD : AIRICE_SOLVE_COLS;
   for (int k = 0; k < nc; k++) a.out[k] = d_out[k];
   a.ok = d_ok; a.nevals = d_nevals;
@@ -333,8 +384,8 @@ int airice_solve_device(airice_ctx* c, int64_t n, const double* d_h, const doubl
 // Host-buffer path: the batch is cut into chunks that alternate between two streams, each with its own device
 // staging slot.  Copies go directly from/to the caller's buffers (no extra host memcpy); with pinned caller memory
 // the H2D of chunk k+1, the kernel of chunk k and the D2H of chunk k-1 run concurrently.
-int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* dist, double depth, double ice,
-                      int units, double* out, uint8_t* ok) {
+int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* dist, const double* straight,
+                      double depth, double ice, int units, double* out, uint8_t* ok) {
   if (!c) return fail(-1, "null context");
   if (units != AIRICE_UNITS_M_DEG && units != AIRICE_UNITS_CM_RAD) return fail(-1, "unknown units");
   if (n == 0) return 0;
@@ -342,7 +393,7 @@ int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* d
   CK(cudaSetDevice(c->device));
   const int nc = units == AIRICE_UNITS_CM_RAD ? AIRICE_SOLVE_COLS_CM_RAD : AIRICE_SOLVE_COLS;
   const int64_t chunk = n < (1 << 20) ? (n > 0 ? n : 1) : (1 << 20);
-  int rc = ensure_slots(c, (size_t)chunk * (sizeof(double) * (2 + nc) + 1) + 64);
+  int rc = ensure_slots(c, (size_t)chunk * (sizeof(double) * (3 + nc) + 1) + 64);
   if (rc) return rc;
   const double sc = (units == AIRICE_UNITS_CM_RAD) ? 100.0 : 1.0;
   const AirIcePlan& p = c->plan(ice / sc, depth / sc);
@@ -357,7 +408,12 @@ int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* d
     std::memset(&a, 0, sizeof(a));
     a.n = m; a.h = dh; a.d = dh + chunk; a.ice = ice; a.depth = depth; a.units = units;
     for (int k = 0; k < nc; k++) a.out[k] = dh + (2 + k) * chunk;
-    a.ok = (uint8_t*)(dh + (2 + nc) * chunk);
+    a.ok = (uint8_t*)(dh + (3 + nc) * chunk);
+    if (straight) {
+      double* ds = dh + (2 + nc) * chunk;
+      CK(cudaMemcpyAsync(ds, straight + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+      a.straight = ds;
+    }
     cudaError_t e = launch_solve(c->medium, p, a, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_solve");
     for (int k = 0; k < nc; k++)

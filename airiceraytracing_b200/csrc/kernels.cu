@@ -104,7 +104,12 @@ __global__ void __launch_bounds__(kThreads) airice_solve_kernel(const AirIceMedi
   const int kc = kt < 0 ? 0 : kt;
   const double ntx = 1.0 + m.B[kc] * exp(-m.C[kc] * h);
   double ta;
-  const double thR = airice_straight_angle(m, h, d, ice, depth, ta);
+  double thR = airice_straight_angle(m, h, d, ice, depth, ta);
+  if (a.straight) {
+    thR = a.straight[i];
+    if (a.units == AIRICE_UNITS_CM_RAD) thR = thR * m.rad2deg;
+    ta = tan((180 - thR) * m.deg2rad);
+  }
   AirIceSolveStat st;
   double th_star;
   const double theta = airice_solve_theta(m, p, kt, h, ntx, d, thR, ta, th_star, st);

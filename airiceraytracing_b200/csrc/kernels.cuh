@@ -51,6 +51,8 @@ struct SolveArgs {
   int64_t n;
   const double* h;  // Tx heights a.s.l.
   const double* d;  // horizontal distances
+  const double* straight;  // optional: caller-supplied straight-line angle per pair [deg] (the StraightAngle argument of
+                           // Air2IceRayTracing, M.h:191); nullptr = computed as at M.cc:952-958
   double ice;       // ice-surface height (same units as h)
   double depth;     // signed receiver depth (negative = in ice), same units
   int units;        // AIRICE_UNITS_M_DEG: metres in, 13 columns out (m, s, deg);

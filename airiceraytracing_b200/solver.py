@@ -163,10 +163,12 @@ class AirIceSolver:
         return Table(self, h, keepalive=cols32)
 
     # ------------------------------------------------------------------ kernel 2
-    def solve(self, h, d, depth, ice, units=_capi.UNITS_CM_RAD, out=None, ok=None, nevals=False):
+    def solve(self, h, d, depth, ice, units=_capi.UNITS_CM_RAD, out=None, ok=None, nevals=False, straight=None):
         """Batched launch-angle solve on device tensors.  Returns (out [ncols, n] f64, ok [n] uint8[, nevals])."""
         h = h.to(self.torch_device, torch.float64).contiguous()
         d = d.to(self.torch_device, torch.float64).contiguous()
+        if straight is not None:
+            straight = straight.to(self.torch_device, torch.float64).contiguous()
         n = h.numel()
         nc = _capi.SOLVE_COLS_CM_RAD if units == _capi.UNITS_CM_RAD else _capi.SOLVE_COLS
         if out is None:
@@ -174,7 +176,8 @@ class AirIceSolver:
         if ok is None:
             ok = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
         nev = torch.empty(n, dtype=torch.int32, device=self.torch_device) if nevals else None
-        check(self.lib.airice_solve_device(self.handle, n, h.data_ptr(), d.data_ptr(), depth, ice, units,
+        check(self.lib.airice_solve_device(self.handle, n, h.data_ptr(), d.data_ptr(),
+                                           straight.data_ptr() if straight is not None else None, depth, ice, units,
                                            ptr_array([out[k].data_ptr() for k in range(nc)]), ok.data_ptr(),
                                            nev.data_ptr() if nevals else None, _stream_ptr(self.torch_device)))
         return (out, ok, nev) if nevals else (out, ok)
@@ -187,8 +190,8 @@ class AirIceSolver:
             out = np.empty((nc, n), dtype=np.float64)
         if ok is None:
             ok = np.empty(n, dtype=np.uint8)
-        check(self.lib.airice_solve_host(self.handle, n, _host_ptr(h), _host_ptr(d), depth, ice, units, _host_ptr(out),
-                                         _host_ptr(ok)))
+        check(self.lib.airice_solve_host(self.handle, n, _host_ptr(h), _host_ptr(d), None, depth, ice, units,
+                                         _host_ptr(out), _host_ptr(ok)))
         return out, ok
 
     # ------------------------------------------------------------------ kernel 3

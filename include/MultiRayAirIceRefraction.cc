@@ -1,0 +1,313 @@
+// MultiRayAirIceRefraction.cc -- host-side mirror of the reference's hot-path API on top of the C ABI
+// (include/airice_b200.h).  Included by callers exactly like the reference file (RunMultiRayCode.C:1), or linked
+// from libMultiRayAirIceRefraction.so.  No arithmetic of the ray solve happens here: this file converts arguments,
+// owns the table handles (the reference's AllTableAllAntData, MultiRayAirIceRefraction.cc:9) and maps output slots.
+#include "MultiRayAirIceRefraction.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sys/stat.h>
+
+#include "airice_b200.h"
+
+double MaxAirTxHeight = 0, MinAirTxHeight = 0;
+double AngleStepSize = 0.1, LoopStartAngle = 90.1, LoopStopAngle = 180.0;
+int TotalAngleSteps = floor((LoopStopAngle - LoopStartAngle) / AngleStepSize) + 1;
+double HeightStepSize = 10, LoopStartHeight = 0, LoopStopHeight = 0;
+int TotalHeightSteps = 0;
+
+namespace MultiRayAirIceRefraction {
+
+double A_ice = 1.78, B_ice = -0.43, C_ice = 0.0132;
+double GridStartTh = 90.05, GridStopTh = 179.95, GridStepSizeH_O = 25, GridStepSizeTh_O = 0.01, GridWidthH = 1000;
+double GridWidthTh = GridStopTh - GridStartTh, GridStartH = 1000, GridStopH = 100000;
+int GridPoints = 100, TotalStepsH_O = 100, TotalStepsTh_O = 100;
+std::vector<double> GridPositionH, GridPositionTh;
+std::vector<double> GridZValue[10];
+
+namespace detail {
+struct State {
+  airice_ctx *ctx = nullptr;
+  int device = 0;
+  std::string atmosphere = "Atmosphere.dat";  // CWD-relative like the reference (MultiRayAirIceRefraction.cc:27,80)
+  std::vector<airice_table *> tables;          // index = order of MakeRayTracingTable calls
+  double ice_set[3] = {1.78, -0.43, 0.0132};
+  long mtime = -1, size = -1;
+};
+inline State &state() {
+  static State s;
+  return s;
+}
+inline bool ensure_ctx() {
+  State &s = state();
+  if (!s.ctx) {
+    if (airice_create(s.atmosphere.c_str(), AIRICE_VARIANT_MULTIRAY, s.device, &s.ctx) != 0) {
+      std::cerr << "MultiRayAirIceRefraction (B200): " << airice_last_error() << std::endl;
+      s.ctx = nullptr;
+      return false;
+    }
+  }
+  if (s.ice_set[0] != A_ice || s.ice_set[1] != B_ice || s.ice_set[2] != C_ice) {
+    airice_set_ice_model(s.ctx, A_ice, B_ice, C_ice);
+    s.ice_set[0] = A_ice; s.ice_set[1] = B_ice; s.ice_set[2] = C_ice;
+  }
+  return true;
+}
+inline void report(const char *what) { std::cerr << "MultiRayAirIceRefraction (B200): " << what << ": " << airice_last_error() << std::endl; }
+}  // namespace detail
+
+void SetDevice(int device) { detail::state().device = device; }
+void SetAtmosphereFile(const std::string &path) { detail::state().atmosphere = path; }
+
+// MultiRayAirIceRefraction.cc:920-942.  The reference re-parses the file (and rebuilds a 23k-point spline) on every
+// call, i.e. once per table; here the parsed medium is kept and only refreshed when the file changed on disk.
+int MakeAtmosphere() {
+  detail::State &s = detail::state();
+  struct stat st;
+  const bool have = ::stat(s.atmosphere.c_str(), &st) == 0;
+  const bool changed = have && ((long)st.st_mtime != s.mtime || (long)st.st_size != s.size);
+  if (s.ctx && changed && s.tables.empty()) {
+    airice_destroy(s.ctx);
+    s.ctx = nullptr;
+    s.ice_set[0] = 1.78; s.ice_set[1] = -0.43; s.ice_set[2] = 0.0132;
+  }
+  if (!detail::ensure_ctx()) return 1;
+  if (have) { s.mtime = (long)st.st_mtime; s.size = (long)st.st_size; }
+  std::cout << "Atmosphere has been generated " << std::endl;
+  return 0;
+}
+
+// MultiRayAirIceRefraction.cc:2019-2158 (cm in).  The table lives on the GPU; index = order of calls.
+int MakeRayTracingTable(double AntennaDepth, double IceLayerHeight, int AntennaNumber) {
+  (void)AntennaNumber;
+  if (MakeAtmosphere() != 0) return 1;
+  detail::State &s = detail::state();
+  AntennaDepth = AntennaDepth / 100;
+  IceLayerHeight = IceLayerHeight / 100;
+  const double AirTxHeight = 100000;
+  TotalAngleSteps = floor((LoopStopAngle - LoopStartAngle) / AngleStepSize) + 1;
+  LoopStartHeight = AirTxHeight;
+  LoopStopHeight = (AntennaDepth < 0) ? IceLayerHeight : IceLayerHeight + AntennaDepth;
+  TotalHeightSteps = floor((LoopStartHeight - LoopStopHeight) / HeightStepSize) + 1;
+  airice_table *t = nullptr;
+  if (airice_table_create(s.ctx, AntennaDepth, IceLayerHeight, AirTxHeight, HeightStepSize, LoopStartAngle, AngleStepSize,
+                          LoopStopAngle, &t) != 0) {
+    detail::report("MakeRayTracingTable");
+    return 1;
+  }
+  s.tables.push_back(t);
+  return 0;
+}
+
+int GetTableColumn(int AntennaNumber, int col, std::vector<float> &out) {
+  detail::State &s = detail::state();
+  if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size()) return 1;
+  int64_t info[4];
+  airice_table_info(s.tables[AntennaNumber], info);
+  out.resize(info[2]);
+  return airice_table_copy_column(s.tables[AntennaNumber], col, out.data());
+}
+
+int GetHorizontalDistanceToIntersectionPointBatch(long n, const double *SrcHeightASL, const double *HorizontalDistanceToRx,
+                                                  double RxDepthBelowIceBoundary, double IceLayerHeight, double *out,
+                                                  unsigned char *ok) {
+  if (!detail::ensure_ctx()) return 1;
+  int rc = airice_solve_host(detail::state().ctx, n, SrcHeightASL, HorizontalDistanceToRx, nullptr, RxDepthBelowIceBoundary,
+                             IceLayerHeight, AIRICE_UNITS_CM_RAD_C, out, ok);
+  if (rc != 0) detail::report("GetHorizontalDistanceToIntersectionPointBatch");
+  return rc;
+}
+
+// MultiRayAirIceRefraction.cc:945-989
+bool GetHorizontalDistanceToIntersectionPoint(double SrcHeightASL, double HorizontalDistanceToRx,
+                                              double RxDepthBelowIceBoundary, double IceLayerHeight,
+                                              double &opticalPathLengthInIce, double &opticalPathLengthInAir,
+                                              double &geometricalPathLengthInIce, double &geometricalPathLengthInAir,
+                                              double &launchAngle, double &horizontalDistanceToIntersectionPoint,
+                                              double &transmissionCoefficientS, double &transmissionCoefficientP,
+                                              double &RecievedAngleInIce) {
+  double o[9];
+  unsigned char ok = 0;
+  if (GetHorizontalDistanceToIntersectionPointBatch(1, &SrcHeightASL, &HorizontalDistanceToRx, RxDepthBelowIceBoundary,
+                                                    IceLayerHeight, o, &ok) != 0)
+    return false;
+  opticalPathLengthInIce = o[0]; opticalPathLengthInAir = o[1];
+  geometricalPathLengthInIce = o[2]; geometricalPathLengthInAir = o[3];
+  launchAngle = o[4]; horizontalDistanceToIntersectionPoint = o[5];
+  transmissionCoefficientS = o[6]; transmissionCoefficientP = o[7]; RecievedAngleInIce = o[8];
+  return ok != 0;
+}
+
+int GetHorizontalDistanceToIntersectionPoint_TableBatch(long n, const double *SrcHeightASL,
+                                                        const double *HorizontalDistanceToRx,
+                                                        double RxDepthBelowIceBoundary, double IceLayerHeight,
+                                                        int AntennaNumber, double *out, unsigned char *ok) {
+  (void)RxDepthBelowIceBoundary; (void)IceLayerHeight;
+  detail::State &s = detail::state();
+  if (!detail::ensure_ctx()) return 1;
+  // antenna -> table remap by depth equality (MultiRayAirIceRefraction.cc:1348-1352)
+  for (size_t j = 0; j < AntennaTableAlreadyMade.size(); j++) {
+    if (AntennaNumber < (int)AntennaDepths.size() && AntennaTableAlreadyMade[j] < (int)AntennaDepths.size() &&
+        AntennaDepths[AntennaNumber] == AntennaDepths[AntennaTableAlreadyMade[j]])
+      AntennaNumber = (int)j;
+  }
+  if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size()) {
+    std::cerr << "MultiRayAirIceRefraction (B200): no table for antenna " << AntennaNumber << std::endl;
+    return 1;
+  }
+  int rc = airice_lookup_host(s.ctx, s.tables[AntennaNumber], n, SrcHeightASL, HorizontalDistanceToRx, out, ok);
+  if (rc != 0) detail::report("GetHorizontalDistanceToIntersectionPoint_TableBatch");
+  return rc;
+}
+
+// MultiRayAirIceRefraction.cc:1305-1462
+bool GetHorizontalDistanceToIntersectionPoint_Table(double SrcHeightASL, double HorizontalDistanceToRx,
+                                                    double RxDepthBelowIceBoundary, double IceLayerHeight,
+                                                    int AntennaNumber, double &opticalPathLengthInIce,
+                                                    double &opticalPathLengthInAir, double &geometricalPathLengthInIce,
+                                                    double &geometricalPathLengthInAir, double &launchAngle,
+                                                    double &horizontalDistanceToIntersectionPoint,
+                                                    double &transmissionCoefficientS, double &transmissionCoefficientP,
+                                                    double &RecievedAngleInIce) {
+  double o[9];
+  unsigned char ok = 0;
+  if (GetHorizontalDistanceToIntersectionPoint_TableBatch(1, &SrcHeightASL, &HorizontalDistanceToRx, RxDepthBelowIceBoundary,
+                                                          IceLayerHeight, AntennaNumber, o, &ok) != 0)
+    return false;
+  opticalPathLengthInIce = o[0]; opticalPathLengthInAir = o[1];
+  geometricalPathLengthInIce = o[2]; geometricalPathLengthInAir = o[3];
+  launchAngle = o[4]; horizontalDistanceToIntersectionPoint = o[5];
+  transmissionCoefficientS = o[6]; transmissionCoefficientP = o[7]; RecievedAngleInIce = o[8];
+  return ok != 0;
+}
+
+// MultiRayAirIceRefraction.cc:1464-1616 (metres / degrees; dummy[0..16])
+void Air2IceRayTracing(double AirTxHeight, double HorizontalDistance, double IceLayerHeight, double AntennaDepth,
+                       double StraightAngle, double dummy[20]) {
+  std::cout << "main function parameters are " << AirTxHeight << " " << HorizontalDistance << " " << IceLayerHeight << " "
+            << AntennaDepth << std::endl;  // the reference prints this per call (MultiRayAirIceRefraction.cc:1466)
+  for (int i = 0; i < 20; i++) dummy[i] = 0;
+  if (!detail::ensure_ctx()) return;
+  double o[AIRICE_SOLVE_COLS];
+  unsigned char ok = 0;
+  if (airice_solve_host(detail::state().ctx, 1, &AirTxHeight, &HorizontalDistance, &StraightAngle, AntennaDepth,
+                        IceLayerHeight, AIRICE_UNITS_M_DEG_C, o, &ok) != 0) {
+    detail::report("Air2IceRayTracing");
+    return;
+  }
+  const double t_air = o[3], t_ice = o[4], t = t_ice + t_air;
+  dummy[0] = AirTxHeight; dummy[1] = o[0]; dummy[2] = o[1]; dummy[3] = o[2];
+  dummy[4] = t * spedc; dummy[5] = t_ice * spedc; dummy[6] = t_air * spedc;
+  dummy[7] = t; dummy[8] = t_ice; dummy[9] = t_air;
+  dummy[10] = o[5]; dummy[11] = o[6]; dummy[12] = o[7]; dummy[13] = o[8];
+  dummy[14] = o[9]; dummy[15] = o[10]; dummy[16] = o[11];
+}
+
+// MultiRayAirIceRefraction.cc:1796-2017 (metres / degrees; dummy[0..17])
+void GetRayTracingSolutions(double RayLaunchAngleInAir, double AirTxHeight, double IceLayerHeight, double AntennaDepth,
+                            double dummy[20], bool &InIce) {
+  for (int i = 0; i < 18; i++) dummy[i] = 0;
+  if (!detail::ensure_ctx()) return;
+  double o[AIRICE_TABLE_COLS64];
+  // InIce decides whether the ice leg is traced; the C ABI encodes it in the sign of the depth
+  const double depth = InIce ? (AntennaDepth < 0 ? AntennaDepth : -AntennaDepth) : 0.0;
+  if (airice_forward_host(detail::state().ctx, 1, &RayLaunchAngleInAir, &AirTxHeight, depth, IceLayerHeight, o) != 0) {
+    detail::report("GetRayTracingSolutions");
+    return;
+  }
+  for (int i = 0; i < AIRICE_TABLE_COLS64; i++) dummy[1 + i] = o[i];
+}
+
+// MultiRayAirIceRefraction.cc:1618-1696: the old solve-per-cell table, one launch of the batched solver over the
+// whole (height x straight-angle) grid.  cm in; nine double columns, -1000 where the solve misses.
+void MakeTable(double IceLayerHeight, double AntennaDepth) {
+  IceLayerHeight = IceLayerHeight / 100;
+  AntennaDepth = AntennaDepth / 100;
+  std::cout << "making the table now " << AntennaDepth << " " << IceLayerHeight << std::endl;
+  if (MakeAtmosphere() != 0) return;
+  GridStartH = IceLayerHeight + 1;
+  GridStopH = 100000;
+  GridWidthH = GridStopH - GridStartH;
+  GridWidthTh = GridStopTh - GridStartTh;
+  TotalStepsH_O = (GridWidthH / GridStepSizeH_O) + 1;
+  TotalStepsTh_O = (GridWidthTh / GridStepSizeTh_O) + 1;
+  GridPoints = TotalStepsH_O * TotalStepsTh_O;
+  GridPositionH.resize(TotalStepsH_O);
+  GridPositionTh.resize(TotalStepsTh_O);
+  const long n = (long)TotalStepsH_O * TotalStepsTh_O;
+  std::vector<double> hh(n), dd(n), th(n), out((size_t)n * AIRICE_SOLVE_COLS);
+  std::vector<unsigned char> ok(n);
+  for (int ih = 0; ih < TotalStepsH_O; ih++) {
+    for (int ith = 0; ith < TotalStepsTh_O; ith++) {
+      double h = GridStartH + GridStepSizeH_O * ih;
+      double t = GridStartTh + GridStepSizeTh_O * ith;
+      if (ih == TotalStepsH_O - 1) h = GridStopH;
+      if (ith == TotalStepsTh_O - 1) t = GridStopTh;
+      GridPositionH[ih] = h;
+      GridPositionTh[ith] = t;
+      const long i = (long)ih * TotalStepsTh_O + ith;
+      hh[i] = h; th[i] = t;
+      dd[i] = (h - IceLayerHeight + AntennaDepth) * tan((180 - t) * (pi / 180.0));  // MultiRayAirIceRefraction.cc:1662
+    }
+  }
+  for (int c = 0; c < 10; c++) GridZValue[c].clear();
+  if (airice_solve_host(detail::state().ctx, n, hh.data(), dd.data(), th.data(), AntennaDepth, IceLayerHeight,
+                        AIRICE_UNITS_M_DEG_C, out.data(), ok.data()) != 0) {
+    detail::report("MakeTable");
+    return;
+  }
+  for (int c = 0; c < 9; c++) GridZValue[c].resize(n);
+  const double *X = &out[0 * n], *Xair = &out[1 * n], *tair = &out[3 * n], *tice = &out[4 * n], *launch = &out[5 * n];
+  const double *ts = &out[7 * n], *tp = &out[8 * n], *inc = &out[11 * n];
+  for (long i = 0; i < n; i++) {
+    const double d = dd[i];
+    // the reference accepts on the distance test alone here (MultiRayAirIceRefraction.cc:1667), without the X<0 veto
+    const bool accept = (fabs(X[i] - d) / d < 0.01 && d <= 100) || (fabs(X[i] - d) < 1 && d > 100);
+    if (accept) {
+      GridZValue[0][i] = hh[i]; GridZValue[1][i] = X[i]; GridZValue[2][i] = tice[i] * spedc; GridZValue[3][i] = tair[i] * spedc;
+      GridZValue[4][i] = launch[i]; GridZValue[5][i] = Xair[i]; GridZValue[6][i] = ts[i]; GridZValue[7][i] = tp[i];
+      GridZValue[8][i] = inc[i];
+    } else {
+      for (int c = 0; c < 9; c++) GridZValue[c][i] = -1000;
+    }
+  }
+}
+
+// MultiRayAirIceRefraction.cc:1700-1794: inverse-distance weighting over the 2x2 nodes below/left of the rounded bin,
+// reproduced as written (the running value is overwritten per node; an exact hit short-circuits).
+double GetInterpolatedValue(double hR, double thR, int rtParameter) {
+  double sum1 = 0, sum2 = 0, NewZValue = -1000;
+  double minHbin = round((hR - GridStartH) / GridStepSizeH_O);
+  double minThbin = round((thR - GridStartTh) / GridStepSizeTh_O);
+  if (minHbin <= 1) minHbin = 1;
+  if (minThbin <= 1) minThbin = 1;
+  if (minHbin + 1 > TotalStepsH_O) minHbin = TotalStepsH_O - 2;
+  if (minThbin + 1 > TotalStepsTh_O) minThbin = TotalStepsTh_O - 2;
+  const int startbinH = minHbin - 1, endbinH = minHbin + 1, startbinTh = minThbin - 1, endbinTh = minThbin + 1;
+  const std::vector<double> &Z = GridZValue[rtParameter];
+  for (int ixn = startbinH; ixn < endbinH; ixn++) {
+    for (int izn = startbinTh; izn < endbinTh; izn++) {
+      const int ich = ixn * TotalStepsTh_O + izn;
+      if (ich >= 0 && ich < GridPoints && ixn < TotalStepsH_O && izn < TotalStepsTh_O && ixn >= 0 && izn >= 0) {
+        const double dist = fabs((hR - GridPositionH[ixn]) * (hR - GridPositionH[ixn]) +
+                                 (thR - GridPositionTh[izn]) * (thR - GridPositionTh[izn]));
+        if (Z[ich] != -1000) {
+          sum1 += (1.0 / dist) * Z[ich];
+          sum2 += (1.0 / dist);
+          NewZValue = sum1 / sum2;
+        } else {
+          NewZValue = -1000;
+        }
+        if (dist == 0) {
+          NewZValue = (Z[ich] != -1000) ? Z[ich] : -1000;
+          izn = minThbin + 3;
+          ixn = minHbin + 3;
+        }
+      }
+    }
+  }
+  return NewZValue;
+}
+
+}  // namespace MultiRayAirIceRefraction

@@ -3,8 +3,8 @@
  * This is the drop-in boundary for the hot path of uzairlatif90/AirIceRayTracing: plain pointers and sizes,
  * no C++/torch types.  Each entry point names the reference interface it replaces (paths are relative to the
  * reference repository root).  Device entry points take DEVICE pointers and a cudaStream_t passed as void*
- * (NULL = default stream) and do not synchronise; host entry points take HOST pointers, stage through pinned
- * memory on the context's own streams and return when the results are in the caller's buffers.
+ * (NULL = default stream) and do not synchronise; host entry points take HOST pointers (pinned or pageable), copy
+ * chunk by chunk on the context's own two streams and return when the results are in the caller's buffers.
  *
  * All functions return 0 on success or a negative error code; airice_last_error() describes the last failure
  * on the calling thread.  A context is bound to one GPU and may be used from one thread at a time.
@@ -58,6 +58,10 @@ int airice_table_build_device(airice_ctx *ctx, double depth_m, double ice_m, dou
 int airice_forward_device(airice_ctx *ctx, int64_t n, const double *d_theta, const double *d_h, double depth_m,
                           double ice_m, double *const *cols64, void *stream);
 
+/* Same through HOST buffers: out is a dense SoA block out[col*n + i] with 17 columns. */
+int airice_forward_host(airice_ctx *ctx, int64_t n, const double *theta, const double *h, double depth_m, double ice_m,
+                        double *out);
+
 /* Library-owned float table for lookups = one entry of AllTableAllAntData (MultiRayAirIceRefraction.cc:9,2136). */
 int airice_table_create(airice_ctx *ctx, double depth_m, double ice_m, double h_top, double h_step, double th_start,
                         double th_step, double th_stop, airice_table **out);
@@ -79,12 +83,15 @@ int airice_table_copy_row_ranges(const airice_table *t, int32_t *host_first, int
  *   (opt ice, opt air, geo ice, geo air, launch[rad], X_air, T_S, T_P, received[rad]);
  * units = M_DEG: inputs in m, 13 columns (X, X_air, X_ice, t_air[s], t_ice[s], launch, received, T_S, T_P, geo air,
  *   geo ice, incident on ice, refracted below surface).  out: array of column pointers, NULL entries are skipped.
- * ok: the reference's bool (|X-d| test, MultiRayAirIceRefraction.cc:974-983).  nevals: optional diagnostics. */
-int airice_solve_device(airice_ctx *ctx, int64_t n, const double *d_h, const double *d_dist, double depth,
-                        double ice, int units, double *const *d_out, uint8_t *d_ok, int32_t *d_nevals, void *stream);
+ * ok: the reference's bool (|X-d| test, MultiRayAirIceRefraction.cc:974-983).  nevals: optional diagnostics.
+ * d_straight: optional per-pair straight-line angle (deg for M_DEG, rad for CM_RAD) = the StraightAngle argument of
+ *   Air2IceRayTracing; NULL = computed from the geometry as GetHorizontalDistanceToIntersectionPoint does. */
+int airice_solve_device(airice_ctx *ctx, int64_t n, const double *d_h, const double *d_dist, const double *d_straight,
+                        double depth, double ice, int units, double *const *d_out, uint8_t *d_ok, int32_t *d_nevals,
+                        void *stream);
 /* Same through HOST buffers: out is a dense SoA block out[col*n + i] with 9 (CM_RAD) or 13 (M_DEG) columns. */
-int airice_solve_host(airice_ctx *ctx, int64_t n, const double *h, const double *dist, double depth, double ice,
-                      int units, double *out, uint8_t *ok);
+int airice_solve_host(airice_ctx *ctx, int64_t n, const double *h, const double *dist, const double *straight,
+                      double depth, double ice, int units, double *out, uint8_t *ok);
 
 /* ---- kernel 3: table lookup = GetHorizontalDistanceToIntersectionPoint_Table
  * (MultiRayAirIceRefraction.cc:1305-1462, .h:189) with FindClosestAirTxHeight / FindClosestTHD / GetParValues

@@ -344,6 +344,36 @@ class Reference:
         return ok.astype(bool), out
 
 
+def _old_table_api(ref):
+    L = ref.lib
+    L.ref_old_grid.argtypes = [C.c_double] * 4
+    L.ref_old_make_table.argtypes = [C.c_double, C.c_double]
+    L.ref_old_info.argtypes = [c_long_p]
+    L.ref_old_col.argtypes = [C.c_int, c_double_p]
+    L.ref_old_interp.restype = C.c_double
+    L.ref_old_interp.argtypes = [C.c_double, C.c_double, C.c_int]
+
+
+def old_make_table(ref, ice_cm, depth_cm, start_th=90.05, stop_th=179.95, step_h=25.0, step_th=0.01):
+    """Reference MakeTable (M.cc:1618-1696) on a chosen grid -> (info dict, [9, n] columns)."""
+    _old_table_api(ref)
+    ref.lib.ref_old_grid(start_th, stop_th, step_h, step_th)
+    with _cwd(ref.dir):
+        ref.lib.ref_old_make_table(ice_cm, depth_cm)
+    info = (C.c_long * 4)()
+    ref.lib.ref_old_info(info)
+    n = info[3]
+    cols = np.zeros((9, n))
+    for k in range(9):
+        ref.lib.ref_old_col(k, _dp(cols[k]))
+    return dict(n_h=info[0], n_th=info[1], points=info[2]), cols
+
+
+def old_interp(ref, h, th, par):
+    _old_table_api(ref)
+    return ref.lib.ref_old_interp(h, th, par)
+
+
 class PyWrapReference:
     """The unmodified reference pythonwrapper library (Py_TraceIceToAir re-parses ./Atmosphere.dat per call)."""
 

@@ -1,0 +1,84 @@
+// TEST: a caller written the way the reference's own drivers are (RunMultiRayCode.C:1-79): it includes
+// "MultiRayAirIceRefraction.cc", defines the two vectors the header declares extern, fills the grid globals, builds
+// one table per distinct antenna depth, then asks for one table lookup and one direct solve.  Output: one
+// "key value" pair per line (%.17g), parsed by tests/test_gpu_compat.py.
+#include "MultiRayAirIceRefraction.cc"
+
+#include <cstdio>
+
+std::vector<double> AntennaDepths;
+std::vector<int> AntennaTableAlreadyMade;
+
+int main(int argc, char **argv) {
+  if (argc > 1) MultiRayAirIceRefraction::SetAtmosphereFile(argv[1]);
+  double AntennaDepth = -200, IceLayerHeight = 3000, AirTxHeight = 5000, HorizontalDistance = 1000;
+  // coarse grid so the oracle side of the test stays quick
+  AngleStepSize = 0.5; LoopStartAngle = 92.0; LoopStopAngle = 180.0; HeightStepSize = 2000.0;
+
+  AntennaDepths.push_back(AntennaDepth * 100);
+  AntennaDepths.push_back(-150.0 * 100);
+  AntennaDepths.push_back(AntennaDepth * 100);  // same depth as antenna 0: must reuse table 0
+  for (size_t i = 0; i < AntennaDepths.size(); i++) {
+    bool make = true;
+    for (size_t j = 0; j < AntennaTableAlreadyMade.size(); j++)
+      if (AntennaDepths[i] == AntennaDepths[AntennaTableAlreadyMade[j]]) make = false;
+    if (make) {
+      MultiRayAirIceRefraction::MakeRayTracingTable(AntennaDepths[i], IceLayerHeight * 100, (int)i);
+      AntennaTableAlreadyMade.push_back((int)i);
+    }
+  }
+  std::printf("tables %zu\n", AntennaTableAlreadyMade.size());
+  std::printf("TotalHeightSteps %d\nTotalAngleSteps %d\n", TotalHeightSteps, TotalAngleSteps);
+
+  double oi, oa, gi, ga, la, hx, ts, tp, ra;
+  for (int ant = 0; ant < 3; ant++) {
+    bool ok = MultiRayAirIceRefraction::GetHorizontalDistanceToIntersectionPoint_Table(
+        AirTxHeight * 100, HorizontalDistance * 100, AntennaDepths[ant], IceLayerHeight * 100, ant, oi, oa, gi, ga, la, hx, ts, tp, ra);
+    std::printf("table%d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", ant, (int)ok, oi, oa, gi, ga, la, hx, ts, tp, ra);
+  }
+  bool ok = MultiRayAirIceRefraction::GetHorizontalDistanceToIntersectionPoint(
+      AirTxHeight * 100, HorizontalDistance * 100, AntennaDepth * 100, IceLayerHeight * 100, oi, oa, gi, ga, la, hx, ts, tp, ra);
+  std::printf("direct %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", (int)ok, oi, oa, gi, ga, la, hx, ts, tp, ra);
+
+  double dummy[20];
+  bool inice = true;
+  MultiRayAirIceRefraction::GetRayTracingSolutions(170, 20000, 3000, -200, dummy, inice);
+  std::printf("forward");
+  for (int i = 0; i < 18; i++) std::printf(" %.17g", dummy[i]);
+  std::printf("\n");
+  const double thR = 180 - (atan(HorizontalDistance / (AirTxHeight - IceLayerHeight - AntennaDepth)) * (180.0 / MultiRayAirIceRefraction::pi));
+  MultiRayAirIceRefraction::Air2IceRayTracing(AirTxHeight, HorizontalDistance, IceLayerHeight, AntennaDepth, thR, dummy);
+  std::printf("air2ice");
+  for (int i = 0; i < 17; i++) std::printf(" %.17g", dummy[i]);
+  std::printf("\n");
+
+  // mutable ice model (MultiRayAirIceRefraction.h:72-74)
+  MultiRayAirIceRefraction::A_ice = 1.775;
+  ok = MultiRayAirIceRefraction::GetHorizontalDistanceToIntersectionPoint(
+      AirTxHeight * 100, HorizontalDistance * 100, AntennaDepth * 100, IceLayerHeight * 100, oi, oa, gi, ga, la, hx, ts, tp, ra);
+  std::printf("direct_A1775 %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", (int)ok, oi, oa, gi, ga, la, hx, ts, tp, ra);
+  MultiRayAirIceRefraction::A_ice = 1.78;
+
+  // old solve-per-cell table on the grid of tests/golden/old_table.npz
+  MultiRayAirIceRefraction::GridStepSizeH_O = 4000.0;
+  MultiRayAirIceRefraction::GridStepSizeTh_O = 1.5;
+  MultiRayAirIceRefraction::MakeTable(IceLayerHeight * 100, AntennaDepth * 100);
+  std::printf("old_dims %d %d %d\n", MultiRayAirIceRefraction::TotalStepsH_O, MultiRayAirIceRefraction::TotalStepsTh_O,
+              (int)MultiRayAirIceRefraction::GridZValue[0].size());
+  for (int c = 0; c < 9; c++) {
+    std::printf("old_col%d", c);
+    for (double v : MultiRayAirIceRefraction::GridZValue[c]) std::printf(" %.17g", v);
+    std::printf("\n");
+  }
+  if (argc > 2) {
+    FILE *f = std::fopen(argv[2], "r");
+    double qh, qt;
+    while (f && std::fscanf(f, "%lf %lf", &qh, &qt) == 2) {
+      std::printf("old_q");
+      for (int p = 0; p < 9; p++) std::printf(" %.17g", MultiRayAirIceRefraction::GetInterpolatedValue(qh, qt, p));
+      std::printf("\n");
+    }
+    if (f) std::fclose(f);
+  }
+  return 0;
+}

@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from oracle.ref import PyWrapReference, Reference  # noqa: E402
+from oracle.ref import PyWrapReference, Reference, old_interp, old_make_table  # noqa: E402
 
 PI_M = 3.1415927
 ICE_CM, DEPTH_CM = 300000.0, -20000.0
@@ -87,6 +87,18 @@ def main():
                         h_cm=hq * 100, d_cm=dq * 100, ok=okq, out=outq, rows_h=rows_h, rows_idx=rows_idx,
                         thd_idx=np.array(thd_idx), depth_cm=DEPTH_CM, ice_cm=ICE_CM, **grid)
     ref.set_grid()  # back to the shipped defaults
+
+    # ---- old solve-per-cell table (MakeTable / GetInterpolatedValue) on a coarse grid
+    og = dict(start_th=90.05, stop_th=179.95, step_h=4000.0, step_th=1.5)
+    info, ocols = old_make_table(ref, ICE_CM, DEPTH_CM, **og)
+    rng = np.random.default_rng(55)
+    qh = rng.uniform(3001, 100000, 400)
+    qt = rng.uniform(90.05, 179.95, 400)
+    qh[:3] = [3001.0, 7001.0, 100000.0]
+    qt[:3] = [90.05, 91.55, 179.95]
+    qv = np.array([[old_interp(ref, float(a), float(b), p) for p in range(9)] for a, b in zip(qh, qt)])
+    np.savez_compressed(os.path.join(HERE, "old_table.npz"), cols=ocols, n_h=info["n_h"], n_th=info["n_th"], qh=qh, qt=qt, qv=qv,
+                        ice_cm=ICE_CM, depth_cm=DEPTH_CM, **og)
 
     # ---- python wrapper C ABI (Py_TraceIceToAir), metres/degrees, pi = 4 atan(1)
     pw = PyWrapReference()

@@ -1,0 +1,137 @@
+"""GPU: the drop-in surfaces above the C ABI -- the source-compatible C++ namespace (a driver shaped like the
+reference's RunMultiRayCode.C is compiled against include/MultiRayAirIceRefraction.{h,cc}) and the python wrapper's
+libAirIceRayTracing.so (loaded by a ctypes stub with the reference's argtypes)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ATMOSPHERE, ATOL_ANGLE_DEG, ROOT, RTOL_DIST, golden
+
+pytestmark = pytest.mark.gpu
+PI_M = 3.1415927
+
+
+@pytest.fixture(scope="module")
+def driver_output(tmp_path_factory, solver):
+    tmp = tmp_path_factory.mktemp("compat")
+    exe = str(tmp / "driver")
+    lib = os.path.join(ROOT, "airiceraytracing_b200", "lib")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "compat", "driver.cc"), "-o", exe, "-L" + lib, "-lairice_b200",
+                           "-Wl,-rpath," + lib])
+    g = golden("old_table.npz")
+    qfile = str(tmp / "queries.txt")
+    np.savetxt(qfile, np.stack([g["qh"], g["qt"]], axis=1), fmt="%.17g")
+    out = subprocess.run([exe, ATMOSPHERE, qfile], capture_output=True, text=True, check=True).stdout
+    rec = {}
+    for line in out.splitlines():
+        p = line.split()
+        if not p:
+            continue
+        try:
+            vals = [float(x) for x in p[1:]]
+        except ValueError:
+            continue
+        rec.setdefault(p[0], []).append(vals)
+    rec["_stdout"] = out
+    return rec
+
+
+def _close9(got, ref, what):
+    got, ref = np.asarray(got), np.asarray(ref)
+    for k in (0, 1, 2, 3, 5):
+        assert abs(got[k] - ref[k]) <= RTOL_DIST * abs(ref[k]), (what, k, got[k], ref[k])
+    for k in (4, 8):
+        assert abs(got[k] - ref[k]) * 180 / PI_M <= ATOL_ANGLE_DEG, (what, k)
+    for k in (6, 7):
+        assert abs(got[k] - ref[k]) <= 1e-9, (what, k)
+
+
+def test_driver_direct_solve_and_forward(driver_output, oracle):
+    ok, ref = oracle.solve_cm(500000.0, 100000.0, -20000.0, 300000.0)
+    d = driver_output["direct"][0]
+    assert int(d[0]) == int(ok) == 1
+    _close9(d[1:], ref, "direct")
+    f = np.array(driver_output["forward"][0])
+    want = oracle.forward(170.0, 20000.0, 3000.0, -200.0)
+    assert np.allclose(f[[2, 3, 4, 5, 6, 7, 8, 9, 10, 16, 17]], want[[2, 3, 4, 5, 6, 7, 8, 9, 10, 16, 17]], rtol=RTOL_DIST, atol=0)
+    assert np.abs(f[[11, 12, 13]] - want[[11, 12, 13]]).max() <= ATOL_ANGLE_DEG
+    thR = 180 - np.degrees(np.arctan(1000.0 / (5000 - 3000 + 200))) * (np.pi / PI_M)
+    a2i, _ = oracle.air2ice(5000.0, 1000.0, 3000.0, -200.0, 180 - (np.arctan(1000.0 / 2200.0) * (180.0 / PI_M)))
+    got = np.array(driver_output["air2ice"][0])
+    assert np.allclose(got[[1, 2, 3, 4, 5, 6, 7, 8, 9, 14, 15]], a2i[[1, 2, 3, 4, 5, 6, 7, 8, 9, 14, 15]], rtol=RTOL_DIST)
+    assert np.abs(got[[10, 11, 16]] - a2i[[10, 11, 16]]).max() <= ATOL_ANGLE_DEG
+    assert "main function parameters are 5000 1000 3000 -200" in driver_output["_stdout"]  # M.cc:1466
+    # the mutable ice model reaches the kernels: A_ice = 1.775 changes the ice leg
+    assert driver_output["direct_A1775"][0][1] != d[1]
+
+
+def test_driver_tables_and_lookup(driver_output, oracle):
+    assert driver_output["tables"][0] == [2.0]  # antenna 2 shares antenna 0's depth -> two tables (RunMultiRayCode.C:38-52)
+    assert driver_output["TotalHeightSteps"][0] == [49.0] and driver_output["TotalAngleSteps"][0] == [177.0]
+    for ant, depth_cm in ((0, -20000.0), (1, -15000.0), (2, -20000.0)):
+        t = oracle.table_build(depth_cm, 300000.0, 0.5, 92.0, 180.0, 2000.0)
+        ok, ref = t.lookup_cm(500000.0, 100000.0, depth_cm, 300000.0)
+        got = driver_output["table%d" % ant][0]
+        assert int(got[0]) == int(ok) == 1
+        g, r = np.array(got[1:]), ref
+        # float table: our cells may differ from the oracle's by one float ulp, so compare at float precision
+        assert np.allclose(g, r, rtol=3e-7, atol=0)
+        t.free()
+    assert driver_output["table0"][0] == driver_output["table2"][0]
+
+
+def test_driver_old_table_and_idw(driver_output):
+    g = golden("old_table.npz")
+    assert driver_output["old_dims"][0] == [float(g["n_h"]), float(g["n_th"]), float(g["cols"].shape[1])]
+    for c in range(9):
+        got = np.array(driver_output["old_col%d" % c][0])
+        ref = g["cols"][c]
+        assert np.array_equal(got == -1000, ref == -1000), "sentinel cells differ in column %d" % c
+        m = ref != -1000
+        tol = ATOL_ANGLE_DEG if c in (4, 8) else None
+        if tol:
+            assert np.abs(got[m] - ref[m]).max() <= tol
+        else:
+            assert (np.abs(got[m] - ref[m]) / np.abs(ref[m])).max() <= RTOL_DIST
+    q = np.array(driver_output["old_q"])
+    ref = g["qv"]
+    assert q.shape == ref.shape
+    assert np.array_equal(q == -1000, ref == -1000)
+    m = ref != -1000
+    assert (np.abs(q[m] - ref[m]) / np.maximum(np.abs(ref[m]), 1e-300)).max() <= 1e-8
+
+
+def test_python_wrapper_library(solver):
+    """Run in a fresh interpreter the way TraceIceToAir.py does: cwd holds Atmosphere.dat, ctypes stub next to the .so."""
+    code = r'''
+import ctypes, sys, numpy as np
+sys.path.insert(0, %r)
+from AirIceRayTracing import Py_TraceIceToAir, Py_TraceIceToAirBatch
+g = np.load(%r)
+ii = ctypes.c_double * 10
+worst = [0.0, 0.0, 0.0]
+for a, want in zip(g["args"], g["out"]):
+    arr = ii(*([1.0] * 10))
+    Py_TraceIceToAir(float(a[0]), float(a[1]), float(a[2]), float(a[3]), arr)
+    got = np.array(list(arr))
+    assert (got[0] == -1000) == (want[0] == -1000), (a, got, want)
+    if want[0] != -1000:
+        assert got[0] == want[0] and got[1] == want[1] and got[8] == 0 and got[9] == 0
+        worst[0] = max(worst[0], np.abs(got[[2, 3, 6]] - want[[2, 3, 6]]).max() / 1.0 if False else (np.abs(got[[2, 3, 6]] - want[[2, 3, 6]]) / np.abs(want[[2, 3, 6]])).max())
+        worst[1] = max(worst[1], np.abs(got[[4, 5, 7]] - want[[4, 5, 7]]).max())
+    else:
+        assert np.all(got == -1000)
+sel = g["args"][:, 0] == g["args"][5, 0]
+b = Py_TraceIceToAirBatch(float(g["args"][5, 0]), 3000.0, g["args"][sel, 2], g["args"][sel, 3])
+assert b.shape == (sel.sum(), 10)
+print("WORST", worst[0], worst[1])
+''' % (os.path.join(ROOT, "airiceraytracing_b200", "pythonwrapper"), os.path.join(ROOT, "tests", "golden", "pywrap.npz"))
+    out = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(ATMOSPHERE), capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst = [float(x) for x in out.stdout.strip().splitlines()[-1].split()[1:]]
+    assert worst[0] <= RTOL_DIST and worst[1] <= ATOL_ANGLE_DEG
+    assert "We have a solution!!!" in out.stdout and "We do NOT have a solution!!!" in out.stdout
