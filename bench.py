@@ -111,7 +111,7 @@ def run_reference_arm(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "each step = a bounded sample (%d pairs) of the workload, all %d host cores" % (per_core * cores, cores)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -345,12 +345,31 @@ def run_ours(args):
                 "gpu_launches": args.steps, "kernels_per_step": ["airice_solve_kernel"],
                 "solved_fraction": solved, "roofline": roofline, "cpu_baseline": cpu}
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Route everything libraries print to fd 1 (NCCL's version banner, torchrun notes) to stderr and keep a private
+    handle for the ONE JSON line the contract asks for."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    global _JSON_OUT
+    _JSON_OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
