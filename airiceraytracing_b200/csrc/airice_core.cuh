@@ -27,6 +27,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "airice_math.cuh"
+
 #if defined(__CUDACC__)
 #define AIRICE_HD __host__ __device__ __forceinline__
 #define AIRICE_HD_NOINLINE __host__ __device__ __noinline__
@@ -58,6 +60,7 @@ struct AirIceMedium {
   double deg2rad;                     // pi/180.0, rounded once like the reference expression
   double rad2deg;                     // 180/pi
   double c;                           // 299792458 (M.h:30)
+  double tan16;                       // tan(16 deg) in the variant's pi: tangent step of the 16-deg bracket (M.cc:1487)
 };
 
 // Per-(ice height, receiver depth) plan: every ray-independent number of the layer walk, computed on
@@ -69,6 +72,7 @@ struct AirIcePlan {
   double ice_h;    // ice-surface height after the depth>=0 fold (M.cc:1472-1476)
   double depth;    // receiver depth, positive, 0 when the receiver sits in air
   double neg_c[AIRICE_MAX_LAYERS + 1];    // C' = -C of the segment's medium
+  double inv_neg_c[AIRICE_MAX_LAYERS + 1];  // 1/C' (Newton phase only)
   double stop_x[AIRICE_MAX_LAYERS + 1];   // lower end: ice_h for k==kb else hlo[k] (M.cc:722-728); ice leg: depth
   double stop_n[AIRICE_MAX_LAYERS + 1];
   double start_x[AIRICE_MAX_LAYERS + 1];  // upper end when entered from above: hlo[k+1]-1e-5 (M.cc:715); ice leg: 0
@@ -93,16 +97,16 @@ struct AirIceRay {   // everything the reference reports for one ray (metres, se
   double trans_s, trans_p;
 };
 
-// Horizontal distance only (the root function's X), with optional dX/dL for Newton.  The solver path carries L
-// unchanged through all layers and into the ice (M.cc:757-771, 894-902).
-template <bool DERIV>
-AIRICE_HD double airice_x_total(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
-                                double& dXdL) {
+// Horizontal distance X(L) with reference-like rounding (the root function's X, MinimizeforLaunchAngle M.cc:873-917):
+// F(stop) and F(start) are formed and rounded separately as GetRayHorizontalPath does (M.cc:463).  The solver path
+// carries L unchanged through all layers and into the ice (M.cc:757-771, 894-902).  Used for the rare real
+// evaluations inside the bisection replay, where the SIGN of d - X must agree with the reference's.
+AIRICE_HD double airice_x_exact(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L) {
   const double L2 = L * L;
-  const double sAir = sqrt(1.0 * 1.0 - L2), sIce = sqrt(m.A_ice * m.A_ice - L2);
+  const double sAir = AIRICE_SQRT(1.0 * 1.0 - L2), sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
   const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
   const int nseg = nair + (p.has_ice ? 1 : 0);
-  double X = 0.0, dX = 0.0;
+  double X = 0.0;
 #pragma unroll 1
   for (int j = 0; j < nseg; j++) {
     const bool air = j < nair;
@@ -114,18 +118,51 @@ AIRICE_HD double airice_x_total(const AirIceMedium& m, const AirIcePlan& p, int 
     const double xt = top ? h : p.start_x[k];
     const double nt = top ? n_tx : p.start_n[k];
     const double xb = p.stop_x[k], nb = p.stop_n[k];
-    const double Rb = sqrt(nb * nb - L2), Rt = sqrt(nt * nt - L2);
-    const double Tb = A * nb - L2 + sA * Rb, Tt = A * nt - L2 + sA * Rt;
-    const double Gb = Cn * xb - log(Tb), Gt = Cn * xt - log(Tt);
-    const double inv_sA = 1.0 / sA;
-    const double mult = (L / Cn) * inv_sA;
-    const double seg = AIRICE_MUL(mult, Gb) - AIRICE_MUL(mult, Gt);   // F(stop) - F(start) as GetRayHorizontalPath forms it (M.cc:463)
+    const double Rb = AIRICE_SQRT(nb * nb - L2), Rt = AIRICE_SQRT(nt * nt - L2);
+    const double Gb = Cn * xb - AIRICE_LOG(A * nb - L2 + sA * Rb), Gt = Cn * xt - AIRICE_LOG(A * nt - L2 + sA * Rt);
+    const double mult = AIRICE_DIV(L, Cn) * AIRICE_RCP(sA);
+    const double seg = AIRICE_MUL(mult, Gb) - AIRICE_MUL(mult, Gt);
     X += air ? -seg : seg;
-    if (DERIV) {
-      const double qb = (sA + Rb) * (sA + Rb) / (Tb * Rb), qt = (sA + Rt) * (sA + Rt) / (Tt * Rt);
-      const double dseg = (1.0 / Cn) * inv_sA * (A * A * inv_sA * inv_sA * (Gb - Gt) + L2 * inv_sA * (qb - qt));
-      dX += air ? -dseg : dseg;
-    }
+  }
+  return X;
+}
+
+// X(L) and dX/dL for the Newton phase.  Only the converged root matters here (it is re-derived to ~1e-13 deg by the
+// iteration itself and the reported numbers come from airice_ray_full), so this version is arranged for throughput:
+// one log per segment (ln T_stop - ln T_start = ln(T_stop/T_start)), host-precomputed 1/C', and derivative terms
+// from low-precision reciprocals.  dG/dL = L (sA+R)^2 / (T sA R) follows from dT/dL = -L (sA+R)^2/(sA R).
+AIRICE_HD double airice_x_newton(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
+                                 double& dXdL) {
+  const double L2 = L * L;
+  double sAir, yAir, sIce, yIce;
+  AIRICE_SQRT_RSQRT(1.0 * 1.0 - L2, sAir, yAir);
+  AIRICE_SQRT_RSQRT(m.A_ice * m.A_ice - L2, sIce, yIce);
+  const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
+  const int nseg = nair + (p.has_ice ? 1 : 0);
+  double X = 0.0, dX = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < nseg; j++) {
+    const bool air = j < nair;
+    const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
+    const double A = air ? 1.0 : m.A_ice;
+    const double sA = air ? sAir : sIce;
+    const double inv_sA = air ? yAir : yIce;
+    const bool top = (j == 0) && air;
+    const double xt = top ? h : p.start_x[k];
+    const double nt = top ? n_tx : p.start_n[k];
+    const double xb = p.stop_x[k], nb = p.stop_n[k];
+    double Rb, yb, Rt, yt;
+    AIRICE_SQRT_RSQRT(nb * nb - L2, Rb, yb);
+    AIRICE_SQRT_RSQRT(nt * nt - L2, Rt, yt);
+    const double Tb = A * nb - L2 + sA * Rb, Tt = A * nt - L2 + sA * Rt;
+    const double rTt = AIRICE_RCP(Tt);
+    const double dG = p.neg_c[k] * (xb - xt) - AIRICE_LOG(Tb * rTt);
+    const double c1 = p.inv_neg_c[k] * inv_sA;           // 1/(C' sA)
+    const double seg = (L * c1) * dG;
+    const double qb = (sA + Rb) * (sA + Rb) * (AIRICE_RCP_APPROX(Tb) * yb), qt = (sA + Rt) * (sA + Rt) * (rTt * yt);
+    const double dseg = c1 * (A * A * inv_sA * inv_sA * dG + L2 * inv_sA * (qb - qt));
+    X += air ? -seg : seg;
+    dX += air ? -dseg : dseg;
   }
   dXdL = dX;
   return X;
@@ -151,27 +188,29 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
     if (RELAY && air && !top) Lk = Lk * p.relay[k];
     const double A = air ? 1.0 : m.A_ice;
     const double L2 = Lk * Lk;
-    const double sA = sqrt(A * A - L2), inv_sA = 1.0 / sA;
+    const double sA = AIRICE_SQRT(A * A - L2), inv_sA = AIRICE_RCP(sA);
     const double Cn = p.neg_c[k];
     const double xt = top ? h : p.start_x[k];
     const double nt = top ? n_tx : p.start_n[k];
     const double xb = p.stop_x[k], nb = p.stop_n[k];
     const double Db = nb * nb - L2, Dt = nt * nt - L2;
-    const double Rb = sqrt(Db), Rt = sqrt(Dt);
-    const double Gb = Cn * xb - log(A * nb - L2 + sA * Rb), Gt = Cn * xt - log(A * nt - L2 + sA * Rt);
-    const double Hb = log(nb + Rb), Ht = log(nt + Rt);
-    const double mult = (Lk / Cn) * inv_sA;
+    const double Rb = AIRICE_SQRT(Db), Rt = AIRICE_SQRT(Dt);
+    const double Gb = Cn * xb - AIRICE_LOG(A * nb - L2 + sA * Rb), Gt = Cn * xt - AIRICE_LOG(A * nt - L2 + sA * Rt);
+    const double Hb = AIRICE_LOG(nb + Rb), Ht = AIRICE_LOG(nt + Rt);
+    const double mult = AIRICE_DIV(Lk, Cn) * inv_sA;
     const double xs = AIRICE_MUL(mult, Gb) - AIRICE_MUL(mult, Gt);
-    const double tb = AIRICE_MUL(1.0 / ((m.c * Cn) * Rb), (Db + (Gb * (A * A * Rb)) / sA) + (A * Rb) * Hb);
-    const double tt = AIRICE_MUL(1.0 / ((m.c * Cn) * Rt), (Dt + (Gt * (A * A * Rt)) / sA) + (A * Rt) * Ht);
+    const double cC = m.c * Cn;
+    const double tb = AIRICE_MUL(AIRICE_RCP(cC * Rb), (Db + AIRICE_MUL(Gb * (A * A * Rb), inv_sA)) + (A * Rb) * Hb);
+    const double tt = AIRICE_MUL(AIRICE_RCP(cC * Rt), (Dt + AIRICE_MUL(Gt * (A * A * Rt), inv_sA)) + (A * Rt) * Ht);
     const double ts = tb - tt;
-    const double gs = (Hb + (A * inv_sA) * Gb) / Cn - (Ht + (A * inv_sA) * Gt) / Cn;
+    const double iC = AIRICE_RCP(Cn);
+    const double gs = AIRICE_MUL(Hb + (A * inv_sA) * Gb, iC) - AIRICE_MUL(Ht + (A * inv_sA) * Gt, iC);
     if (air) {
       xa += -xs; ta += -ts; ga += -gs;
       Rsurf = Rb;  // after the last air segment: sqrt(n_air(surface)^2 - L^2) = n1 cos(incidence)
     } else {
       xi = xs; ti = ts; gi = gs;
-      r.recv_deg = asin(Lk / nb) * m.rad2deg;  // M.cc:824 / 583-589
+      r.recv_deg = asin(AIRICE_DIV(Lk, nb)) * m.rad2deg;  // M.cc:824 / 583-589
     }
   }
   r.x_air = xa; r.t_air = ta; r.p_air = ga;
@@ -181,16 +220,17 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
   const double n1 = p.stop_n[p.kb < AIRICE_MAX_LAYERS ? p.kb : 0];
   const double n2 = p.start_n[AIRICE_ICE_SLOT];  // n_ice(0)
   const double Lsurf = in_ice ? Lk : Lk;
-  const double si = Lsurf / n1;
+  const double si = AIRICE_DIV(Lsurf, n1);
   r.inc_ice_deg = asin(si) * m.rad2deg;
   // Fresnel field transmission, air->ice at the surface (M.cc:285-301, 321-337) without trig:
   // sin(theta_i) = L/n1, n1 cos(theta_i) = sqrt(n1^2-L^2) = R of the bottom end.
-  const double u = (n1 / n2) * si;
-  const double sq = sqrt(1.0 - u * u);
+  const double n12 = AIRICE_DIV(n1, n2);
+  const double u = n12 * si;
+  const double sq = AIRICE_SQRT(1.0 - u * u);
   const double c1 = Rsurf;
-  double trs = 1.0 + (c1 - n2 * sq) / (c1 + n2 * sq);
-  const double c2 = c1 / n1;  // cos(theta_i)
-  double trp = (1.0 - (n1 * sq - n2 * c2) / (n1 * sq + n2 * c2)) * (n1 / n2);
+  double trs = 1.0 + AIRICE_DIV(c1 - n2 * sq, c1 + n2 * sq);
+  const double c2 = AIRICE_DIV(c1, n1);  // cos(theta_i)
+  double trp = (1.0 - AIRICE_DIV(n1 * sq - n2 * c2, n1 * sq + n2 * c2)) * n12;
   if (trs != trs) trs = 0.0;
   if (trp != trp) trp = 0.0;
   r.trans_s = trs; r.trans_p = trp;

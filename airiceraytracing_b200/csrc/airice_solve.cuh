@@ -58,11 +58,11 @@ AIRICE_HD void airice_bracket(const AirIceMedium& m, const AirIcePlan& p, int kt
       lo = lo + 0.05;
     }
     finite_lo = walk && (1.0 - L * L > 0.0);
-    t_cap = L / sqrt(n_tx * n_tx - L * L);
+    t_cap = AIRICE_DIV(L, AIRICE_SQRT(n_tx * n_tx - L * L));
   } else {
     // lo = thR-16 exactly: tan(inc_lo) = tan(inc_hi + 16 deg) by the addition formula, no trig call
-    const double t16 = tan(16 * m.deg2rad);
-    t_cap = (ta + t16) / (1.0 - ta * t16);
+    const double t16 = m.tan16;
+    t_cap = AIRICE_DIV(ta + t16, 1.0 - ta * t16);
     finite_lo = walk && (t_cap * t_cap * (n_tx * n_tx - 1.0) < 1.0);
   }
   if (hi < 90.001 && hi > 90.00) hi = 90.05;  // M.cc:1513-1516
@@ -92,10 +92,12 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
     ts = NAN;
 #pragma unroll 1
     for (int it = 0; it < AIRICE_NEWTON_MAXIT; it++) {
-      const double w = 1.0 / sqrt(1.0 + t * t);
+      double sq1, w;
+      AIRICE_SQRT_RSQRT(1.0 + t * t, sq1, w);
+      w = AIRICE_RCP(sq1);
       const double L = n_tx * t * w;
       double dXdL;
-      const double X = airice_x_total<true>(m, p, kt, h, n_tx, L, dXdL);
+      const double X = airice_x_newton(m, p, kt, h, n_tx, L, dXdL);
       st.n_newton++;
       const double g = X - d;
       if (g == 0.0) { ts = t; break; }
@@ -106,7 +108,7 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
         thi = t;
       }
       const double dgdt = dXdL * n_tx * w * w * w;
-      double tn = t - g / dgdt;
+      double tn = t - AIRICE_DIV(g, dgdt);
       const double hi_t = thi < t_cap ? thi : t_cap;
       bool newton_step = true;
       if (!(tn > tlo) || !(tn < hi_t)) {
@@ -144,8 +146,7 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
       if (fabs(x - th) > guard) {
         s = (x < th) ? -1 : 1;
       } else {
-        double du;
-        const double f = d - airice_x_total<false>(m, p, kt, h, n_tx, airice_L_of_theta(m, n_tx, x), du);
+        const double f = d - airice_x_exact(m, p, kt, h, n_tx, airice_L_of_theta(m, n_tx, x));
         st.n_replay++;
         s = (f < 0.0) ? -1 : ((f > 0.0) ? 1 : 0);
       }

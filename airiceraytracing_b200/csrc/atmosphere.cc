@@ -146,6 +146,7 @@ int load_medium(const char* path, int variant, AirIceMedium* out, double* n0_out
   m.deg2rad = m.pi / 180.0;
   m.rad2deg = 180 / m.pi;
   m.c = 299792458.0;
+  m.tan16 = std::tan(16 * m.deg2rad);
   m.A_ice = 1.78; m.B_ice = -0.43; m.C_ice = 0.0132;
   for (int k = 0; k < 5; k++) m.hlo[k] = atmlay_cm[k] / 100;
   m.hlo[5] = atmlay_cm[4] / 100;
@@ -204,9 +205,9 @@ void make_plan(const AirIceMedium& m, double ice_h, double depth_signed, AirIceP
     if (ice_h >= m.hlo[k] && ice_h < m.hlo[k + 1]) { p.kb = k; break; }
   }
   for (int k = 0; k <= AIRICE_MAX_LAYERS; k++) {
-    p.neg_c[k] = -1; p.stop_x[k] = 0; p.stop_n[k] = 1; p.start_x[k] = 0; p.start_n[k] = 1; p.relay[k] = 1;
+    p.neg_c[k] = -1; p.inv_neg_c[k] = -1; p.stop_x[k] = 0; p.stop_n[k] = 1; p.start_x[k] = 0; p.start_n[k] = 1; p.relay[k] = 1;
   }
-  for (int k = 0; k < m.nlayers; k++) p.neg_c[k] = -m.C[k];
+  for (int k = 0; k < m.nlayers; k++) { p.neg_c[k] = -m.C[k]; p.inv_neg_c[k] = 1.0 / p.neg_c[k]; }
   for (int k = p.kb; k < m.nlayers; k++) {
     p.stop_x[k] = (k == p.kb) ? ice_h : m.hlo[k];
     p.stop_n[k] = n_air(m, p.stop_x[k]);
@@ -216,6 +217,7 @@ void make_plan(const AirIceMedium& m, double ice_h, double depth_signed, AirIceP
   for (int k = p.kb; k + 1 < m.nlayers; k++) p.relay[k] = p.start_n[k] / p.stop_n[k + 1];
   // ice leg: surface (x=0) down to the receiver (x=depth), GetIcePropagationPar (M.cc:807-869)
   p.neg_c[AIRICE_ICE_SLOT] = -m.C_ice;
+  p.inv_neg_c[AIRICE_ICE_SLOT] = 1.0 / p.neg_c[AIRICE_ICE_SLOT];
   p.start_x[AIRICE_ICE_SLOT] = 0.0;
   p.start_n[AIRICE_ICE_SLOT] = n_ice(m, 0.0);
   p.stop_x[AIRICE_ICE_SLOT] = p.depth;

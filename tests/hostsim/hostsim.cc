@@ -70,6 +70,6 @@ void sim_forward_batch(long n, const double* th, const double* h, double ice, do
 // d/dL check: returns X and analytic dX/dL
 double sim_x_total(double h, double ice, double depth, double L, double* dXdL) {
   AirIcePlan p; make_plan(g_m, ice, depth, &p);
-  return airice_x_total<true>(g_m, p, top_layer(h), h, n_air(g_m, h), L, *dXdL);
+  return airice_x_newton(g_m, p, top_layer(h), h, n_air(g_m, h), L, *dXdL);
 }
 }
