@@ -129,14 +129,15 @@ AIRICE_HD double airice_x_exact(const AirIceMedium& m, const AirIcePlan& p, int 
 
 // X(L) and dX/dL for the Newton phase.  Only the converged root matters here (it is re-derived to ~1e-13 deg by the
 // iteration itself and the reported numbers come from airice_ray_full), so this version is arranged for throughput:
-// one log per segment (ln T_stop - ln T_start = ln(T_stop/T_start)), host-precomputed 1/C', and derivative terms
-// from low-precision reciprocals.  dG/dL = L (sA+R)^2 / (T sA R) follows from dT/dL = -L (sA+R)^2/(sA R).
+// one log per segment (ln T_stop - ln T_start = ln(T_stop/T_start)), host-precomputed 1/C', 1/R from the sqrt's own
+// refined seed.  dG/dL = L (sA+R)^2 / (T sA R) follows from dT/dL = -L (sA+R)^2/(sA R).
 AIRICE_HD double airice_x_newton(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
                                  double& dXdL) {
   const double L2 = L * L;
-  double sAir, yAir, sIce, yIce;
-  AIRICE_SQRT_RSQRT(1.0 * 1.0 - L2, sAir, yAir);
-  AIRICE_SQRT_RSQRT(m.A_ice * m.A_ice - L2, sIce, yIce);
+  // X must be good to ~1e-13 relative (the root inherits its error), so 1/sA is a full-precision reciprocal; the
+  // per-end 1/R below only enters the derivative and the Hermite slopes, where ~1e-12 is ample.
+  const double sAir = AIRICE_SQRT(1.0 * 1.0 - L2), sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
+  const double yAir = AIRICE_RCP(sAir), yIce = AIRICE_RCP(sIce);
   const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
   const int nseg = nair + (p.has_ice ? 1 : 0);
   double X = 0.0, dX = 0.0;
@@ -159,7 +160,7 @@ AIRICE_HD double airice_x_newton(const AirIceMedium& m, const AirIcePlan& p, int
     const double dG = p.neg_c[k] * (xb - xt) - AIRICE_LOG(Tb * rTt);
     const double c1 = p.inv_neg_c[k] * inv_sA;           // 1/(C' sA)
     const double seg = (L * c1) * dG;
-    const double qb = (sA + Rb) * (sA + Rb) * (AIRICE_RCP_APPROX(Tb) * yb), qt = (sA + Rt) * (sA + Rt) * (rTt * yt);
+    const double qb = (sA + Rb) * (sA + Rb) * (AIRICE_RCP(Tb) * yb), qt = (sA + Rt) * (sA + Rt) * (rTt * yt);
     const double dseg = c1 * (A * A * inv_sA * inv_sA * dG + L2 * inv_sA * (qb - qt));
     X += air ? -seg : seg;
     dX += air ? -dseg : dseg;

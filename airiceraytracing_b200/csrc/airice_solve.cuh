@@ -18,6 +18,9 @@
 
 #define AIRICE_SOLVE_GUARD_DEG 1.0e-10
 #define AIRICE_NEWTON_MAXIT 40
+#ifndef AIRICE_HERMITE_ACCEPT
+#define AIRICE_HERMITE_ACCEPT 1.0e-6   // (pending step [deg]) x (previous step [deg]) below which the Hermite root is taken
+#endif
 
 struct AirIceSolveStat {
   int n_newton;  // distance evaluations spent in the Newton phase
@@ -81,14 +84,20 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
   if (!(lo <= hi)) return NAN;      // gsl_root_fsolver_set rejects lo>hi; the reference result is undefined
   if (!finite_lo) return lo;        // f(lo) not finite: solver state never set (UB cases)
 
-  // ---- phase 1: theta* by safeguarded Newton on t = tan(incidence at Tx)
+  // ---- phase 1: theta* by safeguarded Newton on t = tan(incidence at Tx), finished by two-point inverse Hermite
+  // interpolation: with (t,g,g') at the last two iterates, the cubic t(g) through both points and slopes is
+  // evaluated at g=0.  Its error is ~ e_prev^2 e_cur^2, so once the pending Newton step is small the Hermite root is
+  // already converged and the confirming evaluation (a third of the Newton work, and the cause of most intra-warp
+  // iteration-count divergence) is skipped.
   double ts;                                        // root in t, or +-inf
   if (!(d > 0.0)) {
     ts = (d == 0.0) ? 0.0 : -INFINITY;  // X>=0: d<0 means f<0 everywhere
   } else {
     double tlo = 0.0, thi = INFINITY;  // g(tlo)<0<g(thi), g = X-d
-    double t = d / ((h - p.ice_h) + 0.55 * p.depth);
+    double t = AIRICE_DIV(d, (h - p.ice_h) + 0.55 * p.depth);
     if (!(t < t_cap)) t = t_cap;
+    double t_prev = 0.0, g_prev = 0.0, dg_prev = 0.0, step_prev_deg = INFINITY;
+    bool have_prev = false;
     ts = NAN;
 #pragma unroll 1
     for (int it = 0; it < AIRICE_NEWTON_MAXIT; it++) {
@@ -108,7 +117,8 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
         thi = t;
       }
       const double dgdt = dXdL * n_tx * w * w * w;
-      double tn = t - AIRICE_DIV(g, dgdt);
+      const double inv_dg = AIRICE_RCP(dgdt);
+      double tn = t - g * inv_dg;
       const double hi_t = thi < t_cap ? thi : t_cap;
       bool newton_step = true;
       if (!(tn > tlo) || !(tn < hi_t)) {
@@ -117,8 +127,19 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
         if (thi == INFINITY && g < 0.0) tn = t_cap; else tn = 0.5 * (tlo + hi_t);
       }
       const double step_deg = fabs(tn - t) * w * w * m.rad2deg;
+      if (newton_step && step_deg < 1.0e-7) { ts = tn; break; }
+      if (newton_step && have_prev && step_deg * step_prev_deg < AIRICE_HERMITE_ACCEPT) {
+        // inverse Hermite through (g_prev, t_prev, 1/g'_prev) and (g, t, 1/g'), evaluated at g = 0
+        const double dy = g - g_prev;
+        const double sfrac = -g_prev * AIRICE_RCP(dy);
+        const double s2 = sfrac * sfrac, s3 = s2 * sfrac;
+        const double h00 = 2.0 * s3 - 3.0 * s2 + 1.0, h10 = s3 - 2.0 * s2 + sfrac, h01 = 3.0 * s2 - 2.0 * s3, h11 = s3 - s2;
+        const double th_ = h00 * t_prev + h10 * dy * AIRICE_RCP(dg_prev) + h01 * t + h11 * dy * inv_dg;
+        if (th_ > tlo && th_ < hi_t) { ts = th_; break; }
+      }
+      have_prev = newton_step;
+      t_prev = t; g_prev = g; dg_prev = dgdt; step_prev_deg = step_deg;
       t = tn;
-      if (newton_step && step_deg < 1.0e-7) { ts = t; break; }
       if (thi < INFINITY && thi - tlo <= 4.0e-16 * thi) { ts = 0.5 * (tlo + thi); break; }
     }
     if (ts != ts) ts = t;  // iteration cap: take the last iterate
@@ -129,13 +150,34 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
   else theta_star = 180 - atan(ts) * m.rad2deg;
 
   // ---- phase 2: replay of gsl_root_fsolver_bisection + gsl_root_test_interval (M.cc:355-369).
-  // One loop serves the two endpoint signs (steps -2, -1: gsl_root_fsolver_set) and the halvings (steps >= 0),
-  // so the rare "evaluate f for real" path (MinimizeforLaunchAngle, M.cc:873-917) exists once in the code.
+  // Fast form first: as long as no probe (lo, hi or a midpoint) comes within `guard` of theta*, sign f(x) is just the
+  // side of theta* that x lies on, and GSL's update rule "keep the half whose ends differ in sign" becomes
+  //   below = mid < theta*;  take_hi = (lo_below != below);  hi = take_hi ? mid : hi;  lo = take_hi ? lo : mid.
+  // The returned root is the midpoint of the final bracket (GSL: root = 0.5*(lo+mid) or 0.5*(mid+hi)).
   const double guard = AIRICE_SOLVE_GUARD_DEG;
   const double th = theta_star;
+  {
+    double flo = lo, fhi = hi;
+    bool near = !(fabs(flo - th) > guard) || !(fabs(fhi - th) > guard);
+    bool lo_below = flo < th;
+#pragma unroll 1
+    for (int iter = 0; iter < 40; iter++) {
+      const double mid = (flo + fhi) / 2.0;
+      near = near || !(fabs(mid - th) > guard);
+      const bool below = mid < th;
+      const bool take_hi = (lo_below != below);
+      fhi = take_hi ? mid : fhi;
+      flo = take_hi ? flo : mid;
+      lo_below = take_hi ? lo_below : below;
+      if (fhi - flo < 0.000000001 * flo) break;   // gsl_root_test_interval with 0 < lo < hi
+    }
+    if (!near && flo > 0.0) return 0.5 * (flo + fhi);
+  }
+  // Careful form (about 0.2 % of solves): a probe sits within `guard` of theta*, so f is evaluated there for real
+  // (MinimizeforLaunchAngle, M.cc:873-917), including GSL's exact-zero exits.  One loop serves the two endpoint
+  // signs (steps -2, -1: gsl_root_fsolver_set) and the halvings (steps >= 0).
   int s_lo = 1, s_hi = 1;
   double root = 0.5 * (lo + hi);
-  int iter = 0;
 #pragma unroll 1
   for (int step = -2; step < 40; step++) {
     const bool probing = step < 0;
@@ -153,7 +195,6 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
     }
     if (step == -2) { s_lo = s; continue; }
     if (step == -1) { s_hi = s; continue; }
-    iter++;
     if (s_lo == 0) { root = lo; hi = lo; }
     else if (s_hi == 0) { root = hi; lo = hi; }
     else if (s == 0) { root = x; lo = x; hi = x; }
@@ -163,7 +204,6 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
     const double mn = ((lo > 0.0 && hi > 0.0) || (lo < 0.0 && hi < 0.0)) ? (al < au ? al : au) : 0.0;
     if (fabs(hi - lo) < 0.000000001 * mn) break;
   }
-  (void)iter;
   return root;
 }
 

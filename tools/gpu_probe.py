@@ -53,6 +53,7 @@ for kind, seed in (("loop", 20260418), ("coreas", 20260419)):
     ss, oks, nev = out.cpu().numpy().T, ok.cpu().numpy().astype(bool), nev.cpu().numpy()
     m = oko & oks
     dth = np.abs(ss[m, 4] - so[m, 4]) * 180 / 3.1415927
+    print(f"   angle mismatches >1e-9 deg: {(dth > 1e-9).sum()}, >1e-12: {(dth > 1e-12).sum()}")
     print(f"solve[{kind}] flags equal {np.array_equal(oko, oks)} ({(oko != oks).sum()} differ); angle max {dth.max():.3e} deg, >1e-7: {(dth > 1e-7).sum()}, bit-equal {(ss[m, 4] == so[m, 4]).mean():.5f}; evals mean {nev.mean():.3f} max {nev.max()}")
     for k, nm in {0: 'optIce', 1: 'optAir', 2: 'geoIce', 3: 'geoAir', 5: 'Xair'}.items():
         rel = np.abs(ss[m, k] - so[m, k]) / np.abs(so[m, k]); print(f"  {nm:7s} max rel {rel.max():.3e} >1e-9: {(rel > 1e-9).sum()}")
