@@ -173,9 +173,11 @@ AIRICE_HD double airice_x_newton(const AirIceMedium& m, const AirIcePlan& p, int
 // RELAY = true  -> forward tracer / table cell (GetRayTracingSolutions, M.cc:1796-2017): L is handed from layer to
 //                  layer through Snell at the boundary (L *= n_start[k]/n_stop[k+1]).
 // RELAY = false -> tail of a launch-angle solve (Air2IceRayTracing, M.cc:1524-1614): one L throughout.
+// want_inc / want_refr: whether the incidence angle on the surface and the refracted angle below it are reported by
+// the caller (each is an asin the other outputs do not need).
 template <bool RELAY>
 AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
-                               bool in_ice, AirIceRay& r) {
+                               bool in_ice, bool want_inc, bool want_refr, AirIceRay& r) {
   const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
   const int nseg = nair + (in_ice ? 1 : 0);
   double xa = 0.0, ta = 0.0, ga = 0.0, xi = 0.0, ti = 0.0, gi = 0.0;
@@ -222,7 +224,7 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
   const double n2 = p.start_n[AIRICE_ICE_SLOT];  // n_ice(0)
   const double Lsurf = in_ice ? Lk : Lk;
   const double si = AIRICE_DIV(Lsurf, n1);
-  r.inc_ice_deg = asin(si) * m.rad2deg;
+  r.inc_ice_deg = want_inc ? asin(si) * m.rad2deg : 0.0;
   // Fresnel field transmission, air->ice at the surface (M.cc:285-301, 321-337) without trig:
   // sin(theta_i) = L/n1, n1 cos(theta_i) = sqrt(n1^2-L^2) = R of the bottom end.
   const double n12 = AIRICE_DIV(n1, n2);
@@ -235,5 +237,5 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
   if (trs != trs) trs = 0.0;
   if (trp != trp) trp = 0.0;
   r.trans_s = trs; r.trans_p = trp;
-  r.refr_deg = asin(u) * m.rad2deg;  // refracted angle just below the surface (P.cc:1081)
+  r.refr_deg = want_refr ? asin(u) * m.rad2deg : 0.0;  // refracted angle just below the surface (P.cc:1081)
 }

@@ -67,14 +67,19 @@ struct airice_ctx {
 struct airice_table {
   airice_ctx* ctx = nullptr;
   bool owns = false;
-  float* cols[AIRICE_TABLE_NCOLS32] = {nullptr};
+  float* cols[AIRICE_TABLE_NCOLS32] = {nullptr};   // reference layout (column-major), owned or wrapped
+  // lookup layout, always owned: dense X, 48-byte records, per-row height, per-row trim ranges (one allocation)
+  void* pack = nullptr;
+  float* x = nullptr;
+  float4* rec = nullptr;
+  float* row_h = nullptr;
   int* row_first = nullptr;
   int* row_last = nullptr;
   int64_t n_h = 0, n_th = 0, cells = 0;
   double loop_stop_h = 0, h_step = 0;
   LookupTable view() const {
     LookupTable t;
-    for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t.col[k] = cols[k];
+    t.x = x; t.rec = rec; t.row_h = row_h;
     t.cells = cells; t.n_h = (int)n_h; t.n_th = (int)n_th;
     t.loop_stop_h = loop_stop_h; t.h_step = h_step;
     t.row_first = row_first; t.row_last = row_last;
@@ -83,6 +88,26 @@ struct airice_table {
 };
 
 namespace {
+
+// Allocate and fill the lookup layout of a table from its column-major form.
+int pack_table(airice_table* t) {
+  const size_t rec_bytes = sizeof(float4) * 3 * (size_t)t->cells;
+  const size_t x_bytes = (sizeof(float) * (size_t)t->cells + 255) / 256 * 256;
+  const size_t rowh_bytes = (sizeof(float) * (size_t)t->n_h + 255) / 256 * 256;
+  const size_t range_bytes = (sizeof(int) * (size_t)t->n_h + 255) / 256 * 256;
+  cudaError_t e = cudaMalloc(&t->pack, rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(lookup layout)");
+  char* base = (char*)t->pack;
+  t->rec = (float4*)base;
+  t->x = (float*)(base + rec_bytes);
+  t->row_h = (float*)(base + rec_bytes + x_bytes);
+  t->row_first = (int*)(base + rec_bytes + x_bytes + rowh_bytes);
+  t->row_last = (int*)(base + rec_bytes + x_bytes + rowh_bytes + range_bytes);
+  e = launch_pack_table(t->cols, t->cells, (int)t->n_h, (int)t->n_th, t->x, t->rec, t->row_h, t->row_first, t->row_last, nullptr);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+  if (e != cudaSuccess) return cuda_fail(e, "pack table");
+  return 0;
+}
 
 int ensure_slots(airice_ctx* c, size_t bytes) {
   if (c->slot_bytes >= bytes) return 0;
@@ -244,15 +269,8 @@ int airice_table_create(airice_ctx* c, double depth_m, double ice_m, double h_to
   cudaError_t e = cudaMalloc((void**)&block, sizeof(float) * t->cells * AIRICE_TABLE_NCOLS32);
   if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(table)"); }
   for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t->cols[k] = block + (int64_t)k * t->cells;
-  e = cudaMalloc((void**)&t->row_first, sizeof(int) * 2 * t->n_h);
-  if (e != cudaSuccess) { cudaFree(block); delete t; return cuda_fail(e, "cudaMalloc(row ranges)"); }
-  t->row_last = t->row_first + t->n_h;
   rc = build_rows(c, g, 0, t->n_h, nullptr, t->cols, nullptr);
-  if (rc == 0) {
-    e = launch_row_ranges(t->view(), t->row_first, t->row_last, nullptr);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
-    if (e != cudaSuccess) rc = cuda_fail(e, "row ranges");
-  }
+  if (rc == 0) rc = pack_table(t);
   if (rc) { airice_table_destroy(t); return rc; }
   *out = t;
   return 0;
@@ -267,12 +285,8 @@ int airice_table_wrap(airice_ctx* c, const float* const* d_cols32, int64_t n_h, 
   t->ctx = c; t->owns = false;
   for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t->cols[k] = const_cast<float*>(d_cols32[k]);
   t->n_h = n_h; t->n_th = n_th; t->cells = n_h * n_th; t->loop_stop_h = loop_stop_h; t->h_step = h_step;
-  cudaError_t e = cudaMalloc((void**)&t->row_first, sizeof(int) * 2 * n_h);
-  if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(row ranges)"); }
-  t->row_last = t->row_first + n_h;
-  e = launch_row_ranges(t->view(), t->row_first, t->row_last, nullptr);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
-  if (e != cudaSuccess) { airice_table_destroy(t); return cuda_fail(e, "row ranges"); }
+  int rc = pack_table(t);
+  if (rc) { airice_table_destroy(t); return rc; }
   *out = t;
   return 0;
 }
@@ -281,7 +295,7 @@ void airice_table_destroy(airice_table* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
   if (t->owns && t->cols[0]) cudaFree(t->cols[0]);
-  if (t->row_first) cudaFree(t->row_first);
+  if (t->pack) cudaFree(t->pack);
   delete t;
 }
 

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kThreads) airice_table_kernel(const AirIceMedi
   const double theta = theta_of_bin(a, j);
   const double L = airice_L_of_theta(m, ntx, theta);
   AirIceRay r;
-  airice_ray_full<true>(m, p, kt, h, ntx, L, a.in_ice != 0, r);
+  airice_ray_full<true>(m, p, kt, h, ntx, L, a.in_ice != 0, W64 && a.c64[11] != nullptr, false, r);
   const double x = r.x_air + r.x_ice;
   const double t = r.t_ice + r.t_air;
   const double opt_air = r.t_air * m.c, opt_ice = r.t_ice * m.c;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kThreads) airice_forward_kernel(const AirIceMe
   const double ntx = 1.0 + m.B[kc] * exp(-m.C[kc] * h);
   const double L = airice_L_of_theta(m, ntx, theta);
   AirIceRay r;
-  airice_ray_full<true>(m, p, kt, h, ntx, L, a.in_ice != 0, r);
+  airice_ray_full<true>(m, p, kt, h, ntx, L, a.in_ice != 0, a.c64[11] != nullptr, false, r);
   const double t = r.t_ice + r.t_air;
   const double v[AIRICE_TABLE_NCOLS64] = {h, r.x_air + r.x_ice, r.x_air, r.x_ice, t * m.c, r.t_air * m.c, r.t_ice * m.c,
                                           t * 1.0e9, r.t_air * 1.0e9, r.t_ice * 1.0e9, theta, r.inc_ice_deg, r.recv_deg,
@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(kThreads) airice_forward_kernel(const AirIceMe
     if (a.c64[k]) a.c64[k][i] = v[k];
 }
 
-__global__ void __launch_bounds__(kThreads) airice_solve_kernel(const AirIceMedium m, const AirIcePlan p, const SolveArgs a) {
+#ifndef AIRICE_SOLVE_MINBLOCKS
+#define AIRICE_SOLVE_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(kThreads, AIRICE_SOLVE_MINBLOCKS) airice_solve_kernel(const AirIceMedium m, const AirIcePlan p, const SolveArgs a) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.n) return;
   double h = a.h[i], d = a.d[i];
@@ -115,7 +118,8 @@ __global__ void __launch_bounds__(kThreads) airice_solve_kernel(const AirIceMedi
   const double theta = airice_solve_theta(m, p, kt, h, ntx, d, thR, ta, th_star, st);
   const double L = airice_L_of_theta(m, ntx, theta);
   AirIceRay r;
-  airice_ray_full<false>(m, p, kt, h, ntx, L, p.has_ice != 0, r);
+  const bool full_rec = (a.units != AIRICE_UNITS_CM_RAD);
+  airice_ray_full<false>(m, p, kt, h, ntx, L, p.has_ice != 0, full_rec && a.out[11] != nullptr, full_rec && a.out[12] != nullptr, r);
   const double thd = r.x_ice + r.x_air;
   if (a.ok) a.ok[i] = airice_check_solution(thd, d) ? 1 : 0;
   if (a.nevals) a.nevals[i] = st.n_newton + st.n_replay;
@@ -155,16 +159,31 @@ __device__ __forceinline__ bool usable_x(double v) {
 // Per-row trim of FindClosestAirTxHeight (M.cc:1050-1072) done once per table instead of once per query:
 // row_last = highest bin <= row end with a usable X, row_first = lowest bin >= row start with a usable X.
 // The scans run past the row like the reference's do (bounded by the table here).
-__global__ void airice_row_range_kernel(const LookupTable t, int* row_first, int* row_last) {
+__global__ void airice_row_range_kernel(const float* __restrict__ X, int64_t cells, int n_h, int n_th, int* row_first,
+                                        int* row_last) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= t.n_h) return;
-  const int64_t lo = (int64_t)r * t.n_th, hi = lo + t.n_th - 1;
+  if (r >= n_h) return;
+  const int64_t lo = (int64_t)r * n_th, hi = lo + n_th - 1;
   int64_t s = hi;
-  while (s >= 0 && !usable_x((double)t.col[1][s])) s--;
+  while (s >= 0 && !usable_x((double)X[s])) s--;
   int64_t e = lo;
-  while (e < t.cells && !usable_x((double)t.col[1][e])) e++;
+  while (e < cells && !usable_x((double)X[e])) e++;
   row_last[r] = (int)s;
   row_first[r] = (int)e;
+}
+
+// column-major reference layout -> lookup layout (dense X + 48-byte records + per-row height)
+__global__ void airice_pack_kernel(const float* c0, const float* c1, const float* c2, const float* c3, const float* c4,
+                                   const float* c5, const float* c6, const float* c7, const float* c8, const float* c9,
+                                   const float* c10, int64_t cells, int n_th, float* x, float4* rec, float* row_h) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cells) return;
+  const float xv = c1[i];
+  x[i] = xv;
+  rec[3 * i + 0] = make_float4(xv, c2[i], c3[i], c4[i]);
+  rec[3 * i + 1] = make_float4(c5[i], c6[i], c7[i], c8[i]);
+  rec[3 * i + 2] = make_float4(c9[i], c10[i], 0.f, 0.f);
+  if (i % n_th == 0) row_h[i / n_th] = c0[i];
 }
 
 // FindClosestTHD (M.cc:1128-1169): <=8 index halvings while the window is >=3 wide, then a linear scan.
@@ -194,35 +213,41 @@ __device__ __forceinline__ void find_thd(const float* __restrict__ X, double d, 
   i1 = index1; i2 = index2; cv = minimum;
 }
 
+__device__ __forceinline__ void load_rec(const float4* __restrict__ rec, int i, double* v) {
+  const float4 a = __ldg(rec + 3 * (int64_t)i), b = __ldg(rec + 3 * (int64_t)i + 1), c = __ldg(rec + 3 * (int64_t)i + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; v[8] = c.x; v[9] = c.y;
+}
+
 // One row of GetParValues (M.cc:1196-1240): ten parameters at distance d, or "out of range".
 __device__ __forceinline__ bool row_params(const LookupTable& t, double d, int s0, int e0, double* par) {
-  const double maxthd = (double)__ldg(t.col[1] + s0);
+  const double maxthd = (double)__ldg(t.x + s0);
   if (!(d <= maxthd)) return false;
   int i1, i2;
   double cv;
-  find_thd(t.col[1], d, s0, e0, i1, i2, cv);
+  find_thd(t.x, d, s0, e0, i1, i2, cv);
   if (cv != 0) {
-    const double x1 = (double)__ldg(t.col[1] + i1), x2 = (double)__ldg(t.col[1] + i2);
-    const double w = (d - x1) / (x2 - x1);
+    double y1[10], y2[10];
+    load_rec(t.rec, i1, y1);
+    load_rec(t.rec, i2, y2);
+    const double w = (d - y1[0]) / (y2[0] - y1[0]);
 #pragma unroll
-    for (int ip = 0; ip < 10; ip++) {
-      const double y1 = (double)__ldg(t.col[1 + ip] + i1), y2 = (double)__ldg(t.col[1 + ip] + i2);
-      par[ip] = y1 + (y2 - y1) * w;  // oneDLinearInterpolation (M.cc:992-995)
-    }
+    for (int ip = 0; ip < 10; ip++) par[ip] = y1[ip] + (y2[ip] - y1[ip]) * w;  // oneDLinearInterpolation (M.cc:992-995)
   } else {
-    const int sidx = i1 + 1;
-#pragma unroll
-    for (int ip = 0; ip < 10; ip++) par[ip] = (double)__ldg(t.col[1 + ip] + sidx);
+    load_rec(t.rec, i1 + 1, par);
   }
   return true;
 }
 
-__global__ void __launch_bounds__(kThreads) airice_lookup_kernel(const AirIceMedium m, const LookupTable t, const LookupArgs a) {
+#ifndef AIRICE_LOOKUP_MINBLOCKS
+#define AIRICE_LOOKUP_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_lookup_kernel(const AirIceMedium m, const LookupTable t, const LookupArgs a) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.n) return;
   const double h = a.h_cm[i] / 100, d = a.d_cm[i] / 100;  // M.cc:1307-1308
   const int total = (int)t.cells - 1;
-  const double maxh = (double)__ldg(t.col[0]), minh = (double)__ldg(t.col[0] + total);
+  // column 0 holds the row's Tx height in every cell: col0[c] == row_h[c / n_th]
+  const double maxh = (double)__ldg(t.row_h), minh = (double)__ldg(t.row_h + total / t.n_th);
   double PI[10];
 #pragma unroll
   for (int k = 0; k < 10; k++) PI[k] = 0.0;
@@ -232,17 +257,17 @@ __global__ void __launch_bounds__(kThreads) airice_lookup_kernel(const AirIceMed
     const int cur = (int)floor((h - t.loop_stop_h) / t.h_step);
     const int row = t.n_h - cur - 1;
     const int s1 = __ldg(t.row_first + row), e1 = __ldg(t.row_last + row);
-    const double cv0 = fabs((double)__ldg(t.col[0] + row) - h);  // column 0 indexed with the ROW index, as written (M.cc:1076)
+    const double cv0 = fabs((double)__ldg(t.row_h + row / t.n_th) - h);  // column 0 indexed with the ROW index, as written (M.cc:1076)
     int s2 = s1 - t.n_th, e2 = e1 - t.n_th;
     if (s2 < 0) s2 = s1 + t.n_th;
     if (e2 < 0) e2 = e1 + t.n_th;
     double P1[10], P2[10];
-    const double h1 = (double)__ldg(t.col[0] + s1);
+    const double h1 = (double)__ldg(t.row_h + s1 / t.n_th);
     oor1 = !row_params(t, d, s1, e1, P1);
     double h2;
     bool two = (cv0 != 0 && h > minh && s2 < total);
     if (two) {
-      h2 = (double)__ldg(t.col[0] + s2);
+      h2 = (double)__ldg(t.row_h + s2 / t.n_th);
       oor2 = !row_params(t, d, s2, e2, P2);
     } else {
       h2 = h1;
@@ -338,9 +363,15 @@ cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const Solve
   return cudaGetLastError();
 }
 
-cudaError_t launch_row_ranges(const LookupTable& t, int* row_first, int* row_last, cudaStream_t s) {
-  const int blocks = (t.n_h + 127) / 128;
-  airice_row_range_kernel<<<blocks, 128, 0, s>>>(t, row_first, row_last);
+cudaError_t launch_pack_table(const float* const* c, int64_t cells, int n_h, int n_th, float* x, float4* rec,
+                              float* row_h, int* row_first, int* row_last, cudaStream_t s) {
+  const int64_t blocks = (cells + 255) / 256;
+  if (blocks > 2147483647LL) return cudaErrorInvalidValue;
+  airice_pack_kernel<<<dim3((unsigned)blocks), 256, 0, s>>>(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10],
+                                                           cells, n_th, x, rec, row_h);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  airice_row_range_kernel<<<(n_h + 127) / 128, 128, 0, s>>>(x, cells, n_h, n_th, row_first, row_last);
   return cudaGetLastError();
 }
 

@@ -67,14 +67,23 @@ struct SolveArgs {
 cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const SolveArgs& a, cudaStream_t s);
 
 // ---- kernel 3: table lookup (GetHorizontalDistanceToIntersectionPoint_Table, M.cc:1305-1462)
+// Lookup-side layout (built once per table by launch_pack_table): the reference's column-major float table makes one
+// query touch 40+ different 32-byte sectors (10 parameters x 2 bins x 2 rows, one useful float per sector; ncu showed
+// 2.3 KB of DRAM traffic per lookup).  Here the THD column stays dense for the index search, and the ten
+// interpolated parameters of a cell sit together in one 48-byte record, so the two bins of a row are one contiguous
+// 96-byte read.
 struct LookupTable {
-  const float* col[AIRICE_TABLE_NCOLS32];
+  const float* x;          // column 1 (total horizontal distance), dense, for FindClosestTHD
+  const float4* rec;       // 3 float4 per cell: {X, opt_ice, opt_air, launch | X_air, T_S, T_P, geo_air | geo_ice, received, 0, 0}
+  const float* row_h;      // Tx height of each row (column 0 is constant along a row)
   int64_t cells;
   int n_h, n_th;
   double loop_stop_h, h_step;
   const int* row_first;  // per row: first/last bin with a usable X (trim of M.cc:1050-1072), precomputed
   const int* row_last;
 };
+cudaError_t launch_pack_table(const float* const* cols32, int64_t cells, int n_h, int n_th, float* x, float4* rec,
+                              float* row_h, int* row_first, int* row_last, cudaStream_t s);
 struct LookupArgs {
   int64_t n;
   const double* h_cm;
@@ -82,7 +91,6 @@ struct LookupArgs {
   double* out[AIRICE_LOOKUP_NCOLS];  // same 9 slots as the CM_RAD solve
   uint8_t* ok;                       // solution flag (M.cc:1356-1449)
 };
-cudaError_t launch_row_ranges(const LookupTable& t, int* row_first, int* row_last, cudaStream_t s);
 cudaError_t launch_lookup(const AirIceMedium& m, const LookupTable& t, const LookupArgs& a, cudaStream_t s);
 
 // ---- FP64 FMA peak probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)

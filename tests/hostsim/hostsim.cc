@@ -33,7 +33,7 @@ void sim_forward(double theta, double h, double ice, double depth, int inice, do
   const double ntx = n_air(g_m, h);
   const double L = airice_L_of_theta(g_m, ntx, theta);
   AirIceRay r;
-  airice_ray_full<true>(g_m, p, kt, h, ntx, L, inice != 0, r);
+  airice_ray_full<true>(g_m, p, kt, h, ntx, L, inice != 0, true, true, r);
   for (int i = 0; i < 18; i++) out[i] = 0;
   out[1] = h; out[2] = r.x_air + r.x_ice; out[3] = r.x_air; out[4] = r.x_ice;
   out[5] = (r.t_ice + r.t_air) * g_m.c; out[6] = r.t_air * g_m.c; out[7] = r.t_ice * g_m.c;
@@ -53,7 +53,7 @@ int sim_solve_cm(double h_cm, double d_cm, double depth_cm, double ice_cm, doubl
   const double theta = airice_solve_theta(g_m, p, kt, h, ntx, d, thR, ta, ths, st);
   const double L = airice_L_of_theta(g_m, ntx, theta);
   AirIceRay r;
-  airice_ray_full<false>(g_m, p, kt, h, ntx, L, p.has_ice != 0, r);
+  airice_ray_full<false>(g_m, p, kt, h, ntx, L, p.has_ice != 0, true, true, r);
   out[0] = (r.t_ice * g_m.c) * 100; out[1] = (r.t_air * g_m.c) * 100; out[2] = r.p_ice * 100; out[3] = r.p_air * 100;
   out[4] = theta * (g_m.pi / 180); out[5] = r.x_air * 100; out[6] = r.trans_s; out[7] = r.trans_p;
   out[8] = r.recv_deg * (g_m.pi / 180);
