@@ -1,0 +1,393 @@
+// airice_inice.cuh -- in-ice ray solver (Tx and Rx both in the ice): direct, reflected and up to two refracted
+// rays per Tx->Rx pair, one thread per pair.
+//
+// Reference: /root/reference/IceRayTracing.cc -- IceRayTracing() :1745-1919, GetDirectRayPar :626-742,
+// GetReflectedRayPar :745-920, GetRefractedRayPar :923-1253, root functions fDa/fRa/fRaa :411-607, fDnfR_L :368-379,
+// GetZmax :346-353, FindFunctionRoot (GSL falsepos, |f|<1e-6, <=100 it) :261-300, FindFunctionRootZmax :303-335,
+// FindFunctionRootFDF (GSL newton + gsl_deriv_central) :222-258.  TransitionBoundary == 0 (IceRayTracing.hh:49).
+//
+// Unlike the air->ice solve, nothing here can be short-cut: the reference stops its false-position iteration as
+// soon as |f| < 1e-6 m, so the L it returns (and with it every launch angle to ~1e-6 deg, and the accept/reject
+// decision |f|<0.5 that defines the solution-branch count) is a property of the ITERATION, not of the root.  The
+// kernel therefore runs the same recurrences -- regula falsi with GSL's bisection safeguard, the nested falsepos for
+// the turning depth z_max(L), Newton with the 5-point numerical derivative, and the retry ladder for the second
+// refracted ray -- on registers.  What changes is the cost of each function evaluation: n(z0), n(z1), n(1e-7) are
+// computed once per pair instead of 2-3 exp() per evaluation, and heap/indirection is gone.
+#pragma once
+#include "airice_core.cuh"
+
+struct AirIceInIce {      // ice model + constants of the IceRayTracing namespace
+  double A, B, C;         // IceRayTracing.hh:45-56
+  double pi;              // 3.14159265359 (IceRayTracing.hh:41, sic)
+  double c;               // 299792458
+};
+
+struct InIcePair {
+  double A, B, C, z0, z1, x1;   // z0 <= z1 after the flip (Tx deeper), both negative
+  double n0, n1, ns;            // n(z0), n(z1), n(1e-7)
+};
+
+AIRICE_HD double inice_nz(const AirIceInIce& m, double z) { z = fabs(z); return m.A + m.B * exp(-m.C * z); }
+
+// fDnfR_L (IceRayTracing.cc:368-379) with n(Z) supplied
+AIRICE_HD double inice_fL(double A, double L, double Cp, double Z, double nZ) {
+  return (L / Cp) * (1.0 / sqrt(A * A - L * L)) * (Cp * Z - log(A * nZ - L * L + sqrt(A * A - L * L) * sqrt(nZ * nZ - L * L)));
+}
+
+// ---- GSL pieces, restated (see oracle/gsl_standin/gsl_standin.c for the same algorithms on the test side)
+struct InIceBracket { double f_lower, f_upper, root, x_lower, x_upper; };
+
+template <class F>
+AIRICE_HD void inice_falsepos_set(const F& f, InIceBracket& s, double lo, double hi) {
+  s.f_lower = 0.0; s.f_upper = 0.0;            // zero-initialised solver state
+  s.root = 0.5 * (lo + hi); s.x_lower = lo; s.x_upper = hi;
+  const double fl = f(lo);
+  if (!isfinite(fl)) return;                    // GSL_EBADFUNC: state left as it was
+  const double fu = f(hi);
+  if (!isfinite(fu)) return;
+  s.f_lower = fl; s.f_upper = fu;
+}
+
+template <class F>
+AIRICE_HD void inice_falsepos_iterate(const F& f, InIceBracket& s) {
+  const double xl = s.x_lower, xr = s.x_upper, fl = s.f_lower, fu = s.f_upper;
+  if (fl == 0.0) { s.root = xl; s.x_upper = xl; return; }
+  if (fu == 0.0) { s.root = xr; s.x_lower = xr; return; }
+  const double x_lin = xr - (fu * (xl - xr) / (fl - fu));
+  const double f_lin = f(x_lin);
+  if (!isfinite(f_lin)) return;
+  if (f_lin == 0.0) { s.root = x_lin; s.x_lower = x_lin; s.x_upper = x_lin; return; }
+  double w;
+  if ((fl > 0.0 && f_lin < 0.0) || (fl < 0.0 && f_lin > 0.0)) { s.root = x_lin; s.x_upper = x_lin; s.f_upper = f_lin; w = x_lin - xl; }
+  else { s.root = x_lin; s.x_lower = x_lin; s.f_lower = f_lin; w = xr - x_lin; }
+  if (w < 0.5 * (xr - xl)) return;
+  const double xb = 0.5 * (xl + xr);
+  const double fb = f(xb);
+  if (!isfinite(fb)) return;
+  if ((fl > 0.0 && fb < 0.0) || (fl < 0.0 && fb > 0.0)) {
+    s.x_upper = xb; s.f_upper = fb;
+    if (s.root > xb) s.root = 0.5 * (xl + xb);
+  } else {
+    s.x_lower = xb; s.f_lower = fb;
+    if (s.root < xb) s.root = 0.5 * (xb + xr);
+  }
+}
+
+// FindFunctionRoot (IceRayTracing.cc:261-300)
+template <class F>
+AIRICE_HD double inice_find_root(const F& f, double lo, double hi) {
+  InIceBracket s;
+  if (lo > hi) {            // gsl_root_fsolver_set refuses; solver has no bracket (zeroed): every iterate reports 0
+    s.f_lower = 0; s.f_upper = 0; s.root = 0; s.x_lower = 0; s.x_upper = 0;
+  } else {
+    inice_falsepos_set(f, s, lo, hi);
+  }
+  double r = 0;
+#pragma unroll 1
+  for (int iter = 0; iter < 100; iter++) {
+    inice_falsepos_iterate(f, s);
+    r = s.root;
+    const double check = f(r);
+    if (fabs(check) < 1e-6) break;
+  }
+  return r;
+}
+
+// GetZmax (IceRayTracing.cc:346-353) = FindFunctionRootZmax(GetMinnz, 0, 5000) (IceRayTracing.cc:303-335)
+struct InIceMinnz {
+  double A, B, C, L;
+  AIRICE_HD double operator()(double x) const { return A + B * exp(-C * x) - L; }   // raw x, not |x| (IceRayTracing.cc:342)
+};
+AIRICE_HD double inice_zmax(double A, double B, double C, double L) {
+  InIceMinnz f = {A, B, C, L};
+  InIceBracket s;
+  inice_falsepos_set(f, s, 0.0, 5000.0);
+  double r = 0;
+#pragma unroll 1
+  for (int iter = 0; iter < 100; iter++) {
+    inice_falsepos_iterate(f, s);
+    r = s.root;
+    const double lo = s.x_lower, hi = s.x_upper;
+    if (lo > hi) break;  // GSL_EINVAL != GSL_CONTINUE
+    const double al = fabs(lo), au = fabs(hi);
+    const double mn = ((lo > 0.0 && hi > 0.0) || (lo < 0.0 && hi < 0.0)) ? (al < au ? al : au) : 0.0;
+    if (fabs(hi - lo) < 1e-6 + 1e-6 * mn) break;
+  }
+  return r;
+}
+
+// root functions of L (IceRayTracing.cc:411-607), TransitionBoundary == 0 branches
+struct InIceFDa {
+  InIcePair g;
+  AIRICE_HD double operator()(double L) const {
+    return (inice_fL(g.A, L, g.C, g.z1, g.n1) - inice_fL(g.A, L, g.C, g.z0, g.n0)) - g.x1;
+  }
+};
+struct InIceFRa {
+  InIcePair g;
+  AIRICE_HD double operator()(double L) const {
+    const double fb = inice_fL(g.A, L, -g.C, -g.z0, g.n0);
+    const double d01 = inice_fL(g.A, L, -g.C, -g.z1, g.n1) - fb;
+    const double d0s = inice_fL(g.A, L, -g.C, 1e-7, g.ns) - fb;
+    return d01 - 2 * (d0s) - g.x1;
+  }
+};
+struct InIceFRaa {
+  InIcePair g;
+  AIRICE_HD double operator()(double L) const {
+    const double zmax = inice_zmax(g.A, g.B, g.C, L) + 1e-7;
+    if (!(zmax > 0)) return 1e9;
+    const double nzm = g.A + g.B * exp(-g.C * fabs(zmax));
+    const double fb = inice_fL(g.A, L, -g.C, -g.z0, g.n0);
+    double d01 = inice_fL(g.A, L, -g.C, -g.z1, g.n1) - fb;
+    double d0s = inice_fL(g.A, L, -g.C, zmax, nzm) - fb;
+    if (d01 != d01) d01 = 1e9;
+    if (d0s != d0s) d0s = 1e9;
+    return d01 - 2 * (d0s) - g.x1;
+  }
+};
+
+// gsl_deriv_central (deriv/deriv.c)
+template <class F>
+AIRICE_HD void inice_central(const F& f, double x, double h, double& result, double& round, double& trunc) {
+  const double fm1 = f(x - h), fp1 = f(x + h), fmh = f(x - h / 2), fph = f(x + h / 2);
+  const double r3 = 0.5 * (fp1 - fm1);
+  const double r5 = (4.0 / 3.0) * (fph - fmh) - (1.0 / 3.0) * r3;
+  const double e3 = (fabs(fp1) + fabs(fm1)) * 2.2204460492503131e-16;
+  const double e5 = 2.0 * (fabs(fph) + fabs(fmh)) * 2.2204460492503131e-16 + e3;
+  const double a = fabs(r3 / h), b = fabs(r5 / h);
+  const double dy = (a > b ? a : b) * (fabs(x) / h) * 2.2204460492503131e-16;
+  result = r5 / h;
+  trunc = fabs((r5 - r3) / h);
+  round = fabs(e5 / h) + dy;
+}
+template <class F>
+AIRICE_HD double inice_deriv_central(const F& f, double x, double h) {
+  double r0, round, trunc;
+  inice_central(f, x, h, r0, round, trunc);
+  double error = round + trunc;
+  if (round < trunc && (round > 0 && trunc > 0)) {
+    double ro, round_o, trunc_o;
+    const double h_opt = h * pow(round / (2.0 * trunc), 1.0 / 3.0);
+    inice_central(f, x, h_opt, ro, round_o, trunc_o);
+    const double error_o = round_o + trunc_o;
+    if (error_o < error && fabs(ro - r0) < 4.0 * error) { r0 = ro; error = error_o; }
+  }
+  return r0;
+}
+
+// FindFunctionRootFDF (IceRayTracing.cc:222-258): GSL newton with df from gsl_deriv_central(h=1e-8)
+template <class F>
+AIRICE_HD double inice_newton_root(const F& f, double lo, double hi) {
+  double x = (lo + hi) / 2;
+  double fv = f(x), df = inice_deriv_central(f, x, 1e-8);
+  double root = x;
+#pragma unroll 1
+  for (int iter = 0; iter < 100; iter++) {
+    if (df != 0.0) {                       // else GSL_EZERODIV: root unchanged
+      const double rn = root - (fv / df);
+      root = rn;
+      fv = f(rn);
+      df = inice_deriv_central(f, rn, 1e-8);
+    }
+    const double x0 = x;
+    x = root;
+    if (fabs(x - x0) < 1e-6 * fabs(x) || x == x0) break;
+  }
+  return x;
+}
+
+// fDnfR as a function of depth (IceRayTracing.cc:355-365), n(x) evaluated per call like the reference
+struct InIceFDepth {
+  double A, B, C, Cp, L;
+  AIRICE_HD double operator()(double x) const {
+    const double n = A + B * exp(-C * fabs(x));
+    return (L / Cp) * (1.0 / sqrt(A * A - L * L)) * (Cp * x - log(A * n - L * L + sqrt(A * A - L * L) * sqrt(n * n - L * L)));
+  }
+};
+
+// ftimeD / fpathD (IceRayTracing.cc:382-408) through the identities of airice_core.cuh
+AIRICE_HD void inice_time_path(const AirIceInIce& m, double x, double Cp, double L, double& t, double& p) {
+  const double A = m.A;
+  const double n = inice_nz(m, x);
+  const double D = n * n - L * L, R = sqrt(D), sA = sqrt(A * A - L * L);
+  const double G = Cp * x - log(A * n - L * L + sA * R), H = log(n + R);
+  t = (1.0 / ((m.c * Cp) * R)) * ((D + (G * (A * A * R)) / sA) + (A * R) * H);
+  p = (H + (A / sA) * G) / Cp;
+}
+
+// IceRayTracing::IceRayTracing(0, z0, x1, z1) -> out[29] (IceRayTracing.cc:1745-1919).  Slots 12..17 are written only
+// when the branch exists in the reference; here absent ones are 0.  Returns the 4-bit branch mask (D,R,Ra1,Ra2).
+AIRICE_HD int inice_solve(const AirIceInIce& m, double z0_in, double x1, double z1_in, double* out) {
+  const double k180pi = 180.0 / m.pi, kpi180 = m.pi / 180.0;
+  // common flip: the tracer wants the transmitter deeper than the receiver (IceRayTracing.cc:631-637)
+  double z0 = z0_in, z1 = z1_in;
+  const bool flip = z0 > z1;
+  if (flip) { z0 = z1_in; z1 = z0_in; }
+  InIcePair g;
+  g.A = m.A; g.B = m.B; g.C = m.C; g.z0 = z0; g.z1 = z1; g.x1 = x1;
+  g.n0 = inice_nz(m, z0); g.n1 = inice_nz(m, z1); g.ns = inice_nz(m, 1e-7);
+
+  // ---------------- direct ray (IceRayTracing.cc:626-742)
+  double RangD, LangD, timeD, pathD, lvalueD, checkD;
+  {
+    InIceFDa f = {g};
+    const double up = g.n1 < g.n0 ? g.n1 : g.n0;   // min_element keeps the first of equals; values equal then
+    lvalueD = inice_find_root(f, 1e-7, up);
+    LangD = asin(lvalueD / g.n0) * k180pi;
+    checkD = f(lvalueD);
+    double ta, pa, tb, pb;
+    inice_time_path(m, -z0, -m.C, lvalueD, ta, pa);
+    inice_time_path(m, -z1, -m.C, lvalueD, tb, pb);
+    timeD = ta - tb; pathD = pa - pb;
+    InIceFDepth fd = {m.A, m.B, m.C, -m.C, lvalueD};
+    RangD = atan(inice_deriv_central(fd, -z1, 1e-8)) * k180pi;
+    if (z1 == z0 && RangD != RangD) RangD = 180 - LangD;
+    if (checkD != checkD) checkD = -1000;
+  }
+  double outD0 = RangD, outD1 = LangD;
+  if (flip) { outD0 = 180 - LangD; outD1 = 180 - RangD; }
+
+  // ---------------- reflected ray (IceRayTracing.cc:745-920)
+  double RangR, LangR, timeR, timeR1, timeR2, pathR, lvalueR, checkR, incAng;
+  {
+    InIceFRa f = {g};
+    double up = g.n1;
+    if (g.n0 < up) up = g.n0;
+    if (g.ns < up) up = g.ns;
+    lvalueR = inice_find_root(f, 1e-7, up);
+    LangR = asin(lvalueR / g.n0) * k180pi;
+    checkR = f(lvalueR);
+    double ts, ps, ta, pa, tb, pb;
+    inice_time_path(m, -1e-7, m.C, lvalueR, ts, ps);
+    inice_time_path(m, z0, m.C, lvalueR, ta, pa);
+    inice_time_path(m, z1, m.C, lvalueR, tb, pb);
+    timeR1 = ts - ta; timeR2 = ts - tb;
+    double pathR1 = ps - pa, pathR2 = ps - pb;
+    timeR = timeR1 + timeR2; pathR = pathR1 + pathR2;
+    if (flip) { const double d = timeR2; timeR2 = timeR1; timeR1 = d; }
+    InIceFDepth fd = {m.A, m.B, m.C, m.C, lvalueR};
+    RangR = 180 - atan(inice_deriv_central(fd, z1, 1e-8)) * k180pi;
+    if (z1 == z0 && RangR != RangR) RangR = 180 - LangR;
+    if (z1 != z0 && RangR != RangR) RangR = 90;
+    if (checkR != checkR) checkR = -1000;
+    incAng = atan(inice_deriv_central(fd, -1e-7, 1e-8)) * k180pi;
+  }
+  double outR0 = RangR, outR1 = LangR;
+  if (flip) { outR0 = 180 - LangR; outR1 = 180 - RangR; }
+
+  // ---------------- refracted rays (IceRayTracing.cc:923-1253), only when D or R is missing (IceRayTracing.cc:1806)
+  double RangRa[2] = {0, 0}, LangRa[2] = {0, 0}, timeRa[2] = {0, 0}, lvalueRa[2] = {0, 0}, checkRa[2] = {-1000, -1000};
+  double timeRa1[2] = {0, 0}, timeRa2[2] = {0, 0}, zmaxv[2] = {0, 0}, pathRa[2] = {0, 0};
+  if (fabs(checkR) > 0.5 || fabs(checkD) > 0.5) {
+    // the callee receives the (already un-flipped) outputs of the reflected ray and flips them back (IceRayTracing.cc:937-941)
+    double LangR_in = outR1;
+    if (flip) LangR_in = 180 - outR0;
+    InIceFRaa f = {g};
+    double lv[2] = {0, 0}, La[2] = {0, 0}, cz[2] = {-1000, -1000}, zm[2] = {10, 10};
+    const double up = g.n0 < g.n1 ? g.n0 : g.n1;
+    double lower = g.n0 * sin((64.0 * kpi180));
+    if (lower > up) lower = g.n0 * sin((LangR_in * kpi180));
+    lv[0] = inice_find_root(f, lower, up);
+    La[0] = asin(lv[0] / g.n0) * k180pi;
+    cz[0] = f(lv[0]);
+    zm[0] = inice_zmax(m.A, m.B, m.C, lv[0]) + 1e-7;
+    if (fabs(cz[0]) > 0.5) {
+      lv[0] = inice_newton_root(f, lower, up);
+      La[0] = asin(lv[0] / g.n0) * k180pi;
+      cz[0] = f(lv[0]);
+      zm[0] = inice_zmax(m.A, m.B, m.C, lv[0]) + 1e-7;
+    }
+    if (lv[0] < 0) cz[0] = -1000;
+#define INICE_RETRY(expr_root)                                   \
+  do {                                                           \
+    lv[1] = (expr_root);                                         \
+    La[1] = asin(lv[1] / g.n0) * k180pi;                         \
+    cz[1] = f(lv[1]);                                            \
+    zm[1] = inice_zmax(m.A, m.B, m.C, lv[1]) + 1e-7;             \
+  } while (0)
+#define INICE_BAD1 (fabs(cz[1]) > 0.5 || cz[1] != cz[1] || fabs(lv[1] - lv[0]) < 1e-4)
+    if (fabs(cz[0]) < 0.5 && fabs(checkD) > 0.5 && fabs(checkR) > 0.5) {
+      INICE_RETRY(inice_find_root(f, lv[0] - 0.23, lv[0] - 0.023));
+      if (INICE_BAD1) INICE_RETRY(inice_find_root(f, lv[0] - 0.15, lv[0] - 0.023));
+      if (INICE_BAD1) {
+        if (lv[0] + 0.005 < up) INICE_RETRY(inice_find_root(f, lv[0] + 0.005, up));
+        else INICE_RETRY(inice_find_root(f, lv[0] - 0.1, lv[0] - 0.01));
+      }
+      if (INICE_BAD1) {
+        const double tmp = inice_newton_root(f, lv[0] - 0.23, lv[0] - 0.023);
+        if (fabs(tmp) < m.A) INICE_RETRY(tmp);   // the reference solves the same problem twice (IceRayTracing.cc:1029-1031)
+      }
+      if (INICE_BAD1) {
+        const double tmp = inice_newton_root(f, lv[0] - 0.1, lv[0] - 0.023);
+        if (fabs(tmp) < m.A) INICE_RETRY(tmp);
+      }
+      if (lv[1] < 0) cz[1] = -1000;
+      if (fabs(cz[1]) < 0.5 && fabs(cz[0]) < 0.5 && fabs(lv[1] - lv[0]) < 1e-4) cz[1] = -1000;
+      if (La[0] != La[0]) La[0] = 0;
+      if (La[1] != La[1]) La[1] = 0;
+      if (La[1] < La[0] && fabs(cz[0]) < 0.5 && fabs(cz[1]) < 0.5) {
+        double t;
+        t = lv[1]; lv[1] = lv[0]; lv[0] = t;
+        t = La[1]; La[1] = La[0]; La[0] = t;
+        t = cz[1]; cz[1] = cz[0]; cz[0] = t;
+        t = zm[1]; zm[1] = zm[0]; zm[0] = t;
+      }
+    } else {
+      lv[1] = 0; La[1] = 0; cz[1] = -1000; zm[1] = -1000;
+    }
+#undef INICE_RETRY
+#undef INICE_BAD1
+    double tRa[2] = {0, 0}, tRa1[2] = {0, 0}, tRa2[2] = {0, 0}, pRa[2] = {0, 0}, Ra[2] = {0, 0};
+#pragma unroll 1
+    for (int i = 0; i < 2; i++) {
+      if (cz[i] != cz[i]) cz[i] = -1000;
+      if (zm[i] == 1e-7 || zm[i] <= 0) cz[i] = -1000;
+      if ((z0 < -zm[i] || zm[i] < -z1)) {
+        double tm, pm, ta, pa, tb, pb;
+        inice_time_path(m, -zm[i], m.C, lv[i], tm, pm);
+        inice_time_path(m, z0, m.C, lv[i], ta, pa);
+        inice_time_path(m, z1, m.C, lv[i], tb, pb);
+        tRa1[i] = tm - ta; tRa2[i] = tm - tb;
+        tRa[i] = tRa1[i] + tRa2[i];
+        pRa[i] = (pm - pa) + (pm - pb);
+        if (flip) { const double d = tRa2[i]; tRa2[i] = tRa1[i]; tRa1[i] = d; }
+      }
+      InIceFDepth fd = {m.A, m.B, m.C, m.C, lv[i]};
+      Ra[i] = 180 - atan(inice_deriv_central(fd, z1, 1e-8)) * k180pi;
+      if (z1 == z0 && Ra[i] != Ra[i]) Ra[i] = 180 - La[i];
+      if (z1 != z0 && Ra[i] != Ra[i]) Ra[i] = 90;
+    }
+    if (cz[0] != cz[0]) cz[0] = -1000;
+    if (cz[1] != cz[1]) cz[1] = -1000;
+    // callee outputs (IceRayTracing.cc:1215-1250): angles un-flipped
+    for (int i = 0; i < 2; i++) {
+      double o0 = Ra[i], o1 = La[i];
+      if (flip) { o0 = 180 - La[i]; o1 = 180 - Ra[i]; }
+      const bool take = (i == 0) || (fabs(checkR) > 0.5 && fabs(checkD) > 0.5);  // IceRayTracing.cc:1816
+      if (take) {
+        RangRa[i] = o0; LangRa[i] = o1; timeRa[i] = tRa[i]; lvalueRa[i] = lv[i]; checkRa[i] = cz[i];
+        timeRa1[i] = tRa1[i]; timeRa2[i] = tRa2[i]; zmaxv[i] = zm[i];
+      }
+      pathRa[i] = pRa[i];
+    }
+  }
+
+  out[0] = outD1; out[1] = outR1; out[2] = LangRa[0]; out[3] = LangRa[1];
+  out[4] = timeD; out[5] = timeR; out[6] = timeRa[0]; out[7] = timeRa[1];
+  out[8] = outD0; out[9] = outR0; out[10] = RangRa[0]; out[11] = RangRa[1];
+  out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 0; out[16] = 0; out[17] = 0;
+  if (fabs(checkR) < 0.5) { out[12] = timeR1; out[13] = timeR2; }
+  if (fabs(checkRa[0]) < 0.5) { out[14] = timeRa1[0]; out[15] = timeRa2[0]; }
+  if (fabs(checkRa[1]) < 0.5) { out[16] = timeRa1[1]; out[17] = timeRa2[1]; }
+  out[18] = incAng;
+  out[19] = lvalueD; out[20] = lvalueR; out[21] = lvalueRa[0]; out[22] = lvalueRa[1];
+  out[23] = zmaxv[0]; out[24] = zmaxv[1];
+  out[25] = pathD; out[26] = pathR; out[27] = pathRa[0]; out[28] = pathRa[1];
+  int mask = 15;
+  if (fabs(checkD) > 0.5) { out[8] = -1000; mask &= ~1; }
+  if (fabs(checkR) > 0.5) { out[9] = -1000; mask &= ~2; }
+  if (fabs(checkRa[0]) > 0.5) { out[10] = -1000; mask &= ~4; }
+  if (fabs(checkRa[1]) > 0.5) { out[11] = -1000; mask &= ~8; }
+  return mask;
+}

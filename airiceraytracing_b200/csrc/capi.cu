@@ -486,6 +486,58 @@ int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const do
   return 0;
 }
 
+int airice_inice_solve_device(airice_ctx* c, int64_t n, const double* d_z0, const double* d_x1, const double* d_z1,
+                              double* const* d_out, uint8_t* d_mask, void* stream) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!d_z0 || !d_x1 || !d_z1 || !d_out) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  InIceArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n; a.z0 = d_z0; a.x1 = d_x1; a.z1 = d_z1;
+  a.A = c->medium.A_ice; a.B = c->medium.B_ice; a.C = c->medium.C_ice;
+  for (int k = 0; k < AIRICE_INICE_NCOLS; k++) a.out[k] = d_out[k];
+  a.mask = d_mask;
+  cudaError_t e = launch_inice(a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_inice");
+  return 0;
+}
+
+int airice_inice_solve_host(airice_ctx* c, int64_t n, const double* z0, const double* x1, const double* z1, double* out,
+                            uint8_t* mask) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!z0 || !x1 || !z1 || !out || !mask) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int nc = AIRICE_INICE_NCOLS;
+  const int64_t chunk = n < (1 << 19) ? n : (1 << 19);
+  int rc = ensure_slots(c, (size_t)chunk * (sizeof(double) * (3 + nc) + 1) + 64);
+  if (rc) return rc;
+  int slot = 0;
+  for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    double* dh = (double*)c->dev[slot];
+    cudaStream_t s = c->streams[slot];
+    CK(cudaMemcpyAsync(dh, z0 + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, x1 + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + 2 * chunk, z1 + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    InIceArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = m; a.z0 = dh; a.x1 = dh + chunk; a.z1 = dh + 2 * chunk;
+    a.A = c->medium.A_ice; a.B = c->medium.B_ice; a.C = c->medium.C_ice;
+    for (int k = 0; k < nc; k++) a.out[k] = dh + (3 + k) * chunk;
+    a.mask = (uint8_t*)(dh + (3 + nc) * chunk);
+    cudaError_t e = launch_inice(a, s);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_inice");
+    for (int k = 0; k < nc; k++)
+      CK(cudaMemcpyAsync(out + (int64_t)k * n + off, a.out[k], sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(mask + off, a.mask, (size_t)m, cudaMemcpyDeviceToHost, s));
+  }
+  for (int s = 0; s < airice_ctx::kSlots; s++)
+    if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
+  return 0;
+}
+
 int airice_fp64_peak_tflops(airice_ctx* c, double* tflops) {
   if (!c || !tflops) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));

@@ -93,6 +93,19 @@ struct LookupArgs {
 };
 cudaError_t launch_lookup(const AirIceMedium& m, const LookupTable& t, const LookupArgs& a, cudaStream_t s);
 
+// ---- kernel 4: in-ice direct / reflected / refracted solver (IceRayTracing::IceRayTracing, IceRayTracing.cc:1745-1919)
+#define AIRICE_INICE_NCOLS 29
+struct InIceArgs {
+  int64_t n;
+  const double* z0;   // Tx depth (negative), Rx depth (negative), horizontal distance; Tx at x = 0
+  const double* x1;
+  const double* z1;
+  double A, B, C;     // ice model n(z) = A + B exp(-C |z|)
+  double* out[AIRICE_INICE_NCOLS];  // the 29 slots of the reference's output array, SoA; nullptr = skip
+  uint8_t* mask;      // bit0 D, bit1 R, bit2 Ra1, bit3 Ra2: which branches exist (receive-angle slot != -1000)
+};
+cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s);
+
 // ---- FP64 FMA peak probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
 cudaError_t fp64_peak_probe(double* tflops_out, int iters, cudaStream_t s);
 

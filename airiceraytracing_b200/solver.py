@@ -219,6 +219,38 @@ class AirIceSolver:
         return out, ok
 
 
+INICE_COLUMNS = ["launch_d", "launch_r", "launch_ra1", "launch_ra2", "t_d", "t_r", "t_ra1", "t_ra2", "recv_d", "recv_r",
+                 "recv_ra1", "recv_ra2", "t_r_1", "t_r_2", "t_ra1_1", "t_ra1_2", "t_ra2_1", "t_ra2_2", "incidence",
+                 "L_d", "L_r", "L_ra1", "L_ra2", "zmax_1", "zmax_2", "path_d", "path_r", "path_ra1", "path_ra2"]
+
+
+def _inice_solve(self, z0, x1, z1):
+    """In-ice D/R/Ra solver on device tensors -> (out [29, n] f64, mask [n] uint8)."""
+    z0 = z0.to(self.torch_device, torch.float64).contiguous()
+    x1 = x1.to(self.torch_device, torch.float64).contiguous()
+    z1 = z1.to(self.torch_device, torch.float64).contiguous()
+    n = z0.numel()
+    out = torch.empty((_capi.INICE_COLS, n), dtype=torch.float64, device=self.torch_device)
+    mask = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
+    check(self.lib.airice_inice_solve_device(self.handle, n, z0.data_ptr(), x1.data_ptr(), z1.data_ptr(),
+                                             ptr_array([out[k].data_ptr() for k in range(_capi.INICE_COLS)]),
+                                             mask.data_ptr(), _stream_ptr(self.torch_device)))
+    return out, mask
+
+
+def _inice_solve_host(self, z0, x1, z1):
+    n = int(z0.shape[0])
+    out = np.empty((_capi.INICE_COLS, n), dtype=np.float64)
+    mask = np.empty(n, dtype=np.uint8)
+    check(self.lib.airice_inice_solve_host(self.handle, n, _host_ptr(z0), _host_ptr(x1), _host_ptr(z1), _host_ptr(out),
+                                           _host_ptr(mask)))
+    return out, mask
+
+
+AirIceSolver.inice_solve = _inice_solve
+AirIceSolver.inice_solve_host = _inice_solve_host
+
+
 def _host_ptr(a):
     if isinstance(a, torch.Tensor):
         assert a.device.type == "cpu" and a.is_contiguous()

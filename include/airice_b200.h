@@ -101,6 +101,18 @@ int airice_lookup_device(airice_ctx *ctx, const airice_table *t, int64_t n, cons
 int airice_lookup_host(airice_ctx *ctx, const airice_table *t, int64_t n, const double *h_cm, const double *dist_cm,
                        double *out, uint8_t *ok);
 
+/* ---- kernel 4: in-ice solver = IceRayTracing::IceRayTracing(0, z0, x1, z1) (IceRayTracing.cc:1745-1919; direct,
+ * reflected and up to two refracted rays by GetDirectRayPar :626, GetReflectedRayPar :745, GetRefractedRayPar :923).
+ * Depths negative, metres; out: 29 column pointers = the 29 slots of the reference's output array (launch angles 0-3,
+ * times 4-7, receive angles 8-11 with -1000 = branch absent, sub-times 12-17, incidence 18, L 19-22, z_max 23-24,
+ * geometric paths 25-28); mask bit0..3 = D, R, Ra1, Ra2 present (the solution-branch count is its popcount).
+ * The ice model is the context's (airice_set_ice_model; IceRayTracing::SetA/SetB/SetC in the reference). */
+#define AIRICE_INICE_COLS 29
+int airice_inice_solve_device(airice_ctx *ctx, int64_t n, const double *d_z0, const double *d_x1, const double *d_z1,
+                              double *const *d_out, uint8_t *d_mask, void *stream);
+int airice_inice_solve_host(airice_ctx *ctx, int64_t n, const double *z0, const double *x1, const double *z1, double *out,
+                            uint8_t *mask);
+
 /* ---- measurement helpers */
 int airice_fp64_peak_tflops(airice_ctx *ctx, double *tflops); /* dependent-free DFMA probe, roofline denominator */
 int airice_sync(airice_ctx *ctx);

@@ -404,3 +404,19 @@ class PyWrapReference:
         out = np.zeros(15)
         self.lib.pyref_air2ice(h, d, ice, depth, thR, _dp(out))
         return out
+
+
+class IceRayReference:
+    """The unmodified reference IceRayTracing.cc (in-ice direct / reflected / refracted solver)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(REFDIR, "libiceray_ref.so"))
+        self.lib.iceref_solve_batch.argtypes = [C.c_long, c_double_p, c_double_p, c_double_p, c_double_p]
+
+    def solve_batch(self, z0, x1, z1):
+        z0 = np.ascontiguousarray(z0, dtype=np.float64)
+        x1 = np.ascontiguousarray(x1, dtype=np.float64)
+        z1 = np.ascontiguousarray(z1, dtype=np.float64)
+        out = np.zeros((z0.size, 29))
+        self.lib.iceref_solve_batch(z0.size, _dp(z0), _dp(x1), _dp(z1), _dp(out))
+        return out

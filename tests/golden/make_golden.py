@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from oracle.ref import PyWrapReference, Reference, old_interp, old_make_table  # noqa: E402
+from oracle.ref import IceRayReference, PyWrapReference, Reference, old_interp, old_make_table  # noqa: E402
 
 PI_M = 3.1415927
 ICE_CM, DEPTH_CM = 300000.0, -20000.0
@@ -99,6 +99,19 @@ def main():
     qv = np.array([[old_interp(ref, float(a), float(b), p) for p in range(9)] for a, b in zip(qh, qt)])
     np.savez_compressed(os.path.join(HERE, "old_table.npz"), cols=ocols, n_h=info["n_h"], n_th=info["n_th"], qh=qh, qt=qt, qv=qv,
                         ice_cm=ICE_CM, depth_cm=DEPTH_CM, **og)
+
+    # ---- in-ice solver IceRayTracing::IceRayTracing(0, z0, x1, z1): 29 outputs per pair
+    rng = np.random.default_rng(3)
+    n = 4000
+    z0 = rng.uniform(-1501, -1, n)
+    z1 = rng.uniform(-201, -1, n)
+    x1 = rng.uniform(1, 3001, n)
+    sw = rng.random(n) < 0.3                       # Tx shallower than Rx: exercises the flip (IceRayTracing.cc:631)
+    z0, z1 = np.where(sw, z1, z0), np.where(sw, z0, z1)
+    z0[:6] = [-180.0, -1000.0, -200.0, -100.0, -50.0, -5.0]     # SURVEY.md 8c known answers + same-depth + near surface
+    x1[:6] = [100.0, 2000.0, 1500.0, 100.0, 20.0, 300.0]
+    z1[:6] = [-5.0, -200.0, -150.0, -100.0, -50.0, -3.0]
+    np.savez_compressed(os.path.join(HERE, "inice.npz"), z0=z0, x1=x1, z1=z1, out=IceRayReference().solve_batch(z0, x1, z1))
 
     # ---- python wrapper C ABI (Py_TraceIceToAir), metres/degrees, pi = 4 atan(1)
     pw = PyWrapReference()

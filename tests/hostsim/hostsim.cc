@@ -6,6 +6,7 @@
 
 #include "airice_host.hpp"
 #include "airice_solve.cuh"
+#include "airice_inice.cuh"
 
 using namespace airice;
 
@@ -71,5 +72,27 @@ void sim_forward_batch(long n, const double* th, const double* h, double ice, do
 double sim_x_total(double h, double ice, double depth, double L, double* dXdL) {
   AirIcePlan p; make_plan(g_m, ice, depth, &p);
   return airice_x_newton(g_m, p, top_layer(h), h, n_air(g_m, h), L, *dXdL);
+}
+// in-ice solver: IceRayTracing::IceRayTracing(0,z0,x1,z1) layout, out[29] per pair; returns nothing
+void sim_inice_batch(long n, const double* z0, const double* x1, const double* z1, double* out, int* mask) {
+  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  for (long i = 0; i < n; i++) mask[i] = inice_solve(m, z0[i], x1[i], z1[i], out + 29 * i);
+}
+}
+extern "C" {
+double sim_inice_zmax(double L) { return inice_zmax(1.78, -0.43, 0.0132, L); }
+double sim_inice_fraa(double L, double z0, double x1, double z1) {
+  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  InIcePair g; g.A = m.A; g.B = m.B; g.C = m.C; g.z0 = z0; g.z1 = z1; g.x1 = x1;
+  g.n0 = inice_nz(m, z0); g.n1 = inice_nz(m, z1); g.ns = inice_nz(m, 1e-7);
+  InIceFRaa f = {g};
+  return f(L);
+}
+double sim_inice_dfraa(double L, double z0, double x1, double z1) {
+  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  InIcePair g; g.A = m.A; g.B = m.B; g.C = m.C; g.z0 = z0; g.z1 = z1; g.x1 = x1;
+  g.n0 = inice_nz(m, z0); g.n1 = inice_nz(m, z1); g.ns = inice_nz(m, 1e-7);
+  InIceFRaa f = {g};
+  return inice_deriv_central(f, L, 1e-8);
 }
 }
