@@ -78,6 +78,13 @@ struct AirIcePlan {
   double start_x[AIRICE_MAX_LAYERS + 1];  // upper end when entered from above: hlo[k+1]-1e-5 (M.cc:715); ice leg: 0
   double start_n[AIRICE_MAX_LAYERS + 1];
   double relay[AIRICE_MAX_LAYERS + 1];    // n_start[k]/n_stop[k+1]: Snell hand-over of the table path (M.cc:1871)
+  // single-precision companions for the FP32 pre-iteration of the solver (host-computed in double, then rounded):
+  // q = n^2 - A^2 and pa = A (n - A) at both ends of a segment keep the small differences (n-1 ~ 3e-4 in air) exact,
+  // so that R^2 = q + sA^2 and T = pa + sA (sA + R) stay accurate in float even for grazing rays.
+  float f_q_stop[AIRICE_MAX_LAYERS + 1], f_pa_stop[AIRICE_MAX_LAYERS + 1];
+  float f_q_start[AIRICE_MAX_LAYERS + 1], f_pa_start[AIRICE_MAX_LAYERS + 1];
+  float f_cdx[AIRICE_MAX_LAYERS + 1];       // C' (x_stop - x_start) of a full segment
+  float f_inv_neg_c[AIRICE_MAX_LAYERS + 1];
 };
 
 AIRICE_HD double airice_n_air(const AirIceMedium& m, int k, double z) { return 1.0 + m.B[k] * exp(-m.C[k] * z); }
@@ -166,6 +173,86 @@ AIRICE_HD double airice_x_newton(const AirIceMedium& m, const AirIcePlan& p, int
     dX += air ? -dseg : dseg;
   }
   dXdL = dX;
+  return X;
+}
+
+// X(L) only, FP64, arranged like airice_x_newton but without derivative terms: the work horse of the solver's
+// chord iteration (the slope comes from the FP32 pre-iteration or from a secant).
+AIRICE_HD double airice_x_fast(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L) {
+  const double L2 = L * L;
+  const double sAir = AIRICE_SQRT(1.0 * 1.0 - L2), sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
+  const double yAir = AIRICE_RCP(sAir), yIce = AIRICE_RCP(sIce);
+  const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
+  const int nseg = nair + (p.has_ice ? 1 : 0);
+  double X = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < nseg; j++) {
+    const bool air = j < nair;
+    const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
+    const double A = air ? 1.0 : m.A_ice;
+    const double sA = air ? sAir : sIce;
+    const double inv_sA = air ? yAir : yIce;
+    const bool top = (j == 0) && air;
+    const double xt = top ? h : p.start_x[k];
+    const double nt = top ? n_tx : p.start_n[k];
+    const double xb = p.stop_x[k], nb = p.stop_n[k];
+    const double Rb = AIRICE_SQRT(nb * nb - L2), Rt = AIRICE_SQRT(nt * nt - L2);
+    const double Tb = A * nb - L2 + sA * Rb, Tt = A * nt - L2 + sA * Rt;
+    const double dG = p.neg_c[k] * (xb - xt) - AIRICE_LOG(Tb * AIRICE_RCP(Tt));
+    const double seg = (L * (p.inv_neg_c[k] * inv_sA)) * dG;
+    X += air ? -seg : seg;
+  }
+  return X;
+}
+
+// Single-precision X(t) and dX/dt, t = tan(incidence at the transmitter): the pre-iteration that brings the solver
+// within ~1e-4 deg of the root on the FP32/MUFU pipes, which this FP64-bound kernel leaves idle.  dn_tx = n(h_Tx) - 1.
+#if defined(__CUDA_ARCH__)
+#define AIRICE_F_RSQRT(x) rsqrtf(x)
+#define AIRICE_F_RCP(x) __frcp_rn(x)
+#define AIRICE_F_LOG(x) __logf(x)
+#else
+#define AIRICE_F_RSQRT(x) (1.0f / sqrtf(x))
+#define AIRICE_F_RCP(x) (1.0f / (x))
+#define AIRICE_F_LOG(x) logf(x)
+#endif
+AIRICE_HD float airice_x_newton_f32(const AirIceMedium& m, const AirIcePlan& p, int kt, float h_minus_stop_top_cn,
+                                    float dn_tx, float t, float& dXdt) {
+  const float n_tx = 1.0f + dn_tx;
+  const float q_tx = dn_tx * (2.0f + dn_tx);                  // n_tx^2 - 1
+  const float w2 = AIRICE_F_RCP(1.0f + t * t), w = sqrtf(w2);
+  const float L = n_tx * t * w, L2 = L * L;
+  const float sA2_air = w2 * (1.0f - t * t * q_tx);           // 1 - L^2 without cancellation
+  const float Ai = (float)m.A_ice;
+  const float sA2_ice = Ai * Ai - L2;
+  const float yAir = AIRICE_F_RSQRT(sA2_air), yIce = AIRICE_F_RSQRT(sA2_ice);
+  const float sAir = sA2_air * yAir, sIce = sA2_ice * yIce;
+  const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
+  const int nseg = nair + (p.has_ice ? 1 : 0);
+  float X = 0.0f, dX = 0.0f;
+#pragma unroll 1
+  for (int j = 0; j < nseg; j++) {
+    const bool air = j < nair;
+    const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
+    const float A = air ? 1.0f : Ai;
+    const float sA2 = air ? sA2_air : sA2_ice, sA = air ? sAir : sIce, inv_sA = air ? yAir : yIce;
+    const bool top = (j == 0) && air;
+    const float qt = top ? q_tx : p.f_q_start[k], pat = top ? dn_tx : p.f_pa_start[k];
+    const float cdx = top ? h_minus_stop_top_cn : p.f_cdx[k];
+    const float Rb2 = p.f_q_stop[k] + sA2, Rt2 = qt + sA2;
+    const float yb = AIRICE_F_RSQRT(Rb2), yt = AIRICE_F_RSQRT(Rt2);
+    const float Rb = Rb2 * yb, Rt = Rt2 * yt;
+    const float Tb = p.f_pa_stop[k] + sA * (sA + Rb), Tt = pat + sA * (sA + Rt);
+    const float rTb = AIRICE_F_RCP(Tb), rTt = AIRICE_F_RCP(Tt);
+    const float dG = cdx - AIRICE_F_LOG(Tb * rTt);
+    const float c1 = p.f_inv_neg_c[k] * inv_sA;
+    const float seg = (L * c1) * dG;
+    const float qb_ = (sA + Rb) * (sA + Rb) * (rTb * yb), qt_ = (sA + Rt) * (sA + Rt) * (rTt * yt);
+    const float dseg = c1 * (A * A * inv_sA * inv_sA * dG + L2 * inv_sA * (qb_ - qt_));
+    X += air ? -seg : seg;
+    dX += air ? -dseg : dseg;
+  }
+  dXdt = dX * n_tx * w2 * w;   // dL/dt = n_tx / (1+t^2)^{3/2}
   return X;
 }
 

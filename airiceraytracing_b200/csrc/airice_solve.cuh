@@ -6,9 +6,9 @@
 // 1e-9*min(|lo|,|hi|) (about 1.5e-7 deg, ~27 halvings, each a full layer walk), return the midpoint of
 // the last bracket, then evaluate the ray once more at that angle.
 //
-// What this does instead: (1) find the true root theta* of f with a safeguarded Newton iteration on
-// t = tan(incidence at the transmitter), in which X is almost linear, using the analytic dX/dL that
-// falls out of the closed forms (3-5 evaluations); (2) REPLAY the reference's bisection without
+// What this does instead: (1) find the true root theta* of f on t = tan(incidence at the transmitter), in which X
+// is almost linear: two single-precision Newton iterations (analytic dX/dL from the closed forms), then a
+// safeguarded FP64 chord iteration (typically 2 evaluations); (2) REPLAY the reference's bisection without
 // evaluating f: for a monotone f the sign of f(mid) is the side of theta* that mid lies on, so the ~27
 // halvings cost a compare each.  Only a midpoint that falls within `guard` degrees of theta* is
 // evaluated for real.  The replay lands on the very bracket the reference ends in, so the returned
@@ -18,9 +18,6 @@
 
 #define AIRICE_SOLVE_GUARD_DEG 1.0e-10
 #define AIRICE_NEWTON_MAXIT 40
-#ifndef AIRICE_HERMITE_ACCEPT
-#define AIRICE_HERMITE_ACCEPT 1.0e-6   // (pending step [deg]) x (previous step [deg]) below which the Hermite root is taken
-#endif
 
 struct AirIceSolveStat {
   int n_newton;  // distance evaluations spent in the Newton phase
@@ -84,19 +81,41 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
   if (!(lo <= hi)) return NAN;      // gsl_root_fsolver_set rejects lo>hi; the reference result is undefined
   if (!finite_lo) return lo;        // f(lo) not finite: solver state never set (UB cases)
 
-  // ---- phase 1: theta* by safeguarded Newton on t = tan(incidence at Tx), finished by two-point inverse Hermite
-  // interpolation: with (t,g,g') at the last two iterates, the cubic t(g) through both points and slopes is
-  // evaluated at g=0.  Its error is ~ e_prev^2 e_cur^2, so once the pending Newton step is small the Hermite root is
-  // already converged and the confirming evaluation (a third of the Newton work, and the cause of most intra-warp
-  // iteration-count divergence) is skipped.
+  // ---- phase 1: theta* on t = tan(incidence at Tx), in which X(t) is almost linear.
+  //  (a) two Newton iterations in SINGLE precision (X and dX/dt from airice_x_newton_f32) bring t within ~1e-4 deg of
+  //      the root and leave a slope good to ~1e-5; they run on the FP32/MUFU pipes this FP64-bound kernel leaves idle;
+  //  (b) a safeguarded chord iteration in FP64 (X only, airice_x_fast) with that slope -- or a secant slope when a
+  //      step was long enough to measure one -- finishes: error after a step = (slope error) x step + O(step^2), so a
+  //      step below 1e-7 deg with a good slope leaves ~1e-12 deg.  Typically 2 FP64 evaluations, the same for every
+  //      lane of a warp.
   double ts;                                        // root in t, or +-inf
   if (!(d > 0.0)) {
     ts = (d == 0.0) ? 0.0 : -INFINITY;  // X>=0: d<0 means f<0 everywhere
   } else {
     double tlo = 0.0, thi = INFINITY;  // g(tlo)<0<g(thi), g = X-d
-    double t = AIRICE_DIV(d, (h - p.ice_h) + 0.55 * p.depth);
+    const double hgt = (h - p.ice_h) + 0.55 * p.depth;
+    double t = AIRICE_DIV(d, hgt);
     if (!(t < t_cap)) t = t_cap;
-    double t_prev = 0.0, g_prev = 0.0, dg_prev = 0.0, step_prev_deg = INFINITY;
+    double slope = hgt;                 // dX/dt ~ height for a straight ray; replaced below
+    bool slope_good = false;
+    if (kt >= p.kb) {
+      const int kc = kt < 0 ? 0 : kt;
+      const float dn_tx = (float)(n_tx - 1.0);
+      const float cdx_top = (float)(p.neg_c[kc] * (p.stop_x[kc] - h));
+      const float df = (float)d, capf = (float)t_cap;
+      float tf = (float)t, sf = 0.0f;
+      bool okf = true;
+#pragma unroll 1
+      for (int it = 0; it < 2 && okf; it++) {
+        float dXdt;
+        const float Xf = airice_x_newton_f32(m, p, kt, cdx_top, dn_tx, tf, dXdt);
+        const float tn = tf - (Xf - df) / dXdt;
+        okf = (tn > 0.0f) && (tn < capf) && (dXdt > 0.0f);
+        if (okf) { tf = tn; sf = dXdt; }
+      }
+      if (sf > 0.0f) { t = (double)tf; slope = (double)sf; slope_good = true; }
+    }
+    double t_prev = 0.0, g_prev = 0.0;
     bool have_prev = false;
     ts = NAN;
 #pragma unroll 1
@@ -105,8 +124,7 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
       AIRICE_SQRT_RSQRT(1.0 + t * t, sq1, w);
       w = AIRICE_RCP(sq1);
       const double L = n_tx * t * w;
-      double dXdL;
-      const double X = airice_x_newton(m, p, kt, h, n_tx, L, dXdL);
+      const double X = airice_x_fast(m, p, kt, h, n_tx, L);
       st.n_newton++;
       const double g = X - d;
       if (g == 0.0) { ts = t; break; }
@@ -116,29 +134,21 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
       } else {
         thi = t;
       }
-      const double dgdt = dXdL * n_tx * w * w * w;
-      const double inv_dg = AIRICE_RCP(dgdt);
-      double tn = t - g * inv_dg;
+      if (have_prev && fabs(t - t_prev) > 1.0e-5 * t) {   // long enough step: the secant measures the slope
+        const double sec = AIRICE_DIV(g - g_prev, t - t_prev);
+        if (sec > 0.0) { slope = sec; slope_good = fabs(t - t_prev) < 1.0e-2 * t; }
+      }
+      double tn = t - AIRICE_DIV(g, slope);
       const double hi_t = thi < t_cap ? thi : t_cap;
-      bool newton_step = true;
+      bool chord_step = true;
       if (!(tn > tlo) || !(tn < hi_t)) {
         // outside the bracket (or NaN): probe the cap once if it is still untested, else bisect
-        newton_step = false;
+        chord_step = false;
         if (thi == INFINITY && g < 0.0) tn = t_cap; else tn = 0.5 * (tlo + hi_t);
       }
       const double step_deg = fabs(tn - t) * w * w * m.rad2deg;
-      if (newton_step && step_deg < 1.0e-7) { ts = tn; break; }
-      if (newton_step && have_prev && step_deg * step_prev_deg < AIRICE_HERMITE_ACCEPT) {
-        // inverse Hermite through (g_prev, t_prev, 1/g'_prev) and (g, t, 1/g'), evaluated at g = 0
-        const double dy = g - g_prev;
-        const double sfrac = -g_prev * AIRICE_RCP(dy);
-        const double s2 = sfrac * sfrac, s3 = s2 * sfrac;
-        const double h00 = 2.0 * s3 - 3.0 * s2 + 1.0, h10 = s3 - 2.0 * s2 + sfrac, h01 = 3.0 * s2 - 2.0 * s3, h11 = s3 - s2;
-        const double th_ = h00 * t_prev + h10 * dy * AIRICE_RCP(dg_prev) + h01 * t + h11 * dy * inv_dg;
-        if (th_ > tlo && th_ < hi_t) { ts = th_; break; }
-      }
-      have_prev = newton_step;
-      t_prev = t; g_prev = g; dg_prev = dgdt; step_prev_deg = step_deg;
+      if (chord_step && slope_good && step_deg < 1.0e-7) { ts = tn; break; }
+      have_prev = true; t_prev = t; g_prev = g;
       t = tn;
       if (thi < INFINITY && thi - tlo <= 4.0e-16 * thi) { ts = 0.5 * (tlo + thi); break; }
     }

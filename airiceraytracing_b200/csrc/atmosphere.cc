@@ -222,6 +222,15 @@ void make_plan(const AirIceMedium& m, double ice_h, double depth_signed, AirIceP
   p.start_n[AIRICE_ICE_SLOT] = n_ice(m, 0.0);
   p.stop_x[AIRICE_ICE_SLOT] = p.depth;
   p.stop_n[AIRICE_ICE_SLOT] = n_ice(m, p.depth);
+  for (int k = 0; k <= AIRICE_MAX_LAYERS; k++) {
+    const double A = (k == AIRICE_ICE_SLOT) ? m.A_ice : 1.0;
+    p.f_q_stop[k] = (float)((p.stop_n[k] - A) * (p.stop_n[k] + A));
+    p.f_pa_stop[k] = (float)(A * (p.stop_n[k] - A));
+    p.f_q_start[k] = (float)((p.start_n[k] - A) * (p.start_n[k] + A));
+    p.f_pa_start[k] = (float)(A * (p.start_n[k] - A));
+    p.f_cdx[k] = (float)(p.neg_c[k] * (p.stop_x[k] - p.start_x[k]));
+    p.f_inv_neg_c[k] = (float)p.inv_neg_c[k];
+  }
   *plan = p;
 }
 
