@@ -31,8 +31,12 @@ def build(force=False, verbose_ptxas=False):
 
     core = os.path.join(LIBDIR, "libairice_b200.so")
     core_src = [os.path.join(CSRC, f) for f in ("kernels.cu", "capi.cu", "atmosphere.cc")]
-    if force or _newer(core, core_src + headers):
-        _run(["nvcc"] + NVCC_FLAGS + extra + ["-shared", "-o", core] + core_src)
+    inice_src = os.path.join(CSRC, "inice_kernels.cu")
+    inice_obj = os.path.join(LIBDIR, "inice_kernels.o")
+    if force or _newer(core, core_src + [inice_src] + headers):
+        # the in-ice solver replays the reference's iterations and must round like its x86 build: no FMA contraction
+        _run(["nvcc"] + NVCC_FLAGS + extra + ["-fmad=false", "-c", "-o", inice_obj, inice_src])
+        _run(["nvcc"] + NVCC_FLAGS + extra + ["-shared", "-o", core] + core_src + [inice_obj])
 
     # source-compatible C++ API (namespace MultiRayAirIceRefraction) on top of the C ABI
     compat = os.path.join(LIBDIR, "libMultiRayAirIceRefraction.so")

@@ -35,7 +35,10 @@ AIRICE_HD double inice_fL(double A, double L, double Cp, double Z, double nZ) {
 }
 
 // ---- GSL pieces, restated (see oracle/gsl_standin/gsl_standin.c for the same algorithms on the test side)
-struct InIceBracket { double f_lower, f_upper, root, x_lower, x_upper; };
+struct InIceBracket {
+  double f_lower, f_upper, root, x_lower, x_upper;
+  double f_root;     // f(root) when the iterate has just evaluated it (root == x_linear), else NaN
+};
 
 template <class F>
 AIRICE_HD void inice_falsepos_set(const F& f, InIceBracket& s, double lo, double hi) {
@@ -51,11 +54,13 @@ AIRICE_HD void inice_falsepos_set(const F& f, InIceBracket& s, double lo, double
 template <class F>
 AIRICE_HD void inice_falsepos_iterate(const F& f, InIceBracket& s) {
   const double xl = s.x_lower, xr = s.x_upper, fl = s.f_lower, fu = s.f_upper;
+  s.f_root = NAN;
   if (fl == 0.0) { s.root = xl; s.x_upper = xl; return; }
   if (fu == 0.0) { s.root = xr; s.x_lower = xr; return; }
   const double x_lin = xr - (fu * (xl - xr) / (fl - fu));
   const double f_lin = f(x_lin);
   if (!isfinite(f_lin)) return;
+  s.f_root = f_lin;
   if (f_lin == 0.0) { s.root = x_lin; s.x_lower = x_lin; s.x_upper = x_lin; return; }
   double w;
   if ((fl > 0.0 && f_lin < 0.0) || (fl < 0.0 && f_lin > 0.0)) { s.root = x_lin; s.x_upper = x_lin; s.f_upper = f_lin; w = x_lin - xl; }
@@ -66,10 +71,10 @@ AIRICE_HD void inice_falsepos_iterate(const F& f, InIceBracket& s) {
   if (!isfinite(fb)) return;
   if ((fl > 0.0 && fb < 0.0) || (fl < 0.0 && fb > 0.0)) {
     s.x_upper = xb; s.f_upper = fb;
-    if (s.root > xb) s.root = 0.5 * (xl + xb);
+    if (s.root > xb) { s.root = 0.5 * (xl + xb); s.f_root = NAN; }
   } else {
     s.x_lower = xb; s.f_lower = fb;
-    if (s.root < xb) s.root = 0.5 * (xb + xr);
+    if (s.root < xb) { s.root = 0.5 * (xb + xr); s.f_root = NAN; }
   }
 }
 
@@ -83,12 +88,21 @@ AIRICE_HD double inice_find_root(const F& f, double lo, double hi) {
     inice_falsepos_set(f, s, lo, hi);
   }
   double r = 0;
+  s.f_root = NAN;
 #pragma unroll 1
   for (int iter = 0; iter < 100; iter++) {
+    const InIceBracket before = s;
     inice_falsepos_iterate(f, s);
     r = s.root;
-    const double check = f(r);
+    // the reference re-evaluates f(root) for its residual test (IceRayTracing.cc:285); when root is the regula-falsi
+    // point the iterate has that very value already (f is deterministic)
+    const double check = (s.f_root == s.f_root) ? s.f_root : f(r);
     if (fabs(check) < 1e-6) break;
+    // a step that changed nothing (e.g. the regula-falsi point fell outside the domain, f not finite: GSL returns
+    // before touching its state) will change nothing the next 99 times either
+    if (s.root == before.root && s.x_lower == before.x_lower && s.x_upper == before.x_upper &&
+        s.f_lower == before.f_lower && s.f_upper == before.f_upper)
+      break;
   }
   return r;
 }
@@ -146,6 +160,42 @@ struct InIceFRaa {
     return d01 - 2 * (d0s) - g.x1;
   }
 };
+
+// Horizontal reach of a refracted ray with parameter L in exact form: X_Ra(L) = F(-z1) + F(-z0) - 2 F(z_max), with the
+// turning depth z_max = -ln((L-A)/B)/C where n(z_max) = L (there R = 0 and T = L (A - L)).
+AIRICE_HD double inice_xra_exact(const InIcePair& g, double L) {
+  const double zmax = -log((L - g.A) / g.B) / g.C;
+  const double sA = sqrt(g.A * g.A - L * L);
+  const double fm = (L / -g.C) * (1.0 / sA) * (-g.C * zmax - log(L * (g.A - L)));
+  return inice_fL(g.A, L, -g.C, -g.z1, g.n1) + inice_fL(g.A, L, -g.C, -g.z0, g.n0) - 2.0 * fm;
+}
+
+// Certificate that NO refracted ray can be accepted: fRaa(L) = X_Ra(L) - x1 wherever it is not a 1e9 penalty, the
+// reference's version differs from the exact one only through its ~1e-6 m error in z_max (worth < 1e-2 m in X), and a
+// branch is accepted only if |fRaa| < 0.5 at the returned L (IceRayTracing.cc:1905-1916).  So if the exact X_Ra stays
+// more than `margin` below x1 on the whole admissible range (A+B, min(n0,n1)], every path through the reference's
+// falsepos / Newton retry ladder ends with the branch rejected, and the ladder (hundreds of evaluations, each with a
+// nested falsepos for z_max: two thirds of the reference's total run time) need not be walked.
+AIRICE_HD bool inice_no_refracted_possible(const InIcePair& g, double margin) {
+  const double lo = g.A + g.B, hi = (g.n0 < g.n1 ? g.n0 : g.n1);
+  if (!(hi > lo)) return false;
+  // X_Ra is smooth with one interior maximum on (lo, hi); sample it, then polish around the best sample, and add a
+  // curvature-based slack so that the bound holds between samples.
+  const int N = 24;
+  double best = -INFINITY, bestL = lo;
+  double prev = -INFINITY, prev2 = -INFINITY, slack = 0.0;
+#pragma unroll 1
+  for (int i = 1; i <= N; i++) {
+    const double L = lo + (hi - lo) * ((double)i - 0.5) / (double)N;
+    const double x = inice_xra_exact(g, L);
+    if (!(x == x)) return false;
+    if (x > best) { best = x; bestL = L; }
+    if (i >= 3) { const double c = fabs(x - 2.0 * prev + prev2); if (c > slack) slack = c; }
+    prev2 = prev; prev = x;
+  }
+  // the maximum lies within one sample spacing of the best sample; |second difference| bounds how far X can rise there
+  return best + 2.0 * slack + margin < g.x1 && bestL == bestL;
+}
 
 // gsl_deriv_central (deriv/deriv.c)
 template <class F>
@@ -216,18 +266,28 @@ AIRICE_HD void inice_time_path(const AirIceInIce& m, double x, double Cp, double
   p = (H + (A / sA) * G) / Cp;
 }
 
-// IceRayTracing::IceRayTracing(0, z0, x1, z1) -> out[29] (IceRayTracing.cc:1745-1919).  Slots 12..17 are written only
-// when the branch exists in the reference; here absent ones are 0.  Returns the 4-bit branch mask (D,R,Ra1,Ra2).
-AIRICE_HD int inice_solve(const AirIceInIce& m, double z0_in, double x1, double z1_in, double* out) {
-  const double k180pi = 180.0 / m.pi, kpi180 = m.pi / 180.0;
-  // common flip: the tracer wants the transmitter deeper than the receiver (IceRayTracing.cc:631-637)
+// The solver is split in two so that the kernel can run the cheap, uniform part (direct + reflected ray) for every pair
+// and the long, irregular part (the refracted-ray ladder) only for the pairs that need it, packed densely into warps.
+
+AIRICE_HD InIcePair inice_make_pair(const AirIceInIce& m, double z0_in, double x1, double z1_in, bool& flip) {
+  // the tracer wants the transmitter deeper than the receiver (IceRayTracing.cc:631-637)
   double z0 = z0_in, z1 = z1_in;
-  const bool flip = z0 > z1;
+  flip = z0 > z1;
   if (flip) { z0 = z1_in; z1 = z0_in; }
   InIcePair g;
   g.A = m.A; g.B = m.B; g.C = m.C; g.z0 = z0; g.z1 = z1; g.x1 = x1;
   g.n0 = inice_nz(m, z0); g.n1 = inice_nz(m, z1); g.ns = inice_nz(m, 1e-7);
+  return g;
+}
 
+// Direct + reflected ray (GetDirectRayPar :626-742, GetReflectedRayPar :745-920) and the IceRayTracing() bookkeeping for
+// them; all 29 slots are written, the refracted ones as "absent".  needs_ra: the refracted ladder has to run
+// (IceRayTracing.cc:1806) and is not ruled out by inice_no_refracted_possible.  Returns mask bits 0 (D) and 1 (R).
+AIRICE_HD int inice_solve_dr(const AirIceInIce& m, double z0_in, double x1, double z1_in, double* out, bool& needs_ra) {
+  const double k180pi = 180.0 / m.pi;
+  bool flip;
+  const InIcePair g = inice_make_pair(m, z0_in, x1, z1_in, flip);
+  const double z0 = g.z0, z1 = g.z1;
   // ---------------- direct ray (IceRayTracing.cc:626-742)
   double RangD, LangD, timeD, pathD, lvalueD, checkD;
   {
@@ -276,13 +336,41 @@ AIRICE_HD int inice_solve(const AirIceInIce& m, double z0_in, double x1, double 
   double outR0 = RangR, outR1 = LangR;
   if (flip) { outR0 = 180 - LangR; outR1 = 180 - RangR; }
 
-  // ---------------- refracted rays (IceRayTracing.cc:923-1253), only when D or R is missing (IceRayTracing.cc:1806)
+  (void)LangR; (void)RangR;
+  out[0] = outD1; out[1] = outR1; out[2] = 0; out[3] = 0;
+  out[4] = timeD; out[5] = timeR; out[6] = 0; out[7] = 0;
+  out[8] = outD0; out[9] = outR0; out[10] = -1000; out[11] = -1000;
+  out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 0; out[16] = 0; out[17] = 0;
+  if (fabs(checkR) < 0.5) { out[12] = timeR1; out[13] = timeR2; }
+  out[18] = incAng;
+  out[19] = lvalueD; out[20] = lvalueR; out[21] = 0; out[22] = 0;
+  out[23] = 0; out[24] = 0;
+  out[25] = pathD; out[26] = pathR; out[27] = 0; out[28] = 0;
+  int mask = 3;
+  if (fabs(checkD) > 0.5) { out[8] = -1000; mask &= ~1; }
+  if (fabs(checkR) > 0.5) { out[9] = -1000; mask &= ~2; }
+  needs_ra = (mask != 3) && !inice_no_refracted_possible(g, 2.0);
+  return mask;
+}
+
+// Refracted rays (GetRefractedRayPar :923-1253) for a pair whose direct and/or reflected ray is missing; fills the
+// refracted slots of out[] (2,3,6,7,10,11,14-17,21-24,27,28).  d_absent / r_absent: |checkzero| > 0.5 of the direct /
+// reflected ray; lvalueR: the reflected ray's L (slot 20), from which the callee's LangR is re-derived exactly.
+// Returns mask bits 2 (Ra1) and 3 (Ra2).
+AIRICE_HD int inice_solve_ra(const AirIceInIce& m, double z0_in, double x1, double z1_in, bool d_absent, bool r_absent,
+                             double lvalueR, double* out) {
+  const double k180pi = 180.0 / m.pi, kpi180 = m.pi / 180.0;
+  bool flip;
+  const InIcePair g = inice_make_pair(m, z0_in, x1, z1_in, flip);
+  const double z0 = g.z0, z1 = g.z1;
+  const double checkD = d_absent ? 1.0 : 0.0, checkR = r_absent ? 1.0 : 0.0;  // only |.| > 0.5 is ever asked
   double RangRa[2] = {0, 0}, LangRa[2] = {0, 0}, timeRa[2] = {0, 0}, lvalueRa[2] = {0, 0}, checkRa[2] = {-1000, -1000};
   double timeRa1[2] = {0, 0}, timeRa2[2] = {0, 0}, zmaxv[2] = {0, 0}, pathRa[2] = {0, 0};
-  if (fabs(checkR) > 0.5 || fabs(checkD) > 0.5) {
-    // the callee receives the (already un-flipped) outputs of the reflected ray and flips them back (IceRayTracing.cc:937-941)
-    double LangR_in = outR1;
-    if (flip) LangR_in = 180 - outR0;
+  {
+    // the callee gets the reflected ray's launch angle back in the flipped frame (IceRayTracing.cc:937-941): that is
+    // the internal LangR = asin(L_R / n(z0))
+    double LangR_in = asin(lvalueR / g.n0) * k180pi;
+    if (flip) LangR_in = 180 - (180 - LangR_in);   // it travels out as 180-LangR and is flipped back, with both roundings
     InIceFRaa f = {g};
     double lv[2] = {0, 0}, La[2] = {0, 0}, cz[2] = {-1000, -1000}, zm[2] = {10, 10};
     const double up = g.n0 < g.n1 ? g.n0 : g.n1;
@@ -373,21 +461,26 @@ AIRICE_HD int inice_solve(const AirIceInIce& m, double z0_in, double x1, double 
     }
   }
 
-  out[0] = outD1; out[1] = outR1; out[2] = LangRa[0]; out[3] = LangRa[1];
-  out[4] = timeD; out[5] = timeR; out[6] = timeRa[0]; out[7] = timeRa[1];
-  out[8] = outD0; out[9] = outR0; out[10] = RangRa[0]; out[11] = RangRa[1];
-  out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 0; out[16] = 0; out[17] = 0;
-  if (fabs(checkR) < 0.5) { out[12] = timeR1; out[13] = timeR2; }
+  out[2] = LangRa[0]; out[3] = LangRa[1];
+  out[6] = timeRa[0]; out[7] = timeRa[1];
+  out[10] = RangRa[0]; out[11] = RangRa[1];
+  out[14] = 0; out[15] = 0; out[16] = 0; out[17] = 0;
   if (fabs(checkRa[0]) < 0.5) { out[14] = timeRa1[0]; out[15] = timeRa2[0]; }
   if (fabs(checkRa[1]) < 0.5) { out[16] = timeRa1[1]; out[17] = timeRa2[1]; }
-  out[18] = incAng;
-  out[19] = lvalueD; out[20] = lvalueR; out[21] = lvalueRa[0]; out[22] = lvalueRa[1];
+  out[21] = lvalueRa[0]; out[22] = lvalueRa[1];
   out[23] = zmaxv[0]; out[24] = zmaxv[1];
-  out[25] = pathD; out[26] = pathR; out[27] = pathRa[0]; out[28] = pathRa[1];
-  int mask = 15;
-  if (fabs(checkD) > 0.5) { out[8] = -1000; mask &= ~1; }
-  if (fabs(checkR) > 0.5) { out[9] = -1000; mask &= ~2; }
+  out[27] = pathRa[0]; out[28] = pathRa[1];
+  int mask = 12;
   if (fabs(checkRa[0]) > 0.5) { out[10] = -1000; mask &= ~4; }
   if (fabs(checkRa[1]) > 0.5) { out[11] = -1000; mask &= ~8; }
+  return mask;
+}
+
+// IceRayTracing::IceRayTracing(0, z0, x1, z1) -> out[29] (IceRayTracing.cc:1745-1919).  Slots 12..17 are written only
+// when the branch exists in the reference; here absent ones are 0.  Returns the 4-bit branch mask (D,R,Ra1,Ra2).
+AIRICE_HD int inice_solve(const AirIceInIce& m, double z0_in, double x1, double z1_in, double* out) {
+  bool needs_ra;
+  int mask = inice_solve_dr(m, z0_in, x1, z1_in, out, needs_ra);
+  if (needs_ra) mask |= inice_solve_ra(m, z0_in, x1, z1_in, (mask & 1) == 0, (mask & 2) == 0, out[20], out);
   return mask;
 }

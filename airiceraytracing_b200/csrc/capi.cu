@@ -45,6 +45,9 @@ struct airice_ctx {
   size_t slot_bytes = 0;
   // per-row transmitter data (height, n(h), top layer) of the last table grid built: uploaded once, reused by
   // every rebuild of the same rows (MakeRayTracingTable is called once per antenna depth on the same grid)
+  // in-ice solver scratch: compaction list + counter (+ private mask / L_R columns when the caller passes none)
+  void* inice_scratch = nullptr;
+  size_t inice_bytes = 0;
   struct RowCache {
     double key[7] = {0, 0, 0, 0, 0, 0, 0};
     int64_t r0 = -1, r1 = -1;
@@ -208,6 +211,7 @@ void airice_destroy(airice_ctx* c) {
   }
   if (c->rows.d_rows) cudaFree(c->rows.d_rows);
   if (c->rows.d_kt) cudaFree(c->rows.d_kt);
+  if (c->inice_scratch) cudaFree(c->inice_scratch);
   delete c;
 }
 
@@ -486,11 +490,33 @@ int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const do
   return 0;
 }
 
+namespace {
+// scratch layout: [count:int32 pad to 256][list:int32 x n][mask:u8 x n][L_R:f64 x n]
+int inice_scratch(airice_ctx* c, int64_t n, InIceArgs* a, cudaStream_t s) {
+  const size_t list_b = ((size_t)n * 4 + 255) / 256 * 256, mask_b = ((size_t)n + 255) / 256 * 256, lr_b = (size_t)n * 8;
+  const size_t need = 256 + list_b + mask_b + lr_b;
+  if (c->inice_bytes < need) {
+    CK(cudaStreamSynchronize(s));
+    if (c->inice_scratch) cudaFree(c->inice_scratch);
+    c->inice_scratch = nullptr; c->inice_bytes = 0;
+    CK(cudaMalloc(&c->inice_scratch, need));
+    c->inice_bytes = need;
+  }
+  char* base = (char*)c->inice_scratch;
+  a->ra_count = (int32_t*)base;
+  a->ra_list = (int32_t*)(base + 256);
+  if (!a->mask) a->mask = (uint8_t*)(base + 256 + list_b);
+  if (!a->out[20]) a->out[20] = (double*)(base + 256 + list_b + mask_b);
+  return 0;
+}
+}  // namespace
+
 int airice_inice_solve_device(airice_ctx* c, int64_t n, const double* d_z0, const double* d_x1, const double* d_z1,
                               double* const* d_out, uint8_t* d_mask, void* stream) {
   if (!c) return fail(-1, "null context");
   if (n == 0) return 0;
   if (!d_z0 || !d_x1 || !d_z1 || !d_out) return fail(-1, "null argument");
+  if (n >= 2147483647LL) return fail(-5, "at most 2^31-1 pairs per call");
   CK(cudaSetDevice(c->device));
   InIceArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -498,6 +524,7 @@ int airice_inice_solve_device(airice_ctx* c, int64_t n, const double* d_z0, cons
   a.A = c->medium.A_ice; a.B = c->medium.B_ice; a.C = c->medium.C_ice;
   for (int k = 0; k < AIRICE_INICE_NCOLS; k++) a.out[k] = d_out[k];
   a.mask = d_mask;
+  { int rc = inice_scratch(c, n, &a, (cudaStream_t)stream); if (rc) return rc; }
   cudaError_t e = launch_inice(a, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_inice");
   return 0;
@@ -527,6 +554,9 @@ int airice_inice_solve_host(airice_ctx* c, int64_t n, const double* z0, const do
     a.A = c->medium.A_ice; a.B = c->medium.B_ice; a.C = c->medium.C_ice;
     for (int k = 0; k < nc; k++) a.out[k] = dh + (3 + k) * chunk;
     a.mask = (uint8_t*)(dh + (3 + nc) * chunk);
+    // one compaction scratch per context: chunks of the two streams must not overlap in pass 1/2
+    if (off > 0) CK(cudaStreamSynchronize(c->streams[slot ^ 1]));
+    { int rcs = inice_scratch(c, chunk, &a, s); if (rcs) return rcs; }
     cudaError_t e = launch_inice(a, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_inice");
     for (int k = 0; k < nc; k++)

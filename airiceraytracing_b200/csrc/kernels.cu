@@ -10,7 +10,6 @@
 #include <math_constants.h>
 
 #include "airice_solve.cuh"
-#include "airice_inice.cuh"
 #include "kernels.cuh"
 
 namespace airice {
@@ -310,20 +309,6 @@ __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_look
     if (a.out[k]) a.out[k][i] = o[k];
 }
 
-// ---------------------------------------------------------------------------------------- in-ice solver
-__global__ void __launch_bounds__(kThreads) airice_inice_kernel(const InIceArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= a.n) return;
-  AirIceInIce m;
-  m.A = a.A; m.B = a.B; m.C = a.C; m.pi = 3.14159265359; m.c = 299792458.0;  // IceRayTracing.hh:41-43
-  double o[AIRICE_INICE_NCOLS];
-  const int mask = inice_solve(m, a.z0[i], a.x1[i], a.z1[i], o);
-  if (a.mask) a.mask[i] = (uint8_t)mask;
-#pragma unroll
-  for (int k = 0; k < AIRICE_INICE_NCOLS; k++)
-    if (a.out[k]) a.out[k][i] = o[k];
-}
-
 // ---------------------------------------------------------------------------------------- FP64 peak probe
 __global__ void __launch_bounds__(256) fp64_fma_kernel(double* sink, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -395,14 +380,6 @@ cudaError_t launch_lookup(const AirIceMedium& m, const LookupTable& t, const Loo
   const int64_t blocks = (a.n + kThreads - 1) / kThreads;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
   airice_lookup_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(m, t, a);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s) {
-  if (a.n <= 0) return cudaSuccess;
-  const int64_t blocks = (a.n + kThreads - 1) / kThreads;
-  if (blocks > 2147483647LL) return cudaErrorInvalidValue;
-  airice_inice_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 

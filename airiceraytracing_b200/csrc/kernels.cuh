@@ -103,6 +103,11 @@ struct InIceArgs {
   double A, B, C;     // ice model n(z) = A + B exp(-C |z|)
   double* out[AIRICE_INICE_NCOLS];  // the 29 slots of the reference's output array, SoA; nullptr = skip
   uint8_t* mask;      // bit0 D, bit1 R, bit2 Ra1, bit3 Ra2: which branches exist (receive-angle slot != -1000)
+  // scratch owned by the caller (context): compaction list of the pairs whose refracted-ray ladder must run, and its
+  // length.  Pass 1 (all pairs: direct + reflected) appends to it; pass 2 walks it, so the long irregular searches are
+  // packed densely into warps instead of idling 31 lanes behind one.
+  int32_t* ra_list;   // [n]
+  int32_t* ra_count;  // [1], zeroed by launch_inice
 };
 cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s);
 

@@ -89,6 +89,32 @@ def cpu_reference_rate(h_cm, d_cm, per_core, cores=None):
     return rate, cores, kind, sample, wall, max(r[0] for r in res)
 
 
+def _cpu_inice_worker(seed):
+    from oracle.ref import IceRayReference
+    rng = np.random.default_rng(seed)
+    n = 3000
+    z0, z1, x1 = rng.uniform(-1501, -1, n), rng.uniform(-201, -1, n), rng.uniform(1, 3001, n)
+    ref = IceRayReference()
+    t0 = time.perf_counter()
+    ref.solve_batch(z0, x1, z1)
+    return time.perf_counter() - t0, n
+
+
+def cpu_inice_rate(cores):
+    """The unmodified reference IceRayTracing.cc on the host cores (3000 random geometries per process)."""
+    from oracle.ref import reference_available
+    if not reference_available("libiceray_ref.so"):
+        return None
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_inice_worker, [1000 + i for i in range(cores)])
+        wall = time.perf_counter() - t0
+    n = sum(r[1] for r in res)
+    return {"value": n / wall, "unit": "solves/s", "cores": cores, "kind": "reference",
+            "sample": "%d random in-ice geometries, %d per process, unmodified IceRayTracing.cc + GSL stand-in at -O2" % (n, 3000)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -320,8 +346,20 @@ def run_ours(args):
         T = solver.table_create(-200.0, 3000.0)
         ms = time_ms(lambda: solver.lookup(T, h, d, out=out, ok=ok))
         extras["lookup"] = {"table": "reference grid 9701x900 float", "lookups": n, "ms": ms, "lookups_per_s": world * n / ms * 1e3,
-                            "algorithmic_gbs": n * (16 + 73 + 176) / ms / 1e6, "solved": float(ok.float().mean())}
+                            "algorithmic_gbs": n * (16 + 73 + 192) / ms / 1e6,
+                            "layout": "dense THD column for the index search + 48-byte records (4 cells x 48 B gathered per query)", "solved": float(ok.float().mean())}
         T.close()
+        # in-ice direct/reflected/refracted solver (IceRayTracing::IceRayTracing), SURVEY.md 8a geometry distribution
+        ni = 2_000_000
+        gi = torch.Generator(device=dev).manual_seed(20260421 + rank)
+        z0 = -1.0 - 1500.0 * torch.rand(ni, generator=gi, device=dev, dtype=torch.float64)
+        z1 = -1.0 - 200.0 * torch.rand(ni, generator=gi, device=dev, dtype=torch.float64)
+        x1 = 1.0 + 3000.0 * torch.rand(ni, generator=gi, device=dev, dtype=torch.float64)
+        ms = max_over_ranks(time_ms(lambda: solver.inice_solve(z0, x1, z1), reps=2, warm=1))
+        _, mk = solver.inice_solve(z0, x1, z1)
+        popc = torch.tensor([bin(i).count("1") for i in range(16)], device=dev)[mk.long()]
+        extras["inice"] = {"pairs_per_gpu": ni, "ms": ms, "solves_per_s": world * ni / ms * 1e3,
+                           "branch_count_fractions": [float((popc == k).double().mean()) for k in range(3)]}
         if world > 1:
             # result reassembly: one all-gather of the 9 output columns
             gathered = torch.empty((world, 9, n), dtype=torch.float64, device=dev)
@@ -333,6 +371,8 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.skip_cpu:
         rate, cores, kind, sample, wall, _ = cpu_reference_rate(h_np, d_np, 20000)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "wall_s": wall}
+        if "inice" in extras:
+            extras["inice"]["cpu_baseline"] = cpu_inice_rate(cores)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
