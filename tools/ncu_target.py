@@ -27,5 +27,12 @@ if which in ("all", "lookup"):
     o2 = torch.empty((9, n), dtype=torch.float64, device="cuda")
     for _ in range(3):
         S.lookup(T, dh, dd, out=o2, ok=ok)
+if which in ("all", "inice"):
+    ni = min(n, 500_000)
+    rng2 = np.random.default_rng(7)
+    z0 = torch.from_numpy(rng2.uniform(-1501, -1, ni)).cuda(); z1 = torch.from_numpy(rng2.uniform(-201, -1, ni)).cuda()
+    x1 = torch.from_numpy(rng2.uniform(1, 3001, ni)).cuda()
+    for _ in range(2):
+        S.inice_solve(z0, x1, z1)
 torch.cuda.synchronize()
 print("done", which, n)
