@@ -38,6 +38,12 @@
 #endif
 
 #define AIRICE_MAX_LAYERS 5
+#ifndef AIRICE_UNROLL_XFAST
+#define AIRICE_UNROLL_XFAST 1
+#endif
+#ifndef AIRICE_UNROLL_FULL
+#define AIRICE_UNROLL_FULL 1
+#endif
 
 // Product rounded on its own (never contracted into an FMA with a following add).  Used where the reference forms
 // F(stop)-F(start) from two separately rounded products: for a zero-thickness segment (Tx exactly on the ice surface,
@@ -185,7 +191,8 @@ AIRICE_HD double airice_x_fast(const AirIceMedium& m, const AirIcePlan& p, int k
   const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
   const int nseg = nair + (p.has_ice ? 1 : 0);
   double X = 0.0;
-#pragma unroll 1
+  constexpr int kUnrollX = AIRICE_UNROLL_XFAST;
+#pragma unroll kUnrollX
   for (int j = 0; j < nseg; j++) {
     const bool air = j < nair;
     const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
@@ -270,7 +277,8 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
   double xa = 0.0, ta = 0.0, ga = 0.0, xi = 0.0, ti = 0.0, gi = 0.0;
   double Lk = L, Rsurf = 0.0;
   r.recv_deg = 0.0;
-#pragma unroll 1
+  constexpr int kUnrollF = AIRICE_UNROLL_FULL;
+#pragma unroll kUnrollF
   for (int j = 0; j < nseg; j++) {
     const bool air = j < nair;
     const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
