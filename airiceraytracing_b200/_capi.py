@@ -25,7 +25,7 @@ EXPORTS = [
     "airice_set_ice_model", "airice_table_dims", "airice_table_build_device", "airice_forward_device",
     "airice_forward_host", "airice_table_create", "airice_table_wrap", "airice_table_destroy", "airice_table_info",
     "airice_table_copy_column", "airice_table_column_ptr", "airice_table_copy_row_ranges", "airice_solve_device",
-    "airice_solve_host", "airice_lookup_device", "airice_lookup_host", "airice_inice_solve_device",
+    "airice_solve_multi_device", "airice_solve_host", "airice_lookup_device", "airice_lookup_host", "airice_inice_solve_device",
     "airice_inice_solve_host", "airice_fp64_peak_tflops", "airice_sync",
 ]
 
@@ -61,6 +61,7 @@ def load():
     lib.airice_table_column_ptr.argtypes = [vp, i, pp]
     lib.airice_table_copy_row_ranges.argtypes = [vp, vp, vp]
     lib.airice_solve_device.argtypes = [vp, i64, vp, vp, vp, d, d, i, pp, vp, vp, vp]
+    lib.airice_solve_multi_device.argtypes = [vp, i64, i, vp, vp, C.POINTER(d), d, i, pp, vp, vp]
     lib.airice_solve_host.argtypes = [vp, i64, vp, vp, vp, d, d, i, vp, vp]
     lib.airice_forward_host.argtypes = [vp, i64, vp, vp, d, d, vp]
     lib.airice_lookup_device.argtypes = [vp, vp, i64, vp, vp, pp, vp, vp]

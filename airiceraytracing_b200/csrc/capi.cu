@@ -399,6 +399,26 @@ int airice_solve_device(airice_ctx* c, int64_t n, const double* d_h, const doubl
   return 0;
 }
 
+// Multi-antenna form (BASELINE config 5: shower points x in-ice receivers): one launch per receiver depth over the
+// same Tx heights; distances and outputs are antenna-major ([antenna][point]).
+int airice_solve_multi_device(airice_ctx* c, int64_t n_points, int n_ant, const double* d_h, const double* d_dist,
+                              const double* depths_host, double ice, int units, double* const* d_out, uint8_t* d_ok,
+                              void* stream) {
+  if (!c) return fail(-1, "null context");
+  if (n_ant < 0 || n_points < 0) return fail(-1, "negative size");
+  if (n_ant == 0 || n_points == 0) return 0;
+  if (!d_h || !d_dist || !depths_host || !d_out) return fail(-1, "null argument");
+  const int nc = units == AIRICE_UNITS_CM_RAD ? AIRICE_SOLVE_COLS_CM_RAD : AIRICE_SOLVE_COLS;
+  for (int a = 0; a < n_ant; a++) {
+    double* cols[AIRICE_SOLVE_NCOLS];
+    for (int k = 0; k < nc; k++) cols[k] = d_out[k] ? d_out[k] + (int64_t)a * n_points : nullptr;
+    int rc = airice_solve_device(c, n_points, d_h, d_dist + (int64_t)a * n_points, nullptr, depths_host[a], ice, units, cols,
+                                 d_ok ? d_ok + (int64_t)a * n_points : nullptr, nullptr, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 // Host-buffer path: the batch is cut into chunks that alternate between two streams, each with its own device
 // staging slot.  Copies go directly from/to the caller's buffers (no extra host memcpy); with pinned caller memory
 // the H2D of chunk k+1, the kernel of chunk k and the D2H of chunk k-1 run concurrently.

@@ -182,6 +182,23 @@ class AirIceSolver:
                                            nev.data_ptr() if nevals else None, _stream_ptr(self.torch_device)))
         return (out, ok, nev) if nevals else (out, ok)
 
+    def solve_multi(self, h, d, depths, ice, units=_capi.UNITS_CM_RAD, out=None, ok=None):
+        """n_points Tx heights against len(depths) receivers; d is [n_ant, n_points]; returns (out [ncols, n_ant, n_points], ok)."""
+        h = h.to(self.torch_device, torch.float64).contiguous()
+        d = d.to(self.torch_device, torch.float64).contiguous()
+        n_ant, n = int(d.shape[0]), int(h.numel())
+        assert d.shape[1] == n and len(depths) == n_ant
+        nc = _capi.SOLVE_COLS_CM_RAD if units == _capi.UNITS_CM_RAD else _capi.SOLVE_COLS
+        if out is None:
+            out = torch.empty((nc, n_ant, n), dtype=torch.float64, device=self.torch_device)
+        if ok is None:
+            ok = torch.empty((n_ant, n), dtype=torch.uint8, device=self.torch_device)
+        dep = (C.c_double * n_ant)(*[float(x) for x in depths])
+        check(self.lib.airice_solve_multi_device(self.handle, n, n_ant, h.data_ptr(), d.data_ptr(), dep, ice, units,
+                                                 ptr_array([out[k].data_ptr() for k in range(nc)]), ok.data_ptr(),
+                                                 _stream_ptr(self.torch_device)))
+        return out, ok
+
     def solve_host(self, h, d, depth, ice, units=_capi.UNITS_CM_RAD, out=None, ok=None):
         """Same through host buffers (numpy arrays or pinned torch CPU tensors); copies happen inside the call."""
         n = int(h.shape[0])

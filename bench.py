@@ -360,6 +360,35 @@ def run_ours(args):
         popc = torch.tensor([bin(i).count("1") for i in range(16)], device=dev)[mk.long()]
         extras["inice"] = {"pairs_per_gpu": ni, "ms": ms, "solves_per_s": world * ni / ms * 1e3,
                            "branch_count_fractions": [float((popc == k).double().mean()) for k in range(3)]}
+        # BASELINE config 5: 1e6 shower points x 64 in-ice receiver depths (points sharded over ranks): direct solves,
+        # one table per depth, table-interpolated solutions
+        n5, n_ant = 1_000_000 // world, 64
+        depths_cm = [-100.0 * (200.0 * (k + 1) / n_ant) for k in range(n_ant)]      # -(3.1 .. 200) m, equally spaced
+        g5 = torch.Generator(device=dev).manual_seed(20260420 + rank)
+        h5 = (3001 + (100000 - 3001) * torch.rand(n5, generator=g5, device=dev, dtype=torch.float64)) * 100
+        a5 = 90.2 + (179.8 - 90.2) * torch.rand((n_ant, n5), generator=g5, device=dev, dtype=torch.float64)
+        d5 = (h5.unsqueeze(0) - ICE_CM - torch.tensor(depths_cm, device=dev, dtype=torch.float64).unsqueeze(1)) * \
+            torch.tan((180 - a5) * (PI_M / 180))
+        del a5
+        o5 = torch.empty((9, n_ant, n5), dtype=torch.float64, device=dev)
+        k5 = torch.empty((n_ant, n5), dtype=torch.uint8, device=dev)
+        barrier()
+        ms_direct = max_over_ranks(time_ms(lambda: solver.solve_multi(h5, d5, depths_cm, ICE_CM, UNITS_CM_RAD, out=o5, ok=k5),
+                                           reps=2, warm=1))
+
+        def tables_and_lookups():
+            for a in range(n_ant):
+                Ta = solver.table_create(depths_cm[a] / 100.0, ICE_CM / 100.0)
+                solver.lookup(Ta, h5, d5[a], out=o5[:, a], ok=k5[a])
+                Ta.close()
+        barrier()
+        ms_table = max_over_ranks(time_ms(tables_and_lookups, reps=1, warm=1))
+        extras["c5_multi_antenna"] = {"points": n5 * world, "antennas": n_ant, "pairs": n5 * world * n_ant,
+                                      "direct_ms": ms_direct, "direct_solves_per_s": world * n5 * n_ant / ms_direct * 1e3,
+                                      "tables_plus_lookups_ms": ms_table,
+                                      "table_solutions_per_s": world * n5 * n_ant / ms_table * 1e3,
+                                      "note": "64 reference-grid tables (9701x900) built, packed and freed per pass"}
+        del o5, k5, d5, h5
         if world > 1:
             # result reassembly: one all-gather of the 9 output columns
             gathered = torch.empty((world, 9, n), dtype=torch.float64, device=dev)

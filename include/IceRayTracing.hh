@@ -1,0 +1,35 @@
+// IceRayTracing.hh -- source-compatible host API of the in-ice solver on top of the B200 C ABI.
+//
+// Replaces, for the hot path only, /root/reference/IceRayTracing.hh / IceRayTracing.cc: the 4-argument
+// IceRayTracing::IceRayTracing(x0, z0, x1, z1) defined at IceRayTracing.cc:1745 (the reference header declares a
+// 5-argument form at IceRayTracing.hh:186; both are offered here), and the ice-model setters SetA/SetB/SetC
+// (IceRayTracing.cc:7-17).  The returned array has the reference's 29 slots and is owned by the caller (delete[]),
+// as in the reference.  Attenuation, focusing, ray-path dumps, the in-ice interpolation table and the constant-n
+// variants are outside the hot path and are not provided.
+#ifndef IRT_HEAD_B200
+#define IRT_HEAD_B200
+#include <string>
+
+namespace IceRayTracing {
+
+static constexpr double pi = 3.14159265359;       // IceRayTracing.hh:41 (sic)
+static constexpr double c_light_ms = 299792458;   // IceRayTracing.hh:43
+extern double A_ice, B_ice, C_ice;                // IceRayTracing.hh:54-56
+
+void SetA(double &A);
+void SetB(double &B);
+void SetC(double &C);
+void SetDevice(int device);                       // B200 extra
+void SetAtmosphereFile(const std::string &path);  // B200 extra: the shared context parses one (default ./Atmosphere.dat)
+
+// out[0..3] launch angles D,R,Ra1,Ra2; [4..7] times; [8..11] receive angles (-1000 = branch absent); [12..17] sub-times;
+// [18] incidence on the surface; [19..22] L; [23..24] z_max; [25..28] geometric paths.  x0 must be 0 (as in the reference's
+// own callers); it is accepted for signature compatibility.
+double *IceRayTracing(double x0, double z0, double x1, double z1);
+double *IceRayTracing(double x0, double z0, double x1, double z1, bool PlotRayPaths);
+
+// batch form (new): n pairs, out[col*n + i] with 29 columns, mask[i] bit0..3 = D,R,Ra1,Ra2 present
+int IceRayTracingBatch(long n, const double *z0, const double *x1, const double *z1, double *out, unsigned char *mask);
+
+}  // namespace IceRayTracing
+#endif

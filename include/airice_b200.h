@@ -89,6 +89,12 @@ int airice_table_copy_row_ranges(const airice_table *t, int32_t *host_first, int
 int airice_solve_device(airice_ctx *ctx, int64_t n, const double *d_h, const double *d_dist, const double *d_straight,
                         double depth, double ice, int units, double *const *d_out, uint8_t *d_ok, int32_t *d_nevals,
                         void *stream);
+/* Multi-antenna form (CoREAS: n_points shower points x n_ant receivers, the shape of RunMultiRayCode_loop.C with
+ * several AntennaDepths): d_dist and every output column are antenna-major [n_ant][n_points]; depths_host[n_ant] is a
+ * HOST array of signed receiver depths.  One kernel launch per receiver on the given stream. */
+int airice_solve_multi_device(airice_ctx *ctx, int64_t n_points, int n_ant, const double *d_h, const double *d_dist,
+                              const double *depths_host, double ice, int units, double *const *d_out, uint8_t *d_ok,
+                              void *stream);
 /* Same through HOST buffers: out is a dense SoA block out[col*n + i] with 9 (CM_RAD) or 13 (M_DEG) columns. */
 int airice_solve_host(airice_ctx *ctx, int64_t n, const double *h, const double *dist, const double *straight,
                       double depth, double ice, int units, double *out, uint8_t *ok);

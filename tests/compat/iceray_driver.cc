@@ -1,0 +1,18 @@
+// TEST: a caller of the in-ice entry point written like the reference's users (MakeMultiRayPlot.C style):
+// includes "IceRayTracing.cc", calls IceRayTracing::IceRayTracing(0, z0, x1, z1), deletes the result.
+#include "IceRayTracing.cc"
+
+#include <cstdio>
+
+int main(int argc, char **argv) {
+  if (argc > 1) IceRayTracing::SetAtmosphereFile(argv[1]);
+  const double cases[3][3] = {{-180, 100, -5}, {-1000, 2000, -200}, {-200, 1500, -150}};
+  for (auto &c : cases) {
+    double *r = IceRayTracing::IceRayTracing(0, c[0], c[1], c[2]);
+    std::printf("case");
+    for (int i = 0; i < 29; i++) std::printf(" %.17g", r[i]);
+    std::printf("\n");
+    delete[] r;
+  }
+  return 0;
+}

@@ -135,3 +135,22 @@ print("WORST", worst[0], worst[1])
     worst = [float(x) for x in out.stdout.strip().splitlines()[-1].split()[1:]]
     assert worst[0] <= RTOL_DIST and worst[1] <= ATOL_ANGLE_DEG
     assert "We have a solution!!!" in out.stdout and "We do NOT have a solution!!!" in out.stdout
+
+
+def test_iceray_driver(tmp_path, solver):
+    """SURVEY.md 8c known answers through the source-compatible IceRayTracing::IceRayTracing()."""
+    exe = str(tmp_path / "iceray")
+    lib = os.path.join(ROOT, "airiceraytracing_b200", "lib")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "compat", "iceray_driver.cc"), "-o", exe, "-L" + lib, "-lairice_b200",
+                           "-Wl,-rpath," + lib])
+    out = subprocess.run([exe, ATMOSPHERE], capture_output=True, text=True, check=True).stdout
+    rows = [np.array([float(x) for x in line.split()[1:]]) for line in out.splitlines() if line.startswith("case")]
+    g = golden("inice.npz")["out"]
+    assert len(rows) == 3
+    for k, r in enumerate(rows):
+        assert np.array_equal(r[8:12] != -1000, g[k, 8:12] != -1000)
+    assert abs(rows[0][19] - 0.80023300831165) < 1e-12 and abs(rows[0][20] - 0.759040146127282) < 1e-12
+    assert abs(rows[0][0] - 27.380168714) < 1e-7 and abs(rows[0][1] - 25.8628862578) < 1e-7
+    assert abs(rows[1][19] - 1.64977154594608) < 1e-12 and abs(rows[1][21] - 1.46757200401104) < 5e-9
+    assert (rows[2][8:12] != -1000).sum() == 0

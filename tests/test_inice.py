@@ -108,3 +108,28 @@ def test_kernel_matches_live_reference_20k(solver):
     counts = check_inice(out.cpu().numpy().T, ref, recv_tol_deg=5e-3, max_flag_mismatch=4, flipped=z0 > z1, ra_rtol=5e-8)
     hist = np.bincount(counts, minlength=3) / n
     assert 0.3 < hist[0] < 0.45 and 0.5 < hist[2] < 0.7   # 38.7 % / 2.9 % / 58.4 %
+
+
+@pytest.mark.gpu
+def test_kernel_edge_cases(solver):
+    """Empty and ragged batches, same-depth pairs, Tx shallower than Rx, a changed ice model."""
+    import torch
+    out, mask = solver.inice_solve(torch.empty(0, dtype=torch.float64), torch.empty(0, dtype=torch.float64),
+                                   torch.empty(0, dtype=torch.float64))
+    assert out.shape == (29, 0) and mask.numel() == 0
+    g = golden("inice.npz")
+    for n in (1, 31, 129):
+        o, m = solver.inice_solve(torch.from_numpy(g["z0"][:n]), torch.from_numpy(g["x1"][:n]), torch.from_numpy(g["z1"][:n]))
+        check_inice(o.cpu().numpy().T, g["out"][:n], recv_tol_deg=5e-3, max_flag_mismatch=0, flipped=g["z0"][:n] > g["z1"][:n],
+                    ra_rtol=5e-8)
+    # symmetric pair: swapping Tx and Rx swaps launch and receive angles (the reference's flip, IceRayTracing.cc:631-740)
+    a, _ = solver.inice_solve(torch.tensor([-180.0]), torch.tensor([100.0]), torch.tensor([-5.0]))
+    b, _ = solver.inice_solve(torch.tensor([-5.0]), torch.tensor([100.0]), torch.tensor([-180.0]))
+    a, b = a.cpu().numpy()[:, 0], b.cpu().numpy()[:, 0]
+    assert abs(a[4] - b[4]) < 1e-15 and abs(a[19] - b[19]) < 1e-15          # same time, same L
+    assert abs((180 - a[8]) - b[0]) < 1e-12 and abs((180 - a[0]) - b[8]) < 1e-12
+    # SetA / SetB / SetC analogue
+    solver.set_ice_model(1.775, -0.43, 0.0132)
+    c, _ = solver.inice_solve(torch.tensor([-180.0]), torch.tensor([100.0]), torch.tensor([-5.0]))
+    solver.set_ice_model(1.78, -0.43, 0.0132)
+    assert abs(c.cpu().numpy()[19, 0] - a[19]) > 1e-6
