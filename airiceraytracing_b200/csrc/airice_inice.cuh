@@ -146,19 +146,23 @@ struct InIceFRa {
     return d01 - 2 * (d0s) - g.x1;
   }
 };
+// zm: the turning depth (+1e-7) this evaluation used -- the same number GetRefractedRayPar computes again right after
+// every root search (IceRayTracing.cc:957,985...), so callers that just evaluated f at the root can keep it
+AIRICE_HD double inice_fraa_eval(const InIcePair& g, double L, double& zm) {
+  const double zmax = inice_zmax(g.A, g.B, g.C, L) + 1e-7;
+  zm = zmax;
+  if (!(zmax > 0)) return 1e9;
+  const double nzm = g.A + g.B * exp(-g.C * fabs(zmax));
+  const double fb = inice_fL(g.A, L, -g.C, -g.z0, g.n0);
+  double d01 = inice_fL(g.A, L, -g.C, -g.z1, g.n1) - fb;
+  double d0s = inice_fL(g.A, L, -g.C, zmax, nzm) - fb;
+  if (d01 != d01) d01 = 1e9;
+  if (d0s != d0s) d0s = 1e9;
+  return d01 - 2 * (d0s) - g.x1;
+}
 struct InIceFRaa {
   InIcePair g;
-  AIRICE_HD double operator()(double L) const {
-    const double zmax = inice_zmax(g.A, g.B, g.C, L) + 1e-7;
-    if (!(zmax > 0)) return 1e9;
-    const double nzm = g.A + g.B * exp(-g.C * fabs(zmax));
-    const double fb = inice_fL(g.A, L, -g.C, -g.z0, g.n0);
-    double d01 = inice_fL(g.A, L, -g.C, -g.z1, g.n1) - fb;
-    double d0s = inice_fL(g.A, L, -g.C, zmax, nzm) - fb;
-    if (d01 != d01) d01 = 1e9;
-    if (d0s != d0s) d0s = 1e9;
-    return d01 - 2 * (d0s) - g.x1;
-  }
+  AIRICE_HD double operator()(double L) const { double zm; return inice_fraa_eval(g, L, zm); }
 };
 
 // Horizontal reach of a refracted ray with parameter L in exact form: X_Ra(L) = F(-z1) + F(-z0) - 2 F(z_max), with the
@@ -353,114 +357,126 @@ AIRICE_HD int inice_solve_dr(const AirIceInIce& m, double z0_in, double x1, doub
   return mask;
 }
 
-// Refracted rays (GetRefractedRayPar :923-1253) for a pair whose direct and/or reflected ray is missing; fills the
-// refracted slots of out[] (2,3,6,7,10,11,14-17,21-24,27,28).  d_absent / r_absent: |checkzero| > 0.5 of the direct /
-// reflected ray; lvalueR: the reflected ray's L (slot 20), from which the callee's LangR is re-derived exactly.
-// Returns mask bits 2 (Ra1) and 3 (Ra2).
-AIRICE_HD int inice_solve_ra(const AirIceInIce& m, double z0_in, double x1, double z1_in, bool d_absent, bool r_absent,
-                             double lvalueR, double* out) {
+// Refracted rays (GetRefractedRayPar :923-1253) for a pair whose direct and/or reflected ray is missing, in two parts:
+// the root-search LADDER (falsepos, Newton retry, up to five more searches for a second root) and the FINISH (times,
+// paths, angles, bookkeeping).  The ladder is the long irregular part; it exists twice: literally below, and as a
+// resumable state machine in airice_inice_machine.cuh that the GPU kernel steps (same evaluations, same order).
+struct InIceRaLadder { double lv[2], cz[2], zm[2]; };   // L, f(L) and z_max(L)+1e-7 of the two candidate roots
+
+// bracket of the first search (IceRayTracing.cc:937-950); LangR_in: the reflected ray's launch angle as the callee sees it
+AIRICE_HD void inice_ra_first_bracket(const AirIceInIce& m, const InIcePair& g, bool flip, double lvalueR, double& lower,
+                                      double& up) {
   const double k180pi = 180.0 / m.pi, kpi180 = m.pi / 180.0;
-  bool flip;
-  const InIcePair g = inice_make_pair(m, z0_in, x1, z1_in, flip);
-  const double z0 = g.z0, z1 = g.z1;
-  const double checkD = d_absent ? 1.0 : 0.0, checkR = r_absent ? 1.0 : 0.0;  // only |.| > 0.5 is ever asked
-  double RangRa[2] = {0, 0}, LangRa[2] = {0, 0}, timeRa[2] = {0, 0}, lvalueRa[2] = {0, 0}, checkRa[2] = {-1000, -1000};
-  double timeRa1[2] = {0, 0}, timeRa2[2] = {0, 0}, zmaxv[2] = {0, 0}, pathRa[2] = {0, 0};
-  {
-    // the callee gets the reflected ray's launch angle back in the flipped frame (IceRayTracing.cc:937-941): that is
-    // the internal LangR = asin(L_R / n(z0))
-    double LangR_in = asin(lvalueR / g.n0) * k180pi;
-    if (flip) LangR_in = 180 - (180 - LangR_in);   // it travels out as 180-LangR and is flipped back, with both roundings
-    InIceFRaa f = {g};
-    double lv[2] = {0, 0}, La[2] = {0, 0}, cz[2] = {-1000, -1000}, zm[2] = {10, 10};
-    const double up = g.n0 < g.n1 ? g.n0 : g.n1;
-    double lower = g.n0 * sin((64.0 * kpi180));
-    if (lower > up) lower = g.n0 * sin((LangR_in * kpi180));
-    lv[0] = inice_find_root(f, lower, up);
-    La[0] = asin(lv[0] / g.n0) * k180pi;
+  // the callee gets the reflected ray's launch angle back in the flipped frame (IceRayTracing.cc:937-941): that is
+  // the internal LangR = asin(L_R / n(z0))
+  double LangR_in = asin(lvalueR / g.n0) * k180pi;
+  if (flip) LangR_in = 180 - (180 - LangR_in);   // it travels out as 180-LangR and is flipped back, with both roundings
+  up = g.n0 < g.n1 ? g.n0 : g.n1;
+  lower = g.n0 * sin((64.0 * kpi180));
+  if (lower > up) lower = g.n0 * sin((LangR_in * kpi180));
+}
+
+AIRICE_HD InIceRaLadder inice_ra_ladder(const AirIceInIce& m, const InIcePair& g, bool flip, bool d_absent, bool r_absent,
+                                        double lvalueR) {
+  InIceFRaa f = {g};
+  double lv[2] = {0, 0}, cz[2] = {-1000, -1000}, zm[2] = {10, 10};
+  double lower, up;
+  inice_ra_first_bracket(m, g, flip, lvalueR, lower, up);
+  lv[0] = inice_find_root(f, lower, up);
+  cz[0] = f(lv[0]);
+  zm[0] = inice_zmax(m.A, m.B, m.C, lv[0]) + 1e-7;
+  if (fabs(cz[0]) > 0.5) {
+    lv[0] = inice_newton_root(f, lower, up);
     cz[0] = f(lv[0]);
     zm[0] = inice_zmax(m.A, m.B, m.C, lv[0]) + 1e-7;
-    if (fabs(cz[0]) > 0.5) {
-      lv[0] = inice_newton_root(f, lower, up);
-      La[0] = asin(lv[0] / g.n0) * k180pi;
-      cz[0] = f(lv[0]);
-      zm[0] = inice_zmax(m.A, m.B, m.C, lv[0]) + 1e-7;
-    }
-    if (lv[0] < 0) cz[0] = -1000;
+  }
+  if (lv[0] < 0) cz[0] = -1000;
 #define INICE_RETRY(expr_root)                                   \
   do {                                                           \
     lv[1] = (expr_root);                                         \
-    La[1] = asin(lv[1] / g.n0) * k180pi;                         \
     cz[1] = f(lv[1]);                                            \
     zm[1] = inice_zmax(m.A, m.B, m.C, lv[1]) + 1e-7;             \
   } while (0)
 #define INICE_BAD1 (fabs(cz[1]) > 0.5 || cz[1] != cz[1] || fabs(lv[1] - lv[0]) < 1e-4)
-    if (fabs(cz[0]) < 0.5 && fabs(checkD) > 0.5 && fabs(checkR) > 0.5) {
-      INICE_RETRY(inice_find_root(f, lv[0] - 0.23, lv[0] - 0.023));
-      if (INICE_BAD1) INICE_RETRY(inice_find_root(f, lv[0] - 0.15, lv[0] - 0.023));
-      if (INICE_BAD1) {
-        if (lv[0] + 0.005 < up) INICE_RETRY(inice_find_root(f, lv[0] + 0.005, up));
-        else INICE_RETRY(inice_find_root(f, lv[0] - 0.1, lv[0] - 0.01));
-      }
-      if (INICE_BAD1) {
-        const double tmp = inice_newton_root(f, lv[0] - 0.23, lv[0] - 0.023);
-        if (fabs(tmp) < m.A) INICE_RETRY(tmp);   // the reference solves the same problem twice (IceRayTracing.cc:1029-1031)
-      }
-      if (INICE_BAD1) {
-        const double tmp = inice_newton_root(f, lv[0] - 0.1, lv[0] - 0.023);
-        if (fabs(tmp) < m.A) INICE_RETRY(tmp);
-      }
-      if (lv[1] < 0) cz[1] = -1000;
-      if (fabs(cz[1]) < 0.5 && fabs(cz[0]) < 0.5 && fabs(lv[1] - lv[0]) < 1e-4) cz[1] = -1000;
-      if (La[0] != La[0]) La[0] = 0;
-      if (La[1] != La[1]) La[1] = 0;
-      if (La[1] < La[0] && fabs(cz[0]) < 0.5 && fabs(cz[1]) < 0.5) {
-        double t;
-        t = lv[1]; lv[1] = lv[0]; lv[0] = t;
-        t = La[1]; La[1] = La[0]; La[0] = t;
-        t = cz[1]; cz[1] = cz[0]; cz[0] = t;
-        t = zm[1]; zm[1] = zm[0]; zm[0] = t;
-      }
-    } else {
-      lv[1] = 0; La[1] = 0; cz[1] = -1000; zm[1] = -1000;
+  if (fabs(cz[0]) < 0.5 && d_absent && r_absent) {
+    INICE_RETRY(inice_find_root(f, lv[0] - 0.23, lv[0] - 0.023));
+    if (INICE_BAD1) INICE_RETRY(inice_find_root(f, lv[0] - 0.15, lv[0] - 0.023));
+    if (INICE_BAD1) {
+      if (lv[0] + 0.005 < up) INICE_RETRY(inice_find_root(f, lv[0] + 0.005, up));
+      else INICE_RETRY(inice_find_root(f, lv[0] - 0.1, lv[0] - 0.01));
     }
+    if (INICE_BAD1) {
+      const double tmp = inice_newton_root(f, lv[0] - 0.23, lv[0] - 0.023);
+      if (fabs(tmp) < m.A) INICE_RETRY(tmp);   // the reference solves the same problem twice (IceRayTracing.cc:1029-1031)
+    }
+    if (INICE_BAD1) {
+      const double tmp = inice_newton_root(f, lv[0] - 0.1, lv[0] - 0.023);
+      if (fabs(tmp) < m.A) INICE_RETRY(tmp);
+    }
+    if (lv[1] < 0) cz[1] = -1000;
+    if (fabs(cz[1]) < 0.5 && fabs(cz[0]) < 0.5 && fabs(lv[1] - lv[0]) < 1e-4) cz[1] = -1000;
+  } else {
+    lv[1] = 0; cz[1] = -1000; zm[1] = -1000;
+  }
 #undef INICE_RETRY
 #undef INICE_BAD1
-    double tRa[2] = {0, 0}, tRa1[2] = {0, 0}, tRa2[2] = {0, 0}, pRa[2] = {0, 0}, Ra[2] = {0, 0};
-#pragma unroll 1
-    for (int i = 0; i < 2; i++) {
-      if (cz[i] != cz[i]) cz[i] = -1000;
-      if (zm[i] == 1e-7 || zm[i] <= 0) cz[i] = -1000;
-      if ((z0 < -zm[i] || zm[i] < -z1)) {
-        double tm, pm, ta, pa, tb, pb;
-        inice_time_path(m, -zm[i], m.C, lv[i], tm, pm);
-        inice_time_path(m, z0, m.C, lv[i], ta, pa);
-        inice_time_path(m, z1, m.C, lv[i], tb, pb);
-        tRa1[i] = tm - ta; tRa2[i] = tm - tb;
-        tRa[i] = tRa1[i] + tRa2[i];
-        pRa[i] = (pm - pa) + (pm - pb);
-        if (flip) { const double d = tRa2[i]; tRa2[i] = tRa1[i]; tRa1[i] = d; }
-      }
-      InIceFDepth fd = {m.A, m.B, m.C, m.C, lv[i]};
-      Ra[i] = 180 - atan(inice_deriv_central(fd, z1, 1e-8)) * k180pi;
-      if (z1 == z0 && Ra[i] != Ra[i]) Ra[i] = 180 - La[i];
-      if (z1 != z0 && Ra[i] != Ra[i]) Ra[i] = 90;
-    }
-    if (cz[0] != cz[0]) cz[0] = -1000;
-    if (cz[1] != cz[1]) cz[1] = -1000;
-    // callee outputs (IceRayTracing.cc:1215-1250): angles un-flipped
-    for (int i = 0; i < 2; i++) {
-      double o0 = Ra[i], o1 = La[i];
-      if (flip) { o0 = 180 - La[i]; o1 = 180 - Ra[i]; }
-      const bool take = (i == 0) || (fabs(checkR) > 0.5 && fabs(checkD) > 0.5);  // IceRayTracing.cc:1816
-      if (take) {
-        RangRa[i] = o0; LangRa[i] = o1; timeRa[i] = tRa[i]; lvalueRa[i] = lv[i]; checkRa[i] = cz[i];
-        timeRa1[i] = tRa1[i]; timeRa2[i] = tRa2[i]; zmaxv[i] = zm[i];
-      }
-      pathRa[i] = pRa[i];
-    }
-  }
+  InIceRaLadder r;
+  r.lv[0] = lv[0]; r.lv[1] = lv[1]; r.cz[0] = cz[0]; r.cz[1] = cz[1]; r.zm[0] = zm[0]; r.zm[1] = zm[1];
+  return r;
+}
 
+// fills the refracted slots of out[] (2,3,6,7,10,11,14-17,21-24,27,28); returns mask bits 2 (Ra1) and 3 (Ra2)
+AIRICE_HD int inice_ra_finish(const AirIceInIce& m, const InIcePair& g, bool flip, bool d_absent, bool r_absent,
+                              const InIceRaLadder& lad, double* out) {
+  const double k180pi = 180.0 / m.pi;
+  const double z0 = g.z0, z1 = g.z1;
+  const bool both = d_absent && r_absent;
+  double lv[2] = {lad.lv[0], lad.lv[1]}, cz[2] = {lad.cz[0], lad.cz[1]}, zm[2] = {lad.zm[0], lad.zm[1]};
+  double La[2] = {asin(lv[0] / g.n0) * k180pi, asin(lv[1] / g.n0) * k180pi};
+  if (fabs(cz[0]) < 0.5 && both) {     // the second root was searched for (cz[0] does not change in that branch)
+    if (La[0] != La[0]) La[0] = 0;
+    if (La[1] != La[1]) La[1] = 0;
+    if (La[1] < La[0] && fabs(cz[0]) < 0.5 && fabs(cz[1]) < 0.5) {
+      double t;
+      t = lv[1]; lv[1] = lv[0]; lv[0] = t;
+      t = La[1]; La[1] = La[0]; La[0] = t;
+      t = cz[1]; cz[1] = cz[0]; cz[0] = t;
+      t = zm[1]; zm[1] = zm[0]; zm[0] = t;
+    }
+  } else {
+    La[1] = 0;
+  }
+  double RangRa[2] = {0, 0}, LangRa[2] = {0, 0}, timeRa[2] = {0, 0}, lvalueRa[2] = {0, 0}, checkRa[2] = {-1000, -1000};
+  double timeRa1[2] = {0, 0}, timeRa2[2] = {0, 0}, zmaxv[2] = {0, 0}, pathRa[2] = {0, 0};
+#pragma unroll 1
+  for (int i = 0; i < 2; i++) {
+    double tRa = 0, tRa1 = 0, tRa2 = 0, pRa = 0;
+    if (cz[i] != cz[i]) cz[i] = -1000;
+    if (zm[i] == 1e-7 || zm[i] <= 0) cz[i] = -1000;
+    if ((z0 < -zm[i] || zm[i] < -z1)) {
+      double tm, pm, ta, pa, tb, pb;
+      inice_time_path(m, -zm[i], m.C, lv[i], tm, pm);
+      inice_time_path(m, z0, m.C, lv[i], ta, pa);
+      inice_time_path(m, z1, m.C, lv[i], tb, pb);
+      tRa1 = tm - ta; tRa2 = tm - tb;
+      tRa = tRa1 + tRa2;
+      pRa = (pm - pa) + (pm - pb);
+      if (flip) { const double d = tRa2; tRa2 = tRa1; tRa1 = d; }
+    }
+    InIceFDepth fd = {m.A, m.B, m.C, m.C, lv[i]};
+    double Ra = 180 - atan(inice_deriv_central(fd, z1, 1e-8)) * k180pi;
+    if (z1 == z0 && Ra != Ra) Ra = 180 - La[i];
+    if (z1 != z0 && Ra != Ra) Ra = 90;
+    // callee outputs (IceRayTracing.cc:1215-1250): angles un-flipped
+    double o0 = Ra, o1 = La[i];
+    if (flip) { o0 = 180 - La[i]; o1 = 180 - Ra; }
+    const bool take = (i == 0) || both;  // IceRayTracing.cc:1816
+    if (take) {
+      RangRa[i] = o0; LangRa[i] = o1; timeRa[i] = tRa; lvalueRa[i] = lv[i]; checkRa[i] = cz[i];
+      timeRa1[i] = tRa1; timeRa2[i] = tRa2; zmaxv[i] = zm[i];
+    }
+    pathRa[i] = pRa;
+  }
   out[2] = LangRa[0]; out[3] = LangRa[1];
   out[6] = timeRa[0]; out[7] = timeRa[1];
   out[10] = RangRa[0]; out[11] = RangRa[1];
@@ -474,6 +490,16 @@ AIRICE_HD int inice_solve_ra(const AirIceInIce& m, double z0_in, double x1, doub
   if (fabs(checkRa[0]) > 0.5) { out[10] = -1000; mask &= ~4; }
   if (fabs(checkRa[1]) > 0.5) { out[11] = -1000; mask &= ~8; }
   return mask;
+}
+
+// d_absent / r_absent: |checkzero| > 0.5 of the direct / reflected ray; lvalueR: the reflected ray's L (slot 20), from
+// which the callee's LangR is re-derived exactly.
+AIRICE_HD int inice_solve_ra(const AirIceInIce& m, double z0_in, double x1, double z1_in, bool d_absent, bool r_absent,
+                             double lvalueR, double* out) {
+  bool flip;
+  const InIcePair g = inice_make_pair(m, z0_in, x1, z1_in, flip);
+  const InIceRaLadder lad = inice_ra_ladder(m, g, flip, d_absent, r_absent, lvalueR);
+  return inice_ra_finish(m, g, flip, d_absent, r_absent, lad, out);
 }
 
 // IceRayTracing::IceRayTracing(0, z0, x1, z1) -> out[29] (IceRayTracing.cc:1745-1919).  Slots 12..17 are written only

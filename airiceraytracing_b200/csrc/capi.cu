@@ -511,10 +511,10 @@ int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const do
 }
 
 namespace {
-// scratch layout: [count:int32 pad to 256][list:int32 x n][mask:u8 x n][L_R:f64 x n]
+// scratch layout: [counters:int32 x2 pad to 256][list:int32 x n][mask:u8 x n][L_R:f64 x n][ladder:f64 x 6n]
 int inice_scratch(airice_ctx* c, int64_t n, InIceArgs* a, cudaStream_t s) {
   const size_t list_b = ((size_t)n * 4 + 255) / 256 * 256, mask_b = ((size_t)n + 255) / 256 * 256, lr_b = (size_t)n * 8;
-  const size_t need = 256 + list_b + mask_b + lr_b;
+  const size_t need = 256 + list_b + mask_b + lr_b + 6 * lr_b;
   if (c->inice_bytes < need) {
     CK(cudaStreamSynchronize(s));
     if (c->inice_scratch) cudaFree(c->inice_scratch);
@@ -527,6 +527,7 @@ int inice_scratch(airice_ctx* c, int64_t n, InIceArgs* a, cudaStream_t s) {
   a->ra_list = (int32_t*)(base + 256);
   if (!a->mask) a->mask = (uint8_t*)(base + 256 + list_b);
   if (!a->out[20]) a->out[20] = (double*)(base + 256 + list_b + mask_b);
+  a->ra_lad = (double*)(base + 256 + list_b + mask_b + lr_b);
   return 0;
 }
 }  // namespace

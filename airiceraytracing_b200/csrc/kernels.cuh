@@ -104,10 +104,11 @@ struct InIceArgs {
   double* out[AIRICE_INICE_NCOLS];  // the 29 slots of the reference's output array, SoA; nullptr = skip
   uint8_t* mask;      // bit0 D, bit1 R, bit2 Ra1, bit3 Ra2: which branches exist (receive-angle slot != -1000)
   // scratch owned by the caller (context): compaction list of the pairs whose refracted-ray ladder must run, and its
-  // length.  Pass 1 (all pairs: direct + reflected) appends to it; pass 2 walks it, so the long irregular searches are
-  // packed densely into warps instead of idling 31 lanes behind one.
+  // length.  Pass 1 (all pairs: direct + reflected) appends to it; pass 2 (persistent lanes stepping the root-search
+  // state machine, each taking the next list entry when its own is finished) and pass 3 (times, paths, angles) walk it.
   int32_t* ra_list;   // [n]
-  int32_t* ra_count;  // [1], zeroed by launch_inice
+  int32_t* ra_count;  // [2], zeroed by launch_inice: [0] list length (pass 1), [1] next list entry to hand out (pass 2)
+  double* ra_lad;     // [6][n] ladder results (L, f(L), z_max of the two candidate roots) per list entry, pass 2 -> pass 3
 };
 cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s);
 

@@ -7,6 +7,7 @@
 #include "airice_host.hpp"
 #include "airice_solve.cuh"
 #include "airice_inice.cuh"
+#include "airice_inice_machine.cuh"
 
 using namespace airice;
 
@@ -77,6 +78,31 @@ double sim_x_total(double h, double ice, double depth, double L, double* dXdL) {
 void sim_inice_batch(long n, const double* z0, const double* x1, const double* z1, double* out, int* mask) {
   AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
   for (long i = 0; i < n; i++) mask[i] = inice_solve(m, z0[i], x1[i], z1[i], out + 29 * i);
+}
+}
+extern "C" {
+// literal ladder vs stepped state machine for every pair whose refracted search runs: writes both 6-value results,
+// returns how many pairs ran the ladder; evals[i] = fRaa evaluations the machine consumed (-1: ladder not needed)
+long sim_inice_ladder_compare(long n, const double* z0, const double* x1, const double* z1, double* direct, double* stepped,
+                              int* evals) {
+  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  long ran = 0;
+  for (long i = 0; i < n; i++) {
+    double o[29]; bool needs;
+    const int mask = inice_solve_dr(m, z0[i], x1[i], z1[i], o, needs);
+    evals[i] = -1;
+    for (int k = 0; k < 6; k++) { direct[6 * i + k] = 0; stepped[6 * i + k] = 0; }
+    if (!needs) continue;
+    bool flip;
+    const InIcePair g = inice_make_pair(m, z0[i], x1[i], z1[i], flip);
+    const InIceRaLadder a = inice_ra_ladder(m, g, flip, (mask & 1) == 0, (mask & 2) == 0, o[20]);
+    const InIceRaLadder b = inice_ra_ladder_stepped(m, g, flip, (mask & 1) == 0, (mask & 2) == 0, o[20], &evals[i]);
+    const double da[6] = {a.lv[0], a.lv[1], a.cz[0], a.cz[1], a.zm[0], a.zm[1]};
+    const double db[6] = {b.lv[0], b.lv[1], b.cz[0], b.cz[1], b.zm[0], b.zm[1]};
+    for (int k = 0; k < 6; k++) { direct[6 * i + k] = da[k]; stepped[6 * i + k] = db[k]; }
+    ran++;
+  }
+  return ran;
 }
 }
 extern "C" {

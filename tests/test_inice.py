@@ -81,6 +81,29 @@ def test_hostsim_matches_reference_golden(hostsim):
     assert {0, 1, 2} == set(np.unique(counts))
 
 
+def test_stepped_ladder_equals_literal_ladder(hostsim):
+    """The refracted-ray root-search ladder exists twice: as the literal nested loops (inice_ra_ladder, pinned against the
+    reference by the golden test above) and as the resumable state machine the GPU lanes step
+    (airice_inice_machine.cuh).  Same evaluations in the same order => identical bits, on every pair."""
+    dp = C.POINTER(C.c_double)
+    f = hostsim.lib.sim_inice_ladder_compare
+    f.restype = C.c_long
+    f.argtypes = [C.c_long, dp, dp, dp, dp, dp, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(77)
+    n = 12000
+    z0 = np.concatenate([-rng.uniform(0.5, 2500, n - 2000), -rng.uniform(0.5, 30, 2000)])
+    z1 = np.concatenate([-rng.uniform(0.5, 300, n - 2000), -rng.uniform(0.5, 30, 2000)])
+    x1 = np.concatenate([rng.uniform(1, 6000, n - 2000), rng.uniform(1, 400, 2000)])
+    a, b, ev = np.zeros((n, 6)), np.zeros((n, 6)), np.zeros(n, np.int32)
+    ran = f(n, z0.ctypes.data_as(dp), x1.ctypes.data_as(dp), z1.ctypes.data_as(dp), a.ctypes.data_as(dp),
+            b.ctypes.data_as(dp), ev.ctypes.data_as(C.POINTER(C.c_int)))
+    assert ran > 2000                      # the ladder really ran for a good share of the pairs
+    same = (a.view(np.int64) == b.view(np.int64)) | (np.isnan(a) & np.isnan(b))
+    assert same.all(), f"{(~same.all(1)).sum()} pairs differ, first {np.where(~same.all(1))[0][:3]}"
+    e = ev[ev >= 0]
+    assert e.min() >= 1 and e.max() <= 7 * 100 * 9 + 64   # 7 searches x 100 iterations x (f + 8-point derivative)
+
+
 @pytest.mark.gpu
 def test_kernel_matches_reference_golden(solver):
     import torch
