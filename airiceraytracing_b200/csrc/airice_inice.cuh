@@ -16,6 +16,15 @@
 #pragma once
 #include "airice_core.cuh"
 
+// Building blocks that pass 1 / pass 3 use many times over (fL ~30x, the 8-point derivative 3x, time+path 5x): real calls
+// on the device, so that the kernel (15k instructions when everything is inlined, more than the instruction cache
+// holds: measured 12 "no instruction" stall cycles per issue) is emitted once per block.
+#if defined(__CUDACC__)
+#define AIRICE_INICE_CALL __host__ __device__ __noinline__
+#else
+#define AIRICE_INICE_CALL inline
+#endif
+
 struct AirIceInIce {      // ice model + constants of the IceRayTracing namespace
   double A, B, C;         // IceRayTracing.hh:45-56
   double pi;              // 3.14159265359 (IceRayTracing.hh:41, sic)
@@ -30,7 +39,7 @@ struct InIcePair {
 AIRICE_HD double inice_nz(const AirIceInIce& m, double z) { z = fabs(z); return m.A + m.B * exp(-m.C * z); }
 
 // fDnfR_L (IceRayTracing.cc:368-379) with n(Z) supplied
-AIRICE_HD double inice_fL(double A, double L, double Cp, double Z, double nZ) {
+AIRICE_INICE_CALL double inice_fL(double A, double L, double Cp, double Z, double nZ) {
   return (L / Cp) * (1.0 / sqrt(A * A - L * L)) * (Cp * Z - log(A * nZ - L * L + sqrt(A * A - L * L) * sqrt(nZ * nZ - L * L)));
 }
 
@@ -112,7 +121,7 @@ struct InIceMinnz {
   double A, B, C, L;
   AIRICE_HD double operator()(double x) const { return A + B * exp(-C * x) - L; }   // raw x, not |x| (IceRayTracing.cc:342)
 };
-AIRICE_HD double inice_zmax(double A, double B, double C, double L) {
+AIRICE_HD double inice_zmax_literal(double A, double B, double C, double L) {
   InIceMinnz f = {A, B, C, L};
   InIceBracket s;
   inice_falsepos_set(f, s, 0.0, 5000.0);
@@ -128,6 +137,72 @@ AIRICE_HD double inice_zmax(double A, double B, double C, double L) {
     if (fabs(hi - lo) < 1e-6 + 1e-6 * mn) break;
   }
   return r;
+}
+// The same iteration written for the machine it runs on: this function is ~3/4 of all the work of the refracted-ray
+// search (it sits inside every evaluation of fRaa) and a pure dependency chain, ~13 falsepos steps of two exp() each
+// (or a single step when L is below n(0): the first regula-falsi point is negative and ends the search at once).
+// The regula-falsi point and the bisection point of a step depend only on the bracket the step starts from, so both
+// function values are computed together (the second one is needed in >90% of the steps and simply dropped otherwise),
+// which halves the chain.  The iteration is a struct so that the GPU kernel can run it one step at a time with the
+// lanes of a warp taking the next pending evaluation as soon as their own has converged.
+// Same points, same values, same updates as inice_zmax_literal; tests compare the two.
+struct InIceZmaxIter {
+  double xl, xr, fl, fu, root, L;
+  int iter;
+  // e5000 = exp(-C * 5000.0)
+  AIRICE_HD void init(double A, double B, double e5000, double L_) {
+    L = L_; xl = 0.0; xr = 5000.0; root = 0.5 * (0.0 + 5000.0); fl = 0.0; fu = 0.0; iter = 0;
+    const double f0 = A + B * 1.0 - L;          // exp(-C * 0.0) == 1
+    if (isfinite(f0)) {
+      const double f1 = A + B * e5000 - L;
+      if (isfinite(f1)) { fl = f0; fu = f1; }
+    }
+  }
+  // one falsepos iteration and the stopping tests of the loop around it; true = finished (root is the answer)
+  AIRICE_HD bool step(double A, double B, double C) {
+    bool stuck = false;
+    if (fl == 0.0) { root = xl; xr = xl; }
+    else if (fu == 0.0) { root = xr; xl = xr; }
+    else {
+      const double x_lin = xr - (fu * (xl - xr) / (fl - fu));
+      const double xb = 0.5 * (xl + xr);
+      const double f_lin = A + B * exp(-C * x_lin) - L;
+      const double fb = A + B * exp(-C * xb) - L;
+      // f not finite at the regula-falsi point (exp overflow for L far below the physical range): GSL returns before
+      // touching its state, so this and all the remaining iterations up to the 100th change nothing
+      if (!isfinite(f_lin)) stuck = true;
+      else {
+        if (f_lin == 0.0) { root = x_lin; xl = x_lin; xr = x_lin; }
+        else {
+          const double oxl = xl, oxr = xr, ofl = fl;
+          double w;
+          if ((ofl > 0.0 && f_lin < 0.0) || (ofl < 0.0 && f_lin > 0.0)) { root = x_lin; xr = x_lin; fu = f_lin; w = x_lin - oxl; }
+          else { root = x_lin; xl = x_lin; fl = f_lin; w = oxr - x_lin; }
+          if (!(w < 0.5 * (oxr - oxl)) && isfinite(fb)) {
+            if ((ofl > 0.0 && fb < 0.0) || (ofl < 0.0 && fb > 0.0)) {
+              xr = xb; fu = fb;
+              if (root > xb) root = 0.5 * (oxl + xb);
+            } else {
+              xl = xb; fl = fb;
+              if (root < xb) root = 0.5 * (xb + oxr);
+            }
+          }
+        }
+      }
+    }
+    if (xl > xr) return true;  // GSL_EINVAL != GSL_CONTINUE
+    const double al = fabs(xl), au = fabs(xr);
+    const double mn = ((xl > 0.0 && xr > 0.0) || (xl < 0.0 && xr < 0.0)) ? (al < au ? al : au) : 0.0;
+    if (fabs(xr - xl) < 1e-6 + 1e-6 * mn) return true;
+    return stuck || ++iter >= 100;
+  }
+};
+AIRICE_HD double inice_zmax(double A, double B, double C, double L) {
+  InIceZmaxIter z;
+  z.init(A, B, exp(-C * 5000.0), L);
+#pragma unroll 1
+  while (!z.step(A, B, C)) {}
+  return z.root;
 }
 
 // root functions of L (IceRayTracing.cc:411-607), TransitionBoundary == 0 branches
@@ -148,9 +223,7 @@ struct InIceFRa {
 };
 // zm: the turning depth (+1e-7) this evaluation used -- the same number GetRefractedRayPar computes again right after
 // every root search (IceRayTracing.cc:957,985...), so callers that just evaluated f at the root can keep it
-AIRICE_HD double inice_fraa_eval(const InIcePair& g, double L, double& zm) {
-  const double zmax = inice_zmax(g.A, g.B, g.C, L) + 1e-7;
-  zm = zmax;
+AIRICE_HD double inice_fraa_given_zmax(const InIcePair& g, double L, double zmax) {   // zmax = inice_zmax(L) + 1e-7
   if (!(zmax > 0)) return 1e9;
   const double nzm = g.A + g.B * exp(-g.C * fabs(zmax));
   const double fb = inice_fL(g.A, L, -g.C, -g.z0, g.n0);
@@ -159,6 +232,23 @@ AIRICE_HD double inice_fraa_eval(const InIcePair& g, double L, double& zm) {
   if (d01 != d01) d01 = 1e9;
   if (d0s != d0s) d0s = 1e9;
   return d01 - 2 * (d0s) - g.x1;
+}
+AIRICE_HD double inice_fraa_eval(const InIcePair& g, double L, double& zm) {
+  zm = inice_zmax(g.A, g.B, g.C, L) + 1e-7;
+  return inice_fraa_given_zmax(g, L, zm);
+}
+// fRaa outside the physical range of L without the iteration: for L = NaN (a Newton search that has left the domain
+// keeps asking for it) the turning-depth search stops at its first step with root 0, for finite L > A at the first
+// regula-falsi point, beyond 5000 m, where f < 0; in both cases every fL term is NaN and fRaa is its NaN penalty
+// 1e9 - 2e9 - x1.  Returns false when L is not of that kind (nothing written).  Tests compare with inice_fraa_eval.
+AIRICE_HD bool inice_fraa_shortcut(double A, double B, double e5000, double x1, double L, double& y, double& zm) {
+  if (L != L) { y = 1e9 - 2 * (1e9) - x1; zm = 0.0 + 1e-7; return true; }
+  if (L > A && L < 1e300) {
+    const double f0 = A + B * 1.0 - L, f1 = A + B * e5000 - L;          // InIceZmaxIter::init; both < 0
+    const double x_lin = 5000.0 - (f1 * (0.0 - 5000.0) / (f0 - f1));   // first step
+    if (x_lin > 5000.0 && x_lin < 1e300) { y = 1e9 - 2 * (1e9) - x1; zm = x_lin + 1e-7; return true; }
+  }
+  return false;
 }
 struct InIceFRaa {
   InIcePair g;
@@ -216,7 +306,7 @@ AIRICE_HD void inice_central(const F& f, double x, double h, double& result, dou
   round = fabs(e5 / h) + dy;
 }
 template <class F>
-AIRICE_HD double inice_deriv_central(const F& f, double x, double h) {
+AIRICE_INICE_CALL double inice_deriv_central(const F& f, double x, double h) {
   double r0, round, trunc;
   inice_central(f, x, h, r0, round, trunc);
   double error = round + trunc;
@@ -261,7 +351,7 @@ struct InIceFDepth {
 };
 
 // ftimeD / fpathD (IceRayTracing.cc:382-408) through the identities of airice_core.cuh
-AIRICE_HD void inice_time_path(const AirIceInIce& m, double x, double Cp, double L, double& t, double& p) {
+AIRICE_INICE_CALL void inice_time_path(const AirIceInIce& m, double x, double Cp, double L, double& t, double& p) {
   const double A = m.A;
   const double n = inice_nz(m, x);
   const double D = n * n - L * L, R = sqrt(D), sA = sqrt(A * A - L * L);

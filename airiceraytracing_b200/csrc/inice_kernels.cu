@@ -44,39 +44,112 @@ __global__ void __launch_bounds__(kThreads) airice_inice_dr_kernel(const InIceAr
   }
 }
 
-// pass 2: the refracted-ray root-search ladder for the listed pairs.  Persistent lanes: each lane steps the state
-// machine of ONE pair (airice_inice_machine.cuh) -- the warp's common loop body is a single evaluation of fRaa -- and
-// takes the next list entry as soon as its pair is finished, so neither the search a lane is in nor the number of
-// evaluations its pair needs (median 22, mean 78, maximum ~700) leaves the other lanes idle.
+// pass 2: the refracted-ray root-search ladder for the listed pairs.  Persistent lanes: each lane owns the search state
+// of ONE pair (airice_inice_machine.cuh) and takes the next list entry as soon as its pair is finished.  Every step, the
+// lanes of a warp pool the evaluations of fRaa their pairs ask for (1, 2, 4 or 5 each) in shared memory and share them
+// out evenly, so the loop body all lanes run together is one evaluation of fRaa, whatever search each pair is in, and
+// a pair with a long search (the number of evaluations per pair spans 3 ... several thousand) uses idle lanes.
+struct InIceWarpPool {
+  static constexpr int kCap = 32;
+  double x[kCap], y[kCap], zm[kCap];   // request points and results
+  double pair[5][32];                  // z0, z1, x1, n(z0), n(z1) of each lane's pair
+  unsigned char owner[kCap];
+};
+
 __global__ void __launch_bounds__(kThreads) airice_inice_ladder_kernel(const InIceArgs a) {
+  __shared__ InIceWarpPool pools[kThreads / 32];
+  InIceWarpPool& pool = pools[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
   const AirIceInIce m = inice_model(a);
   const int count = a.ra_count[0];
+  const double e5000 = exp(-a.C * 5000.0);
   InIceRaMachine M;
-  InIcePair g;
   int j = 0;
   bool has = false, exhausted = false;
-  M.ph = InIceRaMachine::DONE; M.xq = 0;
+  M.ph = InIceRaMachine::DONE; M.nq = 0; M.xq = 0;
+  double yk[InIceRaMachine::kMaxReq] = {0, 0, 0, 0, 0}, zk[InIceRaMachine::kMaxReq] = {0, 0, 0, 0, 0};
+  int slot[InIceRaMachine::kMaxReq] = {0, 0, 0, 0, 0};
+  int rot = 0;
+  double my_x1 = 0.0;
   for (;;) {
     if (!has && !exhausted) {
       j = atomicAdd(a.ra_count + 1, 1);
       if (j < count) {
         const int64_t i = a.ra_list[j];
         bool flip;
-        g = inice_make_pair(m, a.z0[i], a.x1[i], a.z1[i], flip);
+        const InIcePair g = inice_make_pair(m, a.z0[i], a.x1[i], a.z1[i], flip);
         const int mask_dr = a.mask[i];
         M.init(m, g, flip, (mask_dr & 1) == 0, (mask_dr & 2) == 0, a.out[20][i]);
+        pool.pair[0][lane] = g.z0; pool.pair[1][lane] = g.z1; pool.pair[2][lane] = g.x1;
+        pool.pair[3][lane] = g.n0; pool.pair[4][lane] = g.n1;
+        my_x1 = g.x1;
         has = true;
       } else {
         exhausted = true;
       }
     }
-    if (__all_sync(0xffffffffu, !has)) break;
-    if (has) {
-      if (!M.done()) {
-        double zm;
-        const double y = inice_fraa_eval(g, M.xq, zm);
-        M.advance(y, zm);
+    // Requests outside the physical range of L are settled by their owner: for L = NaN (a Newton search that left the
+    // domain keeps asking for it: 9% of all requests) and for L > A (5%) every fL term is NaN, fRaa is its
+    // "1e9 - 2e9 - x1" penalty, and the turning-depth search ends after one step at a value known in closed form.
+    // The others ("hard": 9-16 falsepos steps for the turning depth plus three fL) go to the warp's pool.
+    const int nq = has ? M.nq : 0;
+    double xk[InIceRaMachine::kMaxReq];
+    int nhard = 0;
+    unsigned hard_bits = 0;
+#pragma unroll
+    for (int k = 0; k < InIceRaMachine::kMaxReq; k++) {
+      xk[k] = 0.0;
+      if (k < nq) {
+        const double L = xk[k] = M.query(k);
+        const bool hard = !inice_fraa_shortcut(a.A, a.B, e5000, my_x1, L, yk[k], zk[k]);
+        if (hard) { hard_bits |= 1u << k; nhard++; }
       }
+    }
+    // The pool takes at most 32 hard requests per trip -- one for every lane, so that the evaluation below is a single
+    // fully occupied pass -- packed greedily in lane order from a start lane that rotates; a pair whose requests do
+    // not fit any more simply waits for the next trip.
+    if (!__any_sync(full, has)) break;   // no lane holds a pair and the list is used up
+    rot = (rot + 11) & 31;
+    int incl = __shfl_sync(full, nhard, (lane + rot) & 31);      // lane p holds the count of virtual position p
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(full, incl, d);
+      if (lane >= d) incl += t;
+    }
+    incl = __shfl_sync(full, incl, (lane - rot) & 31);           // back to the owner: inclusive sum up to its position
+    const bool accepted = incl <= 32 || nhard == 0;
+    const int total = __reduce_max_sync(full, incl <= 32 ? incl : 0);
+    if (accepted) {
+      int hb = incl - nhard;
+#pragma unroll
+      for (int k = 0; k < InIceRaMachine::kMaxReq; k++)
+        if (hard_bits & (1u << k)) { pool.x[hb] = xk[k]; pool.owner[hb] = (unsigned char)lane; slot[k] = hb++; }
+    }
+    __syncwarp();
+    if (lane < total) {
+      const int o = pool.owner[lane];
+      InIcePair g;
+      g.A = a.A; g.B = a.B; g.C = a.C;
+      g.z0 = pool.pair[0][o]; g.z1 = pool.pair[1][o]; g.x1 = pool.pair[2][o]; g.n0 = pool.pair[3][o]; g.n1 = pool.pair[4][o];
+      g.ns = 0;
+      const double x = pool.x[lane];
+      InIceZmaxIter Z;
+      Z.init(a.A, a.B, e5000, x);
+#pragma unroll 1
+      while (!Z.step(a.A, a.B, a.C)) {}
+      const double zm = Z.root + 1e-7;
+      pool.zm[lane] = zm;
+      pool.y[lane] = inice_fraa_given_zmax(g, x, zm);
+    }
+    __syncwarp();
+    if (accepted) {
+#pragma unroll
+      for (int k = 0; k < InIceRaMachine::kMaxReq; k++)
+        if (hard_bits & (1u << k)) { yk[k] = pool.y[slot[k]]; zk[k] = pool.zm[slot[k]]; }
+    }
+    if (has && accepted) {
+      M.advance(yk, zk);
       if (M.done()) {
         const int64_t n = a.n;
         a.ra_lad[0 * n + j] = M.lv0; a.ra_lad[1 * n + j] = M.lv1;
@@ -85,6 +158,7 @@ __global__ void __launch_bounds__(kThreads) airice_inice_ladder_kernel(const InI
         has = false;
       }
     }
+    __syncwarp();
   }
 }
 

@@ -82,21 +82,22 @@ void sim_inice_batch(long n, const double* z0, const double* x1, const double* z
 }
 extern "C" {
 // literal ladder vs stepped state machine for every pair whose refracted search runs: writes both 6-value results,
-// returns how many pairs ran the ladder; evals[i] = fRaa evaluations the machine consumed (-1: ladder not needed)
+// returns how many pairs ran the ladder; evals[i] = fRaa evaluations the machine requested (-1: ladder not needed),
+// steps[i] = machine steps (critical path length)
 long sim_inice_ladder_compare(long n, const double* z0, const double* x1, const double* z1, double* direct, double* stepped,
-                              int* evals) {
+                              int* evals, int* steps) {
   AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
   long ran = 0;
   for (long i = 0; i < n; i++) {
     double o[29]; bool needs;
     const int mask = inice_solve_dr(m, z0[i], x1[i], z1[i], o, needs);
-    evals[i] = -1;
+    evals[i] = -1; steps[i] = -1;
     for (int k = 0; k < 6; k++) { direct[6 * i + k] = 0; stepped[6 * i + k] = 0; }
     if (!needs) continue;
     bool flip;
     const InIcePair g = inice_make_pair(m, z0[i], x1[i], z1[i], flip);
     const InIceRaLadder a = inice_ra_ladder(m, g, flip, (mask & 1) == 0, (mask & 2) == 0, o[20]);
-    const InIceRaLadder b = inice_ra_ladder_stepped(m, g, flip, (mask & 1) == 0, (mask & 2) == 0, o[20], &evals[i]);
+    const InIceRaLadder b = inice_ra_ladder_stepped(m, g, flip, (mask & 1) == 0, (mask & 2) == 0, o[20], &evals[i], &steps[i]);
     const double da[6] = {a.lv[0], a.lv[1], a.cz[0], a.cz[1], a.zm[0], a.zm[1]};
     const double db[6] = {b.lv[0], b.lv[1], b.cz[0], b.cz[1], b.zm[0], b.zm[1]};
     for (int k = 0; k < 6; k++) { direct[6 * i + k] = da[k]; stepped[6 * i + k] = db[k]; }
@@ -107,6 +108,17 @@ long sim_inice_ladder_compare(long n, const double* z0, const double* x1, const 
 }
 extern "C" {
 double sim_inice_zmax(double L) { return inice_zmax(1.78, -0.43, 0.0132, L); }
+// fRaa at L for the pair (z0, x1, z1): full evaluation into y[0], zm[0]; shortcut into y[1], zm[1]; returns 1 if the
+// shortcut applied
+int sim_inice_fraa_shortcut(double L, double z0, double x1, double z1, double* y, double* zm) {
+  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  bool flip;
+  const InIcePair g = inice_make_pair(m, z0, x1, z1, flip);
+  y[0] = inice_fraa_eval(g, L, zm[0]);
+  y[1] = 0; zm[1] = 0;
+  return inice_fraa_shortcut(m.A, m.B, exp(-m.C * 5000.0), g.x1, L, y[1], zm[1]) ? 1 : 0;
+}
+double sim_inice_zmax_literal(double L) { return inice_zmax_literal(1.78, -0.43, 0.0132, L); }
 double sim_inice_fraa(double L, double z0, double x1, double z1) {
   AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
   InIcePair g; g.A = m.A; g.B = m.B; g.C = m.C; g.z0 = z0; g.z1 = z1; g.x1 = x1;

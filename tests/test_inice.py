@@ -81,6 +81,40 @@ def test_hostsim_matches_reference_golden(hostsim):
     assert {0, 1, 2} == set(np.unique(counts))
 
 
+def test_zmax_restructured_equals_literal(hostsim):
+    """inice_zmax (both function values of a falsepos step computed together) against the literal GSL-shaped loop."""
+    a, b = hostsim.lib.sim_inice_zmax, hostsim.lib.sim_inice_zmax_literal
+    for f in (a, b):
+        f.restype = C.c_double
+        f.argtypes = [C.c_double]
+    rng = np.random.default_rng(1)
+    Ls = np.concatenate([rng.uniform(1.0, 1.9, 50000),
+                         [np.nan, np.inf, -np.inf, 0.0, 1.35, 1.78, 1.3500000001, 1.7799999, 2.5, -3.0, 1.35 - 1e-12, -3.2, -3.3,
+                          -5.0, -100.0, 1e6, -1e6, 1e300, -1e300], rng.uniform(-10, 10, 5000)])
+    for L in Ls:
+        x, y = a(L), b(L)
+        assert x == y or (x != x and y != y), (L, x, y)
+
+
+def test_fraa_shortcut_equals_full_evaluation(hostsim):
+    """Requests at L = NaN or L > A are answered by the owning lane in closed form; same bits as the full evaluation."""
+    f = hostsim.lib.sim_inice_fraa_shortcut
+    f.restype = C.c_int
+    f.argtypes = [C.c_double] * 4 + [C.POINTER(C.c_double)] * 2
+    rng = np.random.default_rng(3)
+    Ls = np.concatenate([[np.nan, 1.78, 1.7800000000000002, 1.79, 2.9145161501534642, 10.0, 1e3, 1e8, 1e299, 1e301, np.inf,
+                          -np.inf, 1.5, 1.2, -4.0], rng.uniform(1.78, 4.0, 3000), 1.78 + 10 ** rng.uniform(-15, 6, 3000)])
+    y, zm = (C.c_double * 2)(), (C.c_double * 2)()
+    used = 0
+    for L in Ls:
+        z0, z1, x1 = -rng.uniform(1, 1500), -rng.uniform(1, 200), rng.uniform(1, 3000)
+        if f(L, z0, x1, z1, y, zm):
+            used += 1
+            assert y[0] == y[1] and zm[0] == zm[1], (L, z0, x1, z1, y[:], zm[:])
+    assert used > 5000
+    assert not f(1.5, -100.0, 50.0, -10.0, y, zm) and not f(1.78, -100.0, 50.0, -10.0, y, zm)
+
+
 def test_stepped_ladder_equals_literal_ladder(hostsim):
     """The refracted-ray root-search ladder exists twice: as the literal nested loops (inice_ra_ladder, pinned against the
     reference by the golden test above) and as the resumable state machine the GPU lanes step
@@ -88,20 +122,21 @@ def test_stepped_ladder_equals_literal_ladder(hostsim):
     dp = C.POINTER(C.c_double)
     f = hostsim.lib.sim_inice_ladder_compare
     f.restype = C.c_long
-    f.argtypes = [C.c_long, dp, dp, dp, dp, dp, C.POINTER(C.c_int)]
+    f.argtypes = [C.c_long, dp, dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     rng = np.random.default_rng(77)
     n = 12000
     z0 = np.concatenate([-rng.uniform(0.5, 2500, n - 2000), -rng.uniform(0.5, 30, 2000)])
     z1 = np.concatenate([-rng.uniform(0.5, 300, n - 2000), -rng.uniform(0.5, 30, 2000)])
     x1 = np.concatenate([rng.uniform(1, 6000, n - 2000), rng.uniform(1, 400, 2000)])
-    a, b, ev = np.zeros((n, 6)), np.zeros((n, 6)), np.zeros(n, np.int32)
+    a, b, ev, st = np.zeros((n, 6)), np.zeros((n, 6)), np.zeros(n, np.int32), np.zeros(n, np.int32)
     ran = f(n, z0.ctypes.data_as(dp), x1.ctypes.data_as(dp), z1.ctypes.data_as(dp), a.ctypes.data_as(dp),
-            b.ctypes.data_as(dp), ev.ctypes.data_as(C.POINTER(C.c_int)))
+            b.ctypes.data_as(dp), ev.ctypes.data_as(C.POINTER(C.c_int)), st.ctypes.data_as(C.POINTER(C.c_int)))
     assert ran > 2000                      # the ladder really ran for a good share of the pairs
     same = (a.view(np.int64) == b.view(np.int64)) | (np.isnan(a) & np.isnan(b))
     assert same.all(), f"{(~same.all(1)).sum()} pairs differ, first {np.where(~same.all(1))[0][:3]}"
     e = ev[ev >= 0]
     assert e.min() >= 1 and e.max() <= 7 * 100 * 9 + 64   # 7 searches x 100 iterations x (f + 8-point derivative)
+    assert (st[ev >= 0] <= e).all() and st[ev >= 0].max() <= 7 * 100 * 2 + 16   # independent evaluations share a step
 
 
 @pytest.mark.gpu

@@ -28,7 +28,7 @@ if which in ("all", "lookup"):
     for _ in range(3):
         S.lookup(T, dh, dd, out=o2, ok=ok)
 if which in ("all", "inice"):
-    ni = min(n, 500_000)
+    ni = n
     rng2 = np.random.default_rng(7)
     z0 = torch.from_numpy(rng2.uniform(-1501, -1, ni)).cuda(); z1 = torch.from_numpy(rng2.uniform(-201, -1, ni)).cuda()
     x1 = torch.from_numpy(rng2.uniform(1, 3001, ni)).cuda()
