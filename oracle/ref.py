@@ -406,6 +406,26 @@ class PyWrapReference:
         return out
 
 
+class InIceOracle:
+    """Our plain-C restatement of the in-ice solver (oracle/inice_oracle.c)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(REFDIR, "liboracle_inice.so"))
+        self.lib.inice_oracle_solve_batch.argtypes = [C.c_long, c_double_p, c_double_p, c_double_p, c_double_p]
+        self.lib.inice_oracle_set_model.argtypes = [C.c_double] * 3
+
+    def set_model(self, A, B, Cc):
+        self.lib.inice_oracle_set_model(A, B, Cc)
+
+    def solve_batch(self, z0, x1, z1):
+        z0 = np.ascontiguousarray(z0, dtype=np.float64)
+        x1 = np.ascontiguousarray(x1, dtype=np.float64)
+        z1 = np.ascontiguousarray(z1, dtype=np.float64)
+        out = np.zeros((z0.size, 29))
+        self.lib.inice_oracle_solve_batch(z0.size, _dp(z0), _dp(x1), _dp(z1), _dp(out))
+        return out
+
+
 class IceRayReference:
     """The unmodified reference IceRayTracing.cc (in-ice direct / reflected / refracted solver)."""
 

@@ -67,6 +67,33 @@ def test_golden_known_answers():
     assert (o[2, 8:12] != -1000).sum() == 0
 
 
+def _same_bits(a, b):
+    return (a.view(np.int64) == b.view(np.int64)) | (np.isnan(a) & np.isnan(b))
+
+
+def test_c_oracle_matches_reference_golden():
+    """oracle/inice_oracle.c (plain-C restatement, literal closed forms + GSL stand-in) against the fixture generated
+    from the unmodified reference: all 29 outputs of all 4000 pairs, bit for bit."""
+    from oracle.ref import InIceOracle
+    g = golden("inice.npz")
+    got = InIceOracle().solve_batch(g["z0"], g["x1"], g["z1"])
+    same = _same_bits(got, g["out"])
+    assert same.all(), ("columns", np.where(~same.all(0))[0], "pairs", np.where(~same.all(1))[0][:5])
+
+
+def test_c_oracle_equals_live_reference():
+    from oracle.ref import InIceOracle, IceRayReference, reference_available
+    if not reference_available("libiceray_ref.so"):
+        pytest.skip("oracle/_ref/libiceray_ref.so not present")
+    rng = np.random.default_rng(11)
+    n = 3000
+    z0 = np.concatenate([-rng.uniform(0.5, 2500, n), -rng.uniform(0.5, 30, 500), [-100.0, -5.0]])
+    z1 = np.concatenate([-rng.uniform(0.5, 300, n), -rng.uniform(0.5, 30, 500), [-100.0, -5.0]])
+    x1 = np.concatenate([rng.uniform(1, 6000, n), rng.uniform(0.01, 400, 500), [50.0, 1e-3]])
+    same = _same_bits(InIceOracle().solve_batch(z0, x1, z1), IceRayReference().solve_batch(z0, x1, z1))
+    assert same.all(), ("columns", np.where(~same.all(0))[0], "pairs", np.where(~same.all(1))[0][:5])
+
+
 def test_hostsim_matches_reference_golden(hostsim):
     g = golden("inice.npz")
     dp = C.POINTER(C.c_double)
@@ -155,13 +182,13 @@ def test_kernel_matches_reference_golden(solver):
 @pytest.mark.gpu
 def test_kernel_matches_live_reference_20k(solver):
     import torch
-    from oracle.ref import IceRayReference, reference_available
-    if not reference_available("libiceray_ref.so"):
-        pytest.skip("oracle/_ref/libiceray_ref.so not present")
+    from oracle.ref import InIceOracle, IceRayReference, reference_available
     rng = np.random.default_rng(2024)
     n = 20000
     z0, z1, x1 = rng.uniform(-1501, -1, n), rng.uniform(-201, -1, n), rng.uniform(1, 3001, n)
-    ref = IceRayReference().solve_batch(z0, x1, z1)
+    # the unmodified reference build when it travelled with the repo, else the plain-C oracle (bit-equal to it)
+    checker = IceRayReference() if reference_available("libiceray_ref.so") else InIceOracle()
+    ref = checker.solve_batch(z0, x1, z1)
     out, mask = solver.inice_solve(torch.from_numpy(z0), torch.from_numpy(x1), torch.from_numpy(z1))
     counts = check_inice(out.cpu().numpy().T, ref, recv_tol_deg=5e-3, max_flag_mismatch=4, flipped=z0 > z1, ra_rtol=5e-8)
     hist = np.bincount(counts, minlength=3) / n
