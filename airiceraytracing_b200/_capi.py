@@ -14,6 +14,7 @@ SOLVE_COLS = 13
 SOLVE_COLS_CM_RAD = 9
 LOOKUP_COLS = 9
 INICE_COLS = 29
+INICE_RAYS_COLS = 10
 UNITS_M_DEG = 0
 UNITS_CM_RAD = 1
 VARIANT_MULTIRAY = 0
@@ -26,7 +27,7 @@ EXPORTS = [
     "airice_forward_host", "airice_table_create", "airice_table_wrap", "airice_table_destroy", "airice_table_info",
     "airice_table_copy_column", "airice_table_column_ptr", "airice_table_copy_row_ranges", "airice_solve_device",
     "airice_solve_multi_device", "airice_solve_host", "airice_lookup_device", "airice_lookup_host", "airice_inice_solve_device",
-    "airice_inice_solve_host", "airice_fp64_peak_tflops", "airice_sync",
+    "airice_inice_solve_host", "airice_inice_two_rays_device", "airice_inice_two_rays_host", "airice_fp64_peak_tflops", "airice_sync",
 ]
 
 _lib = None
@@ -68,6 +69,8 @@ def load():
     lib.airice_lookup_host.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.airice_inice_solve_device.argtypes = [vp, i64, vp, vp, vp, pp, vp, vp]
     lib.airice_inice_solve_host.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    lib.airice_inice_two_rays_device.argtypes = [vp, i64, vp, vp, vp, pp, pp, pp, vp]
+    lib.airice_inice_two_rays_host.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     lib.airice_fp64_peak_tflops.argtypes = [vp, C.POINTER(d)]
     lib.airice_sync.argtypes = [vp]
     _lib = lib

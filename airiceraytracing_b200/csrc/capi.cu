@@ -48,6 +48,8 @@ struct airice_ctx {
   // in-ice solver scratch: compaction list + counter (+ private mask / L_R columns when the caller passes none)
   void* inice_scratch = nullptr;
   size_t inice_bytes = 0;
+  double* inice_cols = nullptr;      // 29 columns of one chunk for airice_inice_two_rays_*
+  int64_t inice_cols_n = 0;
   struct RowCache {
     double key[7] = {0, 0, 0, 0, 0, 0, 0};
     int64_t r0 = -1, r1 = -1;
@@ -212,6 +214,7 @@ void airice_destroy(airice_ctx* c) {
   if (c->rows.d_rows) cudaFree(c->rows.d_rows);
   if (c->rows.d_kt) cudaFree(c->rows.d_kt);
   if (c->inice_scratch) cudaFree(c->inice_scratch);
+  if (c->inice_cols) cudaFree(c->inice_cols);
   delete c;
 }
 
@@ -586,6 +589,94 @@ int airice_inice_solve_host(airice_ctx* c, int64_t n, const double* z0, const do
   }
   for (int s = 0; s < airice_ctx::kSlots; s++)
     if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
+  return 0;
+}
+
+namespace {
+constexpr int64_t kRaysChunk = 1 << 20;
+
+// solve + pick for one chunk of DEVICE inputs on stream s; the 29 intermediate columns live in the context
+int two_rays_chunk(airice_ctx* c, int64_t m, const double* d_rx, const double* d_dist, const double* d_tx, double* const* out10,
+                   int32_t* const* ignore2, int32_t* const* type2, cudaStream_t s) {
+  if (c->inice_cols_n < m) {
+    CK(cudaStreamSynchronize(s));
+    if (c->inice_cols) cudaFree(c->inice_cols);
+    c->inice_cols = nullptr; c->inice_cols_n = 0;
+    const int64_t cap = m < kRaysChunk ? m : kRaysChunk;
+    CK(cudaMalloc((void**)&c->inice_cols, sizeof(double) * AIRICE_INICE_NCOLS * (size_t)cap));
+    c->inice_cols_n = cap;
+  }
+  InIceArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = m; a.z0 = d_tx; a.x1 = d_dist; a.z1 = d_rx;     // IceRayTracing(0, TxDepth, Distance, RxDepth), IceRayTracing.cc:2917
+  a.A = c->medium.A_ice; a.B = c->medium.B_ice; a.C = c->medium.C_ice;
+  for (int k = 0; k < AIRICE_INICE_NCOLS; k++) a.out[k] = c->inice_cols + (size_t)k * c->inice_cols_n;
+  { int rc = inice_scratch(c, m, &a, s); if (rc) return rc; }
+  cudaError_t e = launch_inice(a, s);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_inice");
+  InIcePickArgs p;
+  std::memset(&p, 0, sizeof(p));
+  p.n = m; p.rx_depth = d_rx; p.distance = d_dist; p.tx_depth = d_tx;
+  p.A = a.A; p.B = a.B; p.C = a.C;
+  for (int k = 0; k < AIRICE_INICE_NCOLS; k++) p.in[k] = a.out[k];
+  for (int k = 0; k < AIRICE_INICE_RAYS_NCOLS; k++) p.out[k] = out10[k];
+  p.ignore[0] = ignore2[0]; p.ignore[1] = ignore2[1];
+  p.type[0] = type2 ? type2[0] : nullptr; p.type[1] = type2 ? type2[1] : nullptr;
+  e = launch_inice_pick(p, s);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_inice_pick");
+  return 0;
+}
+}  // namespace
+
+int airice_inice_two_rays_device(airice_ctx* c, int64_t n, const double* d_rx_depth, const double* d_distance,
+                                 const double* d_tx_depth, double* const* d_out, int32_t* const* d_ignore,
+                                 int32_t* const* d_type, void* stream) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!d_rx_depth || !d_distance || !d_tx_depth || !d_out || !d_ignore || !d_ignore[0] || !d_ignore[1])
+    return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  for (int64_t off = 0; off < n; off += kRaysChunk) {
+    const int64_t m = (n - off < kRaysChunk) ? (n - off) : kRaysChunk;
+    double* o[AIRICE_INICE_RAYS_NCOLS];
+    for (int k = 0; k < AIRICE_INICE_RAYS_NCOLS; k++) o[k] = d_out[k] ? d_out[k] + off : nullptr;
+    int32_t* ig[2] = {d_ignore[0] + off, d_ignore[1] + off};
+    int32_t* ty[2] = {d_type && d_type[0] ? d_type[0] + off : nullptr, d_type && d_type[1] ? d_type[1] + off : nullptr};
+    const int rc = two_rays_chunk(c, m, d_rx_depth + off, d_distance + off, d_tx_depth + off, o, ig, ty, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int airice_inice_two_rays_host(airice_ctx* c, int64_t n, const double* rx_depth, const double* distance, const double* tx_depth,
+                               double* out, int32_t* ignore) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!rx_depth || !distance || !tx_depth || !out || !ignore) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int nc = AIRICE_INICE_RAYS_NCOLS;
+  const int64_t chunk = n < kRaysChunk ? n : kRaysChunk;
+  int rc = ensure_slots(c, (size_t)chunk * (sizeof(double) * (3 + nc) + 2 * sizeof(int32_t)) + 64);
+  if (rc) return rc;
+  cudaStream_t s = c->streams[0];             // one stream: the 29-column intermediate is shared between chunks
+  double* dh = (double*)c->dev[0];
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    CK(cudaMemcpyAsync(dh, rx_depth + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, distance + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + 2 * chunk, tx_depth + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    double* o[nc];
+    for (int k = 0; k < nc; k++) o[k] = dh + (3 + k) * chunk;
+    int32_t* ig0 = (int32_t*)(dh + (3 + nc) * chunk);
+    int32_t* ig[2] = {ig0, ig0 + chunk};
+    rc = two_rays_chunk(c, m, dh, dh + chunk, dh + 2 * chunk, o, ig, nullptr, s);
+    if (rc) return rc;
+    for (int k = 0; k < nc; k++)
+      CK(cudaMemcpyAsync(out + (int64_t)k * n + off, o[k], sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    for (int k = 0; k < 2; k++)
+      CK(cudaMemcpyAsync(ignore + (int64_t)k * n + off, ig[k], sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
   return 0;
 }
 

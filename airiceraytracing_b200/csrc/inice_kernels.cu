@@ -184,6 +184,26 @@ __global__ void __launch_bounds__(kThreads) airice_inice_ra_finish_kernel(const 
     if (a.out[cols[c]]) a.out[cols[c]][i] = o[cols[c]];
 }
 
+// the two physical rays of each pair out of the four candidates (elementwise; HBM bound: 29 + 3 columns in, 10 + 4 out)
+__global__ void __launch_bounds__(256) airice_inice_pick_kernel(const InIcePickArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.n) return;
+  AirIceInIce m;
+  m.A = a.A; m.B = a.B; m.C = a.C; m.pi = 3.14159265359; m.c = 299792458.0;
+  double o[AIRICE_INICE_NCOLS];
+#pragma unroll
+  for (int k = 0; k < AIRICE_INICE_NCOLS; k++) o[k] = a.in[k][i];
+  double res[AIRICE_INICE_RAYS_NCOLS];
+  int ig[2], ty[2];
+  inice_pick_two_rays(m, o, a.rx_depth[i], a.distance[i], a.tx_depth[i], res, ig, ty);
+#pragma unroll
+  for (int k = 0; k < AIRICE_INICE_RAYS_NCOLS; k++)
+    if (a.out[k]) a.out[k][i] = res[k];
+  a.ignore[0][i] = ig[0]; a.ignore[1][i] = ig[1];
+  if (a.type[0]) a.type[0][i] = ty[0];
+  if (a.type[1]) a.type[1][i] = ty[1];
+}
+
 int ladder_grid() {
   static int blocks = 0;    // per process; every context of a process sits on the same GPU model
   if (blocks == 0) {
@@ -216,6 +236,17 @@ cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s) {
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   airice_inice_ra_finish_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_inice_pick(const InIcePickArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  const int64_t blocks = (a.n + 255) / 256;
+  if (blocks > 2147483647LL) return cudaErrorInvalidValue;
+  for (int k = 0; k < AIRICE_INICE_NCOLS; k++)
+    if (!a.in[k]) return cudaErrorInvalidValue;
+  if (!a.ignore[0] || !a.ignore[1]) return cudaErrorInvalidValue;
+  airice_inice_pick_kernel<<<dim3((unsigned)blocks), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -112,6 +112,22 @@ struct InIceArgs {
 };
 cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s);
 
+// ---- kernel 4b: the two physical rays of a pair (IceRayTracing::GetRayTracingSolutions, IceRayTracing.cc:2907-3210,
+// without its attenuation integrals), from the 29 columns of kernel 4
+#define AIRICE_INICE_RAYS_NCOLS 10
+struct InIcePickArgs {
+  int64_t n;
+  const double* rx_depth;
+  const double* distance;
+  const double* tx_depth;
+  double A, B, C;
+  const double* in[AIRICE_INICE_NCOLS];    // kernel 4 output, SoA
+  double* out[AIRICE_INICE_RAYS_NCOLS];    // TimeRay[2], PathRay[2], LaunchAngle[2], RecieveAngle[2], IncidenceAngleInIce[2]
+  int32_t* ignore[2];                      // IgnoreCh[2]: 1 = ray present
+  int32_t* type[2];                        // RayType[2] (1 D, 2 R, 3 Ra1, 4 Ra2); nullptr = skip
+};
+cudaError_t launch_inice_pick(const InIcePickArgs& a, cudaStream_t s);
+
 // ---- FP64 FMA peak probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
 cudaError_t fp64_peak_probe(double* tflops_out, int iters, cudaStream_t s);
 

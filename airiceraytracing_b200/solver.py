@@ -264,8 +264,40 @@ def _inice_solve_host(self, z0, x1, z1):
     return out, mask
 
 
+INICE_RAYS_COLUMNS = ["time_0", "time_1", "path_0", "path_1", "launch_0", "launch_1", "recv_0", "recv_1", "incidence_0",
+                      "incidence_1"]
+
+
+def _inice_two_rays(self, rx_depth, distance, tx_depth, want_type=False):
+    """IceRayTracing::GetRayTracingSolutions(RxDepth, Distance, TxDepth, ...) on device tensors (attenuation excluded)
+    -> (out [10, n] f64, ignore [2, n] int32[, type [2, n] int32])."""
+    rx = rx_depth.to(self.torch_device, torch.float64).contiguous()
+    ds = distance.to(self.torch_device, torch.float64).contiguous()
+    tx = tx_depth.to(self.torch_device, torch.float64).contiguous()
+    n = rx.numel()
+    out = torch.empty((_capi.INICE_RAYS_COLS, n), dtype=torch.float64, device=self.torch_device)
+    ig = torch.empty((2, n), dtype=torch.int32, device=self.torch_device)
+    ty = torch.empty((2, n), dtype=torch.int32, device=self.torch_device) if want_type else None
+    check(self.lib.airice_inice_two_rays_device(
+        self.handle, n, rx.data_ptr(), ds.data_ptr(), tx.data_ptr(),
+        ptr_array([out[k].data_ptr() for k in range(_capi.INICE_RAYS_COLS)]), ptr_array([ig[0].data_ptr(), ig[1].data_ptr()]),
+        ptr_array([ty[0].data_ptr(), ty[1].data_ptr()]) if want_type else None, _stream_ptr(self.torch_device)))
+    return (out, ig, ty) if want_type else (out, ig)
+
+
+def _inice_two_rays_host(self, rx_depth, distance, tx_depth):
+    n = int(rx_depth.shape[0])
+    out = np.empty((_capi.INICE_RAYS_COLS, n), dtype=np.float64)
+    ig = np.empty((2, n), dtype=np.int32)
+    check(self.lib.airice_inice_two_rays_host(self.handle, n, _host_ptr(rx_depth), _host_ptr(distance), _host_ptr(tx_depth),
+                                              _host_ptr(out), _host_ptr(ig)))
+    return out, ig
+
+
 AirIceSolver.inice_solve = _inice_solve
 AirIceSolver.inice_solve_host = _inice_solve_host
+AirIceSolver.inice_two_rays = _inice_two_rays
+AirIceSolver.inice_two_rays_host = _inice_two_rays_host
 
 
 def _host_ptr(a):

@@ -284,11 +284,13 @@ def run_ours(args):
     peak_tf = max(solver.fp64_peak_tflops() for _ in range(2))
     achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
     traffic = None
+    sass_flop = None
     tpath = os.path.join(ROOT, "profiles", "solve_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             traffic = tj["dram_bytes_per_pair"] * n
+            sass_flop = tj.get("sass_fp64_flop_per_pair")
         except Exception:
             traffic = None
     roofline = {"bound": "fp64", "kernel": "airice_solve_kernel", "achieved": achieved_tf, "peak": peak_tf,
@@ -297,6 +299,7 @@ def run_ours(args):
                                "MEASURED_PEAKS.json carries no FP64 figure",
                 "algorithmic_flop_per_solve": flops / n, "mean_distance_evals_per_solve": mean_evals,
                 "mean_air_segments": mean_segs, "kernel_ms": kernel_ms,
+                "sass_fp64_flop_per_solve": sass_flop,     # executed DADD + DMUL + 2 DFMA per pair, from the ncu capture
                 "hbm": {"algorithmic_bytes_per_solve": 89, "achieved_gbs": 89.0 * n / (kernel_ms * 1e-3) / 1e9}}
 
     # ---- secondary workloads of the same hot path: table build (MakeRayTracingTable) and table lookup
@@ -351,6 +354,22 @@ def run_ours(args):
                             "algorithmic_gbs": n * (16 + 73 + 192) / ms / 1e6,
                             "layout": "dense THD column for the index search + 48-byte records (4 cells x 48 B gathered per query)", "solved": float(ok.float().mean())}
         T.close()
+        # the same C4 batch pre-sorted by straight-line angle (neighbouring lanes then share layer count and
+        # iteration counts), and the "CoREAS-like" mix (low sources, short distances)
+        order = torch.argsort(torch.atan2(d, h - ICE_CM - DEPTH_CM))
+        hs, ds = h[order].contiguous(), d[order].contiguous()
+        ms = max_over_ranks(time_ms(lambda: solver.solve(hs, ds, DEPTH_CM, ICE_CM, UNITS_CM_RAD, out=out, ok=ok)))
+        extras["solve_angle_sorted"] = {"pairs_per_gpu": n, "ms": ms, "solves_per_s": world * n / ms * 1e3,
+                                        "note": "same batch as the headline, sorted by the caller (sort not timed)"}
+        del hs, ds, order
+        rc = np.random.default_rng(20260419 + rank)
+        hc = torch.from_numpy(rc.uniform(3001.0, 23141.0, n) * 100.0).to(dev)
+        dc = torch.from_numpy(rc.uniform(1.0, 20000.0, n) * 100.0).to(dev)
+        ms = max_over_ranks(time_ms(lambda: solver.solve(hc, dc, DEPTH_CM, ICE_CM, UNITS_CM_RAD, out=out, ok=ok)))
+        extras["solve_coreas_like"] = {"pairs_per_gpu": n, "ms": ms, "solves_per_s": world * n / ms * 1e3,
+                                       "solved_fraction": float(ok.float().mean()),
+                                       "mix": "h ~ U(3001, 23141) m, d ~ U(1, 20000) m, seed 20260419, unsorted"}
+        del hc, dc
         # in-ice direct/reflected/refracted solver (IceRayTracing::IceRayTracing), SURVEY.md 8a geometry distribution
         ni = 2_000_000
         gi = torch.Generator(device=dev).manual_seed(20260421 + rank)

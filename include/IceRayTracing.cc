@@ -1,6 +1,7 @@
 // IceRayTracing.cc -- host-side mirror of the reference's in-ice entry point on top of include/airice_b200.h.
 #include "IceRayTracing.hh"
 
+#include <cstdint>
 #include <cstdlib>
 #include <iostream>
 #include <vector>
@@ -62,6 +63,32 @@ double *IceRayTracing(double x0, double z0, double x1, double z1) {
     for (int i = 8; i < 12; i++) output[i] = -1000;
   }
   return output;
+}
+
+int GetRayTracingSolutionsBatch(long n, const double *RxDepth, const double *Distance, const double *TxDepth, double *out,
+                                int *ignore) {
+  static_assert(sizeof(int) == sizeof(int32_t), "IgnoreCh is int32 in the C ABI");
+  if (!detail::ensure_ctx()) return 1;
+  int rc = airice_inice_two_rays_host(detail::state().ctx, n, RxDepth, Distance, TxDepth, out, (int32_t *)ignore);
+  if (rc != 0) std::cerr << "IceRayTracing (B200): " << airice_last_error() << std::endl;
+  return rc;
+}
+
+void GetRayTracingSolutions(double RxDepth, double Distance, double TxDepth, double TimeRay[2], double PathRay[2],
+                            double LaunchAngle[2], double RecieveAngle[2], int IgnoreCh[2], double IncidenceAngleInIce[2],
+                            double A0, double frequency, double AttRay[2]) {
+  (void)A0; (void)frequency;
+  double out[10];
+  int ig[2] = {0, 0};
+  if (GetRayTracingSolutionsBatch(1, &RxDepth, &Distance, &TxDepth, out, ig) != 0) {
+    for (int k = 0; k < 10; k++) out[k] = 0;
+    out[6] = out[7] = -1000;
+  }
+  for (int k = 0; k < 2; k++) {
+    TimeRay[k] = out[0 + k]; PathRay[k] = out[2 + k]; LaunchAngle[k] = out[4 + k]; RecieveAngle[k] = out[6 + k];
+    IncidenceAngleInIce[k] = out[8 + k]; IgnoreCh[k] = ig[k];
+    if (AttRay) AttRay[k] = 0;
+  }
 }
 
 double *IceRayTracing(double x0, double z0, double x1, double z1, bool PlotRayPaths) {

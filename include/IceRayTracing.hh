@@ -3,7 +3,7 @@
 // Replaces, for the hot path only, /root/reference/IceRayTracing.hh / IceRayTracing.cc: the 4-argument
 // IceRayTracing::IceRayTracing(x0, z0, x1, z1) defined at IceRayTracing.cc:1745 (the reference header declares a
 // 5-argument form at IceRayTracing.hh:186; both are offered here), and the ice-model setters SetA/SetB/SetC
-// (IceRayTracing.cc:7-17).  The returned array has the reference's 29 slots and is owned by the caller (delete[]),
+// (IceRayTracing.cc:7-17), and GetRayTracingSolutions (IceRayTracing.cc:2907; two-ray selection).  The returned array has the reference's 29 slots and is owned by the caller (delete[]),
 // as in the reference.  Attenuation, focusing, ray-path dumps, the in-ice interpolation table and the constant-n
 // variants are outside the hot path and are not provided.
 #ifndef IRT_HEAD_B200
@@ -30,6 +30,16 @@ double *IceRayTracing(double x0, double z0, double x1, double z1, bool PlotRayPa
 
 // batch form (new): n pairs, out[col*n + i] with 29 columns, mask[i] bit0..3 = D,R,Ra1,Ra2 present
 int IceRayTracingBatch(long n, const double *z0, const double *x1, const double *z1, double *out, unsigned char *mask);
+
+// The two physical rays of a pair, ordered by arrival time (IceRayTracing.cc:2907-3210, same argument list).  The
+// attenuation integrals are outside the hot path: A0 and frequency are accepted and ignored, AttRay[] is set to 0.
+void GetRayTracingSolutions(double RxDepth, double Distance, double TxDepth, double TimeRay[2], double PathRay[2],
+                            double LaunchAngle[2], double RecieveAngle[2], int IgnoreCh[2], double IncidenceAngleInIce[2],
+                            double A0, double frequency, double AttRay[2]);
+// batch form (new): out[col*n + i], columns TimeRay[0..1], PathRay[0..1], LaunchAngle[0..1], RecieveAngle[0..1],
+// IncidenceAngleInIce[0..1]; ignore[k*n + i] = IgnoreCh[k]
+int GetRayTracingSolutionsBatch(long n, const double *RxDepth, const double *Distance, const double *TxDepth, double *out,
+                                int *ignore);
 
 }  // namespace IceRayTracing
 #endif

@@ -119,6 +119,21 @@ int airice_inice_solve_device(airice_ctx *ctx, int64_t n, const double *d_z0, co
 int airice_inice_solve_host(airice_ctx *ctx, int64_t n, const double *z0, const double *x1, const double *z1, double *out,
                             uint8_t *mask);
 
+/* ---- kernel 4b: the two physical rays of a pair = IceRayTracing::GetRayTracingSolutions(RxDepth, Distance, TxDepth, ...)
+ * (IceRayTracing.cc:2907-3210; declared IceRayTracing.hh) without its attenuation integrals (A0, frequency, AttRay are
+ * post-processing outside the hot path): runs kernel 4 for (0, TxDepth, Distance, RxDepth), selects two of the
+ * candidates D, R, Ra1, Ra2, orders them by arrival time and applies the same-depth straight-line patch.
+ * out: 10 column pointers = TimeRay[0..1] [s], PathRay[0..1] [m], LaunchAngle[0..1], RecieveAngle[0..1] [deg, -1000 =
+ * absent], IncidenceAngleInIce[0..1] [deg, 100 = none]; ignore: 2 int32 columns = IgnoreCh (1 = ray present);
+ * type: optional 2 int32 columns = the reference's internal RayType (1 D, 2 R, 3 Ra1, 4 Ra2), may be NULL. */
+#define AIRICE_INICE_RAYS_COLS 10
+int airice_inice_two_rays_device(airice_ctx *ctx, int64_t n, const double *d_rx_depth, const double *d_distance,
+                                 const double *d_tx_depth, double *const *d_out, int32_t *const *d_ignore,
+                                 int32_t *const *d_type, void *stream);
+/* HOST buffers: out[col*n + i] with 10 columns, ignore[k*n + i] with k = 0, 1 */
+int airice_inice_two_rays_host(airice_ctx *ctx, int64_t n, const double *rx_depth, const double *distance,
+                               const double *tx_depth, double *out, int32_t *ignore);
+
 /* ---- measurement helpers */
 int airice_fp64_peak_tflops(airice_ctx *ctx, double *tflops); /* dependent-free DFMA probe, roofline denominator */
 int airice_sync(airice_ctx *ctx);

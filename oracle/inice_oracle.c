@@ -391,3 +391,61 @@ void inice_oracle_solve_batch(long n, const double *z0, const double *x1, const 
   long i;
   for (i = 0; i < n; i++) inice_oracle_solve(z0[i], x1[i], z1[i], out + 29 * i);
 }
+
+/* GetRayTracingSolutions, IceRayTracing.cc:2907-3210, without the attenuation integrals (:2952-2966; AttRay is not
+ * produced): the two physical rays of a pair.  out10 = TimeRay[2], PathRay[2], LaunchAngle[2], RecieveAngle[2],
+ * IncidenceAngleInIce[2]; ignore2 = IgnoreCh[2]. */
+void inice_oracle_two_rays(double RxDepth, double Distance, double TxDepth, double *out10, int *ignore2) {
+  double r[29];
+  inice_oracle_solve(TxDepth, Distance, RxDepth, r);
+  const double timeD = r[4], timeR = r[5], timeRa[2] = {r[6], r[7]};
+  const double pathD = r[25], pathR = r[26], pathRa[2] = {r[27], r[28]};
+  const double RangD = r[8], RangR = r[9], RangRa[2] = {r[10], r[11]};
+  const double LangD = r[0], LangR = r[1], LangRa[2] = {r[2], r[3]};
+  double TimeRay[2], PathRay[2], RecieveAngle[2], LaunchAngle[2], Inc[2];
+  int IgnoreCh[2];
+  TimeRay[0] = timeD; TimeRay[1] = timeR; PathRay[0] = pathD; PathRay[1] = pathR;
+  RecieveAngle[0] = RangD; RecieveAngle[1] = RangR; LaunchAngle[0] = LangD; LaunchAngle[1] = LangR;
+  Inc[0] = 100; Inc[1] = r[18];
+  if (RangR == -1000) { Inc[0] = 100; Inc[1] = 100; }
+#define USE_D(s)     do { TimeRay[s] = timeD; PathRay[s] = pathD; RecieveAngle[s] = RangD; LaunchAngle[s] = LangD; } while (0)
+#define USE_R(s)     do { TimeRay[s] = timeR; PathRay[s] = pathR; RecieveAngle[s] = RangR; LaunchAngle[s] = LangR; } while (0)
+#define USE_RA(s, i) do { TimeRay[s] = timeRa[i]; PathRay[s] = pathRa[i]; RecieveAngle[s] = RangRa[i]; LaunchAngle[s] = LangRa[i]; } while (0)
+  if (RangD != -1000) USE_D(0);                                            /* :2984-2991 */
+  if (RangR != -1000) USE_R(1);                                            /* :2993-3000 */
+  if (RangRa[0] != -1000 && RangD != -1000) { USE_D(0); USE_RA(1, 0); }    /* :3002-3016 */
+  if (RangRa[0] != -1000 && RangR != -1000) { USE_R(1); USE_RA(0, 0); }    /* :3018-3032 */
+  if (RangRa[1] != -1000 && RangD != -1000) { USE_D(0); USE_RA(1, 1); }    /* :3034-3048 */
+  if (RangRa[1] != -1000 && RangR != -1000) { USE_R(1); USE_RA(0, 1); }    /* :3050-3064 */
+  if (RangRa[1] != -1000 && RangRa[0] != -1000) { USE_RA(1, 1); USE_RA(0, 0); }   /* :3066-3080 */
+  if (RecieveAngle[1] == -1000 && RecieveAngle[0] == -1000 && RangRa[0] != -1000) USE_RA(0, 0);
+  if (RecieveAngle[1] == -1000 && RecieveAngle[0] == -1000 && RangRa[1] != -1000) USE_RA(1, 1);
+#undef USE_D
+#undef USE_R
+#undef USE_RA
+  IgnoreCh[0] = 1; IgnoreCh[1] = 1;
+  if (RecieveAngle[0] == -1000) IgnoreCh[0] = 0;
+  if (RecieveAngle[1] == -1000) IgnoreCh[1] = 0;
+  if (TimeRay[0] > TimeRay[1] && RecieveAngle[0] != -1000 && RecieveAngle[1] != -1000) {   /* :3141-3148 */
+    double t;
+    t = LaunchAngle[0]; LaunchAngle[0] = LaunchAngle[1]; LaunchAngle[1] = t;
+    t = RecieveAngle[0]; RecieveAngle[0] = RecieveAngle[1]; RecieveAngle[1] = t;
+    t = TimeRay[0]; TimeRay[0] = TimeRay[1]; TimeRay[1] = t;
+    t = PathRay[0]; PathRay[0] = PathRay[1]; PathRay[1] = t;
+  }
+  if (RxDepth == TxDepth && TimeRay[0] == 0 && PathRay[0] == 0) {          /* :3190-3200 */
+    if (Distance == 0) { IgnoreCh[0] = 0; IgnoreCh[1] = 0; }
+    PathRay[0] = Distance;
+    TimeRay[0] = Distance / (k_c / nz(TxDepth));
+    LaunchAngle[0] = 90.; RecieveAngle[0] = 90.;
+    IgnoreCh[0] = 1;
+  }
+  out10[0] = TimeRay[0]; out10[1] = TimeRay[1]; out10[2] = PathRay[0]; out10[3] = PathRay[1];
+  out10[4] = LaunchAngle[0]; out10[5] = LaunchAngle[1]; out10[6] = RecieveAngle[0]; out10[7] = RecieveAngle[1];
+  out10[8] = Inc[0]; out10[9] = Inc[1];
+  ignore2[0] = IgnoreCh[0]; ignore2[1] = IgnoreCh[1];
+}
+void inice_oracle_two_rays_batch(long n, const double *rx, const double *dist, const double *tx, double *out10, int *ignore2) {
+  long i;
+  for (i = 0; i < n; i++) inice_oracle_two_rays(rx[i], dist[i], tx[i], out10 + 10 * i, ignore2 + 2 * i);
+}

@@ -413,9 +413,14 @@ class InIceOracle:
         self.lib = C.CDLL(os.path.join(REFDIR, "liboracle_inice.so"))
         self.lib.inice_oracle_solve_batch.argtypes = [C.c_long, c_double_p, c_double_p, c_double_p, c_double_p]
         self.lib.inice_oracle_set_model.argtypes = [C.c_double] * 3
+        self.lib.inice_oracle_two_rays_batch.argtypes = [C.c_long, c_double_p, c_double_p, c_double_p, c_double_p,
+                                                         C.POINTER(C.c_int)]
 
     def set_model(self, A, B, Cc):
         self.lib.inice_oracle_set_model(A, B, Cc)
+
+    def two_rays(self, rx_depth, distance, tx_depth):
+        return _two_rays(self.lib.inice_oracle_two_rays_batch, rx_depth, distance, tx_depth)
 
     def solve_batch(self, z0, x1, z1):
         z0 = np.ascontiguousarray(z0, dtype=np.float64)
@@ -426,12 +431,28 @@ class InIceOracle:
         return out
 
 
+def _two_rays(fn, rx, dist, tx):
+    rx = np.ascontiguousarray(rx, dtype=np.float64)
+    dist = np.ascontiguousarray(dist, dtype=np.float64)
+    tx = np.ascontiguousarray(tx, dtype=np.float64)
+    out = np.zeros((rx.size, 10))
+    ig = np.zeros((rx.size, 2), dtype=np.int32)
+    fn(rx.size, _dp(rx), _dp(dist), _dp(tx), _dp(out), ig.ctypes.data_as(C.POINTER(C.c_int)))
+    return out, ig
+
+
 class IceRayReference:
     """The unmodified reference IceRayTracing.cc (in-ice direct / reflected / refracted solver)."""
 
     def __init__(self):
         self.lib = C.CDLL(os.path.join(REFDIR, "libiceray_ref.so"))
         self.lib.iceref_solve_batch.argtypes = [C.c_long, c_double_p, c_double_p, c_double_p, c_double_p]
+        self.lib.iceref_two_rays_batch.argtypes = [C.c_long, c_double_p, c_double_p, c_double_p, c_double_p,
+                                                   C.POINTER(C.c_int)]
+
+    def two_rays(self, rx_depth, distance, tx_depth):
+        """GetRayTracingSolutions(RxDepth, Distance, TxDepth, ...) -> (out[n,10], IgnoreCh[n,2])"""
+        return _two_rays(self.lib.iceref_two_rays_batch, rx_depth, distance, tx_depth)
 
     def solve_batch(self, z0, x1, z1):
         z0 = np.ascontiguousarray(z0, dtype=np.float64)

@@ -34,6 +34,19 @@ void iceref_reflected(double z0, double x1, double z1, double *out11) {
   for (int i = 0; i < 11; i++) out11[i] = r[i];
   delete[] r;
 }
+// IceRayTracing::GetRayTracingSolutions (IceRayTracing.cc:2907-3210).  Its attenuation outputs go through the stand-in's
+// quadrature and are not compared; out10 = TimeRay, PathRay, LaunchAngle, RecieveAngle, IncidenceAngleInIce (2 each).
+void iceref_two_rays_batch(long n, const double *rx, const double *dist, const double *tx, double *out10, int *ignore2) {
+  for (long i = 0; i < n; i++) {
+    double T[2], P[2], La[2], Ra[2], Inc[2], Att[2];
+    int Ig[2];
+    IceRayTracing::GetRayTracingSolutions(rx[i], dist[i], tx[i], T, P, La, Ra, Ig, Inc, 1.0, 0.3, Att);
+    double *o = out10 + 10 * i;
+    o[0] = T[0]; o[1] = T[1]; o[2] = P[0]; o[3] = P[1]; o[4] = La[0]; o[5] = La[1]; o[6] = Ra[0]; o[7] = Ra[1];
+    o[8] = Inc[0]; o[9] = Inc[1];
+    ignore2[2 * i] = Ig[0]; ignore2[2 * i + 1] = Ig[1];
+  }
+}
 double iceref_zmax(double A, double L) { return IceRayTracing::GetZmax(A, L); }
 double iceref_fraa(double L, double z0, double x1, double z1) {
   IceRayTracing::fDanfRa_params p = {IceRayTracing::A_ice, z0, x1, z1};

@@ -14,5 +14,14 @@ int main(int argc, char **argv) {
     std::printf("\n");
     delete[] r;
   }
+  // the two-ray selection of the same three pairs, with the reference's own argument list
+  for (auto &c : cases) {
+    double T[2], P[2], La[2], Ra[2], Inc[2], Att[2];
+    int Ig[2];
+    IceRayTracing::GetRayTracingSolutions(c[2], c[1], c[0], T, P, La, Ra, Ig, Inc, 1.0, 0.3, Att);
+    std::printf("rays %d %d", Ig[0], Ig[1]);
+    for (int k = 0; k < 2; k++) std::printf(" %.17g %.17g %.17g %.17g %.17g", T[k], P[k], La[k], Ra[k], Inc[k]);
+    std::printf("\n");
+  }
   return 0;
 }

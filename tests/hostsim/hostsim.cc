@@ -118,6 +118,16 @@ int sim_inice_fraa_shortcut(double L, double z0, double x1, double z1, double* y
   y[1] = 0; zm[1] = 0;
   return inice_fraa_shortcut(m.A, m.B, exp(-m.C * 5000.0), g.x1, L, y[1], zm[1]) ? 1 : 0;
 }
+// GetRayTracingSolutions(RxDepth, Distance, TxDepth) through the host build of the device code
+void sim_inice_two_rays_batch(long n, const double* rx, const double* dist, const double* tx, double* out10, int* ignore2,
+                              int* type2) {
+  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  for (long i = 0; i < n; i++) {
+    double o[29];
+    inice_solve(m, tx[i], dist[i], rx[i], o);
+    inice_pick_two_rays(m, o, rx[i], dist[i], tx[i], out10 + 10 * i, ignore2 + 2 * i, type2 + 2 * i);
+  }
+}
 double sim_inice_zmax_literal(double L) { return inice_zmax_literal(1.78, -0.43, 0.0132, L); }
 double sim_inice_fraa(double L, double z0, double x1, double z1) {
   AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};

@@ -154,3 +154,17 @@ def test_iceray_driver(tmp_path, solver):
     assert abs(rows[0][0] - 27.380168714) < 1e-7 and abs(rows[0][1] - 25.8628862578) < 1e-7
     assert abs(rows[1][19] - 1.64977154594608) < 1e-12 and abs(rows[1][21] - 1.46757200401104) < 5e-9
     assert (rows[2][8:12] != -1000).sum() == 0
+    # GetRayTracingSolutions(RxDepth, Distance, TxDepth, ...) of the same pairs against the plain-C oracle
+    from oracle.ref import InIceOracle
+    rays = [line.split()[1:] for line in out.splitlines() if line.startswith("rays")]
+    assert len(rays) == 3
+    cases = np.array([[-180, 100, -5], [-1000, 2000, -200], [-200, 1500, -150]], dtype=float)
+    want, ig = InIceOracle().two_rays(cases[:, 2], cases[:, 1], cases[:, 0])
+    for k, r in enumerate(rays):
+        assert [int(r[0]), int(r[1])] == ig[k].tolist()
+        v = np.array([float(x) for x in r[2:]]).reshape(2, 5)        # per ray: T, P, launch, receive, incidence
+        for j in range(2):
+            if ig[k, j]:
+                assert abs(v[j, 0] - want[k, 0 + j]) <= 1e-9 * abs(want[k, 0 + j])
+                assert abs(v[j, 1] - want[k, 2 + j]) <= 1e-9 * abs(want[k, 2 + j])
+                assert abs(v[j, 2] - want[k, 4 + j]) <= 5e-3 and abs(v[j, 3] - want[k, 6 + j]) <= 5e-3

@@ -94,6 +94,60 @@ def test_c_oracle_equals_live_reference():
     assert same.all(), ("columns", np.where(~same.all(0))[0], "pairs", np.where(~same.all(1))[0][:5])
 
 
+def _two_ray_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    tx = np.concatenate([-rng.uniform(1, 1500, n), [-100, -100, -50, -50, -5.0, -180.0]])
+    rx = np.concatenate([-rng.uniform(1, 200, n), [-100, -100, -50, -50, -180.0, -5.0]])
+    dist = np.concatenate([rng.uniform(1, 3000, n), [0.0, 20.0, 1e-9, 300.0, 100.0, 100.0]])
+    return rx, dist, tx
+
+
+def check_two_rays(got, ig_got, want, ig_want, max_flag_mismatch, recv_tol_deg=5e-3):
+    """columns: TimeRay[2], PathRay[2], LaunchAngle[2], RecieveAngle[2], IncidenceAngleInIce[2]"""
+    bad = (ig_got != ig_want).any(1)
+    assert bad.sum() <= max_flag_mismatch, "%d pairs with different IgnoreCh" % bad.sum()
+    for j in range(2):
+        m = ~bad & (ig_want[:, j] == 1)
+        # two rays whose arrival times differ by less than the time tolerance may come out in either order
+        close = np.abs(want[:, 0] - want[:, 1]) <= 1e-8 * np.abs(want[:, 0])
+        m &= ~(close & (ig_want.sum(1) == 2))
+        # relative 5e-8 (the refracted branches' L tolerance) with a floor for the degenerate sub-nanometre pairs
+        for col, tol, floor in ((0 + j, 5e-8, 1e-20), (2 + j, 5e-8, 1e-12)):
+            err = np.abs(got[m, col] - want[m, col]) - floor
+            assert (err <= tol * np.abs(want[m, col])).all(), (col, (err / np.maximum(np.abs(want[m, col]), 1e-300)).max())
+        for col in (4 + j, 6 + j, 8 + j):
+            assert np.abs(got[m, col] - want[m, col]).max() <= recv_tol_deg, (col, np.abs(got[m, col] - want[m, col]).max())
+
+
+def test_two_ray_selection_oracle_equals_reference():
+    """GetRayTracingSolutions (IceRayTracing.cc:2907-3210): plain-C oracle against the unmodified reference."""
+    from oracle.ref import InIceOracle, IceRayReference, reference_available
+    if not reference_available("libiceray_ref.so"):
+        pytest.skip("oracle/_ref/libiceray_ref.so not present")
+    rx, dist, tx = _two_ray_cases(2500, 3)
+    a, ia = InIceOracle().two_rays(rx, dist, tx)
+    b, ib = IceRayReference().two_rays(rx, dist, tx)
+    assert _same_bits(a, b).all() and np.array_equal(ia, ib)
+    assert set(np.unique(ia.sum(1))) == {0, 1, 2}
+
+
+def test_two_ray_selection_host_build(hostsim):
+    from oracle.ref import InIceOracle
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    f = hostsim.lib.sim_inice_two_rays_batch
+    f.argtypes = [C.c_long, dp, dp, dp, dp, ip, ip]
+    rx, dist, tx = _two_ray_cases(3000, 4)
+    n = rx.size
+    got, ig, ty = np.zeros((n, 10)), np.zeros((n, 2), np.int32), np.zeros((n, 2), np.int32)
+    f(n, rx.ctypes.data_as(dp), dist.ctypes.data_as(dp), tx.ctypes.data_as(dp), got.ctypes.data_as(dp), ig.ctypes.data_as(ip),
+      ty.ctypes.data_as(ip))
+    want, ig_want = InIceOracle().two_rays(rx, dist, tx)
+    check_two_rays(got, ig, want, ig_want, max_flag_mismatch=1)
+    assert ((ty >= 1) & (ty <= 4)).all()
+    # same depth, zero distance: the straight-line patch (IceRayTracing.cc:3190-3200)
+    assert ig[n - 6].tolist() == [1, 0] and got[n - 6, 4] == 90.0 and got[n - 6, 2] == 0.0
+
+
 def test_hostsim_matches_reference_golden(hostsim):
     g = golden("inice.npz")
     dp = C.POINTER(C.c_double)
@@ -218,3 +272,22 @@ def test_kernel_edge_cases(solver):
     c, _ = solver.inice_solve(torch.tensor([-180.0]), torch.tensor([100.0]), torch.tensor([-5.0]))
     solver.set_ice_model(1.78, -0.43, 0.0132)
     assert abs(c.cpu().numpy()[19, 0] - a[19]) > 1e-6
+
+
+@pytest.mark.gpu
+def test_two_ray_selection_kernel(solver):
+    import torch
+    from oracle.ref import InIceOracle
+    rx, dist, tx = _two_ray_cases(20000, 5)
+    out, ig, ty = solver.inice_two_rays(torch.from_numpy(rx), torch.from_numpy(dist), torch.from_numpy(tx), want_type=True)
+    want, ig_want = InIceOracle().two_rays(rx, dist, tx)
+    check_two_rays(out.cpu().numpy().T, ig.cpu().numpy().T, want, ig_want, max_flag_mismatch=4)
+    ty = ty.cpu().numpy()
+    assert ((ty >= 1) & (ty <= 4)).all()
+    # host-buffer entry point: same bits as the device entry point
+    oh, ih = solver.inice_two_rays_host(rx, dist, tx)
+    assert np.array_equal(oh, out.cpu().numpy(), equal_nan=True) and np.array_equal(ih, ig.cpu().numpy())
+    # empty batch
+    e, ie = solver.inice_two_rays(torch.empty(0, dtype=torch.float64), torch.empty(0, dtype=torch.float64),
+                                  torch.empty(0, dtype=torch.float64))
+    assert e.shape == (10, 0) and ie.shape == (2, 0)
