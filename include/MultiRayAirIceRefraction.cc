@@ -57,6 +57,79 @@ inline bool ensure_ctx() {
 inline void report(const char *what) { std::cerr << "MultiRayAirIceRefraction (B200): " << what << ": " << airice_last_error() << std::endl; }
 }  // namespace detail
 
+// ---- medium accessors (MultiRayAirIceRefraction.cc:150-263): the layer constants come from the context's parsed
+// atmosphere (airice_get_medium); the layer rule is the reference's half-open [ATMLAY[k], ATMLAY[k+1]) in metres
+namespace detail {
+struct Medium { int nlayers; double lay[5], B[5], C[5]; bool ok; };
+inline Medium medium() {
+  Medium m;
+  m.ok = false; m.nlayers = 0;
+  double v[24];
+  if (!ensure_ctx() || airice_get_medium(state().ctx, v) != 0) return m;
+  m.nlayers = (int)v[0];
+  for (int k = 0; k < 5; k++) { m.lay[k] = v[1 + k]; m.B[k] = v[6 + k]; m.C[k] = v[11 + k]; }
+  m.ok = true;
+  return m;
+}
+inline int air_layer(const Medium &m, double zabs) {
+  int which = 0;
+  for (int il = 0; il < m.nlayers - 1; il++)
+    if (zabs < m.lay[il + 1] / 100 && zabs >= m.lay[il] / 100) { which = il; break; }
+  if (zabs >= m.lay[m.nlayers - 1] / 100) which = m.nlayers - 1;
+  return which;
+}
+}  // namespace detail
+
+double GetB_ice(double z) { (void)z; return B_ice; }
+double GetC_ice(double z) { (void)z; return C_ice; }
+double Getnz_ice(double z) { z = fabs(z); return A_ice + GetB_ice(z) * exp(-GetC_ice(z) * z); }
+double GetB_air(double z) {
+  const detail::Medium m = detail::medium();
+  return m.ok ? m.B[detail::air_layer(m, fabs(z))] : NAN;
+}
+double GetC_air(double z) {
+  const detail::Medium m = detail::medium();
+  return m.ok ? m.C[detail::air_layer(m, fabs(z))] : NAN;
+}
+double Getnz_air(double z) {
+  const detail::Medium m = detail::medium();
+  if (!m.ok) return NAN;
+  const double zabs = fabs(z);
+  const int k = detail::air_layer(m, zabs);
+  return 1.0 + m.B[k] * exp(-m.C[k] * zabs);
+}
+namespace detail {
+inline void fresnel_terms(double thetai, double IceLayerHeight, double &n1, double &n2, double &sqterm) {
+  n1 = Getnz_air(IceLayerHeight);
+  n2 = Getnz_ice(0);
+  sqterm = sqrt(1 - pow((n1 / n2) * (sin(thetai)), 2));
+}
+}  // namespace detail
+double Refl_S(double thetai, double IceLayerHeight) {
+  double n1, n2, sq;
+  detail::fresnel_terms(thetai, IceLayerHeight, n1, n2, sq);
+  const double rS = (n1 * cos(thetai) - n2 * sq) / (n1 * cos(thetai) + n2 * sq);
+  return std::isnan(rS) ? 1 : rS;
+}
+double Trans_S(double thetai, double IceLayerHeight) {
+  double n1, n2, sq;
+  detail::fresnel_terms(thetai, IceLayerHeight, n1, n2, sq);
+  const double tS = 1 + ((n1 * cos(thetai) - n2 * sq) / (n1 * cos(thetai) + n2 * sq));
+  return std::isnan(tS) ? 0 : tS;
+}
+double Refl_P(double thetai, double IceLayerHeight) {
+  double n1, n2, sq;
+  detail::fresnel_terms(thetai, IceLayerHeight, n1, n2, sq);
+  const double rP = -(n1 * sq - n2 * cos(thetai)) / (n1 * sq + n2 * cos(thetai));
+  return std::isnan(rP) ? 1 : rP;
+}
+double Trans_P(double thetai, double IceLayerHeight) {
+  double n1, n2, sq;
+  detail::fresnel_terms(thetai, IceLayerHeight, n1, n2, sq);
+  const double tP = (1 - ((n1 * sq - n2 * cos(thetai)) / (n1 * sq + n2 * cos(thetai)))) * (n1 / n2);
+  return std::isnan(tP) ? 0 : tP;
+}
+
 void SetDevice(int device) { detail::state().device = device; }
 void SetAtmosphereFile(const std::string &path) { detail::state().atmosphere = path; }
 

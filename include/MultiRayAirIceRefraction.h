@@ -66,6 +66,20 @@ void GetRayTracingSolutions(double RayLaunchAngleInAir, double AirTxHeight, doub
 void MakeTable(double IceLayerHeight, double AntennaDepth);
 double GetInterpolatedValue(double hR, double thR, int rtParameter);
 
+// ---- the medium model as the reference exposes it (MultiRayAirIceRefraction.h:90-119): parameters of the parsed
+// atmosphere held by the GPU context (needs MakeAtmosphere(), i.e. a GPU) and of the mutable ice model.  z in metres.
+double GetB_ice(double z);
+double GetC_ice(double z);
+double Getnz_ice(double z);
+double GetB_air(double z);
+double GetC_air(double z);
+double Getnz_air(double z);
+// field Fresnel coefficients air -> ice at the surface, incident angle in rad (MultiRayAirIceRefraction.cc:267-337)
+double Refl_S(double thetai, double IceLayerHeight);
+double Trans_S(double thetai, double IceLayerHeight);
+double Refl_P(double thetai, double IceLayerHeight);
+double Trans_P(double thetai, double IceLayerHeight);
+
 // ---- batch entry points (new): n pairs per call, SoA outputs out[col*n + i] in the order of the by-reference
 // arguments above (opt ice, opt air, geo ice, geo air, launch, X_air, T_S, T_P, received), flags in ok[i].
 int GetHorizontalDistanceToIntersectionPointBatch(long n, const double *SrcHeightASL, const double *HorizontalDistanceToRx,

@@ -59,6 +59,16 @@ int main(int argc, char **argv) {
   std::printf("direct_A1775 %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", (int)ok, oi, oa, gi, ga, la, hx, ts, tp, ra);
   MultiRayAirIceRefraction::A_ice = 1.78;
 
+  // medium accessors and Fresnel coefficients (MultiRayAirIceRefraction.h:90-119)
+  const double zs[] = {0.0, 2999.99, 3000.0, 4000.0, 4000.01, 10000.0, 10000.5, 23141.75, 23141.76, 40000.0, 100000.0, -5000.0};
+  for (double z : zs)
+    std::printf("medium %.17g %.17g %.17g %.17g %.17g\n", z, MultiRayAirIceRefraction::GetB_air(z), MultiRayAirIceRefraction::GetC_air(z),
+                MultiRayAirIceRefraction::Getnz_air(z), MultiRayAirIceRefraction::Getnz_ice(-z / 100));
+  const double ths[] = {0.0, 0.3, 1.0, 1.5, 1.5707};
+  for (double th : ths)
+    std::printf("fresnel %.17g %.17g %.17g %.17g %.17g\n", th, MultiRayAirIceRefraction::Refl_S(th, 3000), MultiRayAirIceRefraction::Trans_S(th, 3000),
+                MultiRayAirIceRefraction::Refl_P(th, 3000), MultiRayAirIceRefraction::Trans_P(th, 3000));
+
   // old solve-per-cell table on the grid of tests/golden/old_table.npz
   MultiRayAirIceRefraction::GridStepSizeH_O = 4000.0;
   MultiRayAirIceRefraction::GridStepSizeTh_O = 1.5;

@@ -69,6 +69,29 @@ def test_driver_direct_solve_and_forward(driver_output, oracle):
     assert driver_output["direct_A1775"][0][1] != d[1]
 
 
+def test_driver_medium_accessors_and_fresnel(driver_output, oracle):
+    """GetB_air/GetC_air/Getnz_air/Getnz_ice and Refl/Trans_S/P of the source-compatible API against the oracle's medium."""
+    med = np.array(driver_output["medium"])
+    assert med.shape == (12, 5)
+    consts = oracle.constants()
+    for z, B, Cc, n_air, n_ice in med:
+        assert n_air == oracle.nz_air(z), (z, n_air, oracle.nz_air(z))
+        assert n_ice == oracle.nz_ice(-z / 100)
+        assert B in consts["B_air"] and Cc in consts["C_air"]
+        assert n_air == 1.0 + B * np.exp(-Cc * abs(z))
+    # bottom and top layer; 23141.75 / 23141.76 m straddle ATMLAY[3] = 23141.7538 m (half-open layers, ">=" on the lower edge)
+    assert med[0, 1] == consts["B_air"][0] and med[10, 1] == consts["B_air"][consts["max_layers"] - 1]
+    lay = np.asarray(consts["atmlay_cm"]) / 100
+    assert 23141.75 < lay[3] < 23141.76 and med[7, 1] == consts["B_air"][2] and med[8, 1] == consts["B_air"][3]
+    n1, n2 = oracle.nz_air(3000.0), oracle.nz_ice(0.0)
+    for th, rS, tS, rP, tP in driver_output["fresnel"]:
+        sq = np.sqrt(1 - ((n1 / n2) * np.sin(th)) ** 2)
+        num, den = n1 * np.cos(th) - n2 * sq, n1 * np.cos(th) + n2 * sq
+        assert abs(rS - num / den) < 1e-14 and abs(tS - (1 + num / den)) < 1e-14
+        nump, denp = n1 * sq - n2 * np.cos(th), n1 * sq + n2 * np.cos(th)
+        assert abs(rP + nump / denp) < 1e-14 and abs(tP - (1 - nump / denp) * (n1 / n2)) < 1e-14
+
+
 def test_driver_tables_and_lookup(driver_output, oracle):
     assert driver_output["tables"][0] == [2.0]  # antenna 2 shares antenna 0's depth -> two tables (RunMultiRayCode.C:38-52)
     assert driver_output["TotalHeightSteps"][0] == [49.0] and driver_output["TotalAngleSteps"][0] == [177.0]
