@@ -49,6 +49,8 @@ struct airice_ctx {
   void* inice_scratch = nullptr;
   size_t inice_bytes = 0;
   double* inice_cols = nullptr;      // 29 columns of one chunk for airice_inice_two_rays_*
+  void* path_plans = nullptr;        // per-ray plans of airice_ray_path_*
+  size_t path_plan_cap = 0;
   int64_t inice_cols_n = 0;
   struct RowCache {
     double key[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -215,6 +217,7 @@ void airice_destroy(airice_ctx* c) {
   if (c->rows.d_kt) cudaFree(c->rows.d_kt);
   if (c->inice_scratch) cudaFree(c->inice_scratch);
   if (c->inice_cols) cudaFree(c->inice_cols);
+  if (c->path_plans) cudaFree(c->path_plans);
   delete c;
 }
 
@@ -677,6 +680,70 @@ int airice_inice_two_rays_host(airice_ctx* c, int64_t n, const double* rx_depth,
       CK(cudaMemcpyAsync(ignore + (int64_t)k * n + off, ig[k], sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s));
   }
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int airice_ray_path_device(airice_ctx* c, int64_t n, const double* d_theta, const double* d_h, double depth_m, double ice_m,
+                           int64_t max_points, double* d_x, double* d_z, int32_t* d_count, void* stream) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!d_theta || !d_h || !d_count || (max_points > 0 && (!d_x || !d_z))) return fail(-1, "null argument");
+  if (max_points < 0) return fail(-3, "max_points < 0");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int in_ice = depth_m < 0 ? 1 : 0;
+  const AirIcePlan& p = c->plan(ice_m, in_ice ? depth_m : 0.0);
+  PathArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n; a.theta = d_theta; a.h = d_h; a.max_points = max_points; a.x = d_x; a.z = d_z; a.count = d_count;
+  // plan scratch owned by the context (grow-only; a context serves one call at a time)
+  const size_t need = path_plan_bytes() * (size_t)n;
+  if (c->path_plan_cap < need) {
+    CK(cudaStreamSynchronize(s));
+    if (c->path_plans) cudaFree(c->path_plans);
+    c->path_plans = nullptr; c->path_plan_cap = 0;
+    CK(cudaMalloc(&c->path_plans, need));
+    c->path_plan_cap = need;
+  }
+  a.plans = (AirIcePathPlan*)c->path_plans;
+  cudaError_t e = launch_ray_path(c->medium, p, a, s);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_ray_path");
+  return 0;
+}
+
+int airice_ray_path_host(airice_ctx* c, int64_t n, const double* theta, const double* h, double depth_m, double ice_m,
+                         int64_t max_points, double* x, double* z, int32_t* count) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!theta || !h || !count || (max_points > 0 && (!x || !z))) return fail(-1, "null argument");
+  if (max_points < 0) return fail(-3, "max_points < 0");
+  CK(cudaSetDevice(c->device));
+  // rays per chunk so that one chunk's x and z rows stay within ~256 MB
+  int64_t chunk = max_points > 0 ? (int64_t)(16 << 20) / max_points : n;
+  if (chunk < 1) chunk = 1;
+  if (chunk > n) chunk = n;
+  int rc = ensure_slots(c, (size_t)chunk * (sizeof(double) * (2 + 2 * (size_t)max_points) + sizeof(int32_t)) + 64);
+  if (rc) return rc;
+  int slot = 0;
+  for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    double* dh = (double*)c->dev[slot];
+    cudaStream_t s = c->streams[slot];
+    double* dx = dh + 2 * chunk;
+    double* dz = dx + chunk * max_points;
+    int32_t* dc = (int32_t*)(dz + chunk * max_points);
+    CK(cudaMemcpyAsync(dh, theta + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, h + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    rc = airice_ray_path_device(c, m, dh, dh + chunk, depth_m, ice_m, max_points, dx, dz, dc, s);
+    if (rc) return rc;
+    if (max_points > 0) {
+      CK(cudaMemcpyAsync(x + off * max_points, dx, sizeof(double) * m * max_points, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(z + off * max_points, dz, sizeof(double) * m * max_points, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaMemcpyAsync(count + off, dc, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s));
+  }
+  for (int s = 0; s < airice_ctx::kSlots; s++)
+    if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
   return 0;
 }
 

@@ -9,6 +9,7 @@
 // whole waves of 148 SMs by the launch wrappers.
 #include <math_constants.h>
 
+#include "airice_path.cuh"
 #include "airice_solve.cuh"
 #include "kernels.cuh"
 
@@ -372,6 +373,41 @@ cudaError_t launch_pack_table(const float* const* c, int64_t cells, int n_h, int
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   airice_row_range_kernel<<<(n_h + 127) / 128, 128, 0, s>>>(x, cells, n_h, n_th, row_first, row_last);
+  return cudaGetLastError();
+}
+
+// ---- kernel 5: ray paths.  Step 1: one thread per ray plans its segments; step 2: one thread per point.
+__global__ void __launch_bounds__(128) airice_path_plan_kernel(const AirIceMedium m, const AirIcePlan p, const PathArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (r >= a.n) return;
+  AirIcePathPlan pl;
+  const int total = airice_path_plan(m, p, a.theta[r], a.h[r], pl);
+  if (total <= 0) { pl.nseg = 0; pl.first[0] = 0; }
+  a.plans[r] = pl;
+  a.count[r] = total;
+}
+__global__ void __launch_bounds__(256) airice_path_fill_kernel(const AirIceMedium m, const AirIcePlan p, const PathArgs a) {
+  const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (q >= a.max_points) return;
+  for (int64_t r = blockIdx.y; r < a.n; r += gridDim.y) {
+    const AirIcePathPlan& pl = a.plans[r];
+    double x = CUDART_NAN, z = CUDART_NAN;
+    if (q < (int64_t)pl.first[pl.nseg]) airice_path_point(m, p, pl, (int)q, x, z);
+    a.x[r * a.max_points + q] = x;
+    a.z[r * a.max_points + q] = z;
+  }
+}
+size_t path_plan_bytes() { return sizeof(AirIcePathPlan); }
+cudaError_t launch_ray_path(const AirIceMedium& m, const AirIcePlan& p, const PathArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  if (a.max_points < 0 || a.max_points > 2000000000LL) return cudaErrorInvalidValue;
+  const int64_t pb = (a.n + 127) / 128;
+  if (pb > 2147483647LL) return cudaErrorInvalidValue;
+  airice_path_plan_kernel<<<dim3((unsigned)pb), 128, 0, s>>>(m, p, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || a.max_points == 0) return e;
+  const unsigned gx = (unsigned)((a.max_points + 255) / 256), gy = (unsigned)(a.n < 65535 ? a.n : 65535);
+  airice_path_fill_kernel<<<dim3(gx, gy), 256, 0, s>>>(m, p, a);
   return cudaGetLastError();
 }
 

@@ -5,6 +5,8 @@
 
 #include "airice_core.cuh"
 
+struct AirIcePathPlan;   // airice_path.cuh
+
 #define AIRICE_TABLE_NCOLS64 17
 #define AIRICE_TABLE_NCOLS32 11
 #define AIRICE_SOLVE_NCOLS 13
@@ -127,6 +129,20 @@ struct InIcePickArgs {
   int32_t* type[2];                        // RayType[2] (1 D, 2 R, 3 Ra1, 4 Ra2); nullptr = skip
 };
 cudaError_t launch_inice_pick(const InIcePickArgs& a, cudaStream_t s);
+
+// ---- kernel 5: ray-path emission (SingleRayAirIceRefraction.C:226-299), airice_path.cuh
+struct PathArgs {
+  int64_t n;             // rays
+  const double* theta;   // launch angle, deg from the upward vertical (> 90)
+  const double* h;       // Tx height, m
+  int64_t max_points;    // row length of x / z
+  double* x;             // [n][max_points] horizontal distance from the Tx; unused tail entries are NaN
+  double* z;             // [n][max_points] height above sea level
+  int32_t* count;        // [n] points of the full path (may exceed max_points: the row then holds the first max_points)
+  ::AirIcePathPlan* plans; // [n] scratch
+};
+size_t path_plan_bytes();
+cudaError_t launch_ray_path(const AirIceMedium& m, const AirIcePlan& p, const PathArgs& a, cudaStream_t s);
 
 // ---- FP64 FMA peak probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
 cudaError_t fp64_peak_probe(double* tflops_out, int iters, cudaStream_t s);

@@ -294,6 +294,39 @@ def _inice_two_rays_host(self, rx_depth, distance, tx_depth):
     return out, ig
 
 
+def _ray_path(self, theta, h, depth_m, ice_m, max_points=None):
+    """Ray-path polylines (SingleRayAirIceRefraction.C:226-299) of n rays on device tensors.
+    max_points=None sizes the rows to the longest path.  -> (x [n, max_points], z [n, max_points], count [n] int32)"""
+    theta = theta.to(self.torch_device, torch.float64).contiguous()
+    h = h.to(self.torch_device, torch.float64).contiguous()
+    n = theta.numel()
+    count = torch.empty(n, dtype=torch.int32, device=self.torch_device)
+    sp = _stream_ptr(self.torch_device)
+    if max_points is None:
+        check(self.lib.airice_ray_path_device(self.handle, n, theta.data_ptr(), h.data_ptr(), depth_m, ice_m, 0, None, None,
+                                              count.data_ptr(), sp))
+        max_points = int(count.max().item()) if n else 0
+    x = torch.empty((n, max_points), dtype=torch.float64, device=self.torch_device)
+    z = torch.empty((n, max_points), dtype=torch.float64, device=self.torch_device)
+    check(self.lib.airice_ray_path_device(self.handle, n, theta.data_ptr(), h.data_ptr(), depth_m, ice_m, max_points,
+                                          x.data_ptr() if max_points else None, z.data_ptr() if max_points else None,
+                                          count.data_ptr(), sp))
+    return x, z, count
+
+
+def _ray_path_host(self, theta, h, depth_m, ice_m, max_points):
+    n = int(theta.shape[0])
+    x = np.empty((n, max_points), dtype=np.float64)
+    z = np.empty((n, max_points), dtype=np.float64)
+    count = np.empty(n, dtype=np.int32)
+    check(self.lib.airice_ray_path_host(self.handle, n, _host_ptr(theta), _host_ptr(h), depth_m, ice_m, max_points,
+                                        _host_ptr(x) if max_points else None, _host_ptr(z) if max_points else None,
+                                        _host_ptr(count)))
+    return x, z, count
+
+
+AirIceSolver.ray_path = _ray_path
+AirIceSolver.ray_path_host = _ray_path_host
 AirIceSolver.inice_solve = _inice_solve
 AirIceSolver.inice_solve_host = _inice_solve_host
 AirIceSolver.inice_two_rays = _inice_two_rays

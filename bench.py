@@ -370,6 +370,24 @@ def run_ours(args):
                                        "solved_fraction": float(ok.float().mean()),
                                        "mix": "h ~ U(3001, 23141) m, d ~ U(1, 20000) m, seed 20260419, unsorted"}
         del hc, dc
+        # ray-path emission (BASELINE config 1 shape: Tx 20 km -> ice 3000 m -> Rx -200 m, 17 206 points per ray), 2048 rays
+        nr = 2048
+        tr = torch.full((nr,), 170.0, dtype=torch.float64, device=dev) - 40.0 * torch.rand(nr, device=dev, dtype=torch.float64)
+        hr = torch.full((nr,), 20000.0, dtype=torch.float64, device=dev)
+        px, pz, pc = solver.ray_path(tr, hr, -200.0, 3000.0)
+        mp = px.shape[1]
+
+        def paths():
+            check_rc = solver.lib.airice_ray_path_device(solver.handle, nr, tr.data_ptr(), hr.data_ptr(), -200.0, 3000.0, mp,
+                                                         px.data_ptr(), pz.data_ptr(), pc.data_ptr(),
+                                                         torch.cuda.current_stream(dev).cuda_stream)
+            assert check_rc == 0
+        ms = max_over_ranks(time_ms(paths))
+        pts = int(pc.sum().item())
+        extras["ray_path"] = {"rays_per_gpu": nr, "points_per_gpu": pts, "ms": ms, "points_per_s": world * pts / ms * 1e3,
+                              "store_gbs_per_gpu": 16.0 * nr * mp / ms / 1e6,
+                              "hbm_frac_of_measured_copy_peak": 16.0 * nr * mp / ms / 1e6 / hbm_peak}
+        del px, pz, pc, tr, hr
         # in-ice direct/reflected/refracted solver (IceRayTracing::IceRayTracing), SURVEY.md 8a geometry distribution
         ni = 2_000_000
         gi = torch.Generator(device=dev).manual_seed(20260421 + rank)

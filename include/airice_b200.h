@@ -134,6 +134,20 @@ int airice_inice_two_rays_device(airice_ctx *ctx, int64_t n, const double *d_rx_
 int airice_inice_two_rays_host(airice_ctx *ctx, int64_t n, const double *rx_depth, const double *distance,
                                const double *tx_depth, double *out, int32_t *ignore);
 
+/* ---- kernel 5: ray-path emission = the RayPathinAirnIce.txt dump of the reference's CLI
+ * (SingleRayAirIceRefraction.C:226-299 on the layer walk of :133-152; `./SingleRayAirIceRefraction 200 170 20000 3000`
+ * writes 17206 points), batched: for every ray (launch angle theta in deg from the upward vertical, Tx height h in m)
+ * the polyline at 1 m height steps through the air layers (last point of a layer clamped to the layer edge, next layer
+ * entered 1e-5 m lower) and, for depth_m < 0, on at 1 m depth steps to the receiver depth (depth_m >= 0: the path ends on
+ * the ice surface).
+ * x, z: [n][max_points] row-major (horizontal distance from the Tx, height above sea level); entries past the end of a
+ * path are NaN.  count[i] = points of ray i's full path (0: the ray does not exist; larger than max_points: truncated).
+ * Call with max_points = 0 (x = z = NULL) to get the counts only. */
+int airice_ray_path_device(airice_ctx *ctx, int64_t n, const double *d_theta, const double *d_h, double depth_m, double ice_m,
+                           int64_t max_points, double *d_x, double *d_z, int32_t *d_count, void *stream);
+int airice_ray_path_host(airice_ctx *ctx, int64_t n, const double *theta, const double *h, double depth_m, double ice_m,
+                         int64_t max_points, double *x, double *z, int32_t *count);
+
 /* ---- measurement helpers */
 int airice_fp64_peak_tflops(airice_ctx *ctx, double *tflops); /* dependent-free DFMA probe, roofline denominator */
 int airice_sync(airice_ctx *ctx);

@@ -766,3 +766,47 @@ void oracle_lookup_cm_batch(const oracle_atm *a, const oracle_table *t, long n, 
   long i;
   for (i = 0; i < n; i++) ok[i] = (unsigned char)oracle_lookup_cm(a, t, h_cm[i], d_cm[i], depth_cm, ice_cm, out + 9 * i);
 }
+
+/* Ray-path dump of the reference's CLI, SingleRayAirIceRefraction.C:133-152 (layer walk carrying the first layer's L)
+ * and :226-299 (1 m polyline in air, then in ice).  depth_pos > 0 as the CLI takes it; x/z receive at most max_points
+ * entries; returns the number of points of the full path.  The file the CLI writes holds "index x z" with 6 digits. */
+static double path_F(double x, double A, double B, double C, double L, double n) { /* R.cc fDnfR with n supplied */
+  return (L / C) * (1.0 / sqrt(A * A - L * L)) * (C * x - log(A * n - L * L + sqrt(A * A - L * L) * sqrt(pow(n, 2) - L * L)));
+}
+long oracle_ray_path(const oracle_atm *a, double theta, double h, double ice, double depth_pos, long max_points, double *x, double *z) {
+  int above, below, il, top, first = 1;
+  double walk[5 * 5 + 2];
+  double L, last_x = 0, last_h = 0, rx = 0, i;
+  long ip = 0;
+  skip_layers(a, h, ice, &above, &below);
+  top = a->max_layers - above - 1;
+  oracle_air_walk(a, theta, h, ice, walk);
+  L = walk[2];                                  /* Lvalue = GetHitPar[2] of the first layer, reused below (:140,:148) */
+  for (il = top; il > below - 1; il--) {
+    double start = first ? h : last_h - 0.00001;
+    double stop = (il == (below - 1) + 1) ? ice : a->atmlay_cm[il] / 100;
+    for (i = start; i > stop - 1; i = i - 1) {
+      int k;
+      double B, C;
+      if (i < stop) i = stop;
+      k = oracle_layer_of(a, i);                /* GetB_air(-i), GetC_air(-i): parameters looked up at the point itself */
+      B = a->B_air[k]; C = a->C_air[k];
+      rx = path_F(-i, a->A_air, B, C, L, oracle_nz_air(a, -i)) - path_F(-start, a->A_air, B, C, L, oracle_nz_air(a, -start)) + last_x;
+      if (ip < max_points) { x[ip] = rx; z[ip] = i; }
+      ip++;
+      last_h = i;
+    }
+    last_x = rx;
+    first = 0;
+  }
+  {
+    int ii;
+    for (ii = 0; ii > -(depth_pos + 1); ii--) {
+      double px = last_x - path_F((double)ii, a->A_ice, a->B_ice, a->C_ice, L, oracle_nz_ice(a, (double)ii)) +
+                  path_F(0, a->A_ice, a->B_ice, a->C_ice, L, oracle_nz_ice(a, 0));
+      if (ip < max_points) { x[ip] = px; z[ip] = (double)ii + ice; }
+      ip++;
+    }
+  }
+  return ip;
+}

@@ -20,6 +20,22 @@ PI_M = 3.1415927
 ICE_CM, DEPTH_CM = 300000.0, -20000.0
 
 
+def raypath_from_cli(dst, argv4):
+    import re
+    import shutil
+    import subprocess
+    import tempfile
+    exe = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "SingleRayAirIceRefraction")
+    with tempfile.TemporaryDirectory() as tmp:
+        shutil.copy(os.path.join(HERE, "Atmosphere.dat"), tmp)
+        out = subprocess.run([exe] + ["%g" % v for v in argv4], cwd=tmp, capture_output=True, text=True, check=True).stdout
+        pts = np.loadtxt(os.path.join(tmp, "RayPathinAirnIce.txt"))
+    total = float(re.search(r"Multiple Layer fitting is ([-0-9.eE+]+)", out).group(1))
+    # the file holds "index x z" printed with 6 significant digits
+    np.savez_compressed(dst, argv=np.array(argv4, dtype=float), printed_total_x_air=total, x=pts[:, 1].astype(np.float32),
+                        z=pts[:, 2].astype(np.float32), stdout=out)
+
+
 def main():
     ref = Reference()
     c = ref.constants()
@@ -122,6 +138,10 @@ def main():
         args.append((-float(rng.uniform(1, 200)), 3000.0, float(rng.uniform(3010, 60000)), float(rng.uniform(10, 40000))))
     res = np.array([pw.py_trace(*a) for a in args])
     np.savez(os.path.join(HERE, "pywrap.npz"), args=np.array(args), out=res)
+    # ---- BASELINE config 1: the reference CLI itself, `./SingleRayAirIceRefraction 200 170 20000 3000`, run in a scratch
+    # directory next to a copy of Atmosphere.dat: the total horizontal distance it prints and the ray-path file it writes
+    raypath_from_cli(os.path.join(HERE, "raypath_c1.npz"), (200, 170, 20000, 3000))
+    raypath_from_cli(os.path.join(HERE, "raypath_low.npz"), (57.5, 135, 5000.25, 2800))
     print("golden vectors written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

@@ -7,6 +7,7 @@
 #include "airice_host.hpp"
 #include "airice_solve.cuh"
 #include "airice_inice.cuh"
+#include "airice_path.cuh"
 #include "airice_inice_machine.cuh"
 
 using namespace airice;
@@ -127,6 +128,14 @@ void sim_inice_two_rays_batch(long n, const double* rx, const double* dist, cons
     inice_solve(m, tx[i], dist[i], rx[i], o);
     inice_pick_two_rays(m, o, rx[i], dist[i], tx[i], out10 + 10 * i, ignore2 + 2 * i, type2 + 2 * i);
   }
+}
+// ray-path polyline through the host build of airice_path.cuh; depth negative in ice; returns the point count
+long sim_ray_path(double theta, double h, double ice, double depth, long max_points, double* x, double* z) {
+  AirIcePlan p; make_plan(g_m, ice, depth < 0 ? depth : 0.0, &p);
+  AirIcePathPlan pl;
+  const int total = airice_path_plan(g_m, p, theta, h, pl);
+  for (long q = 0; q < total && q < max_points; q++) airice_path_point(g_m, p, pl, (int)q, x[q], z[q]);
+  return total;
 }
 double sim_inice_zmax_literal(double L) { return inice_zmax_literal(1.78, -0.43, 0.0132, L); }
 double sim_inice_fraa(double L, double z0, double x1, double z1) {
