@@ -1,0 +1,70 @@
+"""Accuracy of the product's own FP64 device math (airice_math.cuh): table-driven log, MUFU-seeded sqrt / reciprocal /
+division.  The parity tolerances (1e-9 relative on distances and times, 1e-7 deg on angles, identical solution flags)
+rest on these staying within ~1 ulp."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def probe(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("math") / "libmathprobe.so")
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared", "-Xcompiler",
+                           "-fPIC", "-I" + os.path.join(ROOT, "airiceraytracing_b200", "csrc"), "-o", so,
+                           os.path.join(ROOT, "tests", "compat", "math_probe.cu")])
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    lib.math_probe.argtypes = [C.c_int, C.c_long, dp, dp, dp]
+
+    def run(op, a, b=None):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(a if b is None else b, dtype=np.float64)
+        out = np.empty_like(a)
+        assert lib.math_probe(op, a.size, a.ctypes.data_as(dp), b.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+        return out
+    return run
+
+
+def ulps(got, exact):
+    """error in units of the last place of the exact value (exact: longdouble, 64-bit mantissa)"""
+    ex = exact.astype(np.float64)
+    return np.abs((got.astype(np.longdouble) - exact) / np.spacing(np.abs(ex)).astype(np.longdouble)).astype(np.float64)
+
+
+@pytest.mark.gpu
+def test_device_log(probe):
+    rng = np.random.default_rng(1)
+    x = np.concatenate([np.exp(rng.uniform(-40, 40, 200000)), rng.uniform(0.5, 2.0, 200000), 1.0 + rng.uniform(-0.02, 0.02, 100000),
+                        1.0 + 10.0 ** rng.uniform(-15, -3, 50000) * rng.choice([-1, 1], 50000),
+                        [1.0, 0.6875, 1.375, np.nextafter(1.0, 0), np.nextafter(1.0, 2), 2.0, 0.5, 1e-300, 1e300]])
+    got = probe(0, x)
+    exact = np.log(x.astype(np.longdouble))
+    assert got[x == 1.0][0] == 0.0                      # exact zero: zero-thickness segments rely on it
+    far = np.abs(x - 1.0) > 0.02
+    assert ulps(got[far], exact[far]).max() <= 1.5
+    near = ~far
+    # next to 1 the result is small; what the ray integrals need there is absolute accuracy (and relative accuracy in
+    # the two table cells that touch 1)
+    assert np.abs(got[near].astype(np.longdouble) - exact[near]).max() <= 1e-17
+    touch = (x >= 0.99609375) & (x < 1.0078125)
+    assert ulps(got[touch], exact[touch]).max() <= 1.0
+    assert np.isnan(probe(0, np.array([-1.0, 0.0, np.nan]))).all()
+
+
+@pytest.mark.gpu
+def test_device_sqrt_rcp_div(probe):
+    rng = np.random.default_rng(2)
+    x = np.concatenate([np.exp(rng.uniform(-200, 200, 200000)), rng.uniform(0.5, 2.0, 100000), [1.0, 4.0, 2.0, 1e-300, 1e300]])
+    s = probe(1, x)
+    assert ulps(s, np.sqrt(x.astype(np.longdouble))).max() <= 1.0
+    assert probe(1, np.array([0.0]))[0] == 0.0 and np.isnan(probe(1, np.array([-1.0]))[0])
+    xr = np.concatenate([np.exp(rng.uniform(-200, 200, 200000)) * rng.choice([-1, 1], 200000), [1.0, -2.0, 3.0]])
+    assert ulps(probe(2, xr), 1.0 / xr.astype(np.longdouble)).max() <= 1.0
+    a = np.exp(rng.uniform(-100, 100, 200000)) * rng.choice([-1, 1], 200000)
+    b = np.exp(rng.uniform(-100, 100, 200000)) * rng.choice([-1, 1], 200000)
+    assert ulps(probe(3, a, b), a.astype(np.longdouble) / b.astype(np.longdouble)).max() <= 1.0
