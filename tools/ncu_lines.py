@@ -4,7 +4,7 @@ usage: ncu_lines.py <report.ncu-rep> <object-or-so with the cubin> <kernel-name-
 import re,csv,sys,subprocess
 from collections import defaultdict
 rep, obj, kern = sys.argv[1], sys.argv[2], sys.argv[3]
-subprocess.run(f"mkdir -p /tmp/cub2 && cd /tmp/cub2 && rm -f *.cubin && cuobjdump -xelf all {obj} >/dev/null && nvdisasm -g -c *.cubin > dis.txt", shell=True, check=True)
+subprocess.run(f"mkdir -p /tmp/cub2 && cd /tmp/cub2 && rm -f *.cubin dis.txt && cuobjdump -xelf all {obj} >/dev/null && for f in *.cubin; do nvdisasm -g -c $f >> dis.txt 2>/dev/null; done", shell=True, check=True)
 subprocess.run(f"ncu -i {rep} --page source --csv > /tmp/cub2/src.csv 2>/dev/null", shell=True, check=True)
 lines=open('/tmp/cub2/dis.txt').read().split('\n')
 start=[i for i,l in enumerate(lines) if l.startswith('.text.') and kern in l][0]
