@@ -144,7 +144,7 @@ for a, want in zip(g["args"], g["out"]):
     assert (got[0] == -1000) == (want[0] == -1000), (a, got, want)
     if want[0] != -1000:
         assert got[0] == want[0] and got[1] == want[1] and got[8] == 0 and got[9] == 0
-        worst[0] = max(worst[0], np.abs(got[[2, 3, 6]] - want[[2, 3, 6]]).max() / 1.0 if False else (np.abs(got[[2, 3, 6]] - want[[2, 3, 6]]) / np.abs(want[[2, 3, 6]])).max())
+        worst[0] = max(worst[0], (np.abs(got[[2, 3, 6]] - want[[2, 3, 6]]) / np.abs(want[[2, 3, 6]])).max())
         worst[1] = max(worst[1], np.abs(got[[4, 5, 7]] - want[[4, 5, 7]]).max())
     else:
         assert np.all(got == -1000)
