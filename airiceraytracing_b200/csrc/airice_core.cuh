@@ -142,7 +142,7 @@ AIRICE_HD double airice_x_exact(const AirIceMedium& m, const AirIcePlan& p, int 
 
 // X(L) and the analytic dX/dL.  The kernels no longer call this (the solver iterates on airice_x_fast after the FP32
 // pre-iteration airice_x_newton_f32); it stays as the FP64 statement of the derivative that the single-precision
-// version is checked against (tests/test_hostsim.py).  Only the converged root matters here (it is re-derived to ~1e-13 deg by the
+// version is checked against by the host-side unit tests.  Only the converged root matters here (it is re-derived to ~1e-13 deg by the
 // iteration itself and the reported numbers come from airice_ray_full), so this version is arranged for throughput:
 // one log per segment (ln T_stop - ln T_start = ln(T_stop/T_start)), host-precomputed 1/C', 1/R from the sqrt's own
 // refined seed.  dG/dL = L (sA+R)^2 / (T sA R) follows from dT/dL = -L (sA+R)^2/(sA R).
