@@ -94,9 +94,12 @@ struct InIceRaMachine {
 
   AIRICE_HD bool bad1() const { return fabs(cz1) > 0.5 || cz1 != cz1 || fabs(lv1 - lv0) < 1e-4; }
 
+  // pow(round / (2 trunc), 1/3) of inice_deriv_central: a real call (pow is ~300 instructions)
+  AIRICE_INICE_CALL static double cube_root_ratio(double round, double trunc) { return pow(round / (2.0 * trunc), 1.0 / 3.0); }
+
   // inice_central on samples f(c-h), f(c+h), f(c-h/2), f(c+h/2)
-  AIRICE_HD static void central(double x, double h, double fm1, double fp1, double fmh, double fph, double& result,
-                                double& round, double& trunc) {
+  AIRICE_INICE_CALL static void central(double x, double h, double fm1, double fp1, double fmh, double fph, double& result,
+                                        double& round, double& trunc) {
     const double r3 = 0.5 * (fp1 - fm1);
     const double r5 = (4.0 / 3.0) * (fph - fmh) - (1.0 / 3.0) * r3;
     const double e3 = (fabs(fp1) + fabs(fm1)) * 2.2204460492503131e-16;
@@ -171,7 +174,7 @@ struct InIceRaMachine {
           central(nw.root, nw.h, y[1], y[2], y[3], y[4], result, round, trunc);
           nw.r0 = result; nw.err0 = round + trunc;
           if (round < trunc && (round > 0 && trunc > 0)) {
-            nw.h = nw.h * pow(round / (2.0 * trunc), 1.0 / 3.0);
+            nw.h = nw.h * cube_root_ratio(round, trunc);
             ph = NW_D2; nq = 4;
             return;
           }
