@@ -277,7 +277,7 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
   const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
   const int nseg = nair + (in_ice ? 1 : 0);
   double xa = 0.0, ta = 0.0, ga = 0.0, xi = 0.0, ti = 0.0, gi = 0.0;
-  double Lk = L, Rsurf = 0.0;
+  double Lk = L, Rsurf = 0.0, sA = 0.0, inv_sA = 0.0;
   r.recv_deg = 0.0;
   constexpr int kUnrollF = AIRICE_UNROLL_FULL;
 #pragma unroll kUnrollF
@@ -288,8 +288,9 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
     if (RELAY && air && !top) Lk = Lk * p.relay[k];
     const double A = air ? 1.0 : m.A_ice;
     const double L2 = Lk * Lk;
-    const double sA = AIRICE_SQRT(A * A - L2), inv_sA = AIRICE_RCP(sA);
-    const double Cn = p.neg_c[k];
+    // sqrt(A^2 - L^2) changes only when L (relay) or the medium (air -> ice) does
+    if (RELAY || j == 0 || !air) { sA = AIRICE_SQRT(A * A - L2); inv_sA = AIRICE_RCP(sA); }
+    const double Cn = p.neg_c[k], iC = p.inv_neg_c[k];
     const double xt = top ? h : p.start_x[k];
     const double nt = top ? n_tx : p.start_n[k];
     const double xb = p.stop_x[k], nb = p.stop_n[k];
@@ -297,13 +298,12 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
     const double Rb = AIRICE_SQRT(Db), Rt = AIRICE_SQRT(Dt);
     const double Gb = Cn * xb - AIRICE_LOG(A * nb - L2 + sA * Rb), Gt = Cn * xt - AIRICE_LOG(A * nt - L2 + sA * Rt);
     const double Hb = AIRICE_LOG(nb + Rb), Ht = AIRICE_LOG(nt + Rt);
-    const double mult = AIRICE_DIV(Lk, Cn) * inv_sA;
+    const double mult = (Lk * iC) * inv_sA;
     const double xs = AIRICE_MUL(mult, Gb) - AIRICE_MUL(mult, Gt);
     const double cC = m.c * Cn;
     const double tb = AIRICE_MUL(AIRICE_RCP(cC * Rb), (Db + AIRICE_MUL(Gb * (A * A * Rb), inv_sA)) + (A * Rb) * Hb);
     const double tt = AIRICE_MUL(AIRICE_RCP(cC * Rt), (Dt + AIRICE_MUL(Gt * (A * A * Rt), inv_sA)) + (A * Rt) * Ht);
     const double ts = tb - tt;
-    const double iC = AIRICE_RCP(Cn);
     const double gs = AIRICE_MUL(Hb + (A * inv_sA) * Gb, iC) - AIRICE_MUL(Ht + (A * inv_sA) * Gt, iC);
     if (air) {
       xa += -xs; ta += -ts; ga += -gs;
