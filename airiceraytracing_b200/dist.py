@@ -64,6 +64,24 @@ def solve_sharded(solve_fn, h, d, group=None, dst=None):
     return full[:-1], full[-1].to(torch.uint8)
 
 
+def pairs_sharded(fn, *arrays, group=None, dst=None):
+    """The same for any per-pair entry point (in-ice solve, two-ray selection, table lookup): `arrays` are equally long
+    1-D inputs, `fn(*slices) -> (out [ncols, m], flags [m] or [nflag, m])`; returns (out, flags) in caller order."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = arrays[0].shape[0]
+    b, e = shard_range(n, rank, world)
+    out, flags = fn(*[a[b:e] for a in arrays])
+    fl = flags if flags.dim() == 2 else flags.unsqueeze(0)
+    packed = torch.cat([out, fl.to(out.dtype)], dim=0)
+    full = gather_columns(packed, n, group, dst)
+    if full is None:
+        return None, None
+    nf = fl.shape[0]
+    got = full[-nf:].to(flags.dtype)
+    return full[:-nf], (got if flags.dim() == 2 else got[0])
+
+
 def table_sharded(build_fn, n_h, n_th, group=None, dst=None):
     """Partition table ROWS contiguously (angles stay whole, so stores stay coalesced and the layer count is uniform
     along a row); `build_fn(row_begin, row_end) -> [ncols, (row_end-row_begin)*n_th]`.  One gather reassembles the

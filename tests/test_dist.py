@@ -28,8 +28,8 @@ def _worker(rank, world, port, n, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from airiceraytracing_b200.dist import gather_columns, shard_range, solve_sharded, table_sharded
-    from oracle.ref import Oracle
+    from airiceraytracing_b200.dist import gather_columns, pairs_sharded, shard_range, solve_sharded, table_sharded
+    from oracle.ref import InIceOracle, Oracle
     o = Oracle(ATMOSPHERE)
     rng = np.random.default_rng(99)
     h = rng.uniform(3001, 100000, n)
@@ -50,12 +50,25 @@ def _worker(rank, world, port, n, q):
         return cols[:, r0 * t.n_th:r1 * t.n_th].clone()
 
     table = table_sharded(build_fn, t.n_h, t.n_th)
+
+    # the in-ice two-ray selection through the generic per-pair sharding (three inputs, two flag rows)
+    io = InIceOracle()
+    m = min(n, 60)
+    tx, rx, dist_m = -rng.uniform(1, 1500, m), -rng.uniform(1, 200, m), rng.uniform(1, 3000, m)
+
+    def rays_fn(rxs, dss, txs):
+        o10, ig = io.two_rays(rxs.numpy(), dss.numpy(), txs.numpy())
+        return torch.from_numpy(o10.T.copy()), torch.from_numpy(ig.T.copy())
+
+    rays, ign = pairs_sharded(rays_fn, torch.from_numpy(rx), torch.from_numpy(dist_m), torch.from_numpy(tx))
     if rank == 0:
         ok_ref, ref = o.solve_cm_batch(h * 100, d * 100, -20000.0, 300000.0)
         q.put(dict(solve_equal=bool(np.array_equal(full.numpy().T, ref, equal_nan=True)),
                    flags_equal=bool(np.array_equal(ok.numpy().astype(bool), ok_ref)),
                    root_equal=bool(root_only is not None and torch.equal(root_only.nan_to_num(), full.nan_to_num())),
                    table_equal=bool(torch.equal(table.nan_to_num(), cols.nan_to_num())),
+                   rays_equal=bool(np.array_equal(rays.numpy().T, io.two_rays(rx, dist_m, tx)[0], equal_nan=True) and
+                                   np.array_equal(ign.numpy().T, io.two_rays(rx, dist_m, tx)[1])),
                    ranges=[shard_range(n, r, world) for r in range(world)]))
     else:
         assert root_only is None
@@ -84,7 +97,7 @@ def test_sharded_solve_and_table_reassemble_in_caller_order(oracle_built, world,
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res is not None
-    assert res["solve_equal"] and res["flags_equal"] and res["root_equal"] and res["table_equal"]
+    assert res["solve_equal"] and res["flags_equal"] and res["root_equal"] and res["table_equal"] and res["rays_equal"]
     rng = res["ranges"]
     assert rng[0][0] == 0 and rng[-1][1] == n and all(a[1] == b[0] for a, b in zip(rng[:-1], rng[1:]))
 
