@@ -205,7 +205,7 @@ void make_plan(const AirIceMedium& m, double ice_h, double depth_signed, AirIceP
     if (ice_h >= m.hlo[k] && ice_h < m.hlo[k + 1]) { p.kb = k; break; }
   }
   for (int k = 0; k <= AIRICE_MAX_LAYERS; k++) {
-    p.neg_c[k] = -1; p.inv_neg_c[k] = -1; p.stop_x[k] = 0; p.stop_n[k] = 1; p.start_x[k] = 0; p.start_n[k] = 1; p.relay[k] = 1;
+    p.neg_c[k] = -1; p.inv_neg_c[k] = -1; p.stop_x[k] = 0; p.stop_n[k] = 1; p.start_x[k] = 0; p.start_n[k] = 1; p.relay[k] = 1; p.ln_relay[k] = 0;
   }
   for (int k = 0; k < m.nlayers; k++) { p.neg_c[k] = -m.C[k]; p.inv_neg_c[k] = 1.0 / p.neg_c[k]; }
   for (int k = p.kb; k < m.nlayers; k++) {
@@ -214,7 +214,10 @@ void make_plan(const AirIceMedium& m, double ice_h, double depth_signed, AirIceP
     p.start_x[k] = m.hlo[k + 1] - 0.00001;
     p.start_n[k] = n_air(m, p.start_x[k]);
   }
-  for (int k = p.kb; k + 1 < m.nlayers; k++) p.relay[k] = p.start_n[k] / p.stop_n[k + 1];
+  for (int k = p.kb; k + 1 < m.nlayers; k++) {
+    p.relay[k] = p.start_n[k] / p.stop_n[k + 1];
+    p.ln_relay[k] = std::log(p.relay[k]);
+  }
   // ice leg: surface (x=0) down to the receiver (x=depth), GetIcePropagationPar (M.cc:807-869)
   p.neg_c[AIRICE_ICE_SLOT] = -m.C_ice;
   p.inv_neg_c[AIRICE_ICE_SLOT] = 1.0 / p.neg_c[AIRICE_ICE_SLOT];
