@@ -50,6 +50,10 @@ struct airice_ctx {
   size_t inice_bytes = 0;
   double* inice_cols = nullptr;      // 29 columns of one chunk for airice_inice_two_rays_*
   void* path_plans = nullptr;        // per-ray plans of airice_ray_path_*
+  // buffers of destroyed tables kept for the next table of the same size (a per-antenna loop creates and destroys 64
+  // tables of 384 + 455 MB: cudaMalloc / cudaFree of that size cost more than building the table, and jitter wildly)
+  struct SpareBuf { void* p; size_t bytes; };
+  std::vector<SpareBuf> spare;
   size_t path_plan_cap = 0;
   int64_t inice_cols_n = 0;
   struct RowCache {
@@ -77,6 +81,7 @@ struct airice_table {
   float* cols[AIRICE_TABLE_NCOLS32] = {nullptr};   // reference layout (column-major), owned or wrapped
   // lookup layout, always owned: dense X, 48-byte records, per-row height, per-row trim ranges (one allocation)
   void* pack = nullptr;
+  size_t cols_bytes = 0, pack_bytes = 0;
   float* x = nullptr;
   float4* rec = nullptr;
   float* row_h = nullptr;
@@ -97,13 +102,42 @@ struct airice_table {
 namespace {
 
 // Allocate and fill the lookup layout of a table from its column-major form.
+// table-sized device buffers: reuse a spare of (nearly) the right size, else allocate
+cudaError_t table_alloc(airice_ctx* c, void** p, size_t bytes) {
+  for (size_t i = 0; i < c->spare.size(); i++) {
+    if (c->spare[i].bytes >= bytes && c->spare[i].bytes <= bytes + bytes / 4) {
+      *p = c->spare[i].p;
+      c->spare.erase(c->spare.begin() + i);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess && !c->spare.empty()) {      // out of memory: give the spares back and retry
+    cudaGetLastError();
+    for (auto& b : c->spare) cudaFree(b.p);
+    c->spare.clear();
+    e = cudaMalloc(p, bytes);
+  }
+  return e;
+}
+void table_release(airice_ctx* c, void* p, size_t bytes) {
+  if (!p) return;
+  if (c->spare.size() < 2 && bytes >= ((size_t)1 << 20)) {
+    cudaDeviceSynchronize();                        // what cudaFree would have waited for
+    c->spare.push_back({p, bytes});
+  } else {
+    cudaFree(p);
+  }
+}
+
 int pack_table(airice_table* t) {
   const size_t rec_bytes = sizeof(float4) * 3 * (size_t)t->cells;
   const size_t x_bytes = (sizeof(float) * (size_t)t->cells + 255) / 256 * 256;
   const size_t rowh_bytes = (sizeof(float) * (size_t)t->n_h + 255) / 256 * 256;
   const size_t range_bytes = (sizeof(int) * (size_t)t->n_h + 255) / 256 * 256;
-  cudaError_t e = cudaMalloc(&t->pack, rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(lookup layout)");
+  t->pack_bytes = rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes;
+  cudaError_t e = table_alloc(t->ctx, &t->pack, t->pack_bytes);
+  if (e != cudaSuccess) { t->pack = nullptr; return cuda_fail(e, "cudaMalloc(lookup layout)"); }
   char* base = (char*)t->pack;
   t->rec = (float4*)base;
   t->x = (float*)(base + rec_bytes);
@@ -218,6 +252,7 @@ void airice_destroy(airice_ctx* c) {
   if (c->inice_scratch) cudaFree(c->inice_scratch);
   if (c->inice_cols) cudaFree(c->inice_cols);
   if (c->path_plans) cudaFree(c->path_plans);
+  for (auto& b : c->spare) cudaFree(b.p);
   delete c;
 }
 
@@ -276,7 +311,8 @@ int airice_table_create(airice_ctx* c, double depth_m, double ice_m, double h_to
   t->loop_stop_h = g.loop_stop_h; t->h_step = g.h_step;
   if (t->cells >= 2147483647LL) { delete t; return fail(-5, "lookup tables are limited to 2^31-1 cells (the reference indexes them with int)"); }
   float* block = nullptr;
-  cudaError_t e = cudaMalloc((void**)&block, sizeof(float) * t->cells * AIRICE_TABLE_NCOLS32);
+  t->cols_bytes = sizeof(float) * (size_t)t->cells * AIRICE_TABLE_NCOLS32;
+  cudaError_t e = table_alloc(c, (void**)&block, t->cols_bytes);
   if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(table)"); }
   for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t->cols[k] = block + (int64_t)k * t->cells;
   rc = build_rows(c, g, 0, t->n_h, nullptr, t->cols, nullptr);
@@ -304,8 +340,8 @@ int airice_table_wrap(airice_ctx* c, const float* const* d_cols32, int64_t n_h, 
 void airice_table_destroy(airice_table* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
-  if (t->owns && t->cols[0]) cudaFree(t->cols[0]);
-  if (t->pack) cudaFree(t->pack);
+  if (t->owns && t->cols[0]) table_release(t->ctx, t->cols[0], t->cols_bytes);
+  if (t->pack) table_release(t->ctx, t->pack, t->pack_bytes);
   delete t;
 }
 
