@@ -67,7 +67,17 @@ struct AirIceMedium {
   double rad2deg;                     // 180/pi
   double c;                           // 299792458 (M.h:30)
   double tan16;                       // tan(16 deg) in the variant's pi: tangent step of the 16-deg bracket (M.cc:1487)
+  // the clamped bracket's scan (M.cc:1490-1511) visits lo_j = 90.001 (+ 0.05 j times, accumulated as the reference
+  // does) and needs sin((180 - lo_j) deg2rad): both are ray-independent, tabulated on the host with the libm the
+  // reference uses.  [AIRICE_CLAMP_N][2] = {lo_j, sin_j}; device memory on the GPU, host memory in host builds.
+  const double* clamp_tab;
 };
+#define AIRICE_CLAMP_N 336             // lo_j up to 106.75 deg: the scan never goes past hi - 0.1 < 105.901
+#if defined(__CUDA_ARCH__)
+#define AIRICE_LDG(p) __ldg(p)
+#else
+#define AIRICE_LDG(p) (*(p))
+#endif
 
 // Per-(ice height, receiver depth) plan: every ray-independent number of the layer walk, computed on
 // the host with the same libm the reference uses.  Slot AIRICE_MAX_LAYERS of the per-segment arrays is the ice leg.

@@ -14,6 +14,7 @@ namespace airice {
 // cubic spline value at h=0 (the only use the reference makes of its 23k-point GSL spline, M.cc:203).
 // Returns 0 or a negative error code; `err` gets a message.
 int load_medium(const char* path, int variant, AirIceMedium* out, double* n0_out, int* npoints_out, std::string* err);
+void make_clamp_table(const AirIceMedium& m, double* tab /* [AIRICE_CLAMP_N][2] */);
 
 // Layer index of a height as GetB_air/GetC_air see it (M.cc:216-256).
 int layer_of(const AirIceMedium& m, double z);

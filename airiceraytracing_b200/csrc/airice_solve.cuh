@@ -38,25 +38,42 @@ AIRICE_HD void airice_bracket(const AirIceMedium& m, const AirIcePlan& p, int kt
   lo = thR - 16;
   hi = thR;
   if (lo < 90.001) {
-    lo = 90.001;
-    // closed-form jump over the NaN zone: X(theta) is NaN exactly while n_tx sin(180-theta) >= 1
-    int k = 0;
+    // The reference scans lo = 90.001, +0.05, ... while the ray does not exist (n_tx sin(180-lo) >= 1) and lo has
+    // not passed hi - 0.1.  The visited angles and their sines do not depend on the ray (m.clamp_tab, accumulated and
+    // evaluated on the host exactly as the reference does), and both stop conditions are monotone in j, so the scan
+    // is two bracketed searches from closed-form estimates: no trigonometry and no loop over the NaN zone here.
+    const double lim = hi - 0.1;
+    const double* tab = m.clamp_tab;
+    int jh = 0;
+    {
+      const double e = ceil((lim - 90.001) / 0.05);
+      jh = e > 0.0 ? (e < (double)(AIRICE_CLAMP_N - 1) ? (int)e : AIRICE_CLAMP_N - 1) : 0;
+#pragma unroll 1
+      while (jh > 0 && AIRICE_LDG(tab + 2 * (jh - 1)) > lim) jh--;
+#pragma unroll 1
+      while (jh < AIRICE_CLAMP_N - 1 && !(AIRICE_LDG(tab + 2 * jh) > lim)) jh++;
+    }
+    int j = jh;
     if (walk && n_tx > 1.0) {
-      const double th_c = 180 - asin(1.0 / n_tx) * m.rad2deg;
-      const double kk = ceil((th_c - 90.001) / 0.05) - 1.0;
-      k = kk > 0.0 ? (int)kk : 0;
-    }
+      // first j with 1 - (n_tx sin_j)^2 > 0: sin_j = cos(lo_j - 90 deg) ~ 1 - eps^2/2 < 1/n_tx  <=>  eps > sqrt(2 (n_tx - 1))
+      const float est = (sqrtf(2.0f * (float)(n_tx - 1.0)) * (float)m.rad2deg - 0.001f) * 20.0f;
+      int jo = est > 0.0f ? (est < (float)jh ? (int)est : jh) : 0;
 #pragma unroll 1
-    for (int i = 0; i < k && !(lo > hi - 0.1); i++) lo = lo + 0.05;
-    // finish with the literal loop (0-2 iterations) so that rounding at the zone edge matches
-    double L = 0.0;
+      while (jo > 0) {
+        const double Lp = n_tx * AIRICE_LDG(tab + 2 * (jo - 1) + 1);
+        if (!(1.0 - Lp * Lp > 0.0)) break;
+        jo--;
+      }
 #pragma unroll 1
-    for (int it = 0; it < 4000; it++) {
-      L = airice_L_of_theta(m, n_tx, lo);
-      const bool okx = walk && (1.0 - L * L > 0.0);
-      if (okx || lo > hi - 0.1) break;
-      lo = lo + 0.05;
+      while (jo < jh) {
+        const double Lp = n_tx * AIRICE_LDG(tab + 2 * jo + 1);
+        if (1.0 - Lp * Lp > 0.0) break;
+        jo++;
+      }
+      j = jo;
     }
+    lo = AIRICE_LDG(tab + 2 * j);
+    const double L = n_tx * AIRICE_LDG(tab + 2 * j + 1);
     finite_lo = walk && (1.0 - L * L > 0.0);
     t_cap = AIRICE_DIV(L, AIRICE_SQRT(n_tx * n_tx - L * L));
   } else {

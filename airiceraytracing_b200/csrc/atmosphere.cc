@@ -147,6 +147,7 @@ int load_medium(const char* path, int variant, AirIceMedium* out, double* n0_out
   m.rad2deg = 180 / m.pi;
   m.c = 299792458.0;
   m.tan16 = std::tan(16 * m.deg2rad);
+  m.clamp_tab = nullptr;   // set by the owner of the medium (make_clamp_table)
   m.A_ice = 1.78; m.B_ice = -0.43; m.C_ice = 0.0132;
   for (int k = 0; k < 5; k++) m.hlo[k] = atmlay_cm[k] / 100;
   m.hlo[5] = atmlay_cm[4] / 100;
@@ -276,6 +277,17 @@ void grid_rows(const AirIceMedium& m, const TableGrid& g, int64_t r0, int64_t r1
     (*h)[r - r0] = hv;
     (*kt)[r - r0] = k;
     (*ntx)[r - r0] = n_air(m, hv);
+  }
+}
+
+// lo_j and sin((180 - lo_j) deg2rad) of the clamped bracket's scan (M.cc:1490-1511): lo accumulates 0.05 exactly as
+// the reference's `lo = lo + 0.05` does
+void make_clamp_table(const AirIceMedium& m, double* tab) {
+  double lo = 90.001;
+  for (int j = 0; j < AIRICE_CLAMP_N; j++) {
+    tab[2 * j] = lo;
+    tab[2 * j + 1] = std::sin((180 - lo) * m.deg2rad);
+    lo = lo + 0.05;
   }
 }
 

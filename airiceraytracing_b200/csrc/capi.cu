@@ -50,6 +50,7 @@ struct airice_ctx {
   size_t inice_bytes = 0;
   double* inice_cols = nullptr;      // 29 columns of one chunk for airice_inice_two_rays_*
   void* path_plans = nullptr;        // per-ray plans of airice_ray_path_*
+  double* clamp_tab = nullptr;       // device copy of the clamped-bracket table (medium.clamp_tab points at it)
   // buffers of destroyed tables kept for the next table of the same size (a per-antenna loop creates and destroys 64
   // tables of 384 + 455 MB: cudaMalloc / cudaFree of that size cost more than building the table, and jitter wildly)
   struct SpareBuf { void* p; size_t bytes; };
@@ -236,6 +237,14 @@ int airice_create(const char* atmosphere_path, int variant, int device, airice_c
   if (rc != 0) { delete c; return fail(rc, err); }
   e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaSetDevice"); }
+  {
+    std::vector<double> tab(2 * AIRICE_CLAMP_N);
+    make_clamp_table(c->medium, tab.data());
+    e = cudaMalloc((void**)&c->clamp_tab, sizeof(double) * tab.size());
+    if (e == cudaSuccess) e = cudaMemcpy(c->clamp_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { if (c->clamp_tab) cudaFree(c->clamp_tab); delete c; return cuda_fail(e, "clamp table"); }
+    c->medium.clamp_tab = c->clamp_tab;
+  }
   *out = c;
   return 0;
 }
@@ -252,6 +261,7 @@ void airice_destroy(airice_ctx* c) {
   if (c->inice_scratch) cudaFree(c->inice_scratch);
   if (c->inice_cols) cudaFree(c->inice_cols);
   if (c->path_plans) cudaFree(c->path_plans);
+  if (c->clamp_tab) cudaFree(c->clamp_tab);
   for (auto& b : c->spare) cudaFree(b.p);
   delete c;
 }

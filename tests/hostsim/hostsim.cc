@@ -17,7 +17,10 @@ static AirIceMedium g_m;
 extern "C" {
 int sim_load(const char* path, int variant) {
   std::string err; double n0; int np;
-  return load_medium(path, variant, &g_m, &n0, &np, &err);
+  const int rc = load_medium(path, variant, &g_m, &n0, &np, &err);
+  static double clamp[2 * AIRICE_CLAMP_N];
+  if (rc == 0) { make_clamp_table(g_m, clamp); g_m.clamp_tab = clamp; }
+  return rc;
 }
 void sim_medium(double* out) {
   out[0] = g_m.nlayers;
