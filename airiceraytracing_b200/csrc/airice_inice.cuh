@@ -42,6 +42,21 @@ AIRICE_HD double inice_nz(const AirIceInIce& m, double z) { z = fabs(z); return 
 AIRICE_INICE_CALL double inice_fL(double A, double L, double Cp, double Z, double nZ) {
   return (L / Cp) * (1.0 / sqrt(A * A - L * L)) * (Cp * Z - log(A * nZ - L * L + sqrt(A * A - L * L) * sqrt(nZ * nZ - L * L)));
 }
+// The same in two parts for the root functions, which evaluate it at two or three depths for ONE L: the factor
+// (L/C)(1/sqrt(A^2-L^2)) and sqrt(A^2-L^2) depend on L only (two divisions and a square root of the two divisions,
+// two square roots and one log a call costs).  The product is formed in the order of the expression above
+// (left to right), so the value of every term is bit-identical to inice_fL's.
+struct InIceFLPre { double t, sA, L2; };
+AIRICE_HD InIceFLPre inice_fL_pre(double A, double L, double Cp) {
+  InIceFLPre q;
+  q.sA = sqrt(A * A - L * L);
+  q.t = (L / Cp) * (1.0 / q.sA);
+  q.L2 = L * L;
+  return q;
+}
+AIRICE_INICE_CALL double inice_fL_at(const InIceFLPre& q, double A, double Cp, double Z, double nZ) {
+  return q.t * (Cp * Z - log(A * nZ - q.L2 + q.sA * sqrt(nZ * nZ - q.L2)));
+}
 
 // ---- GSL pieces, restated (see oracle/gsl_standin/gsl_standin.c for the same algorithms on the test side)
 struct InIceBracket {
@@ -209,15 +224,17 @@ AIRICE_HD double inice_zmax(double A, double B, double C, double L) {
 struct InIceFDa {
   InIcePair g;
   AIRICE_HD double operator()(double L) const {
-    return (inice_fL(g.A, L, g.C, g.z1, g.n1) - inice_fL(g.A, L, g.C, g.z0, g.n0)) - g.x1;
+    const InIceFLPre q = inice_fL_pre(g.A, L, g.C);
+    return (inice_fL_at(q, g.A, g.C, g.z1, g.n1) - inice_fL_at(q, g.A, g.C, g.z0, g.n0)) - g.x1;
   }
 };
 struct InIceFRa {
   InIcePair g;
   AIRICE_HD double operator()(double L) const {
-    const double fb = inice_fL(g.A, L, -g.C, -g.z0, g.n0);
-    const double d01 = inice_fL(g.A, L, -g.C, -g.z1, g.n1) - fb;
-    const double d0s = inice_fL(g.A, L, -g.C, 1e-7, g.ns) - fb;
+    const InIceFLPre q = inice_fL_pre(g.A, L, -g.C);
+    const double fb = inice_fL_at(q, g.A, -g.C, -g.z0, g.n0);
+    const double d01 = inice_fL_at(q, g.A, -g.C, -g.z1, g.n1) - fb;
+    const double d0s = inice_fL_at(q, g.A, -g.C, 1e-7, g.ns) - fb;
     return d01 - 2 * (d0s) - g.x1;
   }
 };
@@ -226,9 +243,10 @@ struct InIceFRa {
 AIRICE_HD double inice_fraa_given_zmax(const InIcePair& g, double L, double zmax) {   // zmax = inice_zmax(L) + 1e-7
   if (!(zmax > 0)) return 1e9;
   const double nzm = g.A + g.B * exp(-g.C * fabs(zmax));
-  const double fb = inice_fL(g.A, L, -g.C, -g.z0, g.n0);
-  double d01 = inice_fL(g.A, L, -g.C, -g.z1, g.n1) - fb;
-  double d0s = inice_fL(g.A, L, -g.C, zmax, nzm) - fb;
+  const InIceFLPre q = inice_fL_pre(g.A, L, -g.C);
+  const double fb = inice_fL_at(q, g.A, -g.C, -g.z0, g.n0);
+  double d01 = inice_fL_at(q, g.A, -g.C, -g.z1, g.n1) - fb;
+  double d0s = inice_fL_at(q, g.A, -g.C, zmax, nzm) - fb;
   if (d01 != d01) d01 = 1e9;
   if (d0s != d0s) d0s = 1e9;
   return d01 - 2 * (d0s) - g.x1;
@@ -259,9 +277,9 @@ struct InIceFRaa {
 // turning depth z_max = -ln((L-A)/B)/C where n(z_max) = L (there R = 0 and T = L (A - L)).
 AIRICE_HD double inice_xra_exact(const InIcePair& g, double L) {
   const double zmax = -log((L - g.A) / g.B) / g.C;
-  const double sA = sqrt(g.A * g.A - L * L);
-  const double fm = (L / -g.C) * (1.0 / sA) * (-g.C * zmax - log(L * (g.A - L)));
-  return inice_fL(g.A, L, -g.C, -g.z1, g.n1) + inice_fL(g.A, L, -g.C, -g.z0, g.n0) - 2.0 * fm;
+  const InIceFLPre q = inice_fL_pre(g.A, L, -g.C);
+  const double fm = q.t * (-g.C * zmax - log(L * (g.A - L)));
+  return inice_fL_at(q, g.A, -g.C, -g.z1, g.n1) + inice_fL_at(q, g.A, -g.C, -g.z0, g.n0) - 2.0 * fm;
 }
 
 // Certificate that NO refracted ray can be accepted: fRaa(L) = X_Ra(L) - x1 wherever it is not a 1e9 penalty, the
