@@ -187,17 +187,27 @@ __global__ void airice_pack_kernel(const float* c0, const float* c1, const float
   if (i % n_th == 0) row_h[i / n_th] = c0[i];
 }
 
-// FindClosestTHD (M.cc:1128-1169): <=8 index halvings while the window is >=3 wide, then a linear scan.
-__device__ __forceinline__ void find_thd(const float* __restrict__ X, double d, int s, int e, int& i1, int& i2, double& cv) {
+// FindClosestTHD (M.cc:1128-1169) = <=8 index halvings while the window is >=3 wide (halve_thd2), then a linear scan
+// (scan_thd).
+__device__ __forceinline__ void load_rec(const float4* __restrict__ rec, int i, double* v) {
+  const float4 a = __ldg(rec + 3 * (int64_t)i), b = __ldg(rec + 3 * (int64_t)i + 1), c = __ldg(rec + 3 * (int64_t)i + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; v[8] = c.x; v[9] = c.y;
+}
+
+// The index halvings of FindClosestTHD for the two rows of a query in lock step: the two chains of dependent loads
+// (eight each, L2 or DRAM latency apiece) overlap instead of running one after the other.
+__device__ __forceinline__ void halve_thd2(const float* __restrict__ X, double d, bool on1, int& s1, int& e1, bool on2, int& s2, int& e2) {
 #pragma unroll 1
   for (int i = 0; i < 8; i++) {
-    if (e - s >= 3) {
-      const int mid = (s + e) / 2;
-      const double v = (double)__ldg(X + mid) - d;
-      if (v > 0) s = mid;
-      if (v < 0) e = mid;
-    }
+    const bool g1 = on1 && (e1 - s1 >= 3), g2 = on2 && (e2 - s2 >= 3);
+    const int m1 = (s1 + e1) / 2, m2 = (s2 + e2) / 2;
+    const float x1 = g1 ? __ldg(X + m1) : 0.f, x2 = g2 ? __ldg(X + m2) : 0.f;
+    if (g1) { const double v = (double)x1 - d; if (v > 0) s1 = m1; if (v < 0) e1 = m1; }
+    if (g2) { const double v = (double)x2 - d; if (v > 0) s2 = m2; if (v < 0) e2 = m2; }
   }
+}
+// the rest of FindClosestTHD (M.cc:1148-1168) on the halved window
+__device__ __forceinline__ void scan_thd(const float* __restrict__ X, double d, int s, int e, int& i1, int& i2, double& cv) {
   double minimum = 100000000000.0;
   int index2 = 0;
 #pragma unroll 1
@@ -213,19 +223,8 @@ __device__ __forceinline__ void find_thd(const float* __restrict__ X, double d, 
   if (minimum > other) minimum = other;
   i1 = index1; i2 = index2; cv = minimum;
 }
-
-__device__ __forceinline__ void load_rec(const float4* __restrict__ rec, int i, double* v) {
-  const float4 a = __ldg(rec + 3 * (int64_t)i), b = __ldg(rec + 3 * (int64_t)i + 1), c = __ldg(rec + 3 * (int64_t)i + 2);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; v[8] = c.x; v[9] = c.y;
-}
-
-// One row of GetParValues (M.cc:1196-1240): ten parameters at distance d, or "out of range".
-__device__ __forceinline__ bool row_params(const LookupTable& t, double d, int s0, int e0, double* par) {
-  const double maxthd = (double)__ldg(t.x + s0);
-  if (!(d <= maxthd)) return false;
-  int i1, i2;
-  double cv;
-  find_thd(t.x, d, s0, e0, i1, i2, cv);
+// ten parameters of one row at distance d from the bracketing records (GetParValues, M.cc:1196-1240)
+__device__ __forceinline__ void row_interp(const LookupTable& t, double d, int i1, int i2, double cv, double* par) {
   if (cv != 0) {
     double y1[10], y2[10];
     load_rec(t.rec, i1, y1);
@@ -236,7 +235,6 @@ __device__ __forceinline__ bool row_params(const LookupTable& t, double d, int s
   } else {
     load_rec(t.rec, i1 + 1, par);
   }
-  return true;
 }
 
 #ifndef AIRICE_LOOKUP_MINBLOCKS
@@ -263,17 +261,22 @@ __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_look
     if (s2 < 0) s2 = s1 + t.n_th;
     if (e2 < 0) e2 = e1 + t.n_th;
     double P1[10], P2[10];
+    const bool two = (cv0 != 0 && h > minh && s2 < total);
     const double h1 = (double)__ldg(t.row_h + s1 / t.n_th);
-    oor1 = !row_params(t, d, s1, e1, P1);
-    double h2;
-    bool two = (cv0 != 0 && h > minh && s2 < total);
-    if (two) {
-      h2 = (double)__ldg(t.row_h + s2 / t.n_th);
-      oor2 = !row_params(t, d, s2, e2, P2);
-    } else {
-      h2 = h1;
-      oor2 = oor1;
-    }
+    const double h2 = two ? (double)__ldg(t.row_h + s2 / t.n_th) : h1;
+    // "out of range": d beyond the row's largest distance (M.cc:1196-1204), else search and interpolate
+    const bool in1 = d <= (double)__ldg(t.x + s1);
+    const bool in2 = two && (d <= (double)__ldg(t.x + s2));
+    int a1 = s1, b1 = e1, a2 = s2, b2 = e2;
+    halve_thd2(t.x, d, in1, a1, b1, in2, a2, b2);
+    int i1 = 0, i2 = 0, j1 = 0, j2 = 0;
+    double c1 = 0.0, c2 = 0.0;
+    if (in1) scan_thd(t.x, d, a1, b1, i1, i2, c1);
+    if (in2) scan_thd(t.x, d, a2, b2, j1, j2, c2);
+    if (in1) row_interp(t, d, i1, i2, c1, P1);
+    if (in2) row_interp(t, d, j1, j2, c2, P2);
+    oor1 = !in1;
+    oor2 = two ? !in2 : oor1;
     // height interpolation (M.cc:1376-1401)
     if (!oor1 && !oor2) {
       if (h1 != h2) {
