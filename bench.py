@@ -199,6 +199,41 @@ def algorithmic_flops(solver, h_cm, nev):
     return float(flops.sum()), float(nev.double().mean()), float(s.mean())
 
 
+def bind_near_gpu(index):
+    """One process per GPU: run on the CPUs NVML reports as local to this GPU, so that the pinned host buffers of the
+    end-to-end leg are first-touched on the GPU's own NUMA node (torchrun does not place its workers)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = None
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+        except Exception:
+            pass
+        h = None
+        if uuid:
+            for cand in ("GPU-" + uuid, uuid):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to GPU %d" % (len(cpus), index)
+    except Exception as e:      # best effort: an unbound process is merely slower end to end
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -211,6 +246,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: airiceraytracing_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -449,7 +485,7 @@ def run_ours(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 73 * n,
                         "api": "airice_solve_host (C ABI, pinned host buffers, 1M-pair chunks on 2 streams)",
-                        "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_matches},
+                        "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_matches, "host_binding": numa},
                 "gpu_launches": args.steps, "kernels_per_step": ["airice_solve_kernel"],
                 "solved_fraction": solved, "roofline": roofline, "cpu_baseline": cpu}
         line.update(extras)
