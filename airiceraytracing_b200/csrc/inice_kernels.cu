@@ -33,15 +33,26 @@ __global__ void __launch_bounds__(kThreads) airice_inice_dr_kernel(const InIceAr
   for (int k = 0; k < AIRICE_INICE_NCOLS; k++)
     if (a.out[k]) a.out[k][i] = o[k];
   if (needs_ra) {
-    // warp-aggregated append
-    const unsigned active = __activemask();
+    // warp-aggregated append.  Pairs that lack BOTH the direct and the reflected ray search for two refracted roots
+    // (mean 150 evaluations against 84) and go to the FRONT of the list, the others to the back: pass 2 hands the list
+    // out front to back, so the long searches start first and the short ones fill the tail.
+    const bool front = (mask == 0);
     const int lane = threadIdx.x & 31;
-    const int leader = __ffs(active) - 1;
+    const unsigned active = __activemask();
+    const unsigned grp = __ballot_sync(active, front);
+    const unsigned mine = front ? grp : (active & ~grp);
+    const int leader = __ffs(mine) - 1;
     int base = 0;
-    if (lane == leader) base = atomicAdd(a.ra_count, __popc(active));
-    base = __shfl_sync(active, base, leader);
-    a.ra_list[base + __popc(active & ((1u << lane) - 1))] = (int32_t)i;
+    if (lane == leader) base = atomicAdd(a.ra_count + (front ? 0 : 2), __popc(mine));
+    base = __shfl_sync(mine, base, leader);
+    const int pos = base + __popc(mine & ((1u << lane) - 1));
+    a.ra_list[front ? pos : (int)(a.n - 1 - pos)] = (int32_t)i;
   }
+}
+
+// list position j (0 <= j < front + back) -> slot of ra_list
+__device__ __forceinline__ int64_t ra_slot(const InIceArgs& a, int j, int n_front) {
+  return j < n_front ? (int64_t)j : a.n - 1 - (int64_t)(j - n_front);
 }
 
 // pass 2: the refracted-ray root-search ladder for the listed pairs.  Persistent lanes: each lane owns the search state
@@ -62,7 +73,7 @@ __global__ void __launch_bounds__(kThreads) airice_inice_ladder_kernel(const InI
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   const AirIceInIce m = inice_model(a);
-  const int count = a.ra_count[0];
+  const int n_front = a.ra_count[0], count = n_front + a.ra_count[2];
   const double e5000 = exp(-a.C * 5000.0);
   InIceRaMachine M;
   int j = 0;
@@ -76,7 +87,7 @@ __global__ void __launch_bounds__(kThreads) airice_inice_ladder_kernel(const InI
     if (!has && !exhausted) {
       j = atomicAdd(a.ra_count + 1, 1);
       if (j < count) {
-        const int64_t i = a.ra_list[j];
+        const int64_t i = a.ra_list[ra_slot(a, j, n_front)];
         bool flip;
         const InIcePair g = inice_make_pair(m, a.z0[i], a.x1[i], a.z1[i], flip);
         const int mask_dr = a.mask[i];
@@ -165,8 +176,9 @@ __global__ void __launch_bounds__(kThreads) airice_inice_ladder_kernel(const InI
 // pass 3: times, paths and angles of the refracted rays found by pass 2
 __global__ void __launch_bounds__(kThreads) airice_inice_ra_finish_kernel(const InIceArgs a) {
   const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (j >= (int64_t)a.ra_count[0]) return;
-  const int64_t i = a.ra_list[j], n = a.n;
+  const int n_front = a.ra_count[0];
+  if (j >= (int64_t)n_front + (int64_t)a.ra_count[2]) return;
+  const int64_t i = a.ra_list[ra_slot(a, (int)j, n_front)], n = a.n;
   const AirIceInIce m = inice_model(a);
   const int mask_dr = a.mask[i];
   bool flip;
@@ -223,7 +235,7 @@ cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s) {
   const int64_t blocks = (a.n + kThreads - 1) / kThreads;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
   if (!a.ra_list || !a.ra_count || !a.ra_lad || !a.mask || !a.out[20]) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(a.ra_count, 0, 2 * sizeof(int32_t), s);
+  cudaError_t e = cudaMemsetAsync(a.ra_count, 0, 3 * sizeof(int32_t), s);
   if (e != cudaSuccess) return e;
   airice_inice_dr_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(a);
   e = cudaGetLastError();

@@ -109,7 +109,8 @@ struct InIceArgs {
   // length.  Pass 1 (all pairs: direct + reflected) appends to it; pass 2 (persistent lanes stepping the root-search
   // state machine, each taking the next list entry when its own is finished) and pass 3 (times, paths, angles) walk it.
   int32_t* ra_list;   // [n]
-  int32_t* ra_count;  // [2], zeroed by launch_inice: [0] list length (pass 1), [1] next list entry to hand out (pass 2)
+  int32_t* ra_count;  // [3], zeroed by launch_inice: [0] entries at the front of the list (pairs searching for two
+                      // refracted rays), [1] next list position to hand out (pass 2), [2] entries at the back
   double* ra_lad;     // [6][n] ladder results (L, f(L), z_max of the two candidate roots) per list entry, pass 2 -> pass 3
 };
 cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s);
