@@ -46,8 +46,8 @@ struct airice_ctx {
   // per-row transmitter data (height, n(h), top layer) of the last table grid built: uploaded once, reused by
   // every rebuild of the same rows (MakeRayTracingTable is called once per antenna depth on the same grid)
   // in-ice solver scratch: compaction list + counter (+ private mask / L_R columns when the caller passes none)
-  void* inice_scratch = nullptr;
-  size_t inice_bytes = 0;
+  void* inice_scratch[kSlots] = {nullptr, nullptr};   // one per staging slot, so that chunks of the host API overlap
+  size_t inice_bytes[kSlots] = {0, 0};
   double* inice_cols = nullptr;      // 29 columns of one chunk for airice_inice_two_rays_*
   void* path_plans = nullptr;        // per-ray plans of airice_ray_path_*
   double* clamp_tab = nullptr;       // device copy of the clamped-bracket table (medium.clamp_tab points at it)
@@ -258,7 +258,8 @@ void airice_destroy(airice_ctx* c) {
   }
   if (c->rows.d_rows) cudaFree(c->rows.d_rows);
   if (c->rows.d_kt) cudaFree(c->rows.d_kt);
-  if (c->inice_scratch) cudaFree(c->inice_scratch);
+  for (int k = 0; k < airice_ctx::kSlots; k++)
+    if (c->inice_scratch[k]) cudaFree(c->inice_scratch[k]);
   if (c->inice_cols) cudaFree(c->inice_cols);
   if (c->path_plans) cudaFree(c->path_plans);
   if (c->clamp_tab) cudaFree(c->clamp_tab);
@@ -564,17 +565,17 @@ int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const do
 
 namespace {
 // scratch layout: [counters:int32 x2 pad to 256][list:int32 x n][mask:u8 x n][L_R:f64 x n][ladder:f64 x 6n]
-int inice_scratch(airice_ctx* c, int64_t n, InIceArgs* a, cudaStream_t s) {
+int inice_scratch(airice_ctx* c, int slot, int64_t n, InIceArgs* a, cudaStream_t s) {
   const size_t list_b = ((size_t)n * 4 + 255) / 256 * 256, mask_b = ((size_t)n + 255) / 256 * 256, lr_b = (size_t)n * 8;
   const size_t need = 256 + list_b + mask_b + lr_b + 6 * lr_b;
-  if (c->inice_bytes < need) {
+  if (c->inice_bytes[slot] < need) {
     CK(cudaStreamSynchronize(s));
-    if (c->inice_scratch) cudaFree(c->inice_scratch);
-    c->inice_scratch = nullptr; c->inice_bytes = 0;
-    CK(cudaMalloc(&c->inice_scratch, need));
-    c->inice_bytes = need;
+    if (c->inice_scratch[slot]) cudaFree(c->inice_scratch[slot]);
+    c->inice_scratch[slot] = nullptr; c->inice_bytes[slot] = 0;
+    CK(cudaMalloc(&c->inice_scratch[slot], need));
+    c->inice_bytes[slot] = need;
   }
-  char* base = (char*)c->inice_scratch;
+  char* base = (char*)c->inice_scratch[slot];
   a->ra_count = (int32_t*)base;
   a->ra_list = (int32_t*)(base + 256);
   if (!a->mask) a->mask = (uint8_t*)(base + 256 + list_b);
@@ -597,7 +598,7 @@ int airice_inice_solve_device(airice_ctx* c, int64_t n, const double* d_z0, cons
   a.A = c->medium.A_ice; a.B = c->medium.B_ice; a.C = c->medium.C_ice;
   for (int k = 0; k < AIRICE_INICE_NCOLS; k++) a.out[k] = d_out[k];
   a.mask = d_mask;
-  { int rc = inice_scratch(c, n, &a, (cudaStream_t)stream); if (rc) return rc; }
+  { int rc = inice_scratch(c, 0, n, &a, (cudaStream_t)stream); if (rc) return rc; }
   cudaError_t e = launch_inice(a, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_inice");
   return 0;
@@ -627,9 +628,7 @@ int airice_inice_solve_host(airice_ctx* c, int64_t n, const double* z0, const do
     a.A = c->medium.A_ice; a.B = c->medium.B_ice; a.C = c->medium.C_ice;
     for (int k = 0; k < nc; k++) a.out[k] = dh + (3 + k) * chunk;
     a.mask = (uint8_t*)(dh + (3 + nc) * chunk);
-    // one compaction scratch per context: chunks of the two streams must not overlap in pass 1/2
-    if (off > 0) CK(cudaStreamSynchronize(c->streams[slot ^ 1]));
-    { int rcs = inice_scratch(c, chunk, &a, s); if (rcs) return rcs; }
+    { int rcs = inice_scratch(c, slot, chunk, &a, s); if (rcs) return rcs; }   // per-slot scratch: chunks overlap
     cudaError_t e = launch_inice(a, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_inice");
     for (int k = 0; k < nc; k++)
@@ -660,7 +659,7 @@ int two_rays_chunk(airice_ctx* c, int64_t m, const double* d_rx, const double* d
   a.n = m; a.z0 = d_tx; a.x1 = d_dist; a.z1 = d_rx;     // IceRayTracing(0, TxDepth, Distance, RxDepth), IceRayTracing.cc:2917
   a.A = c->medium.A_ice; a.B = c->medium.B_ice; a.C = c->medium.C_ice;
   for (int k = 0; k < AIRICE_INICE_NCOLS; k++) a.out[k] = c->inice_cols + (size_t)k * c->inice_cols_n;
-  { int rc = inice_scratch(c, m, &a, s); if (rc) return rc; }
+  { int rc = inice_scratch(c, 0, m, &a, s); if (rc) return rc; }
   cudaError_t e = launch_inice(a, s);
   if (e != cudaSuccess) return cuda_fail(e, "launch_inice");
   InIcePickArgs p;

@@ -255,10 +255,13 @@ def _inice_solve(self, z0, x1, z1):
     return out, mask
 
 
-def _inice_solve_host(self, z0, x1, z1):
+def _inice_solve_host(self, z0, x1, z1, out=None, mask=None):
+    """Host buffers in and out (numpy arrays or CPU tensors; pinned memory lets the chunks' copies overlap the kernels)."""
     n = int(z0.shape[0])
-    out = np.empty((_capi.INICE_COLS, n), dtype=np.float64)
-    mask = np.empty(n, dtype=np.uint8)
+    if out is None:
+        out = np.empty((_capi.INICE_COLS, n), dtype=np.float64)
+    if mask is None:
+        mask = np.empty(n, dtype=np.uint8)
     check(self.lib.airice_inice_solve_host(self.handle, n, _host_ptr(z0), _host_ptr(x1), _host_ptr(z1), _host_ptr(out),
                                            _host_ptr(mask)))
     return out, mask

@@ -435,6 +435,18 @@ def run_ours(args):
         popc = torch.tensor([bin(i).count("1") for i in range(16)], device=dev)[mk.long()]
         extras["inice"] = {"pairs_per_gpu": ni, "ms": ms, "solves_per_s": world * ni / ms * 1e3,
                            "branch_count_fractions": [float((popc == k).double().mean()) for k in range(3)]}
+        # the same through the host-buffer C ABI (pinned memory; 24 B in, 233 B out per pair, copies inside the timing)
+        pz0, px1, pz1 = z0.cpu().pin_memory(), x1.cpu().pin_memory(), z1.cpu().pin_memory()
+        pout = torch.empty((29, ni), dtype=torch.float64).pin_memory()
+        pmask = torch.empty(ni, dtype=torch.uint8).pin_memory()
+        solver.inice_solve_host(pz0, px1, pz1, out=pout, mask=pmask)
+        barrier()
+        t_i0 = time.perf_counter()
+        solver.inice_solve_host(pz0, px1, pz1, out=pout, mask=pmask)
+        e2e_inice = max_over_ranks(time.perf_counter() - t_i0)
+        extras["inice"]["e2e_ms"] = e2e_inice * 1e3
+        extras["inice"]["e2e_solves_per_s"] = world * ni / e2e_inice
+        del pz0, px1, pz1, pout, pmask
         # BASELINE config 5: 1e6 shower points x 64 in-ice receiver depths (points sharded over ranks): direct solves,
         # one table per depth, table-interpolated solutions
         n5, n_ant = 1_000_000 // world, 64

@@ -24,3 +24,14 @@ for _ in range(3):
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
     a.record(); o, mk = S.inice_solve(dz0, dx1, dz1); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
 print(f"in-ice solve {n}: best {min(ts):.2f} ms -> {n/min(ts)*1e3:.3e} solves/s; branch hist", torch.bincount(torch.tensor([bin(i).count('1') for i in range(16)], device='cuda')[mk.long()]).tolist())
+import time
+hz0, hz1, hx1 = dz0.cpu().numpy(), dz1.cpu().numpy(), dx1.cpu().numpy()
+S.inice_solve_host(hz0, hx1, hz1)
+t = time.perf_counter(); oh, mh = S.inice_solve_host(hz0, hx1, hz1); t = time.perf_counter() - t
+print(f"in-ice solve through host buffers {n}: {t*1e3:.1f} ms -> {n/t:.3e} solves/s; equal to device path:",
+      bool(np.array_equal(oh, o.cpu().numpy(), equal_nan=True) and np.array_equal(mh, mk.cpu().numpy())))
+pz0, pz1, px1 = dz0.cpu().pin_memory(), dz1.cpu().pin_memory(), dx1.cpu().pin_memory()
+po, pm = torch.empty((29, n), dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+S.inice_solve_host(pz0, px1, pz1, out=po, mask=pm)
+t = time.perf_counter(); S.inice_solve_host(pz0, px1, pz1, out=po, mask=pm); t = time.perf_counter() - t
+print(f"same with pinned buffers: {t*1e3:.1f} ms -> {n/t:.3e} solves/s; equal:", bool(torch.equal(po.nan_to_num(), o.cpu().nan_to_num())))
