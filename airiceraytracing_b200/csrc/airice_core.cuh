@@ -195,32 +195,43 @@ AIRICE_HD double airice_x_newton(const AirIceMedium& m, const AirIcePlan& p, int
   return X;
 }
 
+// One segment of X(L): (L / (C' sA)) (C' (xb - xt) - ln(T_b / T_t)).  AIR fixes A = 1 at compile time (the products
+// A n are then exact copies of n, so the values are those of the generic form).
+template <bool AIR>
+AIRICE_HD double airice_seg_x(double A, double sA, double inv_sA, double L, double L2, double Cn, double iC, double xt,
+                              double nt, double xb, double nb) {
+  const double Rb = AIRICE_SQRT(nb * nb - L2), Rt = AIRICE_SQRT(nt * nt - L2);
+  const double Tb = (AIR ? nb : A * nb) - L2 + sA * Rb, Tt = (AIR ? nt : A * nt) - L2 + sA * Rt;
+  const double dG = Cn * (xb - xt) - AIRICE_LOG(Tb * AIRICE_RCP(Tt));
+  return (L * (iC * inv_sA)) * dG;
+}
+
 // X(L) only, FP64, arranged like airice_x_newton but without derivative terms: the work horse of the solver's
-// chord iteration (the slope comes from the FP32 pre-iteration or from a secant).
+// chord iteration (the slope comes from the FP32 pre-iteration or from a secant).  The air layers run BOTTOM-UP:
+// every lane of a warp starts at the surface layer kb (uniform), so the per-layer plan values are warp-uniform
+// constant-bank reads (top-down, lanes whose transmitters sit in different layers read different slots in the same
+// trip and the reads serialise); the transmitter's own layer is the last trip of each lane.  The ice leg is a
+// separate instance of the segment, which removes the per-trip air/ice selects.
 AIRICE_HD double airice_x_fast(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L) {
   const double L2 = L * L;
-  const double sAir = AIRICE_SQRT(1.0 * 1.0 - L2), sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
-  const double yAir = AIRICE_RCP(sAir), yIce = AIRICE_RCP(sIce);
-  const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
-  const int nseg = nair + (p.has_ice ? 1 : 0);
   double X = 0.0;
-  constexpr int kUnrollX = AIRICE_UNROLL_XFAST;
-#pragma unroll kUnrollX
-  for (int j = 0; j < nseg; j++) {
-    const bool air = j < nair;
-    const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
-    const double A = air ? 1.0 : m.A_ice;
-    const double sA = air ? sAir : sIce;
-    const double inv_sA = air ? yAir : yIce;
-    const bool top = (j == 0) && air;
-    const double xt = top ? h : p.start_x[k];
-    const double nt = top ? n_tx : p.start_n[k];
-    const double xb = p.stop_x[k], nb = p.stop_n[k];
-    const double Rb = AIRICE_SQRT(nb * nb - L2), Rt = AIRICE_SQRT(nt * nt - L2);
-    const double Tb = A * nb - L2 + sA * Rb, Tt = A * nt - L2 + sA * Rt;
-    const double dG = p.neg_c[k] * (xb - xt) - AIRICE_LOG(Tb * AIRICE_RCP(Tt));
-    const double seg = (L * (p.inv_neg_c[k] * inv_sA)) * dG;
-    X += air ? -seg : seg;
+  if (kt >= p.kb) {
+    const double sAir = AIRICE_SQRT(1.0 * 1.0 - L2);
+    const double yAir = AIRICE_RCP(sAir);
+#pragma unroll 1
+    for (int k = p.kb; k <= kt; k++) {
+      const bool top = (k == kt);
+      const double xt = top ? h : p.start_x[k];
+      const double nt = top ? n_tx : p.start_n[k];
+      X -= airice_seg_x<true>(1.0, sAir, yAir, L, L2, p.neg_c[k], p.inv_neg_c[k], xt, nt, p.stop_x[k], p.stop_n[k]);
+    }
+  }
+  if (p.has_ice) {
+    const double sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
+    const double yIce = AIRICE_RCP(sIce);
+    const int k = AIRICE_ICE_SLOT;
+    X += airice_seg_x<false>(m.A_ice, sIce, yIce, L, L2, p.neg_c[k], p.inv_neg_c[k], p.start_x[k], p.start_n[k],
+                             p.stop_x[k], p.stop_n[k]);
   }
   return X;
 }
@@ -236,41 +247,48 @@ AIRICE_HD double airice_x_fast(const AirIceMedium& m, const AirIcePlan& p, int k
 #define AIRICE_F_RCP(x) (1.0f / (x))
 #define AIRICE_F_LOG(x) logf(x)
 #endif
+template <bool AIR>
+AIRICE_HD void airice_seg_f32(float A, float sA2, float sA, float inv_sA, float L, float L2, float q_stop, float pa_stop,
+                              float qt, float pat, float cdx, float icn, float& X, float& dX) {
+  const float Rb2 = q_stop + sA2, Rt2 = qt + sA2;
+  const float yb = AIRICE_F_RSQRT(Rb2), yt = AIRICE_F_RSQRT(Rt2);
+  const float Rb = Rb2 * yb, Rt = Rt2 * yt;
+  const float Tb = pa_stop + sA * (sA + Rb), Tt = pat + sA * (sA + Rt);
+  const float rTb = AIRICE_F_RCP(Tb), rTt = AIRICE_F_RCP(Tt);
+  const float dG = cdx - AIRICE_F_LOG(Tb * rTt);
+  const float c1 = icn * inv_sA;
+  const float seg = (L * c1) * dG;
+  const float qb_ = (sA + Rb) * (sA + Rb) * (rTb * yb), qt_ = (sA + Rt) * (sA + Rt) * (rTt * yt);
+  const float AA = AIR ? 1.0f : A * A;
+  const float dseg = c1 * (AA * inv_sA * inv_sA * dG + L2 * inv_sA * (qb_ - qt_));
+  if (AIR) { X -= seg; dX -= dseg; } else { X += seg; dX += dseg; }
+}
+
 AIRICE_HD float airice_x_newton_f32(const AirIceMedium& m, const AirIcePlan& p, int kt, float h_minus_stop_top_cn,
                                     float dn_tx, float t, float& dXdt) {
   const float n_tx = 1.0f + dn_tx;
   const float q_tx = dn_tx * (2.0f + dn_tx);                  // n_tx^2 - 1
   const float w2 = AIRICE_F_RCP(1.0f + t * t), w = sqrtf(w2);
   const float L = n_tx * t * w, L2 = L * L;
-  const float sA2_air = w2 * (1.0f - t * t * q_tx);           // 1 - L^2 without cancellation
-  const float Ai = (float)m.A_ice;
-  const float sA2_ice = Ai * Ai - L2;
-  const float yAir = AIRICE_F_RSQRT(sA2_air), yIce = AIRICE_F_RSQRT(sA2_ice);
-  const float sAir = sA2_air * yAir, sIce = sA2_ice * yIce;
-  const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
-  const int nseg = nair + (p.has_ice ? 1 : 0);
   float X = 0.0f, dX = 0.0f;
+  if (kt >= p.kb) {
+    const float sA2 = w2 * (1.0f - t * t * q_tx);             // 1 - L^2 without cancellation
+    const float y = AIRICE_F_RSQRT(sA2), sA = sA2 * y;
 #pragma unroll 1
-  for (int j = 0; j < nseg; j++) {
-    const bool air = j < nair;
-    const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
-    const float A = air ? 1.0f : Ai;
-    const float sA2 = air ? sA2_air : sA2_ice, sA = air ? sAir : sIce, inv_sA = air ? yAir : yIce;
-    const bool top = (j == 0) && air;
-    const float qt = top ? q_tx : p.f_q_start[k], pat = top ? dn_tx : p.f_pa_start[k];
-    const float cdx = top ? h_minus_stop_top_cn : p.f_cdx[k];
-    const float Rb2 = p.f_q_stop[k] + sA2, Rt2 = qt + sA2;
-    const float yb = AIRICE_F_RSQRT(Rb2), yt = AIRICE_F_RSQRT(Rt2);
-    const float Rb = Rb2 * yb, Rt = Rt2 * yt;
-    const float Tb = p.f_pa_stop[k] + sA * (sA + Rb), Tt = pat + sA * (sA + Rt);
-    const float rTb = AIRICE_F_RCP(Tb), rTt = AIRICE_F_RCP(Tt);
-    const float dG = cdx - AIRICE_F_LOG(Tb * rTt);
-    const float c1 = p.f_inv_neg_c[k] * inv_sA;
-    const float seg = (L * c1) * dG;
-    const float qb_ = (sA + Rb) * (sA + Rb) * (rTb * yb), qt_ = (sA + Rt) * (sA + Rt) * (rTt * yt);
-    const float dseg = c1 * (A * A * inv_sA * inv_sA * dG + L2 * inv_sA * (qb_ - qt_));
-    X += air ? -seg : seg;
-    dX += air ? -dseg : dseg;
+    for (int k = p.kb; k <= kt; k++) {                         // bottom-up, see airice_x_fast
+      const bool top = (k == kt);
+      const float qt = top ? q_tx : p.f_q_start[k], pat = top ? dn_tx : p.f_pa_start[k];
+      const float cdx = top ? h_minus_stop_top_cn : p.f_cdx[k];
+      airice_seg_f32<true>(1.0f, sA2, sA, y, L, L2, p.f_q_stop[k], p.f_pa_stop[k], qt, pat, cdx, p.f_inv_neg_c[k], X, dX);
+    }
+  }
+  if (p.has_ice) {
+    const float Ai = (float)m.A_ice;
+    const float sA2 = Ai * Ai - L2;
+    const float y = AIRICE_F_RSQRT(sA2), sA = sA2 * y;
+    const int k = AIRICE_ICE_SLOT;
+    airice_seg_f32<false>(Ai, sA2, sA, y, L, L2, p.f_q_stop[k], p.f_pa_stop[k], p.f_q_start[k], p.f_pa_start[k],
+                          p.f_cdx[k], p.f_inv_neg_c[k], X, dX);
   }
   dXdt = dX * n_tx * w2 * w;   // dL/dt = n_tx / (1+t^2)^{3/2}
   return X;
@@ -282,65 +300,109 @@ AIRICE_HD float airice_x_newton_f32(const AirIceMedium& m, const AirIcePlan& p, 
 // RELAY = false -> tail of a launch-angle solve (Air2IceRayTracing, M.cc:1524-1614): one L throughout.
 // want_inc / want_refr: whether the incidence angle on the surface and the refracted angle below it are reported by
 // the caller (each is an asin the other outputs do not need).
+// Distance, time and geometric path of one segment from the quantities at its two ends (R = sqrt(n^2 - L^2),
+// ln T, H = ln(n + R)); products rounded as the reference forms them.  AIR fixes A = 1 at compile time (exact).
+template <bool AIR>
+AIRICE_HD void airice_seg_sums(double A, double inv_sA, double mult, double cC, double Cn, double iC, double xt, double xb,
+                               double Dt, double Db, double Rt, double Rb, double lnTt, double lnTb, double Ht, double Hb,
+                               double& xs, double& ts, double& gs) {
+  const double Gb = Cn * xb - lnTb, Gt = Cn * xt - lnTt;
+  xs = AIRICE_MUL(mult, Gb) - AIRICE_MUL(mult, Gt);
+  const double AARb = AIR ? Rb : A * A * Rb, AARt = AIR ? Rt : A * A * Rt;
+  const double ARb = AIR ? Rb : A * Rb, ARt = AIR ? Rt : A * Rt;
+  const double Ay = AIR ? inv_sA : A * inv_sA;
+  const double tb = AIRICE_MUL(AIRICE_RCP(cC * Rb), (Db + AIRICE_MUL(Gb * AARb, inv_sA)) + ARb * Hb);
+  const double tt = AIRICE_MUL(AIRICE_RCP(cC * Rt), (Dt + AIRICE_MUL(Gt * AARt, inv_sA)) + ARt * Ht);
+  ts = tb - tt;
+  gs = AIRICE_MUL(Hb + Ay * Gb, iC) - AIRICE_MUL(Ht + Ay * Gt, iC);
+}
+
 template <bool RELAY>
 AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
                                bool in_ice, bool want_inc, bool want_refr, AirIceRay& r) {
-  const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
-  const int nseg = nair + (in_ice ? 1 : 0);
   double xa = 0.0, ta = 0.0, ga = 0.0, xi = 0.0, ti = 0.0, gi = 0.0;
-  double Lk = L, Rsurf = 0.0, sA = 0.0, inv_sA = 0.0;
-  double prevR = 0.0, prevH = 0.0, prevT = 1.0, prevLnT = 0.0;
+  double Lk = L, Rsurf = 0.0;
   r.recv_deg = 0.0;
-  constexpr int kUnrollF = AIRICE_UNROLL_FULL;
+  if (kt >= p.kb) {
+    if (RELAY) {
+      // forward tracer: top-down, L handed from layer to layer
+      double sA = 0.0, inv_sA = 0.0, prevR = 0.0, prevH = 0.0, prevT = 1.0, prevLnT = 0.0;
+      constexpr int kUnrollF = AIRICE_UNROLL_FULL;
 #pragma unroll kUnrollF
-  for (int j = 0; j < nseg; j++) {
-    const bool air = j < nair;
-    const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
-    const bool top = (j == 0) && air;
-    if (RELAY && air && !top) Lk = Lk * p.relay[k];
-    const double A = air ? 1.0 : m.A_ice;
+      for (int k = kt; k >= p.kb; k--) {
+        const bool top = (k == kt);
+        if (!top) Lk = Lk * p.relay[k];
+        const double L2 = Lk * Lk;
+        sA = AIRICE_SQRT(1.0 * 1.0 - L2); inv_sA = AIRICE_RCP(sA);   // changes with every relayed L
+        const double Cn = p.neg_c[k], iC = p.inv_neg_c[k];
+        const double xt = top ? h : p.start_x[k];
+        const double nt = top ? n_tx : p.start_n[k];
+        const double xb = p.stop_x[k], nb = p.stop_n[k];
+        const double Db = nb * nb - L2, Dt = nt * nt - L2;
+        const double Rb = AIRICE_SQRT(Db);
+        const double Tb = nb - L2 + sA * Rb;
+        const double lnTb = AIRICE_LOG(Tb), Hb = AIRICE_LOG(nb + Rb);
+        double Rt, lnTt, Ht;
+        if (!top) {
+          // Snell hand-over at an interior boundary: L' = L rho with rho = n'/n, i.e. the direction L/n is kept, so
+          // R' = sqrt(n'^2 - L'^2) = rho R and ln(n' + R') = ln(n + R) + ln(rho) hold exactly; T' = n' - L'^2 + sA' R'
+          // differs from the T of the layer above by ~3e-13 relative, so ln T' = ln T + log1p((T' - T)/T) needs the
+          // quotient to 3-4 digits only.  Saves one sqrt and two logs per interior boundary (6 of the 20 logs of a cell).
+          Rt = p.relay[k] * prevR;
+          Ht = prevH + p.ln_relay[k];
+          const double u = ((nt - L2 + sA * Rt) - prevT) * AIRICE_RCP_APPROX(prevT);
+          lnTt = prevLnT + (u - 0.5 * u * u);
+        } else {
+          Rt = AIRICE_SQRT(Dt);
+          lnTt = AIRICE_LOG(nt - L2 + sA * Rt);
+          Ht = AIRICE_LOG(nt + Rt);
+        }
+        prevR = Rb; prevH = Hb; prevT = Tb; prevLnT = lnTb;
+        double xs, ts, gs;
+        airice_seg_sums<true>(1.0, inv_sA, (Lk * iC) * inv_sA, m.c * Cn, Cn, iC, xt, xb, Dt, Db, Rt, Rb, lnTt, lnTb, Ht, Hb,
+                              xs, ts, gs);
+        xa += -xs; ta += -ts; ga += -gs;
+        Rsurf = Rb;  // after the last air segment: sqrt(n_air(surface)^2 - L^2) = n1 cos(incidence)
+      }
+    } else {
+      // tail of a solve: one L throughout, so the order of the layers is free; bottom-up keeps the per-layer plan
+      // reads warp-uniform (see airice_x_fast)
+      const double L2 = Lk * Lk;
+      const double sA = AIRICE_SQRT(1.0 * 1.0 - L2), inv_sA = AIRICE_RCP(sA);
+      constexpr int kUnrollF = AIRICE_UNROLL_FULL;
+#pragma unroll kUnrollF
+      for (int k = p.kb; k <= kt; k++) {
+        const bool top = (k == kt);
+        const double Cn = p.neg_c[k], iC = p.inv_neg_c[k];
+        const double xt = top ? h : p.start_x[k];
+        const double nt = top ? n_tx : p.start_n[k];
+        const double xb = p.stop_x[k], nb = p.stop_n[k];
+        const double Db = nb * nb - L2, Dt = nt * nt - L2;
+        const double Rb = AIRICE_SQRT(Db), Rt = AIRICE_SQRT(Dt);
+        const double lnTb = AIRICE_LOG(nb - L2 + sA * Rb), Hb = AIRICE_LOG(nb + Rb);
+        const double lnTt = AIRICE_LOG(nt - L2 + sA * Rt), Ht = AIRICE_LOG(nt + Rt);
+        double xs, ts, gs;
+        airice_seg_sums<true>(1.0, inv_sA, (Lk * iC) * inv_sA, m.c * Cn, Cn, iC, xt, xb, Dt, Db, Rt, Rb, lnTt, lnTb, Ht, Hb,
+                              xs, ts, gs);
+        xa += -xs; ta += -ts; ga += -gs;
+        if (k == p.kb) Rsurf = Rb;
+      }
+    }
+  }
+  if (in_ice) {
+    const int k = AIRICE_ICE_SLOT;
+    const double A = m.A_ice;
     const double L2 = Lk * Lk;
-    // sqrt(A^2 - L^2) changes only when L (relay) or the medium (air -> ice) does
-    if (RELAY || j == 0 || !air) { sA = AIRICE_SQRT(A * A - L2); inv_sA = AIRICE_RCP(sA); }
+    const double sA = AIRICE_SQRT(A * A - L2), inv_sA = AIRICE_RCP(sA);
     const double Cn = p.neg_c[k], iC = p.inv_neg_c[k];
-    const double xt = top ? h : p.start_x[k];
-    const double nt = top ? n_tx : p.start_n[k];
-    const double xb = p.stop_x[k], nb = p.stop_n[k];
+    const double xt = p.start_x[k], nt = p.start_n[k], xb = p.stop_x[k], nb = p.stop_n[k];
     const double Db = nb * nb - L2, Dt = nt * nt - L2;
-    const double Rb = AIRICE_SQRT(Db);
-    const double Tb = A * nb - L2 + sA * Rb;
-    const double lnTb = AIRICE_LOG(Tb), Hb = AIRICE_LOG(nb + Rb);
-    double Rt, lnTt, Ht;
-    if (RELAY && air && !top) {
-      // Snell hand-over at an interior boundary: L' = L rho with rho = n'/n, i.e. the direction L/n is kept, so
-      // R' = sqrt(n'^2 - L'^2) = rho R and ln(n' + R') = ln(n + R) + ln(rho) hold exactly; T' = n' - L'^2 + sA' R'
-      // differs from the T of the layer above by ~3e-13 relative, so ln T' = ln T + log1p((T' - T)/T) needs the
-      // quotient to 3-4 digits only.  Saves one sqrt and two logs per interior boundary (6 of the 20 logs of a cell).
-      Rt = p.relay[k] * prevR;
-      Ht = prevH + p.ln_relay[k];
-      const double u = ((A * nt - L2 + sA * Rt) - prevT) * AIRICE_RCP_APPROX(prevT);
-      lnTt = prevLnT + (u - 0.5 * u * u);
-    } else {
-      Rt = AIRICE_SQRT(Dt);
-      lnTt = AIRICE_LOG(A * nt - L2 + sA * Rt);
-      Ht = AIRICE_LOG(nt + Rt);
-    }
-    prevR = Rb; prevH = Hb; prevT = Tb; prevLnT = lnTb;
-    const double Gb = Cn * xb - lnTb, Gt = Cn * xt - lnTt;
-    const double mult = (Lk * iC) * inv_sA;
-    const double xs = AIRICE_MUL(mult, Gb) - AIRICE_MUL(mult, Gt);
-    const double cC = m.c * Cn;
-    const double tb = AIRICE_MUL(AIRICE_RCP(cC * Rb), (Db + AIRICE_MUL(Gb * (A * A * Rb), inv_sA)) + (A * Rb) * Hb);
-    const double tt = AIRICE_MUL(AIRICE_RCP(cC * Rt), (Dt + AIRICE_MUL(Gt * (A * A * Rt), inv_sA)) + (A * Rt) * Ht);
-    const double ts = tb - tt;
-    const double gs = AIRICE_MUL(Hb + (A * inv_sA) * Gb, iC) - AIRICE_MUL(Ht + (A * inv_sA) * Gt, iC);
-    if (air) {
-      xa += -xs; ta += -ts; ga += -gs;
-      Rsurf = Rb;  // after the last air segment: sqrt(n_air(surface)^2 - L^2) = n1 cos(incidence)
-    } else {
-      xi = xs; ti = ts; gi = gs;
-      r.recv_deg = asin(AIRICE_DIV(Lk, nb)) * m.rad2deg;  // M.cc:824 / 583-589
-    }
+    const double Rb = AIRICE_SQRT(Db), Rt = AIRICE_SQRT(Dt);
+    const double lnTb = AIRICE_LOG(A * nb - L2 + sA * Rb), Hb = AIRICE_LOG(nb + Rb);
+    const double lnTt = AIRICE_LOG(A * nt - L2 + sA * Rt), Ht = AIRICE_LOG(nt + Rt);
+    airice_seg_sums<false>(A, inv_sA, (Lk * iC) * inv_sA, m.c * Cn, Cn, iC, xt, xb, Dt, Db, Rt, Rb, lnTt, lnTb, Ht, Hb,
+                           xi, ti, gi);
+    r.recv_deg = asin(AIRICE_DIV(Lk, nb)) * m.rad2deg;  // M.cc:824 / 583-589
   }
   r.x_air = xa; r.t_air = ta; r.p_air = ga;
   r.x_ice = xi; r.t_ice = ti; r.p_ice = gi;

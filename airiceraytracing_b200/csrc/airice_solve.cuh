@@ -24,6 +24,22 @@ struct AirIceSolveStat {
   int n_replay;  // real evaluations spent inside the guard band during the replay
 };
 
+// floor(log2(x)) of a positive normal double, and x * 2^k (exact while the result stays normal)
+AIRICE_HD int airice_exponent(double x) {
+#if defined(__CUDA_ARCH__)
+  return ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
+#else
+  int e; frexp(x, &e); return e - 1;
+#endif
+}
+AIRICE_HD double airice_scale2(double x, int k) {
+#if defined(__CUDA_ARCH__)
+  return x * __hiloint2double((1023 + k) << 20, 0);
+#else
+  return ldexp(x, k);
+#endif
+}
+
 AIRICE_HD double airice_L_of_theta(const AirIceMedium& m, double n_tx, double theta) {
   // first-segment Snell chain of GetLayerHitPointPar (M.cc:537-589) collapses to n(h_tx) sin(180-theta)
   return n_tx * sin((180 - theta) * m.deg2rad);
@@ -176,37 +192,57 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
   else if (ts == -INFINITY) theta_star = INFINITY;
   else theta_star = 180 - atan(ts) * m.rad2deg;
 
-  // ---- phase 2: replay of gsl_root_fsolver_bisection + gsl_root_test_interval (M.cc:355-369).
-  // Fast form first: as long as no probe (lo, hi or a midpoint) comes within `guard` of theta*, sign f(x) is just the
-  // side of theta* that x lies on, and GSL's update rule "keep the half whose ends differ in sign" becomes
-  //   below = mid < theta*;  take_hi = (lo_below != below);  hi = take_hi ? mid : hi;  lo = take_hi ? lo : mid.
-  // The returned root is the midpoint of the final bracket (GSL: root = 0.5*(lo+mid) or 0.5*(mid+hi)).
+  // ---- phase 2: replay of gsl_root_fsolver_bisection + gsl_root_test_interval (M.cc:355-369) in closed form.
+  // For a monotone f the sign of f(x) is the side of theta* that x lies on, so GSL's rule "keep the half whose ends
+  // differ in sign" keeps the half that contains theta* (and always the UPPER half when theta* is outside the bracket:
+  // f(lo) and f(mid) then have the same sign at every step).  After k halvings the bracket is the cell
+  //   [lo + j W 2^-k, lo + (j+1) W 2^-k],  j = floor((theta* - lo) 2^k / W)   (j = 2^k - 1 when outside),
+  // the loop stops at the first k whose cell is narrower than 1e-9 * (its lower end), and the returned root is the
+  // midpoint of that cell.  The iterated midpoints of the reference sit on this grid to within their rounding
+  // (~3e-14 deg), so the replay costs a few dozen instructions instead of ~27 loop trips.  Left to the careful loop
+  // below: a bracket END within `guard` of theta*, an exact zero of f at a probe, an empty bracket.  A grid point
+  // (= a midpoint the reference probes) within `guard` of theta* gets its sign from one real evaluation of f.
   const double guard = AIRICE_SOLVE_GUARD_DEG;
   const double th = theta_star;
   {
-    double flo = lo, fhi = hi;
-    // `near` sends the solve to the careful form below: an END of the bracket within the guard, or f exactly 0 at a
-    // midpoint.  A MIDPOINT within the guard (0.3 % of solves, one or two of the ~27 halvings) just gets its sign from
-    // a real evaluation of f, in place.
-    bool near = !(fabs(flo - th) > guard) || !(fabs(fhi - th) > guard);
-    bool lo_below = flo < th;
-#pragma unroll 1
-    for (int iter = 0; iter < 40; iter++) {
-      const double mid = (flo + fhi) / 2.0;
-      bool below = mid < th;
-      if (!(fabs(mid - th) > guard)) {
-        const double f = d - airice_x_exact(m, p, kt, h, n_tx, airice_L_of_theta(m, n_tx, mid));
-        st.n_replay++;
-        near = near || !(f < 0.0 || f > 0.0);
-        below = f < 0.0;
+    const double W = hi - lo;
+    bool careful = !(fabs(lo - th) > guard) || !(fabs(hi - th) > guard) || !(W > 0.0) || !(lo > 0.0);
+    if (!careful) {
+      // kb = first k with W 2^-k < 1e-9 hi: no earlier cell can pass the test (its lower end is < hi); cell kb + 1
+      // always passes (lo > hi/2 here: lo >= 90.001, hi - lo <= 16).  At least one halving is made.
+      const double ratio = W * AIRICE_RCP(0.000000001 * hi);
+      int kb = airice_exponent(ratio) + 1;
+      kb = kb < 1 ? 1 : kb;
+      const int kf = kb + 1;
+      const double wf = airice_scale2(W, -kf);            // finest cell width W 2^-kf (exact)
+      const double ncell = airice_scale2(1.0, kf);        // 2^kf
+      double jf = ncell - 1.0;                            // theta* outside (lo, hi): the walk to hi
+      if (th > lo && th < hi) {
+        const double x = (th - lo) * (ncell * AIRICE_RCP(W));
+        const double mr = rint(x);
+        jf = (x < mr) ? mr - 1.0 : mr;                    // floor(x)
+        if (!(fabs(x - mr) * wf > guard)) {
+          // theta* within the guard of grid point mr -- a point the reference evaluates f at (unless it is only on
+          // the finest grid and the loop stops one level earlier: then the evaluation is harmless)
+          if (!(mr > 0.0) || !(mr < ncell)) {
+            careful = true;
+          } else {
+            const double xp = lo + mr * wf;
+            const double f = d - airice_x_exact(m, p, kt, h, n_tx, airice_L_of_theta(m, n_tx, xp));
+            st.n_replay++;
+            if (f < 0.0) jf = mr;                         // grid point below the root: the cell starts there
+            else if (f > 0.0) jf = mr - 1.0;
+            else careful = true;                          // exact zero or NaN: GSL's special exits
+          }
+        }
       }
-      const bool take_hi = (lo_below != below);
-      fhi = take_hi ? mid : fhi;
-      flo = take_hi ? flo : mid;
-      lo_below = take_hi ? lo_below : below;
-      if (fhi - flo < 0.000000001 * flo) break;   // gsl_root_test_interval with 0 < lo < hi
+      if (!careful) {
+        const double jb = floor(0.5 * jf), wb = 2.0 * wf;
+        const double lob = lo + jb * wb, hib = lo + (jb + 1.0) * wb;
+        if (hib - lob < 0.000000001 * lob) return lo + (2.0 * jb + 1.0) * wf;   // stopped after kb halvings
+        return lo + (2.0 * jf + 1.0) * (0.5 * wf);                               // after kb + 1
+      }
     }
-    if (!near && flo > 0.0) return 0.5 * (flo + fhi);
   }
   // Careful form (about 0.2 % of solves): a probe sits within `guard` of theta*, so f is evaluated there for real
   // (MinimizeforLaunchAngle, M.cc:873-917), including GSL's exact-zero exits.  One loop serves the two endpoint
