@@ -247,20 +247,28 @@ AIRICE_HD double airice_x_fast(const AirIceMedium& m, const AirIcePlan& p, int k
 #define AIRICE_F_RCP(x) (1.0f / (x))
 #define AIRICE_F_LOG(x) logf(x)
 #endif
+// One layer END in single precision: R = sqrt(q + sA^2), y = 1/R, T = pa + sA (sA + R), rT = 1/T and the derivative
+// term (sA + R)^2 / (T R).
+struct AirIceEndF32 { float T, rT, g; };
+AIRICE_HD AirIceEndF32 airice_end_f32(float sA2, float sA, float q, float pa) {
+  const float R2 = q + sA2;
+  const float y = AIRICE_F_RSQRT(R2);
+  const float R = R2 * y;
+  AirIceEndF32 e;
+  e.T = pa + sA * (sA + R);
+  e.rT = AIRICE_F_RCP(e.T);
+  e.g = (sA + R) * (sA + R) * (e.rT * y);
+  return e;
+}
+// segment sums from its two ends: X += +-(L c1) dG, dX += +-c1 (A^2 dG / sA^2 + L^2 (g_b - g_t) / sA)
 template <bool AIR>
-AIRICE_HD void airice_seg_f32(float A, float sA2, float sA, float inv_sA, float L, float L2, float q_stop, float pa_stop,
-                              float qt, float pat, float cdx, float icn, float& X, float& dX) {
-  const float Rb2 = q_stop + sA2, Rt2 = qt + sA2;
-  const float yb = AIRICE_F_RSQRT(Rb2), yt = AIRICE_F_RSQRT(Rt2);
-  const float Rb = Rb2 * yb, Rt = Rt2 * yt;
-  const float Tb = pa_stop + sA * (sA + Rb), Tt = pat + sA * (sA + Rt);
-  const float rTb = AIRICE_F_RCP(Tb), rTt = AIRICE_F_RCP(Tt);
-  const float dG = cdx - AIRICE_F_LOG(Tb * rTt);
+AIRICE_HD void airice_seg_f32(float A, float inv_sA, float L, float L2, const AirIceEndF32& eb, const AirIceEndF32& et,
+                              float cdx, float icn, float& X, float& dX) {
+  const float dG = cdx - AIRICE_F_LOG(eb.T * et.rT);
   const float c1 = icn * inv_sA;
   const float seg = (L * c1) * dG;
-  const float qb_ = (sA + Rb) * (sA + Rb) * (rTb * yb), qt_ = (sA + Rt) * (sA + Rt) * (rTt * yt);
   const float AA = AIR ? 1.0f : A * A;
-  const float dseg = c1 * (AA * inv_sA * inv_sA * dG + L2 * inv_sA * (qb_ - qt_));
+  const float dseg = c1 * (AA * inv_sA * inv_sA * dG + L2 * inv_sA * (eb.g - et.g));
   if (AIR) { X -= seg; dX -= dseg; } else { X += seg; dX += dseg; }
 }
 
@@ -274,12 +282,17 @@ AIRICE_HD float airice_x_newton_f32(const AirIceMedium& m, const AirIcePlan& p, 
   if (kt >= p.kb) {
     const float sA2 = w2 * (1.0f - t * t * q_tx);             // 1 - L^2 without cancellation
     const float y = AIRICE_F_RSQRT(sA2), sA = sA2 * y;
+    // bottom-up (see airice_x_fast).  The upper end of a layer and the lower end of the layer above it are the same
+    // point to single precision (1e-5 m and 3e-13 in n apart), so each trip evaluates ONE end and keeps it for the next.
+    AirIceEndF32 eb = airice_end_f32(sA2, sA, p.f_q_stop[p.kb], p.f_pa_stop[p.kb]);
 #pragma unroll 1
-    for (int k = p.kb; k <= kt; k++) {                         // bottom-up, see airice_x_fast
+    for (int k = p.kb; k <= kt; k++) {
       const bool top = (k == kt);
       const float qt = top ? q_tx : p.f_q_start[k], pat = top ? dn_tx : p.f_pa_start[k];
       const float cdx = top ? h_minus_stop_top_cn : p.f_cdx[k];
-      airice_seg_f32<true>(1.0f, sA2, sA, y, L, L2, p.f_q_stop[k], p.f_pa_stop[k], qt, pat, cdx, p.f_inv_neg_c[k], X, dX);
+      const AirIceEndF32 et = airice_end_f32(sA2, sA, qt, pat);
+      airice_seg_f32<true>(1.0f, y, L, L2, eb, et, cdx, p.f_inv_neg_c[k], X, dX);
+      eb = et;
     }
   }
   if (p.has_ice) {
@@ -287,19 +300,14 @@ AIRICE_HD float airice_x_newton_f32(const AirIceMedium& m, const AirIcePlan& p, 
     const float sA2 = Ai * Ai - L2;
     const float y = AIRICE_F_RSQRT(sA2), sA = sA2 * y;
     const int k = AIRICE_ICE_SLOT;
-    airice_seg_f32<false>(Ai, sA2, sA, y, L, L2, p.f_q_stop[k], p.f_pa_stop[k], p.f_q_start[k], p.f_pa_start[k],
-                          p.f_cdx[k], p.f_inv_neg_c[k], X, dX);
+    const AirIceEndF32 eb = airice_end_f32(sA2, sA, p.f_q_stop[k], p.f_pa_stop[k]);
+    const AirIceEndF32 et = airice_end_f32(sA2, sA, p.f_q_start[k], p.f_pa_start[k]);
+    airice_seg_f32<false>(Ai, y, L, L2, eb, et, p.f_cdx[k], p.f_inv_neg_c[k], X, dX);
   }
   dXdt = dX * n_tx * w2 * w;   // dL/dt = n_tx / (1+t^2)^{3/2}
   return X;
 }
 
-// Full evaluation of one ray: distances, times, geometric paths, angles, Fresnel coefficients.
-// RELAY = true  -> forward tracer / table cell (GetRayTracingSolutions, M.cc:1796-2017): L is handed from layer to
-//                  layer through Snell at the boundary (L *= n_start[k]/n_stop[k+1]).
-// RELAY = false -> tail of a launch-angle solve (Air2IceRayTracing, M.cc:1524-1614): one L throughout.
-// want_inc / want_refr: whether the incidence angle on the surface and the refracted angle below it are reported by
-// the caller (each is an asin the other outputs do not need).
 // Distance, time and geometric path of one segment from the quantities at its two ends (R = sqrt(n^2 - L^2),
 // ln T, H = ln(n + R)); products rounded as the reference forms them.  AIR fixes A = 1 at compile time (exact).
 template <bool AIR>
@@ -402,7 +410,8 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
     const double lnTt = AIRICE_LOG(A * nt - L2 + sA * Rt), Ht = AIRICE_LOG(nt + Rt);
     airice_seg_sums<false>(A, inv_sA, (Lk * iC) * inv_sA, m.c * Cn, Cn, iC, xt, xb, Dt, Db, Rt, Rb, lnTt, lnTb, Ht, Hb,
                            xi, ti, gi);
-    r.recv_deg = asin(AIRICE_DIV(Lk, nb)) * m.rad2deg;  // M.cc:824 / 583-589
+    // receive angle asin(L / n(depth)) (M.cc:824 / 583-589) as atan(L / sqrt(n^2 - L^2)): the square root is Rb
+    r.recv_deg = AIRICE_ATAN_Q(Lk, Rb) * m.rad2deg;
   }
   r.x_air = xa; r.t_air = ta; r.p_air = ga;
   r.x_ice = xi; r.t_ice = ti; r.p_ice = gi;
@@ -412,7 +421,8 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
   const double n2 = p.start_n[AIRICE_ICE_SLOT];  // n_ice(0)
   const double Lsurf = in_ice ? Lk : Lk;
   const double si = AIRICE_DIV(Lsurf, n1);
-  r.inc_ice_deg = want_inc ? asin(si) * m.rad2deg : 0.0;
+  // asin(L / n1) = atan(L / sqrt(n1^2 - L^2)) when the ray crossed the air (Rsurf is that square root)
+  r.inc_ice_deg = want_inc ? ((kt >= p.kb) ? AIRICE_ATAN_Q(Lsurf, Rsurf) : asin(si)) * m.rad2deg : 0.0;
   // Fresnel field transmission, air->ice at the surface (M.cc:285-301, 321-337) without trig:
   // sin(theta_i) = L/n1, n1 cos(theta_i) = sqrt(n1^2-L^2) = R of the bottom end.
   const double n12 = AIRICE_DIV(n1, n2);
@@ -425,5 +435,5 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
   if (trs != trs) trs = 0.0;
   if (trp != trp) trp = 0.0;
   r.trans_s = trs; r.trans_p = trp;
-  r.refr_deg = want_refr ? asin(u) * m.rad2deg : 0.0;  // refracted angle just below the surface (P.cc:1081)
+  r.refr_deg = want_refr ? AIRICE_ATAN_Q(u, sq) * m.rad2deg : 0.0;  // refracted angle just below the surface (P.cc:1081)
 }

@@ -190,7 +190,7 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
   // theta* in degrees; +inf in t (root beyond the lower end) maps below the bracket, -inf above it
   if (ts == INFINITY) theta_star = -INFINITY;
   else if (ts == -INFINITY) theta_star = INFINITY;
-  else theta_star = 180 - atan(ts) * m.rad2deg;
+  else theta_star = 180 - AIRICE_ATAN_Q(ts, 1.0) * m.rad2deg;
 
   // ---- phase 2: replay of gsl_root_fsolver_bisection + gsl_root_test_interval (M.cc:355-369) in closed form.
   // For a monotone f the sign of f(x) is the side of theta* that x lies on, so GSL's rule "keep the half whose ends
@@ -283,7 +283,7 @@ AIRICE_HD double airice_straight_angle(const AirIceMedium& m, double h, double d
                                        double& ta) {
   const double den = (depth_signed < 0) ? (h - ice - depth_signed) : (h - (ice + depth_signed));
   ta = d / den;
-  return 180 - (atan(ta) * (180.0 / m.pi));
+  return 180 - (AIRICE_ATAN_Q(ta, 1.0) * (180.0 / m.pi));
 }
 
 // Solution flag of M.cc:974-983.

@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(kThreads, AIRICE_SOLVE_MINBLOCKS) airice_solve
   if (i >= a.n) return;
   double h = a.h[i], d = a.d[i];
   double ice = a.ice, depth = a.depth;
-  if (a.units == AIRICE_UNITS_CM_RAD) { h = h / 100; d = d / 100; ice = ice / 100; depth = depth / 100; }  // M.cc:947-950
+  if (a.units == AIRICE_UNITS_CM_RAD) {  // M.cc:947-950
+    h = AIRICE_DIV100(h); d = AIRICE_DIV100(d); ice = AIRICE_DIV100(ice); depth = AIRICE_DIV100(depth);
+  }
   const int kt = airice_top_layer(m, h);
   const int kc = kt < 0 ? 0 : kt;
   const double ntx = 1.0 + m.B[kc] * exp(-m.C[kc] * h);
@@ -243,7 +245,7 @@ __device__ __forceinline__ void row_interp(const LookupTable& t, double d, int i
 __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_lookup_kernel(const AirIceMedium m, const LookupTable t, const LookupArgs a) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.n) return;
-  const double h = a.h_cm[i] / 100, d = a.d_cm[i] / 100;  // M.cc:1307-1308
+  const double h = AIRICE_DIV100(a.h_cm[i]), d = AIRICE_DIV100(a.d_cm[i]);  // M.cc:1307-1308
   const int total = (int)t.cells - 1;
   // column 0 holds the row's Tx height in every cell: col0[c] == row_h[c / n_th]
   const double maxh = (double)__ldg(t.row_h), minh = (double)__ldg(t.row_h + total / t.n_th);

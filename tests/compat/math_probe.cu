@@ -1,4 +1,4 @@
-// TEST: applies the product's device math (airice_math.cuh: log, sqrt, rcp, div) to arrays, so that
+// TEST: applies the product's device math (airice_math.cuh: log, sqrt, rcp, div, atan, /100) to arrays, so that
 // tests/test_gpu_math.py can measure their error against high-precision references.  Built at test time with nvcc.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -13,7 +13,9 @@ __global__ void probe_kernel(int op, long n, const double* a, const double* b, d
     case 0: r = AIRICE_LOG(a[i]); break;
     case 1: r = AIRICE_SQRT(a[i]); break;
     case 2: r = AIRICE_RCP(a[i]); break;
-    default: r = AIRICE_DIV(a[i], b[i]); break;
+    case 3: r = AIRICE_DIV(a[i], b[i]); break;
+    case 4: r = AIRICE_ATAN_Q(a[i], b[i]); break;
+    default: r = AIRICE_DIV100(a[i]); break;
   }
   out[i] = r;
 }

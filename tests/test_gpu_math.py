@@ -68,3 +68,26 @@ def test_device_sqrt_rcp_div(probe):
     a = np.exp(rng.uniform(-100, 100, 200000)) * rng.choice([-1, 1], 200000)
     b = np.exp(rng.uniform(-100, 100, 200000)) * rng.choice([-1, 1], 200000)
     assert ulps(probe(3, a, b), a.astype(np.longdouble) / b.astype(np.longdouble)).max() <= 1.0
+
+
+@pytest.mark.gpu
+def test_device_atan_and_div100(probe):
+    rng = np.random.default_rng(3)
+    n = 300000
+    # atan(y / x): tangents of every incidence angle (0 .. 1e6), both signs, the range switches, x != 1 (receive angle)
+    y = np.concatenate([np.tan(rng.uniform(0, np.pi / 2, n)), 10.0 ** rng.uniform(-12, 8, n) * rng.choice([-1, 1], n),
+                        [0.0, 1.0, 0.41421356237309503, 2.4142135623730951, 1e300, np.inf, -np.inf, -1.0]])
+    x = np.ones_like(y)
+    got = probe(4, y, x)
+    exact = np.arctan(y.astype(np.longdouble))
+    nz = y != 0
+    assert ulps(got[nz], exact[nz]).max() <= 2.5      # what the solver needs is ~1e-13 deg, i.e. ~1e3 ulp
+    assert got[y == 0][0] == 0.0 and got[-3] == np.pi / 2 and got[-2] == -np.pi / 2
+    yy, xx = rng.uniform(0, 1.8, n), rng.uniform(1e-3, 1.8, n)
+    got = probe(4, yy, xx)
+    assert ulps(got, np.arctan2(yy.astype(np.longdouble), xx.astype(np.longdouble))).max() <= 2.5
+    assert probe(4, np.array([0.7]), np.array([0.0]))[0] == np.pi / 2          # grazing: asin(1)
+    assert np.isnan(probe(4, np.array([np.nan, 0.5]), np.array([1.0, np.nan]))).all()
+    # x / 100 must be THE IEEE quotient (the reference's cm -> m conversion feeds layer tests and exp())
+    v = np.concatenate([rng.uniform(1, 1.5e7, n), 10.0 ** rng.uniform(-3, 9, n) * rng.choice([-1, 1], n), [300000.0, 20000.0, 0.0]])
+    assert np.array_equal(probe(5, v), v / 100)
