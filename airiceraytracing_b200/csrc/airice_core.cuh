@@ -236,6 +236,56 @@ AIRICE_HD double airice_x_fast(const AirIceMedium& m, const AirIcePlan& p, int k
   return X;
 }
 
+// X(L) and dX/dL in FP64, arranged like airice_x_fast (bottom-up air layers, separate ice leg): the ONE evaluation the
+// solver normally spends after the single-precision pre-iteration -- with an analytic slope a Newton step from a point
+// ~1e-6 deg from the root lands ~1e-13 deg from it, which a chord step with the single-precision slope cannot do.
+// dG/dL = L (sA+R)^2 / (T sA R) per end follows from dT/dL = -L (sA+R)^2 / (sA R); 1/R comes from the square root's own
+// refined seed (2^-40), which is ample for a slope.
+template <bool AIR>
+AIRICE_HD void airice_seg_x_dx(double A, double sA, double inv_sA, double L, double L2, double Cn, double iC, double xt,
+                               double nt, double xb, double nb, double& seg, double& dseg) {
+  double Rb, yb, Rt, yt;
+  AIRICE_SQRT_RSQRT(nb * nb - L2, Rb, yb);
+  AIRICE_SQRT_RSQRT(nt * nt - L2, Rt, yt);
+  const double Tb = (AIR ? nb : A * nb) - L2 + sA * Rb, Tt = (AIR ? nt : A * nt) - L2 + sA * Rt;
+  const double rTt = AIRICE_RCP(Tt), rTb = AIRICE_RCP(Tb);
+  const double dG = Cn * (xb - xt) - AIRICE_LOG(Tb * rTt);
+  const double c1 = iC * inv_sA;
+  seg = (L * c1) * dG;
+  const double qb = (sA + Rb) * (sA + Rb) * (rTb * yb), qt = (sA + Rt) * (sA + Rt) * (rTt * yt);
+  const double AA = AIR ? 1.0 : A * A;
+  dseg = c1 * (AA * inv_sA * inv_sA * dG + L2 * inv_sA * (qb - qt));
+}
+AIRICE_HD double airice_x_dx(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
+                             double& dXdL) {
+  const double L2 = L * L;
+  double X = 0.0, dX = 0.0;
+  if (kt >= p.kb) {
+    const double sAir = AIRICE_SQRT(1.0 * 1.0 - L2);
+    const double yAir = AIRICE_RCP(sAir);
+#pragma unroll 1
+    for (int k = p.kb; k <= kt; k++) {
+      const bool top = (k == kt);
+      const double xt = top ? h : p.start_x[k];
+      const double nt = top ? n_tx : p.start_n[k];
+      double seg, dseg;
+      airice_seg_x_dx<true>(1.0, sAir, yAir, L, L2, p.neg_c[k], p.inv_neg_c[k], xt, nt, p.stop_x[k], p.stop_n[k], seg, dseg);
+      X -= seg; dX -= dseg;
+    }
+  }
+  if (p.has_ice) {
+    const double sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
+    const double yIce = AIRICE_RCP(sIce);
+    const int k = AIRICE_ICE_SLOT;
+    double seg, dseg;
+    airice_seg_x_dx<false>(m.A_ice, sIce, yIce, L, L2, p.neg_c[k], p.inv_neg_c[k], p.start_x[k], p.start_n[k], p.stop_x[k],
+                           p.stop_n[k], seg, dseg);
+    X += seg; dX += dseg;
+  }
+  dXdL = dX;
+  return X;
+}
+
 // Single-precision X(t) and dX/dt, t = tan(incidence at the transmitter): the pre-iteration that brings the solver
 // within ~1e-4 deg of the root on the FP32/MUFU pipes, which this FP64-bound kernel leaves idle.  dn_tx = n(h_Tx) - 1.
 #if defined(__CUDA_ARCH__)

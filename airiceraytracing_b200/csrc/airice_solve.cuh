@@ -18,6 +18,9 @@
 
 #define AIRICE_SOLVE_GUARD_DEG 1.0e-10
 #define AIRICE_NEWTON_MAXIT 40
+// error bound below which the Newton step of the single FP64 evaluation is taken as the root; the replay evaluates f
+// for real whenever a probe lies within AIRICE_SOLVE_GUARD_DEG of it, so this only has to stay well below the guard
+#define AIRICE_SOLVE_ACCEPT_DEG 2.0e-11
 
 struct AirIceSolveStat {
   int n_newton;  // distance evaluations spent in the Newton phase
@@ -131,12 +134,15 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
     if (!(t < t_cap)) t = t_cap;
     double slope = hgt;                 // dX/dt ~ height for a straight ray; replaced below
     bool slope_good = false;
+    bool have_kappa = false;
+    double kappa_bound = 0.0;            // |X''/X'| plus its uncertainty, from the single-precision slopes
     if (kt >= p.kb) {
       const int kc = kt < 0 ? 0 : kt;
       const float dn_tx = (float)(n_tx - 1.0);
       const float cdx_top = (float)(p.neg_c[kc] * (p.stop_x[kc] - h));
       const float df = (float)d, capf = (float)t_cap;
       float tf = (float)t, sf = 0.0f;
+      float t_a = 0.0f, s_a = 0.0f, t_b = 0.0f;   // the two evaluation points and the first slope: curvature estimate
       bool okf = true;
 #pragma unroll 1
       for (int it = 0; it < 2 && okf; it++) {
@@ -144,15 +150,56 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
         const float Xf = airice_x_newton_f32(m, p, kt, cdx_top, dn_tx, tf, dXdt);
         const float tn = tf - (Xf - df) / dXdt;
         okf = (tn > 0.0f) && (tn < capf) && (dXdt > 0.0f);
-        if (okf) { tf = tn; sf = dXdt; }
+        if (okf) { t_a = t_b; s_a = sf; t_b = tf; tf = tn; sf = dXdt; }
       }
       if (sf > 0.0f) { t = (double)tf; slope = (double)sf; slope_good = true; }
+      if (okf && s_a > 0.0f) {
+        // both single-precision iterations went through: kappa ~ X''/X' from their two slopes, with the noise of a
+        // single-precision slope (~1e-5 relative) over the distance of the two points as its uncertainty
+        const double dab = (double)t_b - (double)t_a;
+        kappa_bound = AIRICE_DIV(fabs((double)sf - (double)s_a) + 3.0e-5 * (double)sf, fabs(dab) * (double)sf);
+        have_kappa = true;
+      }
     }
     double t_prev = 0.0, g_prev = 0.0;
     bool have_prev = false;
     ts = NAN;
+    if (have_kappa) {
+      // (b1) ONE FP64 evaluation with the analytic slope.  The Newton step from t lands within
+      // 0.5 |X''/X'| dt^2 of the root; with the bound on the curvature from (a) that is below 2e-11 deg for 99.9 % of
+      // pairs (the single-precision landing point is ~1e-6 deg off), well inside the replay's guard band, and the
+      // step is taken as the root.  Otherwise the chord iteration below continues from the step with this slope.
+      double sq1, w;
+      AIRICE_SQRT_RSQRT(1.0 + t * t, sq1, w);
+      w = AIRICE_RCP(sq1);
+      double dXdL;
+      const double X = airice_x_dx(m, p, kt, h, n_tx, n_tx * t * w, dXdL);
+      st.n_newton++;
+      const double g = X - d;
+      const double s = dXdL * n_tx * (w * w * w);          // dL/dt = n_tx / (1+t^2)^{3/2}
+      if (g == 0.0) {
+        ts = t;
+      } else if (g < 0.0 && t >= t_cap) {
+        ts = INFINITY;                                     // even the lower bracket end falls short of d
+      } else {
+        if (g < 0.0) tlo = t; else thi = t;
+        const double hi_t = thi < t_cap ? thi : t_cap;
+        const double dN = -AIRICE_DIV(g, s);
+        double tn = t + dN;
+        const bool inside = (s > 0.0) && (tn > tlo) && (tn < hi_t);
+        const double bound_deg = 0.5 * kappa_bound * (dN * dN) * (w * w) * m.rad2deg;
+        if (inside && bound_deg < AIRICE_SOLVE_ACCEPT_DEG) {
+          ts = tn;
+        } else {
+          if (!inside) tn = (thi == INFINITY && g < 0.0) ? t_cap : 0.5 * (tlo + hi_t);
+          if (s > 0.0) { slope = s; slope_good = true; }
+          have_prev = true; t_prev = t; g_prev = g;
+          t = tn;
+        }
+      }
+    }
 #pragma unroll 1
-    for (int it = 0; it < AIRICE_NEWTON_MAXIT; it++) {
+    for (int it = 0; it < AIRICE_NEWTON_MAXIT && ts != ts; it++) {
       double sq1, w;
       AIRICE_SQRT_RSQRT(1.0 + t * t, sq1, w);
       w = AIRICE_RCP(sq1);
@@ -214,34 +261,32 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
       int kb = airice_exponent(ratio) + 1;
       kb = kb < 1 ? 1 : kb;
       const int kf = kb + 1;
-      const double wf = airice_scale2(W, -kf);            // finest cell width W 2^-kf (exact)
+      const double wf = airice_scale2(W, -kf);            // cell width W 2^-kf after kb + 1 halvings (exact)
       const double ncell = airice_scale2(1.0, kf);        // 2^kf
-      double jf = ncell - 1.0;                            // theta* outside (lo, hi): the walk to hi
-      if (th > lo && th < hi) {
-        const double x = (th - lo) * (ncell * AIRICE_RCP(W));
-        const double mr = rint(x);
-        jf = (x < mr) ? mr - 1.0 : mr;                    // floor(x)
-        if (!(fabs(x - mr) * wf > guard)) {
-          // theta* within the guard of grid point mr -- a point the reference evaluates f at (unless it is only on
-          // the finest grid and the loop stops one level earlier: then the evaluation is harmless)
-          if (!(mr > 0.0) || !(mr < ncell)) {
-            careful = true;
-          } else {
-            const double xp = lo + mr * wf;
-            const double f = d - airice_x_exact(m, p, kt, h, n_tx, airice_L_of_theta(m, n_tx, xp));
-            st.n_replay++;
-            if (f < 0.0) jf = mr;                         // grid point below the root: the cell starts there
-            else if (f > 0.0) jf = mr - 1.0;
-            else careful = true;                          // exact zero or NaN: GSL's special exits
-          }
+      const bool inside = th > lo && th < hi;             // otherwise: the walk to hi, last cell of every level
+      const double x = inside ? (th - lo) * (ncell * AIRICE_RCP(W)) : ncell - 0.5;
+      // does the loop stop after kb halvings?  (cell index there = floor(x / 2))
+      const double jb = floor(0.5 * x), wb = 2.0 * wf;
+      const double lob = lo + jb * wb, hib = lo + (jb + 1.0) * wb;
+      const bool stop_b = hib - lob < 0.000000001 * lob;
+      const double xk = stop_b ? 0.5 * x : x, wk = stop_b ? wb : wf, nk = stop_b ? 0.5 * ncell : ncell;
+      const double mr = rint(xk);
+      double jk = (xk < mr) ? mr - 1.0 : mr;              // floor(xk): the final cell
+      if (inside && !(fabs(xk - mr) * wk > guard)) {
+        // theta* within the guard of grid point mr of the final level: an end of the final cell, i.e. a midpoint the
+        // reference evaluated f at
+        if (!(mr > 0.0) || !(mr < nk)) {
+          careful = true;
+        } else {
+          const double xp = lo + mr * wk;
+          const double f = d - airice_x_exact(m, p, kt, h, n_tx, airice_L_of_theta(m, n_tx, xp));
+          st.n_replay++;
+          if (f < 0.0) jk = mr;                           // grid point below the root: the cell starts there
+          else if (f > 0.0) jk = mr - 1.0;
+          else careful = true;                            // exact zero or NaN: GSL's special exits
         }
       }
-      if (!careful) {
-        const double jb = floor(0.5 * jf), wb = 2.0 * wf;
-        const double lob = lo + jb * wb, hib = lo + (jb + 1.0) * wb;
-        if (hib - lob < 0.000000001 * lob) return lo + (2.0 * jb + 1.0) * wf;   // stopped after kb halvings
-        return lo + (2.0 * jf + 1.0) * (0.5 * wf);                               // after kb + 1
-      }
+      if (!careful) return lo + (2.0 * jk + 1.0) * (0.5 * wk);
     }
   }
   // Careful form (about 0.2 % of solves): a probe sits within `guard` of theta*, so f is evaluated there for real
