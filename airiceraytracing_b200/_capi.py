@@ -24,7 +24,7 @@ VARIANT_PYWRAP = 1
 EXPORTS = [
     "airice_create", "airice_destroy", "airice_last_error", "airice_device_count", "airice_get_medium",
     "airice_set_ice_model", "airice_table_dims", "airice_table_build_device", "airice_forward_device",
-    "airice_forward_host", "airice_table_create", "airice_table_wrap", "airice_table_destroy", "airice_table_info",
+    "airice_forward_host", "airice_table_create", "airice_table_create_multi", "airice_table_wrap", "airice_table_destroy", "airice_table_info",
     "airice_table_copy_column", "airice_table_column_ptr", "airice_table_copy_row_ranges", "airice_solve_device",
     "airice_solve_multi_device", "airice_solve_host", "airice_lookup_device", "airice_lookup_host", "airice_inice_solve_device",
     "airice_inice_solve_host", "airice_inice_two_rays_device", "airice_inice_two_rays_host", "airice_ray_path_device", "airice_ray_path_host", "airice_fp64_peak_tflops", "airice_sync",
@@ -54,6 +54,7 @@ def load():
     lib.airice_table_build_device.argtypes = [vp, d, d, d, d, d, d, d, i64, i64, pp, pp, vp]
     lib.airice_forward_device.argtypes = [vp, i64, vp, vp, d, d, pp, vp]
     lib.airice_table_create.argtypes = [vp, d, d, d, d, d, d, d, pp]
+    lib.airice_table_create_multi.argtypes = [vp, i, C.POINTER(d), d, d, d, d, d, d, pp]
     lib.airice_table_wrap.argtypes = [vp, pp, i64, i64, d, d, pp]
     lib.airice_table_destroy.argtypes = [vp]
     lib.airice_table_destroy.restype = None

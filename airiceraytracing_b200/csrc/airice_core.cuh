@@ -375,12 +375,41 @@ AIRICE_HD void airice_seg_sums(double A, double inv_sA, double mult, double cC, 
   gs = AIRICE_MUL(Hb + Ay * Gb, iC) - AIRICE_MUL(Ht + Ay * Gt, iC);
 }
 
+// incidence angle on the surface, refracted angle below it and the Fresnel coefficients (air side only)
+AIRICE_HD void airice_ray_surface(const AirIceMedium& m, const AirIcePlan& p, int kt, double Lk, double Rsurf, bool want_inc,
+                                  bool want_refr, AirIceRay& r) {
+  // incidence on the ice surface: receive angle of the bottom air segment, asin(L/n(surface)) (M.cc:760, 583-589).
+  // NB: with RELAY the ice leg re-derives L as n_air(surface) sin(incidence) (M.cc:1913, 565-589), which is Lk again.
+  const double n1 = p.stop_n[p.kb < AIRICE_MAX_LAYERS ? p.kb : 0];
+  const double n2 = p.start_n[AIRICE_ICE_SLOT];  // n_ice(0)
+  const double Lsurf = Lk;
+  const double si = AIRICE_DIV(Lsurf, n1);
+  // asin(L / n1) = atan(L / sqrt(n1^2 - L^2)) when the ray crossed the air (Rsurf is that square root)
+  r.inc_ice_deg = want_inc ? ((kt >= p.kb) ? AIRICE_ATAN_Q(Lsurf, Rsurf) : asin(si)) * m.rad2deg : 0.0;
+  // Fresnel field transmission, air->ice at the surface (M.cc:285-301, 321-337) without trig:
+  // sin(theta_i) = L/n1, n1 cos(theta_i) = sqrt(n1^2-L^2) = R of the bottom end.
+  const double n12 = AIRICE_DIV(n1, n2);
+  const double u = n12 * si;
+  const double sq = AIRICE_SQRT(1.0 - u * u);
+  const double c1 = Rsurf;
+  double trs = 1.0 + AIRICE_DIV(c1 - n2 * sq, c1 + n2 * sq);
+  const double c2 = AIRICE_DIV(c1, n1);  // cos(theta_i)
+  double trp = (1.0 - AIRICE_DIV(n1 * sq - n2 * c2, n1 * sq + n2 * c2)) * n12;
+  if (trs != trs) trs = 0.0;
+  if (trp != trp) trp = 0.0;
+  r.trans_s = trs; r.trans_p = trp;
+  r.refr_deg = want_refr ? AIRICE_ATAN_Q(u, sq) * m.rad2deg : 0.0;  // refracted angle just below the surface (P.cc:1081)
+}
+
+// ---- a ray in three pieces, so that the multi-antenna table can run the air walk once and the ice leg per antenna
+// (the air leg does not depend on the receiver depth, M.cc:887-905)
+struct AirIceAirLeg { double x, t, g, L, Rsurf; };   // sums over the air segments, L at the surface, n1 cos(incidence)
+struct AirIceIceTop { double L, L2, sA, inv_sA, Dt, Rt, lnTt, Ht; };   // ray-dependent, depth-independent part of the ice leg
+
 template <bool RELAY>
-AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
-                               bool in_ice, bool want_inc, bool want_refr, AirIceRay& r) {
-  double xa = 0.0, ta = 0.0, ga = 0.0, xi = 0.0, ti = 0.0, gi = 0.0;
+AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L) {
+  double xa = 0.0, ta = 0.0, ga = 0.0;
   double Lk = L, Rsurf = 0.0;
-  r.recv_deg = 0.0;
   if (kt >= p.kb) {
     if (RELAY) {
       // forward tracer: top-down, L handed from layer to layer
@@ -447,43 +476,48 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
       }
     }
   }
+  AirIceAirLeg o;
+  o.x = xa; o.t = ta; o.g = ga; o.L = Lk; o.Rsurf = Rsurf;
+  return o;
+}
+
+// upper end of the ice leg (z = 0): everything that does not depend on the receiver depth
+AIRICE_HD AirIceIceTop airice_ice_top(const AirIceMedium& m, const AirIcePlan& p, double Lk) {
+  const int k = AIRICE_ICE_SLOT;
+  const double A = m.A_ice, nt = p.start_n[k];
+  AirIceIceTop o;
+  o.L = Lk; o.L2 = Lk * Lk;
+  o.sA = AIRICE_SQRT(A * A - o.L2); o.inv_sA = AIRICE_RCP(o.sA);
+  o.Dt = nt * nt - o.L2;
+  o.Rt = AIRICE_SQRT(o.Dt);
+  o.lnTt = AIRICE_LOG(A * nt - o.L2 + o.sA * o.Rt); o.Ht = AIRICE_LOG(nt + o.Rt);
+  return o;
+}
+// ice leg from the surface to depth xb (n(xb) = nb): GetIcePropagationPar (M.cc:807-869)
+AIRICE_HD void airice_ice_leg(const AirIceMedium& m, const AirIcePlan& p, const AirIceIceTop& o, double xb, double nb,
+                              double& xi, double& ti, double& gi, double& recv_deg) {
+  const int k = AIRICE_ICE_SLOT;
+  const double A = m.A_ice;
+  const double Cn = p.neg_c[k], iC = p.inv_neg_c[k];
+  const double Db = nb * nb - o.L2;
+  const double Rb = AIRICE_SQRT(Db);
+  const double lnTb = AIRICE_LOG(A * nb - o.L2 + o.sA * Rb), Hb = AIRICE_LOG(nb + Rb);
+  airice_seg_sums<false>(A, o.inv_sA, (o.L * iC) * o.inv_sA, m.c * Cn, Cn, iC, p.start_x[k], xb, o.Dt, Db, o.Rt, Rb, o.lnTt,
+                         lnTb, o.Ht, Hb, xi, ti, gi);
+  // receive angle asin(L / n(depth)) (M.cc:824 / 583-589) as atan(L / sqrt(n^2 - L^2)): the square root is Rb
+  recv_deg = AIRICE_ATAN_Q(o.L, Rb) * m.rad2deg;
+}
+
+template <bool RELAY>
+AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
+                               bool in_ice, bool want_inc, bool want_refr, AirIceRay& r) {
+  const AirIceAirLeg al = airice_ray_air<RELAY>(m, p, kt, h, n_tx, L);
+  r.x_air = al.x; r.t_air = al.t; r.p_air = al.g;
+  r.x_ice = 0.0; r.t_ice = 0.0; r.p_ice = 0.0;
+  r.recv_deg = 0.0;
   if (in_ice) {
-    const int k = AIRICE_ICE_SLOT;
-    const double A = m.A_ice;
-    const double L2 = Lk * Lk;
-    const double sA = AIRICE_SQRT(A * A - L2), inv_sA = AIRICE_RCP(sA);
-    const double Cn = p.neg_c[k], iC = p.inv_neg_c[k];
-    const double xt = p.start_x[k], nt = p.start_n[k], xb = p.stop_x[k], nb = p.stop_n[k];
-    const double Db = nb * nb - L2, Dt = nt * nt - L2;
-    const double Rb = AIRICE_SQRT(Db), Rt = AIRICE_SQRT(Dt);
-    const double lnTb = AIRICE_LOG(A * nb - L2 + sA * Rb), Hb = AIRICE_LOG(nb + Rb);
-    const double lnTt = AIRICE_LOG(A * nt - L2 + sA * Rt), Ht = AIRICE_LOG(nt + Rt);
-    airice_seg_sums<false>(A, inv_sA, (Lk * iC) * inv_sA, m.c * Cn, Cn, iC, xt, xb, Dt, Db, Rt, Rb, lnTt, lnTb, Ht, Hb,
-                           xi, ti, gi);
-    // receive angle asin(L / n(depth)) (M.cc:824 / 583-589) as atan(L / sqrt(n^2 - L^2)): the square root is Rb
-    r.recv_deg = AIRICE_ATAN_Q(Lk, Rb) * m.rad2deg;
+    const AirIceIceTop it = airice_ice_top(m, p, al.L);
+    airice_ice_leg(m, p, it, p.stop_x[AIRICE_ICE_SLOT], p.stop_n[AIRICE_ICE_SLOT], r.x_ice, r.t_ice, r.p_ice, r.recv_deg);
   }
-  r.x_air = xa; r.t_air = ta; r.p_air = ga;
-  r.x_ice = xi; r.t_ice = ti; r.p_ice = gi;
-  // incidence on the ice surface: receive angle of the bottom air segment, asin(L/n(surface)) (M.cc:760, 583-589).
-  // NB: with RELAY the ice leg re-derives L as n_air(surface) sin(incidence) (M.cc:1913, 565-589), which is Lk again.
-  const double n1 = p.stop_n[p.kb < AIRICE_MAX_LAYERS ? p.kb : 0];
-  const double n2 = p.start_n[AIRICE_ICE_SLOT];  // n_ice(0)
-  const double Lsurf = in_ice ? Lk : Lk;
-  const double si = AIRICE_DIV(Lsurf, n1);
-  // asin(L / n1) = atan(L / sqrt(n1^2 - L^2)) when the ray crossed the air (Rsurf is that square root)
-  r.inc_ice_deg = want_inc ? ((kt >= p.kb) ? AIRICE_ATAN_Q(Lsurf, Rsurf) : asin(si)) * m.rad2deg : 0.0;
-  // Fresnel field transmission, air->ice at the surface (M.cc:285-301, 321-337) without trig:
-  // sin(theta_i) = L/n1, n1 cos(theta_i) = sqrt(n1^2-L^2) = R of the bottom end.
-  const double n12 = AIRICE_DIV(n1, n2);
-  const double u = n12 * si;
-  const double sq = AIRICE_SQRT(1.0 - u * u);
-  const double c1 = Rsurf;
-  double trs = 1.0 + AIRICE_DIV(c1 - n2 * sq, c1 + n2 * sq);
-  const double c2 = AIRICE_DIV(c1, n1);  // cos(theta_i)
-  double trp = (1.0 - AIRICE_DIV(n1 * sq - n2 * c2, n1 * sq + n2 * c2)) * n12;
-  if (trs != trs) trs = 0.0;
-  if (trp != trp) trp = 0.0;
-  r.trans_s = trs; r.trans_p = trp;
-  r.refr_deg = want_refr ? AIRICE_ATAN_Q(u, sq) * m.rad2deg : 0.0;  // refracted angle just below the surface (P.cc:1081)
+  airice_ray_surface(m, p, kt, al.L, al.Rsurf, want_inc, want_refr, r);
 }

@@ -55,6 +55,7 @@ struct airice_ctx {
   // tables of 384 + 455 MB: cudaMalloc / cudaFree of that size cost more than building the table, and jitter wildly)
   struct SpareBuf { void* p; size_t bytes; };
   std::vector<SpareBuf> spare;
+  size_t spare_cap = 0;              // bytes of freed table buffers the context may hold (set on first release)
   size_t path_plan_cap = 0;
   int64_t inice_cols_n = 0;
   struct RowCache {
@@ -123,7 +124,16 @@ cudaError_t table_alloc(airice_ctx* c, void** p, size_t bytes) {
 }
 void table_release(airice_ctx* c, void* p, size_t bytes) {
   if (!p) return;
-  if (c->spare.size() < 2 && bytes >= ((size_t)1 << 20)) {
+  // keep freed table buffers for the next tables of that size (cudaMalloc/cudaFree of a 400 MB block cost more than
+  // building the table): up to a third of the device's memory, 64 antennas' tables (54 GB) included on a B200;
+  // table_alloc hands everything back to the driver when an allocation fails
+  size_t held = 0;
+  for (auto& b : c->spare) held += b.bytes;
+  if (c->spare_cap == 0) {
+    size_t free_b = 0, total_b = 0;
+    c->spare_cap = (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ? total_b / 3 : ((size_t)2 << 30);
+  }
+  if (bytes >= ((size_t)1 << 20) && held + bytes <= c->spare_cap && c->spare.size() < 512) {
     cudaDeviceSynchronize();                        // what cudaFree would have waited for
     c->spare.push_back({p, bytes});
   } else {
@@ -168,7 +178,7 @@ int ensure_slots(airice_ctx* c, size_t bytes) {
 
 // Upload per-row transmitter data for rows [r0,r1) and launch kernel 1 on them.
 int build_rows(airice_ctx* ctx, const TableGrid& g, int64_t r0, int64_t r1, double* const* cols64, float* const* cols32,
-               cudaStream_t s) {
+               cudaStream_t s, TableMultiArgs* multi = nullptr) {
   const int64_t rows_avail = g.first_skipped_row < g.n_h ? g.first_skipped_row : g.n_h;
   if (r0 < 0 || r1 > rows_avail || r0 > r1) return fail(-3, "table rows out of range");
   if (r1 == r0) return 0;
@@ -204,7 +214,9 @@ int build_rows(airice_ctx* ctx, const TableGrid& g, int64_t r0, int64_t r1, doub
   if (cols32) for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) if (!cols32[k]) return fail(-4, "all 11 float columns are required");
   // the table path hands the surface height of the grid (ice, or ice+depth for a receiver in air) to the walk
   const AirIcePlan& p = ctx->plan(g.ice_h, g.depth_signed);
-  cudaError_t e = launch_table(ctx->medium, p, a, s);
+  cudaError_t e;
+  if (multi) { multi->base = a; e = launch_table_multi(ctx->medium, p, *multi, s); }
+  else e = launch_table(ctx->medium, p, a, s);
   if (e != cudaSuccess) return cuda_fail(e, "launch_table");
   return 0;
 }
@@ -330,6 +342,60 @@ int airice_table_create(airice_ctx* c, double depth_m, double ice_m, double h_to
   if (rc == 0) rc = pack_table(t);
   if (rc) { airice_table_destroy(t); return rc; }
   *out = t;
+  return 0;
+}
+
+int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, double ice_m, double h_top, double h_step,
+                              double th_start, double th_step, double th_stop, airice_table** out) {
+  if (!c || !out || !depths_m || n_ant <= 0) return fail(-1, "null argument");
+  for (int q = 0; q < n_ant; q++)
+    if (!(depths_m[q] < 0)) return fail(-6, "airice_table_create_multi: every antenna must sit in the ice (depth < 0); "
+                                            "a receiver in air changes the surface height of the air walk");
+  CK(cudaSetDevice(c->device));
+  TableGrid g; std::string err;
+  int rc = make_grid(depths_m[0], ice_m, h_top, h_step, th_start, th_step, th_stop, &g, &err);   // same grid for every depth < 0
+  if (rc) return fail(rc, err);
+  const int64_t n_h = g.first_skipped_row < g.n_h ? g.first_skipped_row : g.n_h;
+  const int64_t cells = n_h * g.n_th;
+  if (cells >= 2147483647LL) return fail(-5, "lookup tables are limited to 2^31-1 cells (the reference indexes them with int)");
+  for (int q = 0; q < n_ant; q++) out[q] = nullptr;
+  std::vector<double> ant(2 * (size_t)n_ant);
+  std::vector<float*> blocks((size_t)n_ant);
+  double* d_ant = nullptr;
+  float** d_blocks = nullptr;
+  auto cleanup = [&](int code) {
+    for (int q = 0; q < n_ant; q++) { if (out[q]) airice_table_destroy(out[q]); out[q] = nullptr; }
+    if (d_ant) cudaFree(d_ant);
+    if (d_blocks) cudaFree(d_blocks);
+    return code;
+  };
+  for (int q = 0; q < n_ant; q++) {
+    airice_table* t = new airice_table();
+    out[q] = t;
+    t->ctx = c; t->owns = true;
+    t->n_h = n_h; t->n_th = g.n_th; t->cells = cells;
+    t->loop_stop_h = g.loop_stop_h; t->h_step = g.h_step;
+    float* block = nullptr;
+    t->cols_bytes = sizeof(float) * (size_t)cells * AIRICE_TABLE_NCOLS32;
+    cudaError_t e = table_alloc(c, (void**)&block, t->cols_bytes);
+    if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMalloc(table)"));
+    for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t->cols[k] = block + (int64_t)k * cells;
+    blocks[q] = block;
+    ant[2 * q] = -depths_m[q];                       // the plan's positive depth (make_plan)
+    ant[2 * q + 1] = n_ice(c->medium, -depths_m[q]);
+  }
+  cudaError_t e = cudaMalloc((void**)&d_ant, sizeof(double) * ant.size());
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_blocks, sizeof(float*) * blocks.size());
+  if (e == cudaSuccess) e = cudaMemcpy(d_ant, ant.data(), sizeof(double) * ant.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_blocks, blocks.data(), sizeof(float*) * blocks.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cleanup(cuda_fail(e, "antenna arrays"));
+  TableMultiArgs ma;
+  std::memset(&ma, 0, sizeof(ma));
+  ma.n_ant = n_ant; ma.ant = d_ant; ma.blocks = d_blocks; ma.col_stride = cells;
+  rc = build_rows(c, g, 0, n_h, nullptr, nullptr, nullptr, &ma);
+  for (int q = 0; q < n_ant && rc == 0; q++) rc = pack_table(out[q]);   // pack_table synchronises the stream
+  if (rc) return cleanup(rc);
+  cudaFree(d_ant); cudaFree(d_blocks);
   return 0;
 }
 

@@ -76,6 +76,48 @@ __global__ void __launch_bounds__(kThreads) airice_table_kernel(const AirIceMedi
   }
 }
 
+// One thread per cell, all antennas: air walk + surface once, then one ice leg (1 sqrt, 2 log, 1 atan) and 11 float
+// stores per antenna.  Same arithmetic as airice_table_kernel<false, true> per antenna, hence the same bits.
+__global__ void __launch_bounds__(kThreads) airice_table_multi_kernel(const AirIceMedium m, const AirIcePlan p,
+                                                                      const TableMultiArgs ma) {
+  const TableArgs& a = ma.base;
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= a.ncells) return;
+  const int64_t c = a.cell0 + i;
+  const int64_t row = c / a.n_th;
+  const int64_t j = c - row * a.n_th;
+  const double h = __ldg(a.row_h + (row - a.row0));
+  const double ntx = __ldg(a.row_ntx + (row - a.row0));
+  const int kt = __ldg(a.row_kt + (row - a.row0));
+  const double theta = theta_of_bin(a, j);
+  const double L = airice_L_of_theta(m, ntx, theta);
+  const AirIceAirLeg al = airice_ray_air<true>(m, p, kt, h, ntx, L);
+  AirIceRay r;
+  airice_ray_surface(m, p, kt, al.L, al.Rsurf, false, false, r);
+  const AirIceIceTop it = airice_ice_top(m, p, al.L);
+  const float f_h = (float)h, f_th = (float)theta, f_xa = (float)al.x, f_oa = (float)(al.t * m.c), f_ga = (float)al.g;
+  const float f_ts = (float)r.trans_s, f_tp = (float)r.trans_p;
+#pragma unroll 1
+  for (int q = 0; q < ma.n_ant; q++) {
+    const double xb = __ldg(ma.ant + 2 * q), nb = __ldg(ma.ant + 2 * q + 1);
+    double xi, ti, gi, recv;
+    airice_ice_leg(m, p, it, xb, nb, xi, ti, gi, recv);
+    float* o = ma.blocks[q] + i;   // like c32[k][i] of the single-table kernel: blocks start at the launch's first cell
+    const int64_t st = ma.col_stride;
+    o[0] = f_h;
+    o[st] = (float)(al.x + xi);
+    o[2 * st] = (float)(ti * m.c);
+    o[3 * st] = f_oa;
+    o[4 * st] = f_th;
+    o[5 * st] = f_xa;
+    o[6 * st] = f_ts;
+    o[7 * st] = f_tp;
+    o[8 * st] = f_ga;
+    o[9 * st] = (float)gi;
+    o[10 * st] = (float)recv;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) airice_forward_kernel(const AirIceMedium m, const AirIcePlan p, const ForwardArgs a) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.n) return;
@@ -96,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) airice_forward_kernel(const AirIceMe
 }
 
 #ifndef AIRICE_SOLVE_MINBLOCKS
-#define AIRICE_SOLVE_MINBLOCKS 6
+#define AIRICE_SOLVE_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(kThreads, AIRICE_SOLVE_MINBLOCKS) airice_solve_kernel(const AirIceMedium m, const AirIcePlan p, const SolveArgs a) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -350,6 +392,14 @@ cudaError_t launch_table(const AirIceMedium& m, const AirIcePlan& p, const Table
   else if (w64) airice_table_kernel<true, false><<<grid, kThreads, 0, s>>>(m, p, a);
   else if (w32) airice_table_kernel<false, true><<<grid, kThreads, 0, s>>>(m, p, a);
   else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_table_multi(const AirIceMedium& m, const AirIcePlan& p, const TableMultiArgs& a, cudaStream_t s) {
+  if (a.base.ncells <= 0 || a.n_ant <= 0) return cudaSuccess;
+  const int64_t blocks = (a.base.ncells + kThreads - 1) / kThreads;
+  if (blocks > 2147483647LL) return cudaErrorInvalidValue;
+  airice_table_multi_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(m, p, a);
   return cudaGetLastError();
 }
 

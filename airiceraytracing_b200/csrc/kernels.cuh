@@ -36,6 +36,18 @@ struct TableArgs {
 };
 cudaError_t launch_table(const AirIceMedium& m, const AirIcePlan& p, const TableArgs& a, cudaStream_t s);
 
+// kernel 1c: the float tables of several in-ice antennas in one pass: the air walk of a cell does not
+// depend on the receiver depth (M.cc:887-905, 1796-1879), so it runs once and only the ice leg is repeated per antenna.
+// `base` supplies the grid (c64/c32 unused); antenna q gets its 11 float columns at blocks[q] + k * ncols_stride.
+struct TableMultiArgs {
+  TableArgs base;
+  int n_ant;
+  const double* ant;       // device [n_ant][2]: receiver depth (positive, m) and n_ice(depth) (host libm)
+  float* const* blocks;    // device [n_ant]: column-major float block of each antenna's table
+  int64_t col_stride;      // elements between two columns of a block (= cells of the whole table)
+};
+cudaError_t launch_table_multi(const AirIceMedium& m, const AirIcePlan& p, const TableMultiArgs& a, cudaStream_t s);
+
 // kernel 1b: the same forward tracer on arbitrary (theta, h) cells (batched GetRayTracingSolutions, M.cc:1796-2017);
 // n(h) of the transmitter is evaluated on the device here.
 struct ForwardArgs {

@@ -154,6 +154,15 @@ class AirIceSolver:
                                            C.byref(h)))
         return Table(self, h)
 
+    def table_create_multi(self, depths_m, ice_m, h_top=100000.0, h_step=10.0, th_start=90.1, th_step=0.1, th_stop=180.0):
+        """Tables of several in-ice antennas in one pass (the air walk is shared; airice_table_create_multi)."""
+        n = len(depths_m)
+        dep = (C.c_double * n)(*[float(x) for x in depths_m])
+        hs = (C.c_void_p * n)()
+        check(self.lib.airice_table_create_multi(self.handle, n, dep, ice_m, h_top, h_step, th_start, th_step, th_stop,
+                                                 C.cast(hs, C.POINTER(C.c_void_p))))
+        return [Table(self, C.c_void_p(hs[q])) for q in range(n)]
+
     def table_wrap(self, cols32, n_h, n_th, loop_stop_h, h_step):
         """Wrap an [11, n_h*n_th] float32 device tensor (kept alive by the returned Table)."""
         cols32 = cols32.to(self.torch_device, torch.float32).contiguous()

@@ -173,6 +173,38 @@ int MakeRayTracingTable(double AntennaDepth, double IceLayerHeight, int AntennaN
   return 0;
 }
 
+// Batch form of the reference's per-antenna loop `for (i...) MakeRayTracingTable(AntennaDepths[i], IceLayerHeight, i)`
+// (RunMultiRayCode.C): all in-ice antennas in one pass over the grid, the air walk shared (airice_table_create_multi).
+// Tables are appended in the order of `AntennaDepths`, exactly as the loop would; an antenna in air (depth >= 0, cm)
+// falls back to its own MakeRayTracingTable call.
+int MakeRayTracingTables(const std::vector<double> &AntennaDepths_cm, double IceLayerHeight) {
+  if (MakeAtmosphere() != 0) return 1;
+  detail::State &s = detail::state();
+  bool all_in_ice = !AntennaDepths_cm.empty();
+  for (double dcm : AntennaDepths_cm) all_in_ice = all_in_ice && (dcm < 0);
+  if (!all_in_ice) {
+    for (size_t i = 0; i < AntennaDepths_cm.size(); i++)
+      if (MakeRayTracingTable(AntennaDepths_cm[i], IceLayerHeight, (int)i) != 0) return 1;
+    return 0;
+  }
+  std::vector<double> depths_m;
+  for (double dcm : AntennaDepths_cm) depths_m.push_back(dcm / 100);
+  IceLayerHeight = IceLayerHeight / 100;
+  const double AirTxHeight = 100000;
+  TotalAngleSteps = floor((LoopStopAngle - LoopStartAngle) / AngleStepSize) + 1;
+  LoopStartHeight = AirTxHeight;
+  LoopStopHeight = IceLayerHeight;
+  TotalHeightSteps = floor((LoopStartHeight - LoopStopHeight) / HeightStepSize) + 1;
+  std::vector<airice_table *> ts(depths_m.size(), nullptr);
+  if (airice_table_create_multi(s.ctx, (int)depths_m.size(), depths_m.data(), IceLayerHeight, AirTxHeight, HeightStepSize,
+                                LoopStartAngle, AngleStepSize, LoopStopAngle, ts.data()) != 0) {
+    detail::report("MakeRayTracingTables");
+    return 1;
+  }
+  for (airice_table *t : ts) s.tables.push_back(t);
+  return 0;
+}
+
 int GetTableColumn(int AntennaNumber, int col, std::vector<float> &out) {
   detail::State &s = detail::state();
   if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size()) return 1;

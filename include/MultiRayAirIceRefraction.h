@@ -44,6 +44,8 @@ void SetAtmosphereFile(const std::string &path);
 
 int MakeAtmosphere();
 int MakeRayTracingTable(double AntennaDepth, double IceLayerHeight, int AntennaNumber);
+// all antennas in one pass (shared air walk); appends one table per depth, in order (new, not in the reference)
+int MakeRayTracingTables(const std::vector<double> &AntennaDepths_cm, double IceLayerHeight);
 bool GetHorizontalDistanceToIntersectionPoint(double SrcHeightASL, double HorizontalDistanceToRx,
                                               double RxDepthBelowIceBoundary, double IceLayerHeight,
                                               double &opticalPathLengthInIce, double &opticalPathLengthInAir,

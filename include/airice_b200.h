@@ -65,6 +65,12 @@ int airice_forward_host(airice_ctx *ctx, int64_t n, const double *theta, const d
 /* Library-owned float table for lookups = one entry of AllTableAllAntData (MultiRayAirIceRefraction.cc:9,2136). */
 int airice_table_create(airice_ctx *ctx, double depth_m, double ice_m, double h_top, double h_step, double th_start,
                         double th_step, double th_stop, airice_table **out);
+/* The tables of n_ant in-ice antennas (depths_m[q] < 0) in ONE pass: the air walk of a cell does not depend on the
+ * receiver depth (MultiRayAirIceRefraction.cc:887-905, 1796-1879), so it runs once per cell and only the ice leg is
+ * repeated per antenna.  Replaces n_ant calls of MakeRayTracingTable (MultiRayAirIceRefraction.cc:2019-2158; one
+ * AllTableAllAntData entry each, :2136); out[q] is bit-identical to airice_table_create(depths_m[q], ...). */
+int airice_table_create_multi(airice_ctx *ctx, int n_ant, const double *depths_m, double ice_m, double h_top,
+                              double h_step, double th_start, double th_step, double th_stop, airice_table **out);
 /* Wraps 11 caller-owned DEVICE float columns (e.g. a gathered multi-GPU table or a reference-built table). */
 int airice_table_wrap(airice_ctx *ctx, const float *const *d_cols32, int64_t n_h, int64_t n_th, double loop_stop_h,
                       double h_step, airice_table **out);

@@ -5,6 +5,7 @@
 #include "MultiRayAirIceRefraction.cc"
 
 #include <cstdio>
+#include <cstring>
 
 std::vector<double> AntennaDepths;
 std::vector<int> AntennaTableAlreadyMade;
@@ -68,6 +69,26 @@ int main(int argc, char **argv) {
   for (double th : ths)
     std::printf("fresnel %.17g %.17g %.17g %.17g %.17g\n", th, MultiRayAirIceRefraction::Refl_S(th, 3000), MultiRayAirIceRefraction::Trans_S(th, 3000),
                 MultiRayAirIceRefraction::Refl_P(th, 3000), MultiRayAirIceRefraction::Trans_P(th, 3000));
+
+  // batch table build (all antennas in one pass, shared air walk): tables 2..4 must equal the per-antenna tables 0, 1
+  // bit for bit, and a third depth comes along
+  {
+    std::vector<double> depths = {AntennaDepth * 100, -150.0 * 100, -75.0 * 100};
+    const int rc = MultiRayAirIceRefraction::MakeRayTracingTables(depths, IceLayerHeight * 100);
+    long differ = 0, cells = 0;
+    std::vector<float> a, b;
+    for (int k = 0; k < 2 && rc == 0; k++)
+      for (int col = 0; col < 11; col++) {
+        MultiRayAirIceRefraction::GetTableColumn(k, col, a);
+        MultiRayAirIceRefraction::GetTableColumn(2 + k, col, b);
+        cells = (long)a.size();
+        if (a.size() != b.size()) { differ += 1000000; continue; }
+        for (size_t q = 0; q < a.size(); q++) differ += std::memcmp(&a[q], &b[q], sizeof(float)) != 0;
+      }
+    std::vector<float> c;
+    const int rc2 = MultiRayAirIceRefraction::GetTableColumn(4, 10, c);
+    std::printf("multitables %d %ld %ld %d %zu\n", rc, differ, cells, rc2, c.size());
+  }
 
   // old solve-per-cell table on the grid of tests/golden/old_table.npz
   MultiRayAirIceRefraction::GridStepSizeH_O = 4000.0;

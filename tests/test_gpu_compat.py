@@ -107,6 +107,12 @@ def test_driver_tables_and_lookup(driver_output, oracle):
     assert driver_output["table0"][0] == driver_output["table2"][0]
 
 
+def test_driver_batch_tables_equal_per_antenna_tables(driver_output):
+    """MakeRayTracingTables (all antennas in one pass over the grid, air walk shared) against MakeRayTracingTable."""
+    rc, differ, cells, rc2, n = driver_output["multitables"][0]
+    assert rc == 0 and differ == 0 and cells == 49 * 177 and rc2 == 0 and n == cells
+
+
 def test_driver_old_table_and_idw(driver_output):
     g = golden("old_table.npz")
     assert driver_output["old_dims"][0] == [float(g["n_h"]), float(g["n_th"]), float(g["cols"].shape[1])]
