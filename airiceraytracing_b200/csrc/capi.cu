@@ -106,12 +106,18 @@ namespace {
 // Allocate and fill the lookup layout of a table from its column-major form.
 // table-sized device buffers: reuse a spare of (nearly) the right size, else allocate
 cudaError_t table_alloc(airice_ctx* c, void** p, size_t bytes) {
+  // best fit: the column block (384 MB) and the lookup layout (455 MB) of the reference grid fall into each other's
+  // window, and handing the larger one to the smaller request leaves the next larger request without a spare
+  size_t best = c->spare.size();
   for (size_t i = 0; i < c->spare.size(); i++) {
-    if (c->spare[i].bytes >= bytes && c->spare[i].bytes <= bytes + bytes / 4) {
-      *p = c->spare[i].p;
-      c->spare.erase(c->spare.begin() + i);
-      return cudaSuccess;
-    }
+    if (c->spare[i].bytes >= bytes && c->spare[i].bytes <= bytes + bytes / 4 &&
+        (best == c->spare.size() || c->spare[i].bytes < c->spare[best].bytes))
+      best = i;
+  }
+  if (best < c->spare.size()) {
+    *p = c->spare[best].p;
+    c->spare.erase(c->spare.begin() + best);
+    return cudaSuccess;
   }
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess && !c->spare.empty()) {      // out of memory: give the spares back and retry
@@ -141,7 +147,8 @@ void table_release(airice_ctx* c, void* p, size_t bytes) {
   }
 }
 
-int pack_table(airice_table* t) {
+// Allocate the lookup layout of a table (dense X, 48-byte records, per-row height and trim ranges: one block).
+int pack_alloc(airice_table* t) {
   const size_t rec_bytes = sizeof(float4) * 3 * (size_t)t->cells;
   const size_t x_bytes = (sizeof(float) * (size_t)t->cells + 255) / 256 * 256;
   const size_t rowh_bytes = (sizeof(float) * (size_t)t->n_h + 255) / 256 * 256;
@@ -155,7 +162,13 @@ int pack_table(airice_table* t) {
   t->row_h = (float*)(base + rec_bytes + x_bytes);
   t->row_first = (int*)(base + rec_bytes + x_bytes + rowh_bytes);
   t->row_last = (int*)(base + rec_bytes + x_bytes + rowh_bytes + range_bytes);
-  e = launch_pack_table(t->cols, t->cells, (int)t->n_h, (int)t->n_th, t->x, t->rec, t->row_h, t->row_first, t->row_last, nullptr);
+  return 0;
+}
+// ... and fill it from the column-major form.
+int pack_table(airice_table* t) {
+  int rc = pack_alloc(t);
+  if (rc) return rc;
+  cudaError_t e = launch_pack_table(t->cols, t->cells, (int)t->n_h, (int)t->n_th, t->x, t->rec, t->row_h, t->row_first, t->row_last, nullptr);
   if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
   if (e != cudaSuccess) return cuda_fail(e, "pack table");
   return 0;
@@ -362,7 +375,7 @@ int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, 
   std::vector<double> ant(2 * (size_t)n_ant);
   std::vector<float*> blocks((size_t)n_ant);
   double* d_ant = nullptr;
-  float** d_blocks = nullptr;
+  void** d_blocks = nullptr;   // [4][n_ant]: column blocks, records, dense X, row heights
   auto cleanup = [&](int code) {
     for (int q = 0; q < n_ant; q++) { if (out[q]) airice_table_destroy(out[q]); out[q] = nullptr; }
     if (d_ant) cudaFree(d_ant);
@@ -384,16 +397,33 @@ int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, 
     ant[2 * q] = -depths_m[q];                       // the plan's positive depth (make_plan)
     ant[2 * q + 1] = n_ice(c->medium, -depths_m[q]);
   }
+  // the lookup layout of every table is written by the same pass (no separate pack kernel re-reading the columns)
+  std::vector<void*> ptrs(4 * (size_t)n_ant);
+  for (int q = 0; q < n_ant; q++) {
+    rc = pack_alloc(out[q]);
+    if (rc) return cleanup(rc);
+    ptrs[q] = blocks[q];
+    ptrs[(size_t)n_ant + q] = out[q]->rec;
+    ptrs[2 * (size_t)n_ant + q] = out[q]->x;
+    ptrs[3 * (size_t)n_ant + q] = out[q]->row_h;
+  }
   cudaError_t e = cudaMalloc((void**)&d_ant, sizeof(double) * ant.size());
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_blocks, sizeof(float*) * blocks.size());
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_blocks, sizeof(void*) * ptrs.size());
   if (e == cudaSuccess) e = cudaMemcpy(d_ant, ant.data(), sizeof(double) * ant.size(), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d_blocks, blocks.data(), sizeof(float*) * blocks.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_blocks, ptrs.data(), sizeof(void*) * ptrs.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return cleanup(cuda_fail(e, "antenna arrays"));
   TableMultiArgs ma;
   std::memset(&ma, 0, sizeof(ma));
-  ma.n_ant = n_ant; ma.ant = d_ant; ma.blocks = d_blocks; ma.col_stride = cells;
+  ma.n_ant = n_ant; ma.ant = d_ant; ma.blocks = (float* const*)d_blocks; ma.col_stride = cells;
+  ma.rec = (float4* const*)(d_blocks + n_ant);
+  ma.x = (float* const*)(d_blocks + 2 * (size_t)n_ant);
+  ma.row_h = (float* const*)(d_blocks + 3 * (size_t)n_ant);
   rc = build_rows(c, g, 0, n_h, nullptr, nullptr, nullptr, &ma);
-  for (int q = 0; q < n_ant && rc == 0; q++) rc = pack_table(out[q]);   // pack_table synchronises the stream
+  for (int q = 0; q < n_ant && rc == 0; q++) {
+    e = launch_row_ranges(out[q]->x, cells, (int)n_h, (int)g.n_th, out[q]->row_first, out[q]->row_last, nullptr);
+    if (e != cudaSuccess) rc = cuda_fail(e, "row ranges");
+  }
+  if (rc == 0 && (e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "multi-antenna tables");
   if (rc) return cleanup(rc);
   cudaFree(d_ant); cudaFree(d_blocks);
   return 0;

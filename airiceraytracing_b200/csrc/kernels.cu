@@ -115,6 +115,15 @@ __global__ void __launch_bounds__(kThreads) airice_table_multi_kernel(const AirI
     o[8 * st] = f_ga;
     o[9 * st] = (float)gi;
     o[10 * st] = (float)recv;
+    if (ma.rec) {
+      const float f_x = (float)(al.x + xi);
+      float4* rq = ma.rec[q] + 3 * c;
+      ma.x[q][c] = f_x;
+      rq[0] = make_float4(f_x, (float)(ti * m.c), f_oa, f_th);
+      rq[1] = make_float4(f_xa, f_ts, f_tp, f_ga);
+      rq[2] = make_float4((float)gi, (float)recv, 0.f, 0.f);
+      if (j == 0) ma.row_h[q][row] = f_h;
+    }
   }
 }
 
@@ -416,6 +425,11 @@ cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const Solve
   const int64_t blocks = (a.n + kThreads - 1) / kThreads;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
   airice_solve_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(m, p, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_row_ranges(const float* x, int64_t cells, int n_h, int n_th, int* row_first, int* row_last, cudaStream_t s) {
+  airice_row_range_kernel<<<(n_h + 127) / 128, 128, 0, s>>>(x, cells, n_h, n_th, row_first, row_last);
   return cudaGetLastError();
 }
 

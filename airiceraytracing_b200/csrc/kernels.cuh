@@ -45,7 +45,14 @@ struct TableMultiArgs {
   const double* ant;       // device [n_ant][2]: receiver depth (positive, m) and n_ice(depth) (host libm)
   float* const* blocks;    // device [n_ant]: column-major float block of each antenna's table
   int64_t col_stride;      // elements between two columns of a block (= cells of the whole table)
+  // lookup layout of each antenna's table written in the same pass (what airice_pack_kernel derives from the columns);
+  // device [n_ant] each, all three null = columns only.  Indexed by the GLOBAL cell (base.cell0 + i).
+  float4* const* rec;
+  float* const* x;
+  float* const* row_h;
 };
+// per-row trim ranges of a packed table (the part of launch_pack_table the fused pass cannot do per cell)
+cudaError_t launch_row_ranges(const float* x, int64_t cells, int n_h, int n_th, int* row_first, int* row_last, cudaStream_t s);
 cudaError_t launch_table_multi(const AirIceMedium& m, const AirIcePlan& p, const TableMultiArgs& a, cudaStream_t s);
 
 // kernel 1b: the same forward tracer on arbitrary (theta, h) cells (batched GetRayTracingSolutions, M.cc:1796-2017);
