@@ -95,6 +95,9 @@ struct AirIcePlan {
   double start_n[AIRICE_MAX_LAYERS + 1];
   double relay[AIRICE_MAX_LAYERS + 1];    // n_start[k]/n_stop[k+1]: Snell hand-over of the table path (M.cc:1871)
   double ln_relay[AIRICE_MAX_LAYERS + 1]; // log(relay[k]) (~3e-13): the hand-over of ln(n+R) across the boundary
+  // solver path (one L throughout): n_stop[k] - n_start[k-1] and n_stop[k]^2 - n_start[k-1]^2 across the lower boundary
+  // of layer k (~4e-13; 0 for k <= kb): first-order hand-over of R, ln T, H in airice_ray_air<false>
+  double ho_dn[AIRICE_MAX_LAYERS + 1], ho_dn2[AIRICE_MAX_LAYERS + 1];
   // single-precision companions for the FP32 pre-iteration of the solver (host-computed in double, then rounded):
   // q = n^2 - A^2 and pa = A (n - A) at both ends of a segment keep the small differences (n-1 ~ 3e-4 in air) exact,
   // so that R^2 = q + sA^2 and T = pa + sA (sA + R) stay accurate in float even for grazing rays.
@@ -457,6 +460,11 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
       const double L2 = Lk * Lk;
       const double sA = AIRICE_SQRT(1.0 * 1.0 - L2), inv_sA = AIRICE_RCP(sA);
       constexpr int kUnrollF = AIRICE_UNROLL_FULL;
+      // The lower end of layer k and the upper end of layer k-1 are 1e-5 m and ~4e-13 in n apart (M.cc:715), so
+      // R, ln T and H at the lower end follow from the upper end below it to first order in the host-made
+      // differences dn = n_stop[k] - n_start[k-1] and d(n^2): one sqrt and two logs less per interior boundary.
+      // (Second order is (d(n^2)/R^2)^2/8 < 1e-13 while R > 1e-3, i.e. unless the ray grazes that very boundary.)
+      double pR = 0.0, pY = 0.0, pT = 1.0, pLnT = 0.0, pH = 0.0, pN = 1.0;
 #pragma unroll kUnrollF
       for (int k = p.kb; k <= kt; k++) {
         const bool top = (k == kt);
@@ -465,9 +473,22 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
         const double nt = top ? n_tx : p.start_n[k];
         const double xb = p.stop_x[k], nb = p.stop_n[k];
         const double Db = nb * nb - L2, Dt = nt * nt - L2;
-        const double Rb = AIRICE_SQRT(Db), Rt = AIRICE_SQRT(Dt);
-        const double lnTb = AIRICE_LOG(nb - L2 + sA * Rb), Hb = AIRICE_LOG(nb + Rb);
-        const double lnTt = AIRICE_LOG(nt - L2 + sA * Rt), Ht = AIRICE_LOG(nt + Rt);
+        double Rt, yt;
+        AIRICE_SQRT_RSQRT(Dt, Rt, yt);
+        const double Tt = nt - L2 + sA * Rt;
+        const double lnTt = AIRICE_LOG(Tt), Ht = AIRICE_LOG(nt + Rt);
+        double Rb, lnTb, Hb;
+        if (k > p.kb && pR > 1.0e-3) {
+          const double dR = p.ho_dn2[k] * (0.5 * pY);
+          Rb = pR + dR;
+          lnTb = pLnT + (p.ho_dn[k] + sA * dR) * AIRICE_RCP_APPROX(pT);
+          Hb = pH + (p.ho_dn[k] + dR) * AIRICE_RCP_APPROX(pN + pR);
+        } else {
+          Rb = AIRICE_SQRT(Db);
+          lnTb = AIRICE_LOG(nb - L2 + sA * Rb);
+          Hb = AIRICE_LOG(nb + Rb);
+        }
+        pR = Rt; pY = yt; pT = Tt; pLnT = lnTt; pH = Ht; pN = nt;
         double xs, ts, gs;
         airice_seg_sums<true>(1.0, inv_sA, (Lk * iC) * inv_sA, m.c * Cn, Cn, iC, xt, xb, Dt, Db, Rt, Rb, lnTt, lnTb, Ht, Hb,
                               xs, ts, gs);

@@ -219,6 +219,11 @@ void make_plan(const AirIceMedium& m, double ice_h, double depth_signed, AirIceP
     p.relay[k] = p.start_n[k] / p.stop_n[k + 1];
     p.ln_relay[k] = std::log(p.relay[k]);
   }
+  for (int k = 0; k <= AIRICE_MAX_LAYERS; k++) { p.ho_dn[k] = 0; p.ho_dn2[k] = 0; }
+  for (int k = p.kb + 1; k < m.nlayers; k++) {
+    p.ho_dn[k] = p.stop_n[k] - p.start_n[k - 1];
+    p.ho_dn2[k] = (p.stop_n[k] - p.start_n[k - 1]) * (p.stop_n[k] + p.start_n[k - 1]);
+  }
   // ice leg: surface (x=0) down to the receiver (x=depth), GetIcePropagationPar (M.cc:807-869)
   p.neg_c[AIRICE_ICE_SLOT] = -m.C_ice;
   p.inv_neg_c[AIRICE_ICE_SLOT] = 1.0 / p.neg_c[AIRICE_ICE_SLOT];

@@ -13,6 +13,15 @@ namespace airice {
 
 namespace {
 constexpr int kThreads = 128;
+// CTA sizes of pass 1 and pass 2 (instruction fetch is a top stall of both; see the note at airice_solve_kernel)
+#ifndef AIRICE_INICE_DR_THREADS
+#define AIRICE_INICE_DR_THREADS 512
+#endif
+#ifndef AIRICE_INICE_LADDER_THREADS
+#define AIRICE_INICE_LADDER_THREADS 128
+#endif
+constexpr int kDrThreads = AIRICE_INICE_DR_THREADS;
+constexpr int kLadderThreads = AIRICE_INICE_LADDER_THREADS;
 
 __device__ __forceinline__ AirIceInIce inice_model(const InIceArgs& a) {
   AirIceInIce m;
@@ -21,8 +30,8 @@ __device__ __forceinline__ AirIceInIce inice_model(const InIceArgs& a) {
 }
 
 // pass 1: direct + reflected ray for every pair; all 29 columns written (refracted ones as absent)
-__global__ void __launch_bounds__(kThreads) airice_inice_dr_kernel(const InIceArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+__global__ void __launch_bounds__(kDrThreads) airice_inice_dr_kernel(const InIceArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * kDrThreads + threadIdx.x;
   if (i >= a.n) return;
   const AirIceInIce m = inice_model(a);
   double o[AIRICE_INICE_NCOLS];
@@ -67,8 +76,8 @@ struct InIceWarpPool {
   unsigned char owner[kCap];
 };
 
-__global__ void __launch_bounds__(kThreads) airice_inice_ladder_kernel(const InIceArgs a) {
-  __shared__ InIceWarpPool pools[kThreads / 32];
+__global__ void __launch_bounds__(kLadderThreads) airice_inice_ladder_kernel(const InIceArgs a) {
+  __shared__ InIceWarpPool pools[kLadderThreads / 32];
   InIceWarpPool& pool = pools[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
@@ -222,7 +231,7 @@ int ladder_grid() {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, airice_inice_ladder_kernel, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, airice_inice_ladder_kernel, kLadderThreads, 0);
     blocks = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
   }
   return blocks;
@@ -237,14 +246,15 @@ cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s) {
   if (!a.ra_list || !a.ra_count || !a.ra_lad || !a.mask || !a.out[20]) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(a.ra_count, 0, 3 * sizeof(int32_t), s);
   if (e != cudaSuccess) return e;
-  airice_inice_dr_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(a);
+  const int64_t dr_blocks = (a.n + kDrThreads - 1) / kDrThreads;
+  airice_inice_dr_kernel<<<dim3((unsigned)dr_blocks), kDrThreads, 0, s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // the list length stays on the device: pass 2 is a persistent grid (one wave), pass 3 is launched over the worst-case
   // length and its blocks beyond the list exit at once
   int64_t lb = ladder_grid();
   if (lb > blocks) lb = blocks;
-  airice_inice_ladder_kernel<<<dim3((unsigned)lb), kThreads, 0, s>>>(a);
+  airice_inice_ladder_kernel<<<dim3((unsigned)lb), kLadderThreads, 0, s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   airice_inice_ra_finish_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(a);

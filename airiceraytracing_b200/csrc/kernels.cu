@@ -146,11 +146,20 @@ __global__ void __launch_bounds__(kThreads) airice_forward_kernel(const AirIceMe
     if (a.c64[k]) a.c64[k][i] = v[k];
 }
 
-#ifndef AIRICE_SOLVE_MINBLOCKS
-#define AIRICE_SOLVE_MINBLOCKS 8
+// The solve kernel streams through ~3000 instructions once per pair with few loop trips, so instruction fetch is its
+// top stall (ncu: no_instruction 3.4 stall cycles per issue with 8 CTAs of 128 threads).  Warps of one CTA start
+// together and stay roughly in step, so they share the lines the instruction caches hold: 2 CTAs of 512 threads
+// (64 registers) measured 1.56 ms per 1e7 pairs against 1.80 (8 x 128), 1.73 (4 x 256), 1.59 (2 x 384, 85 registers)
+// and 1.72 (1 x 1024: no overlap of a finishing CTA with the next one); a barrier between the phases did not help.
+#ifndef AIRICE_SOLVE_THREADS
+#define AIRICE_SOLVE_THREADS 512
 #endif
-__global__ void __launch_bounds__(kThreads, AIRICE_SOLVE_MINBLOCKS) airice_solve_kernel(const AirIceMedium m, const AirIcePlan p, const SolveArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+#ifndef AIRICE_SOLVE_MINBLOCKS
+#define AIRICE_SOLVE_MINBLOCKS (1024 / AIRICE_SOLVE_THREADS)
+#endif
+constexpr int kSolveThreads = AIRICE_SOLVE_THREADS;
+__global__ void __launch_bounds__(kSolveThreads, AIRICE_SOLVE_MINBLOCKS) airice_solve_kernel(const AirIceMedium m, const AirIcePlan p, const SolveArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * kSolveThreads + threadIdx.x;
   if (i >= a.n) return;
   double h = a.h[i], d = a.d[i];
   double ice = a.ice, depth = a.depth;
@@ -422,9 +431,9 @@ cudaError_t launch_forward(const AirIceMedium& m, const AirIcePlan& p, const For
 
 cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const SolveArgs& a, cudaStream_t s) {
   if (a.n <= 0) return cudaSuccess;
-  const int64_t blocks = (a.n + kThreads - 1) / kThreads;
+  const int64_t blocks = (a.n + kSolveThreads - 1) / kSolveThreads;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
-  airice_solve_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(m, p, a);
+  airice_solve_kernel<<<dim3((unsigned)blocks), kSolveThreads, 0, s>>>(m, p, a);
   return cudaGetLastError();
 }
 

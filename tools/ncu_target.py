@@ -23,6 +23,10 @@ if which in ("all", "table"):
         S.table_build(-200., 3000., h_step=20., th_start=92., th_step=0.5)
     for _ in range(1 if ONCE else 2):
         S.table_build(-200., 3000.)
+if which in ("all", "multi"):
+    Ts = S.table_create_multi([-200.0 * (k + 1) / 8 for k in range(8)], 3000.)
+    for T in Ts:
+        T.close()
 if which in ("all", "lookup"):
     T = S.table_create(-200., 3000.)
     o2 = torch.empty((9, n), dtype=torch.float64, device="cuda")
