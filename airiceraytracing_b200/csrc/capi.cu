@@ -336,6 +336,8 @@ int airice_table_build_device(airice_ctx* c, double depth_m, double ice_m, doubl
 int airice_table_create(airice_ctx* c, double depth_m, double ice_m, double h_top, double h_step, double th_start,
                         double th_step, double th_stop, airice_table** out) {
   if (!c || !out) return fail(-1, "null argument");
+  // a receiver in the ice: the fused pass of airice_table_create_multi (columns + lookup layout in one kernel, same bits)
+  if (depth_m < 0) return airice_table_create_multi(c, 1, &depth_m, ice_m, h_top, h_step, th_start, th_step, th_stop, out);
   CK(cudaSetDevice(c->device));
   TableGrid g; std::string err;
   int rc = make_grid(depth_m, ice_m, h_top, h_step, th_start, th_step, th_stop, &g, &err);

@@ -57,3 +57,24 @@ def test_replayed_angle_is_the_bisection_midpoint_not_the_true_root(hostsim, ora
     launch_deg = out[0, 4] * 180 / PI_M
     assert abs(launch_deg - 169.99999995110377) < 1e-9
     assert abs(st[0, 2] - 170.0) < 1e-9  # theta* of the Newton phase is the true root
+
+
+def test_closed_form_replay_in_the_special_zones(hostsim, oracle):
+    """The bisection replay is a closed form (cell index from theta*, stop level from the bracket width): check it where
+    the bracket is unusual -- straight-line angles within 16 deg of horizontal (clamped lower end, 0.05-deg scan, brackets
+    down to a fraction of a degree), distances no ray reaches (GSL walks to the upper end), near-vertical rays."""
+    rng = np.random.default_rng(20261018)
+    n = 12000
+    h = rng.uniform(3001, 100000, n)
+    ang = np.concatenate([rng.uniform(90.02, 106.2, n // 2), rng.uniform(90.0005, 90.2, n // 4), rng.uniform(179.0, 179.9999, n // 4)])
+    d = (h - 3000 + 200) * np.tan((180 - ang) * PI_M / 180)
+    d[::7] *= rng.uniform(1.5, 30.0, d[::7].size)          # beyond the reach of any ray from that height
+    ok_r, ref = oracle.solve_cm_batch(h * 100, d * 100, -20000.0, 300000.0)
+    ok, out, st = hostsim.solve_cm(h * 100, d * 100, -20000.0, 300000.0)
+    assert np.array_equal(ok, ok_r)
+    # launch angles are compared for EVERY pair here, solved or not: an unsolved pair still returns the end of GSL's walk
+    fin = np.isfinite(ref[:, 4]) & np.isfinite(out[:, 4])
+    assert np.array_equal(np.isfinite(ref[:, 4]), np.isfinite(out[:, 4]))
+    dang = np.abs(out[fin, 4] - ref[fin, 4]) * 180 / PI_M
+    assert (dang > 1e-7).mean() <= 1e-3 and dang.max() <= 2.5e-7
+    assert_solve_close(ok, out, ok_r, ref, PI_M, "special zones", max_tie_frac=1e-3)
