@@ -62,7 +62,8 @@ int airice_forward_device(airice_ctx *ctx, int64_t n, const double *d_theta, con
 int airice_forward_host(airice_ctx *ctx, int64_t n, const double *theta, const double *h, double depth_m, double ice_m,
                         double *out);
 
-/* Library-owned float table for lookups = one entry of AllTableAllAntData (MultiRayAirIceRefraction.cc:9,2136). */
+/* Library-owned float table for lookups = one entry of AllTableAllAntData (MultiRayAirIceRefraction.cc:9,2136).
+ * (A receiver in the ice is built by the fused pass of airice_table_create_multi with one antenna.) */
 int airice_table_create(airice_ctx *ctx, double depth_m, double ice_m, double h_top, double h_step, double th_start,
                         double th_step, double th_stop, airice_table **out);
 /* The tables of n_ant in-ice antennas (depths_m[q] < 0) in ONE pass: the air walk of a cell does not depend on the
