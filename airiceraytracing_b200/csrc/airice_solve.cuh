@@ -20,7 +20,7 @@
 #define AIRICE_NEWTON_MAXIT 40
 // error bound below which the Newton step of the single FP64 evaluation is taken as the root; the replay evaluates f
 // for real whenever a probe lies within AIRICE_SOLVE_GUARD_DEG of it, so this only has to stay well below the guard
-#define AIRICE_SOLVE_ACCEPT_DEG 2.0e-11
+#define AIRICE_SOLVE_ACCEPT_DEG 5.0e-11
 
 struct AirIceSolveStat {
   int n_newton;  // distance evaluations spent in the Newton phase
@@ -65,7 +65,7 @@ AIRICE_HD void airice_bracket(const AirIceMedium& m, const AirIcePlan& p, int kt
     const double* tab = m.clamp_tab;
     int jh = 0;
     {
-      const double e = ceil((lim - 90.001) / 0.05);
+      const double e = ceil((lim - 90.001) * 20.0);   // an estimate: the two loops below settle it
       jh = e > 0.0 ? (e < (double)(AIRICE_CLAMP_N - 1) ? (int)e : AIRICE_CLAMP_N - 1) : 0;
 #pragma unroll 1
       while (jh > 0 && AIRICE_LDG(tab + 2 * (jh - 1)) > lim) jh--;
@@ -166,7 +166,7 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
     ts = NAN;
     if (have_kappa) {
       // (b1) ONE FP64 evaluation with the analytic slope.  The Newton step from t lands within
-      // 0.5 |X''/X'| dt^2 of the root; with the bound on the curvature from (a) that is below 2e-11 deg for 99.9 % of
+      // 0.5 |X''/X'| dt^2 of the root; with the bound on the curvature from (a) that is below 5e-11 deg for 99.9 % of
       // pairs (the single-precision landing point is ~1e-6 deg off), well inside the replay's guard band, and the
       // step is taken as the root.  Otherwise the chord iteration below continues from the step with this slope.
       double sq1, w;

@@ -21,6 +21,13 @@ S.lookup_host(T, h * 100, d * 100)
 T.close()
 T = S.table_create(-150., 3000., h_step=500., th_step=0.5)      # reuses the spare buffers of the table above
 T.close()
+Ts = S.table_create_multi([-200., -1., -37.5], 3000., h_step=500., th_step=0.5)   # shared-air pass, 3 antennas
+S.lookup(Ts[1], th, td)
+for T in Ts:
+    T.close()
+T = S.table_create(50., 3000., h_step=500., th_step=0.5)        # receiver in air: separate table + pack kernels
+S.lookup(T, th, td)
+T.close()
 ni = 3001
 z0, z1, x1 = rng.uniform(-1501, -1, ni), rng.uniform(-201, -1, ni), rng.uniform(1, 3001, ni)
 S.inice_solve(torch.from_numpy(z0), torch.from_numpy(x1), torch.from_numpy(z1))
