@@ -106,10 +106,16 @@ AIRICE_HD void airice_bracket(const AirIceMedium& m, const AirIcePlan& p, int kt
 
 // Returns the launch angle the reference's bisection returns.  theta_star (the converged root, or
 // -inf/+inf when f has one sign on the bracket) is exposed for diagnostics.
-AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx,
-                                    double d, double thR, double ta_straight, double& theta_star,
-                                    AirIceSolveStat& st) {
+// DEFER = true is the first pass of the two-pass launch (kernels.cu): a pair that needs one of the rare slow paths
+// (failed single-precision pre-iteration, rejected Newton step, a real evaluation of f at a tie, the literal bisection
+// loop) is not solved here -- `hard` is set, the result is NaN -- and the slow paths are not even compiled in; the
+// second pass runs those pairs (0.6 % of a random batch) through DEFER = false in dense warps.
+template <bool DEFER>
+AIRICE_HD double airice_solve_theta_t(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx,
+                                      double d, double thR, double ta_straight, double& theta_star,
+                                      AirIceSolveStat& st, bool& hard) {
   st.n_newton = 0; st.n_replay = 0;
+  hard = false;
   theta_star = NAN;
   bool finite_lo;
   double lo, hi, t_cap;
@@ -198,6 +204,7 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
         }
       }
     }
+    if (DEFER && ts != ts) { hard = true; return NAN; }
 #pragma unroll 1
     for (int it = 0; it < AIRICE_NEWTON_MAXIT && ts != ts; it++) {
       double sq1, w;
@@ -275,6 +282,7 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
       if (inside && !(fabs(xk - mr) * wk > guard)) {
         // theta* within the guard of grid point mr of the final level: an end of the final cell, i.e. a midpoint the
         // reference evaluated f at
+        if (DEFER) { hard = true; return NAN; }
         if (!(mr > 0.0) || !(mr < nk)) {
           careful = true;
         } else {
@@ -292,6 +300,7 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
   // Careful form (about 0.2 % of solves): a probe sits within `guard` of theta*, so f is evaluated there for real
   // (MinimizeforLaunchAngle, M.cc:873-917), including GSL's exact-zero exits.  One loop serves the two endpoint
   // signs (steps -2, -1: gsl_root_fsolver_set) and the halvings (steps >= 0).
+  if (DEFER) { hard = true; return NAN; }
   int s_lo = 1, s_hi = 1;
   double root = 0.5 * (lo + hi);
 #pragma unroll 1
@@ -321,6 +330,13 @@ AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, 
     if (fabs(hi - lo) < 0.000000001 * mn) break;
   }
   return root;
+}
+
+AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx,
+                                    double d, double thR, double ta_straight, double& theta_star,
+                                    AirIceSolveStat& st) {
+  bool hard;
+  return airice_solve_theta_t<false>(m, p, kt, h, n_tx, d, thR, ta_straight, theta_star, st, hard);
 }
 
 // Straight-line angle of GetHorizontalDistanceToIntersectionPoint (M.cc:952-958), metres in.  ta = its tangent.

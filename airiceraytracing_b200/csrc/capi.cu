@@ -55,6 +55,10 @@ struct airice_ctx {
   // tables of 384 + 455 MB: cudaMalloc / cudaFree of that size cost more than building the table, and jitter wildly)
   struct SpareBuf { void* p; size_t bytes; };
   std::vector<SpareBuf> spare;
+  // scratch of the solve kernel's two-pass launch, one per stream that has run a solve (launches on one stream are
+  // ordered, so they can share it): a counter in the first 256 bytes, then room for `cap` deferred pair indices
+  struct DeferScratch { int32_t* buf = nullptr; int64_t cap = 0; };
+  std::map<cudaStream_t, DeferScratch> defer;
   size_t spare_cap = 0;              // bytes of freed table buffers the context may hold (set on first release)
   size_t path_plan_cap = 0;
   int64_t inice_cols_n = 0;
@@ -234,6 +238,25 @@ int build_rows(airice_ctx* ctx, const TableGrid& g, int64_t r0, int64_t r1, doub
   return 0;
 }
 
+// Points a SolveArgs at the stream's deferred-list scratch (grown as needed); without it (allocation failure, >= 2^31
+// pairs) launch_solve falls back to the single-pass kernel.
+void attach_defer_scratch(airice_ctx* c, cudaStream_t s, SolveArgs* a) {
+  if (a->n >= 2147483647LL || a->n < 6000000) return;   // launch_solve runs smaller batches in one pass (kTwoPassMinPairs)
+  airice_ctx::DeferScratch& d = c->defer[s];
+  if (d.cap < a->n) {
+    if (d.buf) { cudaStreamSynchronize(s); cudaFree(d.buf); d.buf = nullptr; d.cap = 0; }
+    const int64_t cap = a->n + a->n / 8 + 1024;
+    if (cudaMalloc((void**)&d.buf, sizeof(int32_t) * (size_t)(64 + cap)) != cudaSuccess) {
+      cudaGetLastError();
+      d.buf = nullptr;
+      return;
+    }
+    d.cap = cap;
+  }
+  a->defer_count = d.buf;
+  a->defer_list = d.buf + 64;
+}
+
 }  // namespace
 
 extern "C" {
@@ -289,6 +312,7 @@ void airice_destroy(airice_ctx* c) {
   if (c->path_plans) cudaFree(c->path_plans);
   if (c->clamp_tab) cudaFree(c->clamp_tab);
   for (auto& b : c->spare) cudaFree(b.p);
+  for (auto& d : c->defer) if (d.second.buf) cudaFree(d.second.buf);
   delete c;
 }
 
@@ -545,6 +569,7 @@ int airice_solve_device(airice_ctx* c, int64_t n, const double* d_h, const doubl
   const int nc = units == AIRICE_UNITS_CM_RAD ? AIRICE_SOLVE_COLS_CM_RAD : AIRICE_SOLVE_COLS;
   for (int k = 0; k < nc; k++) a.out[k] = d_out[k];
   a.ok = d_ok; a.nevals = d_nevals;
+  attach_defer_scratch(c, (cudaStream_t)stream, &a);
   cudaError_t e = launch_solve(c->medium, p, a, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_solve");
   return 0;
@@ -603,6 +628,7 @@ int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* d
       CK(cudaMemcpyAsync(ds, straight + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
       a.straight = ds;
     }
+    attach_defer_scratch(c, s, &a);
     cudaError_t e = launch_solve(c->medium, p, a, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_solve");
     for (int k = 0; k < nc; k++)

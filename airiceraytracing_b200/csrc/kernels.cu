@@ -158,9 +158,11 @@ __global__ void __launch_bounds__(kThreads) airice_forward_kernel(const AirIceMe
 #define AIRICE_SOLVE_MINBLOCKS (1024 / AIRICE_SOLVE_THREADS)
 #endif
 constexpr int kSolveThreads = AIRICE_SOLVE_THREADS;
-__global__ void __launch_bounds__(kSolveThreads, AIRICE_SOLVE_MINBLOCKS) airice_solve_kernel(const AirIceMedium m, const AirIcePlan p, const SolveArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * kSolveThreads + threadIdx.x;
-  if (i >= a.n) return;
+constexpr int64_t kTwoPassMinPairs = 6000000;
+// One pair, start to finish.  DEFER (first pass of the two-pass launch): a pair that needs a rare slow path is appended
+// to a.defer_list (0.6 % of a random batch) and what is written for it here is overwritten by the second pass.
+template <bool DEFER>
+__device__ __forceinline__ void solve_one(const AirIceMedium& m, const AirIcePlan& p, const SolveArgs& a, int64_t i) {
   double h = a.h[i], d = a.d[i];
   double ice = a.ice, depth = a.depth;
   if (a.units == AIRICE_UNITS_CM_RAD) {  // M.cc:947-950
@@ -178,7 +180,11 @@ __global__ void __launch_bounds__(kSolveThreads, AIRICE_SOLVE_MINBLOCKS) airice_
   }
   AirIceSolveStat st;
   double th_star;
-  const double theta = airice_solve_theta(m, p, kt, h, ntx, d, thR, ta, th_star, st);
+  bool hard;
+  const double theta = airice_solve_theta_t<DEFER>(m, p, kt, h, ntx, d, thR, ta, th_star, st, hard);
+  // a deferred pair is listed and then carries on with its NaN angle (its outputs are overwritten by the second pass,
+  // which the stream orders after this one): leaving the kernel here instead measured 5 % slower for the whole launch
+  if (DEFER && hard) a.defer_list[atomicAdd(a.defer_count, 1)] = (int32_t)i;
   const double L = airice_L_of_theta(m, ntx, theta);
   AirIceRay r;
   const bool full_rec = (a.units != AIRICE_UNITS_CM_RAD);
@@ -210,6 +216,25 @@ __global__ void __launch_bounds__(kSolveThreads, AIRICE_SOLVE_MINBLOCKS) airice_
     if (a.out[10]) a.out[10][i] = r.p_ice;
     if (a.out[11]) a.out[11][i] = r.inc_ice_deg;
     if (a.out[12]) a.out[12][i] = r.refr_deg;
+  }
+}
+
+// PASS 0: every pair start to finish in one launch (no scratch at hand).
+// PASS 1 + PASS 2: the rare slow paths cost far more than their share of the work when they run inside the main kernel
+// -- one lane of a warp walks through the chord iteration or a real evaluation of f while 31 wait, and their code sits
+// between the pieces every warp runs (measured: the kernel without them is 10 % faster) -- so pass 1 only lists those
+// pairs and pass 2, a fixed grid striding over the list whose length stays on the device, solves them in dense warps
+// (58 us, latency bound).  1e7 pairs: 1.55 ms in one pass, 1.49 ms in two.
+template <int PASS>
+__global__ void __launch_bounds__(kSolveThreads, AIRICE_SOLVE_MINBLOCKS) airice_solve_kernel(const AirIceMedium m, const AirIcePlan p, const SolveArgs a) {
+  if (PASS == 2) {
+    const int count = *a.defer_count;
+    for (int j = blockIdx.x * kSolveThreads + threadIdx.x; j < count; j += gridDim.x * kSolveThreads)
+      solve_one<false>(m, p, a, (int64_t)a.defer_list[j]);
+  } else {
+    const int64_t i = (int64_t)blockIdx.x * kSolveThreads + threadIdx.x;
+    if (i >= a.n) return;
+    solve_one<PASS == 1>(m, p, a, i);
   }
 }
 
@@ -433,7 +458,19 @@ cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const Solve
   if (a.n <= 0) return cudaSuccess;
   const int64_t blocks = (a.n + kSolveThreads - 1) / kSolveThreads;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
-  airice_solve_kernel<<<dim3((unsigned)blocks), kSolveThreads, 0, s>>>(m, p, a);
+  // the second pass is latency bound (~60 us whatever the list length) and the first saves ~8 % of the single-pass
+  // time: two passes pay off from ~5e6 pairs per launch
+  if (!a.defer_count || !a.defer_list || a.n >= 2147483647LL || a.n < kTwoPassMinPairs) {
+    airice_solve_kernel<0><<<dim3((unsigned)blocks), kSolveThreads, 0, s>>>(m, p, a);
+    return cudaGetLastError();
+  }
+  cudaError_t e = cudaMemsetAsync(a.defer_count, 0, sizeof(int32_t), s);
+  if (e != cudaSuccess) return e;
+  airice_solve_kernel<1><<<dim3((unsigned)blocks), kSolveThreads, 0, s>>>(m, p, a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int64_t second = blocks < 2 * 148 ? blocks : 2 * 148;     // one wave of 2 CTAs per SM strides over the list
+  airice_solve_kernel<2><<<dim3((unsigned)second), kSolveThreads, 0, s>>>(m, p, a);
   return cudaGetLastError();
 }
 

@@ -84,6 +84,10 @@ struct SolveArgs {
   double* out[AIRICE_SOLVE_NCOLS];
   uint8_t* ok;        // solution flag (M.cc:974-983)
   int32_t* nevals;    // optional: distance evaluations spent (Newton + replay), diagnostics
+  // scratch of the two-pass launch (both or neither): a device counter and room for n pair indices.  With them,
+  // launch_solve lists the pairs that need a rare slow path in a first pass and solves those in a second, dense one.
+  int32_t* defer_count;
+  int32_t* defer_list;
 };
 cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const SolveArgs& a, cudaStream_t s);
 
