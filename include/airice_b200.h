@@ -92,7 +92,9 @@ int airice_table_copy_row_ranges(const airice_table *t, int32_t *host_first, int
  *   geo ice, incident on ice, refracted below surface).  out: array of column pointers, NULL entries are skipped.
  * ok: the reference's bool (|X-d| test, MultiRayAirIceRefraction.cc:974-983).  nevals: optional diagnostics.
  * d_straight: optional per-pair straight-line angle (deg for M_DEG, rad for CM_RAD) = the StraightAngle argument of
- *   Air2IceRayTracing; NULL = computed from the geometry as GetHorizontalDistanceToIntersectionPoint does. */
+ *   Air2IceRayTracing; NULL = computed from the geometry as GetHorizontalDistanceToIntersectionPoint does.
+ * Launches of 6e6 pairs and more run as two kernels on `stream` (the second solves the ~0.6 % of pairs that need a
+ * rare slow path, listed by the first); their scratch -- 4 bytes per pair -- belongs to the context, one per stream. */
 int airice_solve_device(airice_ctx *ctx, int64_t n, const double *d_h, const double *d_dist, const double *d_straight,
                         double depth, double ice, int units, double *const *d_out, uint8_t *d_ok, int32_t *d_nevals,
                         void *stream);
