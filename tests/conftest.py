@@ -65,6 +65,7 @@ class HostSim:
         L = self.lib
         L.sim_forward_batch.argtypes = [C.c_long, dp, dp, C.c_double, C.c_double, C.c_int, dp]
         L.sim_solve_cm_batch.argtypes = [C.c_long, dp, dp, C.c_double, C.c_double, dp, C.POINTER(C.c_ubyte), dp]
+        L.sim_solve_defer_batch.argtypes = [C.c_long, dp, dp, C.c_double, C.c_double, dp, dp, C.POINTER(C.c_ubyte)]
         L.sim_x_total.restype = C.c_double
         L.sim_x_total.argtypes = [C.c_double] * 4 + [dp]
         assert L.sim_load(ATMOSPHERE.encode(), 0) == 0
@@ -94,6 +95,17 @@ class HostSim:
                                     out.ctypes.data_as(self.dp), ok.ctypes.data_as(C.POINTER(C.c_ubyte)),
                                     st.ctypes.data_as(self.dp))
         return ok.astype(bool), out, st
+
+    def solve_defer(self, h_cm, d_cm, depth_cm, ice_cm):
+        """(theta of the deferring first pass, theta of the complete solve, hard flags)"""
+        h_cm = np.ascontiguousarray(h_cm, dtype=np.float64)
+        d_cm = np.ascontiguousarray(d_cm, dtype=np.float64)
+        n = h_cm.size
+        td, tf, hard = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.uint8)
+        self.lib.sim_solve_defer_batch(n, h_cm.ctypes.data_as(self.dp), d_cm.ctypes.data_as(self.dp), depth_cm, ice_cm,
+                                       td.ctypes.data_as(self.dp), tf.ctypes.data_as(self.dp),
+                                       hard.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return td, tf, hard.astype(bool)
 
 
 @pytest.fixture(scope="session")

@@ -70,6 +70,23 @@ void sim_solve_cm_batch(long n, const double* h_cm, const double* d_cm, double d
                         unsigned char* ok, double* stats) {
   for (long i = 0; i < n; i++) ok[i] = (unsigned char)sim_solve_cm(h_cm[i], d_cm[i], depth_cm, ice_cm, out + 9 * i, stats ? stats + 3 * i : nullptr);
 }
+// first pass of the two-pass launch (DEFER = true) next to the complete solve: theta of both and the `hard` flag
+void sim_solve_defer_batch(long n, const double* h_cm, const double* d_cm, double depth_cm, double ice_cm, double* theta_defer,
+                           double* theta_full, unsigned char* hard) {
+  const double ice = ice_cm / 100, depth = depth_cm / 100;
+  AirIcePlan p; make_plan(g_m, ice, depth, &p);
+  for (long i = 0; i < n; i++) {
+    const double h = h_cm[i] / 100, d = d_cm[i] / 100;
+    const int kt = top_layer(h);
+    const double ntx = 1.0 + g_m.B[kt < 0 ? 0 : kt] * exp(-g_m.C[kt < 0 ? 0 : kt] * h);
+    double ta;
+    const double thR = airice_straight_angle(g_m, h, d, ice, depth, ta);
+    AirIceSolveStat st; double ths; bool hd;
+    theta_defer[i] = airice_solve_theta_t<true>(g_m, p, kt, h, ntx, d, thR, ta, ths, st, hd);
+    hard[i] = hd ? 1 : 0;
+    theta_full[i] = airice_solve_theta(g_m, p, kt, h, ntx, d, thR, ta, ths, st);
+  }
+}
 void sim_forward_batch(long n, const double* th, const double* h, double ice, double depth, int inice, double* out) {
   for (long i = 0; i < n; i++) sim_forward(th[i], h[i], ice, depth, inice, out + 18 * i);
 }

@@ -78,3 +78,20 @@ def test_closed_form_replay_in_the_special_zones(hostsim, oracle):
     dang = np.abs(out[fin, 4] - ref[fin, 4]) * 180 / PI_M
     assert (dang > 1e-7).mean() <= 1e-3 and dang.max() <= 2.5e-7
     assert_solve_close(ok, out, ok_r, ref, PI_M, "special zones", max_tie_frac=1e-3)
+
+
+def test_first_pass_of_the_two_pass_launch(hostsim):
+    """airice_solve_theta_t<DEFER>: the first pass either returns the very angle of the complete solve or flags the pair
+    for the second pass -- and flags few (the slow paths are rare, that is the premise of the two-pass launch)."""
+    rng = np.random.default_rng(7)
+    n = 60000
+    h = rng.uniform(3001, 100000, n)
+    ang = np.concatenate([rng.uniform(90.2, 179.8, n // 2), rng.uniform(90.001, 96.0, n // 4), rng.uniform(170.0, 179.999, n // 4)])
+    d = (h - 3000 + 200) * np.tan((180 - ang) * PI_M / 180)
+    d[::11] *= rng.uniform(1.2, 20.0, d[::11].size)        # unreachable distances: the walk to the upper end
+    td, tf, hard = hostsim.solve_defer(h * 100, d * 100, -20000.0, 300000.0)
+    easy = ~hard
+    assert np.array_equal(td[easy].view(np.int64), tf[easy].view(np.int64))     # NaN results included, bit for bit
+    assert np.isnan(td[hard]).all()
+    assert hard[: n // 2].mean() < 0.015 and hard.mean() < 0.05
+    assert hard.any()                                                          # the test does exercise the flag
