@@ -27,7 +27,7 @@ EXPORTS = [
     "airice_forward_host", "airice_table_create", "airice_table_create_multi", "airice_table_wrap", "airice_table_destroy", "airice_table_info",
     "airice_table_copy_column", "airice_table_column_ptr", "airice_table_copy_row_ranges", "airice_solve_device",
     "airice_solve_multi_device", "airice_solve_host", "airice_lookup_device", "airice_lookup_host", "airice_inice_solve_device",
-    "airice_inice_solve_host", "airice_inice_two_rays_device", "airice_inice_two_rays_host", "airice_ray_path_device", "airice_ray_path_host", "airice_fp64_peak_tflops", "airice_sync",
+    "airice_inice_solve_host", "airice_inice_two_rays_device", "airice_inice_two_rays_host", "airice_ray_path_device", "airice_ray_path_host", "airice_fp64_peak_tflops", "airice_sync", "airice_trim",
 ]
 
 _lib = None
@@ -76,6 +76,7 @@ def load():
     lib.airice_ray_path_host.argtypes = [vp, i64, vp, vp, d, d, i64, vp, vp, vp]
     lib.airice_fp64_peak_tflops.argtypes = [vp, C.POINTER(d)]
     lib.airice_sync.argtypes = [vp]
+    lib.airice_trim.argtypes = [vp]
     _lib = lib
     return lib
 

@@ -931,4 +931,15 @@ int airice_sync(airice_ctx* c) {
   return 0;
 }
 
+int airice_trim(airice_ctx* c) {
+  if (!c) return fail(-1, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  for (auto& b : c->spare) cudaFree(b.p);
+  c->spare.clear();
+  for (auto& d : c->defer) if (d.second.buf) cudaFree(d.second.buf);
+  c->defer.clear();
+  return 0;
+}
+
 }  // extern "C"

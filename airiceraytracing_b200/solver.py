@@ -105,6 +105,10 @@ class AirIceSolver:
     def sync(self):
         check(self.lib.airice_sync(self.handle))
 
+    def trim(self):
+        """Return the context's cached device memory (buffers of closed tables, solve scratch) to the driver."""
+        check(self.lib.airice_trim(self.handle))
+
     # ------------------------------------------------------------------ kernel 1
     def table_dims(self, depth_m, ice_m, h_top=100000.0, h_step=10.0, th_start=90.1, th_step=0.1, th_stop=180.0):
         nh, nth = C.c_int64(), C.c_int64()

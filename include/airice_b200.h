@@ -160,6 +160,10 @@ int airice_ray_path_host(airice_ctx *ctx, int64_t n, const double *theta, const 
 /* ---- measurement helpers */
 int airice_fp64_peak_tflops(airice_ctx *ctx, double *tflops); /* dependent-free DFMA probe, roofline denominator */
 int airice_sync(airice_ctx *ctx);
+/* Gives the device memory the context keeps for reuse back to the driver: the buffers of destroyed tables (up to a
+ * third of the GPU's memory -- 64 antennas' reference-grid tables are 54 GB) and the solve kernel's per-stream
+ * scratch.  Synchronises the device.  The reference has no counterpart (its tables live until the process ends). */
+int airice_trim(airice_ctx *ctx);
 
 #ifdef __cplusplus
 }
