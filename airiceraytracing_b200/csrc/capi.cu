@@ -41,6 +41,7 @@ struct airice_ctx {
   // when those are pinned the H2D of chunk k+1, the kernel of chunk k and the D2H of chunk k-1 overlap)
   static const int kSlots = 2;
   cudaStream_t streams[kSlots] = {nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[kSlots] = {nullptr, nullptr};   // airice_solve_multi_device's fork/join
   void* dev[kSlots] = {nullptr, nullptr};
   size_t slot_bytes = 0;
   // per-row transmitter data (height, n(h), top layer) of the last table grid built: uploaded once, reused by
@@ -313,6 +314,8 @@ void airice_destroy(airice_ctx* c) {
   if (c->clamp_tab) cudaFree(c->clamp_tab);
   for (auto& b : c->spare) cudaFree(b.p);
   for (auto& d : c->defer) if (d.second.buf) cudaFree(d.second.buf);
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+  for (int s = 0; s < airice_ctx::kSlots; s++) if (c->join_ev[s]) cudaEventDestroy(c->join_ev[s]);
   delete c;
 }
 
@@ -585,14 +588,35 @@ int airice_solve_multi_device(airice_ctx* c, int64_t n_points, int n_ant, const 
   if (n_ant == 0 || n_points == 0) return 0;
   if (!d_h || !d_dist || !depths_host || !d_out) return fail(-1, "null argument");
   const int nc = units == AIRICE_UNITS_CM_RAD ? AIRICE_SOLVE_COLS_CM_RAD : AIRICE_SOLVE_COLS;
-  for (int a = 0; a < n_ant; a++) {
+  // The per-antenna launches alternate between the context's two streams, forked from and joined to the caller's
+  // stream by events: a launch of 1e6 pairs is 6.6 waves of CTAs, and the next antenna's CTAs fill its tail.
+  CK(cudaSetDevice(c->device));
+  const bool fork = n_ant > 1;
+  cudaStream_t user = (cudaStream_t)stream;
+  if (fork) {
+    for (int s = 0; s < airice_ctx::kSlots; s++)
+      if (!c->streams[s]) CK(cudaStreamCreateWithFlags(&c->streams[s], cudaStreamNonBlocking));
+    if (!c->fork_ev) CK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+    for (int s = 0; s < airice_ctx::kSlots; s++)
+      if (!c->join_ev[s]) CK(cudaEventCreateWithFlags(&c->join_ev[s], cudaEventDisableTiming));
+    CK(cudaEventRecord(c->fork_ev, user));
+    for (int s = 0; s < airice_ctx::kSlots; s++) CK(cudaStreamWaitEvent(c->streams[s], c->fork_ev, 0));
+  }
+  int rc = 0;
+  for (int a = 0; a < n_ant && rc == 0; a++) {
     double* cols[AIRICE_SOLVE_NCOLS];
     for (int k = 0; k < nc; k++) cols[k] = d_out[k] ? d_out[k] + (int64_t)a * n_points : nullptr;
-    int rc = airice_solve_device(c, n_points, d_h, d_dist + (int64_t)a * n_points, nullptr, depths_host[a], ice, units, cols,
-                                 d_ok ? d_ok + (int64_t)a * n_points : nullptr, nullptr, stream);
-    if (rc) return rc;
+    rc = airice_solve_device(c, n_points, d_h, d_dist + (int64_t)a * n_points, nullptr, depths_host[a], ice, units, cols,
+                             d_ok ? d_ok + (int64_t)a * n_points : nullptr, nullptr,
+                             fork ? (void*)c->streams[a % airice_ctx::kSlots] : stream);
   }
-  return 0;
+  if (fork) {   // join even after an error: the caller's stream must not run ahead of what was launched
+    for (int s = 0; s < airice_ctx::kSlots; s++) {
+      cudaEventRecord(c->join_ev[s], c->streams[s]);
+      cudaStreamWaitEvent(user, c->join_ev[s], 0);
+    }
+  }
+  return rc;
 }
 
 // Host-buffer path: the batch is cut into chunks that alternate between two streams, each with its own device

@@ -100,7 +100,8 @@ int airice_solve_device(airice_ctx *ctx, int64_t n, const double *d_h, const dou
                         void *stream);
 /* Multi-antenna form (CoREAS: n_points shower points x n_ant receivers, the shape of RunMultiRayCode_loop.C with
  * several AntennaDepths): d_dist and every output column are antenna-major [n_ant][n_points]; depths_host[n_ant] is a
- * HOST array of signed receiver depths.  One kernel launch per receiver on the given stream. */
+ * HOST array of signed receiver depths.  One kernel launch per receiver; the launches alternate between two streams
+ * of the context that are forked from `stream` and joined back to it by events before the call returns. */
 int airice_solve_multi_device(airice_ctx *ctx, int64_t n_points, int n_ant, const double *d_h, const double *d_dist,
                               const double *depths_host, double ice, int units, double *const *d_out, uint8_t *d_ok,
                               void *stream);
