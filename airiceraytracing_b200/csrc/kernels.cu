@@ -1,11 +1,15 @@
-// kernels.cu -- the three hand-written sm_100a kernels of the air->ice hot path.
+// kernels.cu -- the hand-written sm_100a kernels of the air->ice hot path.
 //
-//   airice_table_kernel   one thread per table cell; FP64-pipe bound (~1.7 kflop per 104..180 B written)
-//   airice_solve_kernel   one thread per Tx->Rx pair; FP64-pipe bound (~3 distance evaluations + 1 full ray)
-//   airice_lookup_kernel  one thread per query; L2/HBM gather bound (4 cells x 11 float columns)
+//   airice_table_kernel        one thread per table cell; FP64-pipe bound (~1.7 kflop per 104..180 B written)
+//   airice_table_multi_kernel  the tables of several antennas in one pass (shared air walk) + their lookup layout;
+//                              HBM-write bound (96 B per cell and antenna)
+//   airice_solve_kernel<P>     one thread per Tx->Rx pair (2 single-precision iterations, 1 FP64 evaluation with slope,
+//                              closed-form bisection replay, 1 full ray); issue/latency bound; P = 0 single pass,
+//                              P = 1 / 2 the two-pass launch that solves the rare slow-path pairs in dense warps
+//   airice_lookup_kernel       one thread per query; L2/HBM-latency bound gathers
 //
 // No tensor cores (nothing here is a contraction), no shared memory (there is no inter-thread reuse: the only
-// shared data is the ~0.5 KB medium/plan, which lives in the kernel-parameter constant bank), grids sized in
+// shared data is the ~0.7 KB medium/plan, which lives in the kernel-parameter constant bank), grids sized in
 // whole waves of 148 SMs by the launch wrappers.
 #include <math_constants.h>
 
