@@ -15,6 +15,13 @@
 // computed once per pair instead of 2-3 exp() per evaluation, and heap/indirection is gone.
 #pragma once
 #include "airice_core.cuh"
+#include "airice_glibc_math.cuh"
+
+// exp / log / pow of every quantity the reference ITERATES on round like the glibc the reference links (see
+// airice_glibc_math.cuh): the stopping iterate, hence L, hence the branch flags, then equal the x86 build's bit for bit.
+#define INICE_EXP(x) airice_glibc_exp(x)
+#define INICE_LOG(x) airice_glibc_log(x)
+#define INICE_POW(x, y) airice_glibc_pow((x), (y))
 
 // Building blocks that pass 1 / pass 3 use many times over (fL ~30x, the 8-point derivative 3x, time+path 5x): real calls
 // on the device, so that the kernel (15k instructions when everything is inlined, more than the instruction cache
@@ -29,18 +36,27 @@ struct AirIceInIce {      // ice model + constants of the IceRayTracing namespac
   double A, B, C;         // IceRayTracing.hh:45-56
   double pi;              // 3.14159265359 (IceRayTracing.hh:41, sic)
   double c;               // 299792458
+  double sin64;           // sin(64.0 * (pi / 180.0)) of IceRayTracing.cc:979 -- a constant; kept as one so that the device
+                          // does not round it with its own sin()
 };
+AIRICE_HD AirIceInIce inice_make_model(double A, double B, double C) {
+  AirIceInIce m;
+  m.A = A; m.B = B; m.C = C;
+  m.pi = 3.14159265359; m.c = 299792458.0;      // IceRayTracing.hh:41-43
+  m.sin64 = 0x1.cc2ebbb5639ecp-1;               // glibc's sin() and GCC's constant folder agree on it (tests/test_glibc_math.py)
+  return m;
+}
 
 struct InIcePair {
   double A, B, C, z0, z1, x1;   // z0 <= z1 after the flip (Tx deeper), both negative
   double n0, n1, ns;            // n(z0), n(z1), n(1e-7)
 };
 
-AIRICE_HD double inice_nz(const AirIceInIce& m, double z) { z = fabs(z); return m.A + m.B * exp(-m.C * z); }
+AIRICE_HD double inice_nz(const AirIceInIce& m, double z) { z = fabs(z); return m.A + m.B * INICE_EXP(-m.C * z); }
 
 // fDnfR_L (IceRayTracing.cc:368-379) with n(Z) supplied
 AIRICE_INICE_CALL double inice_fL(double A, double L, double Cp, double Z, double nZ) {
-  return (L / Cp) * (1.0 / sqrt(A * A - L * L)) * (Cp * Z - log(A * nZ - L * L + sqrt(A * A - L * L) * sqrt(nZ * nZ - L * L)));
+  return (L / Cp) * (1.0 / sqrt(A * A - L * L)) * (Cp * Z - INICE_LOG(A * nZ - L * L + sqrt(A * A - L * L) * sqrt(nZ * nZ - L * L)));
 }
 // The same in two parts for the root functions, which evaluate it at two or three depths for ONE L: the factor
 // (L/C)(1/sqrt(A^2-L^2)) and sqrt(A^2-L^2) depend on L only (two divisions and a square root of the two divisions,
@@ -55,7 +71,7 @@ AIRICE_HD InIceFLPre inice_fL_pre(double A, double L, double Cp) {
   return q;
 }
 AIRICE_INICE_CALL double inice_fL_at(const InIceFLPre& q, double A, double Cp, double Z, double nZ) {
-  return q.t * (Cp * Z - log(A * nZ - q.L2 + q.sA * sqrt(nZ * nZ - q.L2)));
+  return q.t * (Cp * Z - INICE_LOG(A * nZ - q.L2 + q.sA * sqrt(nZ * nZ - q.L2)));
 }
 
 // ---- GSL pieces, restated (see oracle/gsl_standin/gsl_standin.c for the same algorithms on the test side)
@@ -134,7 +150,7 @@ AIRICE_HD double inice_find_root(const F& f, double lo, double hi) {
 // GetZmax (IceRayTracing.cc:346-353) = FindFunctionRootZmax(GetMinnz, 0, 5000) (IceRayTracing.cc:303-335)
 struct InIceMinnz {
   double A, B, C, L;
-  AIRICE_HD double operator()(double x) const { return A + B * exp(-C * x) - L; }   // raw x, not |x| (IceRayTracing.cc:342)
+  AIRICE_HD double operator()(double x) const { return A + B * INICE_EXP(-C * x) - L; }   // raw x, not |x| (IceRayTracing.cc:342)
 };
 AIRICE_HD double inice_zmax_literal(double A, double B, double C, double L) {
   InIceMinnz f = {A, B, C, L};
@@ -181,8 +197,8 @@ struct InIceZmaxIter {
     else {
       const double x_lin = xr - (fu * (xl - xr) / (fl - fu));
       const double xb = 0.5 * (xl + xr);
-      const double f_lin = A + B * exp(-C * x_lin) - L;
-      const double fb = A + B * exp(-C * xb) - L;
+      const double f_lin = A + B * INICE_EXP(-C * x_lin) - L;
+      const double fb = A + B * INICE_EXP(-C * xb) - L;
       // f not finite at the regula-falsi point (exp overflow for L far below the physical range): GSL returns before
       // touching its state, so this and all the remaining iterations up to the 100th change nothing
       if (!isfinite(f_lin)) stuck = true;
@@ -214,7 +230,7 @@ struct InIceZmaxIter {
 };
 AIRICE_HD double inice_zmax(double A, double B, double C, double L) {
   InIceZmaxIter z;
-  z.init(A, B, exp(-C * 5000.0), L);
+  z.init(A, B, INICE_EXP(-C * 5000.0), L);
 #pragma unroll 1
   while (!z.step(A, B, C)) {}
   return z.root;
@@ -242,7 +258,7 @@ struct InIceFRa {
 // every root search (IceRayTracing.cc:957,985...), so callers that just evaluated f at the root can keep it
 AIRICE_HD double inice_fraa_given_zmax(const InIcePair& g, double L, double zmax) {   // zmax = inice_zmax(L) + 1e-7
   if (!(zmax > 0)) return 1e9;
-  const double nzm = g.A + g.B * exp(-g.C * fabs(zmax));
+  const double nzm = g.A + g.B * INICE_EXP(-g.C * fabs(zmax));
   const InIceFLPre q = inice_fL_pre(g.A, L, -g.C);
   const double fb = inice_fL_at(q, g.A, -g.C, -g.z0, g.n0);
   double d01 = inice_fL_at(q, g.A, -g.C, -g.z1, g.n1) - fb;
@@ -330,7 +346,7 @@ AIRICE_INICE_CALL double inice_deriv_central(const F& f, double x, double h) {
   double error = round + trunc;
   if (round < trunc && (round > 0 && trunc > 0)) {
     double ro, round_o, trunc_o;
-    const double h_opt = h * pow(round / (2.0 * trunc), 1.0 / 3.0);
+    const double h_opt = h * INICE_POW(round / (2.0 * trunc), 1.0 / 3.0);
     inice_central(f, x, h_opt, ro, round_o, trunc_o);
     const double error_o = round_o + trunc_o;
     if (error_o < error && fabs(ro - r0) < 4.0 * error) { r0 = ro; error = error_o; }
@@ -363,8 +379,8 @@ AIRICE_HD double inice_newton_root(const F& f, double lo, double hi) {
 struct InIceFDepth {
   double A, B, C, Cp, L;
   AIRICE_HD double operator()(double x) const {
-    const double n = A + B * exp(-C * fabs(x));
-    return (L / Cp) * (1.0 / sqrt(A * A - L * L)) * (Cp * x - log(A * n - L * L + sqrt(A * A - L * L) * sqrt(n * n - L * L)));
+    const double n = A + B * INICE_EXP(-C * fabs(x));
+    return (L / Cp) * (1.0 / sqrt(A * A - L * L)) * (Cp * x - INICE_LOG(A * n - L * L + sqrt(A * A - L * L) * sqrt(n * n - L * L)));
   }
 };
 
@@ -373,7 +389,7 @@ AIRICE_INICE_CALL void inice_time_path(const AirIceInIce& m, double x, double Cp
   const double A = m.A;
   const double n = inice_nz(m, x);
   const double D = n * n - L * L, R = sqrt(D), sA = sqrt(A * A - L * L);
-  const double G = Cp * x - log(A * n - L * L + sA * R), H = log(n + R);
+  const double G = Cp * x - INICE_LOG(A * n - L * L + sA * R), H = INICE_LOG(n + R);
   t = (1.0 / ((m.c * Cp) * R)) * ((D + (G * (A * A * R)) / sA) + (A * R) * H);
   p = (H + (A / sA) * G) / Cp;
 }
@@ -480,7 +496,7 @@ AIRICE_HD void inice_ra_first_bracket(const AirIceInIce& m, const InIcePair& g, 
   double LangR_in = asin(lvalueR / g.n0) * k180pi;
   if (flip) LangR_in = 180 - (180 - LangR_in);   // it travels out as 180-LangR and is flipped back, with both roundings
   up = g.n0 < g.n1 ? g.n0 : g.n1;
-  lower = g.n0 * sin((64.0 * kpi180));
+  lower = g.n0 * m.sin64;
   if (lower > up) lower = g.n0 * sin((LangR_in * kpi180));
 }
 

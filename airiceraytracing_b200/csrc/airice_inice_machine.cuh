@@ -95,7 +95,7 @@ struct InIceRaMachine {
   AIRICE_HD bool bad1() const { return fabs(cz1) > 0.5 || cz1 != cz1 || fabs(lv1 - lv0) < 1e-4; }
 
   // pow(round / (2 trunc), 1/3) of inice_deriv_central: a real call (pow is ~300 instructions)
-  AIRICE_INICE_CALL static double cube_root_ratio(double round, double trunc) { return pow(round / (2.0 * trunc), 1.0 / 3.0); }
+  AIRICE_INICE_CALL static double cube_root_ratio(double round, double trunc) { return INICE_POW(round / (2.0 * trunc), 1.0 / 3.0); }
 
   // inice_central on samples f(c-h), f(c+h), f(c-h/2), f(c+h/2)
   AIRICE_INICE_CALL static void central(double x, double h, double fm1, double fp1, double fmh, double fph, double& result,

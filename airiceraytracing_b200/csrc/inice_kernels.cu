@@ -4,7 +4,7 @@
 // stopped at loose tolerances), so its arithmetic has to round like the reference's x86 build does -- every product
 // and sum on its own.  A fused n*n - L*L, for instance, turns the exact 0 the reference gets at the bracket end
 // L = min(n(z0), n(z1)) into -1e-17, sqrt() of that into NaN, and the refracted-ray search of the pair into a
-// different branch count.  Transcendentals still come from the CUDA math library (<= 1-2 ulp from glibc).
+// different branch count.  exp / log / pow are glibc's own algorithms (airice_glibc_math.cuh) for the same reason.
 #include "airice_inice.cuh"
 #include "airice_inice_machine.cuh"
 #include "kernels.cuh"
@@ -24,9 +24,7 @@ constexpr int kDrThreads = AIRICE_INICE_DR_THREADS;
 constexpr int kLadderThreads = AIRICE_INICE_LADDER_THREADS;
 
 __device__ __forceinline__ AirIceInIce inice_model(const InIceArgs& a) {
-  AirIceInIce m;
-  m.A = a.A; m.B = a.B; m.C = a.C; m.pi = 3.14159265359; m.c = 299792458.0;  // IceRayTracing.hh:41-43
-  return m;
+  return inice_make_model(a.A, a.B, a.C);
 }
 
 // pass 1: direct + reflected ray for every pair; all 29 columns written (refracted ones as absent)
@@ -83,7 +81,7 @@ __global__ void __launch_bounds__(kLadderThreads) airice_inice_ladder_kernel(con
   const unsigned full = 0xffffffffu;
   const AirIceInIce m = inice_model(a);
   const int n_front = a.ra_count[0], count = n_front + a.ra_count[2];
-  const double e5000 = exp(-a.C * 5000.0);
+  const double e5000 = INICE_EXP(-a.C * 5000.0);
   InIceRaMachine M;
   int j = 0;
   bool has = false, exhausted = false;
@@ -209,8 +207,7 @@ __global__ void __launch_bounds__(kThreads) airice_inice_ra_finish_kernel(const 
 __global__ void __launch_bounds__(256) airice_inice_pick_kernel(const InIcePickArgs a) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= a.n) return;
-  AirIceInIce m;
-  m.A = a.A; m.B = a.B; m.C = a.C; m.pi = 3.14159265359; m.c = 299792458.0;
+  const AirIceInIce m = inice_make_model(a.A, a.B, a.C);
   double o[AIRICE_INICE_NCOLS];
 #pragma unroll
   for (int k = 0; k < AIRICE_INICE_NCOLS; k++) o[k] = a.in[k][i];

@@ -4,6 +4,7 @@
 #include <math.h>
 
 #include "airice_math.cuh"
+#include "airice_glibc_math.cuh"
 
 __global__ void probe_kernel(int op, long n, const double* a, const double* b, double* out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -15,7 +16,10 @@ __global__ void probe_kernel(int op, long n, const double* a, const double* b, d
     case 2: r = AIRICE_RCP(a[i]); break;
     case 3: r = AIRICE_DIV(a[i], b[i]); break;
     case 4: r = AIRICE_ATAN_Q(a[i], b[i]); break;
-    default: r = AIRICE_DIV100(a[i]); break;
+    case 5: r = AIRICE_DIV100(a[i]); break;
+    case 6: r = airice_glibc_exp(a[i]); break;
+    case 7: r = airice_glibc_log(a[i]); break;
+    default: r = airice_glibc_pow(a[i], b[i]); break;
   }
   out[i] = r;
 }

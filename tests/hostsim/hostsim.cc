@@ -97,7 +97,7 @@ double sim_x_total(double h, double ice, double depth, double L, double* dXdL) {
 }
 // in-ice solver: IceRayTracing::IceRayTracing(0,z0,x1,z1) layout, out[29] per pair; returns nothing
 void sim_inice_batch(long n, const double* z0, const double* x1, const double* z1, double* out, int* mask) {
-  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  const AirIceInIce m = inice_make_model(1.78, -0.43, 0.0132);
   for (long i = 0; i < n; i++) mask[i] = inice_solve(m, z0[i], x1[i], z1[i], out + 29 * i);
 }
 }
@@ -107,7 +107,7 @@ extern "C" {
 // steps[i] = machine steps (critical path length)
 long sim_inice_ladder_compare(long n, const double* z0, const double* x1, const double* z1, double* direct, double* stepped,
                               int* evals, int* steps) {
-  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  const AirIceInIce m = inice_make_model(1.78, -0.43, 0.0132);
   long ran = 0;
   for (long i = 0; i < n; i++) {
     double o[29]; bool needs;
@@ -132,7 +132,7 @@ double sim_inice_zmax(double L) { return inice_zmax(1.78, -0.43, 0.0132, L); }
 // fRaa at L for the pair (z0, x1, z1): full evaluation into y[0], zm[0]; shortcut into y[1], zm[1]; returns 1 if the
 // shortcut applied
 int sim_inice_fraa_shortcut(double L, double z0, double x1, double z1, double* y, double* zm) {
-  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  const AirIceInIce m = inice_make_model(1.78, -0.43, 0.0132);
   bool flip;
   const InIcePair g = inice_make_pair(m, z0, x1, z1, flip);
   y[0] = inice_fraa_eval(g, L, zm[0]);
@@ -142,7 +142,7 @@ int sim_inice_fraa_shortcut(double L, double z0, double x1, double z1, double* y
 // GetRayTracingSolutions(RxDepth, Distance, TxDepth) through the host build of the device code
 void sim_inice_two_rays_batch(long n, const double* rx, const double* dist, const double* tx, double* out10, int* ignore2,
                               int* type2) {
-  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  const AirIceInIce m = inice_make_model(1.78, -0.43, 0.0132);
   for (long i = 0; i < n; i++) {
     double o[29];
     inice_solve(m, tx[i], dist[i], rx[i], o);
@@ -159,14 +159,14 @@ long sim_ray_path(double theta, double h, double ice, double depth, long max_poi
 }
 double sim_inice_zmax_literal(double L) { return inice_zmax_literal(1.78, -0.43, 0.0132, L); }
 double sim_inice_fraa(double L, double z0, double x1, double z1) {
-  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  const AirIceInIce m = inice_make_model(1.78, -0.43, 0.0132);
   InIcePair g; g.A = m.A; g.B = m.B; g.C = m.C; g.z0 = z0; g.z1 = z1; g.x1 = x1;
   g.n0 = inice_nz(m, z0); g.n1 = inice_nz(m, z1); g.ns = inice_nz(m, 1e-7);
   InIceFRaa f = {g};
   return f(L);
 }
 double sim_inice_dfraa(double L, double z0, double x1, double z1) {
-  AirIceInIce m = {1.78, -0.43, 0.0132, 3.14159265359, 299792458.0};
+  const AirIceInIce m = inice_make_model(1.78, -0.43, 0.0132);
   InIcePair g; g.A = m.A; g.B = m.B; g.C = m.C; g.z0 = z0; g.z1 = z1; g.x1 = x1;
   g.n0 = inice_nz(m, z0); g.n1 = inice_nz(m, z1); g.ns = inice_nz(m, 1e-7);
   InIceFRaa f = {g};

@@ -91,3 +91,20 @@ def test_device_atan_and_div100(probe):
     # x / 100 must be THE IEEE quotient (the reference's cm -> m conversion feeds layer tests and exp())
     v = np.concatenate([rng.uniform(1, 1.5e7, n), 10.0 ** rng.uniform(-3, 9, n) * rng.choice([-1, 1], n), [300000.0, 20000.0, 0.0]])
     assert np.array_equal(probe(5, v), v / 100)
+
+
+@pytest.mark.gpu
+def test_device_glibc_exp_log_pow_equal_host_libm(probe, tmp_path):
+    """The device build of airice_glibc_math.cuh against the libm of the host this test runs on: bit for bit (the in-ice
+    solver's branch flags depend on it).  Same argument sets as the CPU-only test of the host build."""
+    from test_glibc_math import build_libm_ref, glibc_math_cases, has_fma, same_bits
+    if not has_fma():
+        pytest.skip("host libm runs its non-FMA build")
+    lib, run = build_libm_ref(tmp_path)
+    rng = np.random.default_rng(6)
+    for op, a, b in glibc_math_cases(rng, 1_000_000):
+        want, got = run(lib.libm_v, op, a, b), probe(6 + op, a, b)
+        ok = same_bits(want, got)
+        # outside the restated fast paths the device falls back to CUDA's own function (|x| >= 512, subnormal results)
+        fast = np.abs(a) < 512 if op == 0 else (np.abs(b * np.log(np.maximum(a, 1e-300))) < 512 if op == 2 else np.ones_like(ok))
+        assert ok[fast].all(), (op, a[fast & ~ok][:3], want[fast & ~ok][:3], got[fast & ~ok][:3])

@@ -1,7 +1,12 @@
 """In-ice solver (IceRayTracing::IceRayTracing): solution-branch flags must be bit-exact, launch angles / times / L
 within the north-star tolerances.  Receive and incidence angles come from gsl_deriv_central with h = 1e-8 m in the
-reference and are noise-limited there (hard part 6): against a different libm they agree only to
-~1e-4 deg, which is asserted as such."""
+reference and are noise-limited there (hard part 6): they are reproduced only by an implementation
+whose every iterate has the reference's bits.  The kernels evaluate exp / log / pow with glibc's own algorithms
+(airice_glibc_math.cuh), so they do: on a B200 the direct and reflected rays' L and times are bit-equal to the x86 build
+and the "noisy" angles agree to 3e-14 deg.  The one libm dependence left is the fallback lower bracket of the first
+refracted search, n(z0) sin(asin(L_R / n(z0)) ...) (IceRayTracing.cc:979-983), formed with CUDA's asin / sin: for ~3 in
+10 000 refracted rays the search starts one ulp off, L lands 1e-12 away, and that pair's derivative-noise angles differ by
+up to ~1e-4 deg -- the only exception left, bounded below by `noisy_frac`."""
 import ctypes as C
 
 import numpy as np
@@ -15,10 +20,18 @@ LAUNCH, TIMES, RECV, LVAL, ZMAX, PATHS = (0, 1, 2, 3), (4, 5, 6, 7, 12, 13, 14, 
     (19, 20, 21, 22), (23, 24), (25, 26, 27, 28)
 
 
-def check_inice(got, ref, recv_tol_deg, max_flag_mismatch=0, flipped=None, ra_rtol=RTOL_DIST):
+def check_inice(got, ref, recv_tol_deg, max_flag_mismatch=0, flipped=None, ra_rtol=RTOL_DIST, noisy_frac=0.0, noisy_tol_deg=5e-3):
     """flipped: boolean per pair, Tx shallower than Rx.  For those the reference reports 180 - (receive angle) as the
     launch angle (IceRayTracing.cc:737-740), so the launch angle inherits the numerical-derivative noise too.
-    ra_rtol: tolerance for the refracted branches, whose L is amplified by the turning-point square root."""
+    ra_rtol: tolerance for the refracted branches, whose L is amplified by the turning-point square root.
+    noisy_frac: share of the REFRACTED rays whose derivative-noise angles may miss recv_tol_deg (by at most noisy_tol_deg)."""
+    def angles_ok(d, refracted, what):
+        if refracted and noisy_frac > 0:
+            assert d.max() <= noisy_tol_deg, (what, d.max())
+            assert (d > recv_tol_deg).sum() <= max(1, int(noisy_frac * d.size)), (what, (d > recv_tol_deg).sum(), d.size)
+        else:
+            assert d.max() <= recv_tol_deg, (what, d.max())
+
     fr, fg = ref[:, 8:12] != -1000, got[:, 8:12] != -1000
     if flipped is None:
         flipped = np.zeros(ref.shape[0], dtype=bool)
@@ -40,9 +53,9 @@ def check_inice(got, ref, recv_tol_deg, max_flag_mismatch=0, flipped=None, ra_rt
             if (~fl).any():
                 assert d[~fl].max() <= tol, ("launch angle", k, d[~fl].max())
             if fl.any():
-                assert d[fl].max() <= max(recv_tol_deg, tol), ("launch angle of a flipped pair", k, d[fl].max())
+                angles_ok(np.maximum(d[fl] - tol, 0), refracted, ("launch angle of a flipped pair", k))
         elif k in RECV:
-            assert np.abs(a - r).max() <= recv_tol_deg, ("receive/incidence angle", k, np.abs(a - r).max())
+            angles_ok(np.abs(a - r), refracted, ("receive/incidence angle", k))
         elif k in TIMES or k in PATHS or k in LVAL:
             # sub-times of the two legs (12-17) are scaled by the whole ray's time: a leg ending next to the turning
             # point is short and its own relative error is not meaningful
@@ -102,8 +115,9 @@ def _two_ray_cases(n, seed):
     return rx, dist, tx
 
 
-def check_two_rays(got, ig_got, want, ig_want, max_flag_mismatch, recv_tol_deg=5e-3):
-    """columns: TimeRay[2], PathRay[2], LaunchAngle[2], RecieveAngle[2], IncidenceAngleInIce[2]"""
+def check_two_rays(got, ig_got, want, ig_want, max_flag_mismatch, recv_tol_deg=5e-3, noisy=0):
+    """columns: TimeRay[2], PathRay[2], LaunchAngle[2], RecieveAngle[2], IncidenceAngleInIce[2]
+    noisy: number of rays whose derivative-noise angles may miss recv_tol_deg (by at most 5e-3 deg), see the module docstring"""
     bad = (ig_got != ig_want).any(1)
     assert bad.sum() <= max_flag_mismatch, "%d pairs with different IgnoreCh" % bad.sum()
     for j in range(2):
@@ -111,12 +125,13 @@ def check_two_rays(got, ig_got, want, ig_want, max_flag_mismatch, recv_tol_deg=5
         # two rays whose arrival times differ by less than the time tolerance may come out in either order
         close = np.abs(want[:, 0] - want[:, 1]) <= 1e-8 * np.abs(want[:, 0])
         m &= ~(close & (ig_want.sum(1) == 2))
-        # relative 5e-8 (the refracted branches' L tolerance) with a floor for the degenerate sub-nanometre pairs
-        for col, tol, floor in ((0 + j, 5e-8, 1e-20), (2 + j, 5e-8, 1e-12)):
+        # north-star tolerance, with a floor for the degenerate sub-nanometre pairs
+        for col, tol, floor in ((0 + j, RTOL_DIST, 1e-20), (2 + j, RTOL_DIST, 1e-12)):
             err = np.abs(got[m, col] - want[m, col]) - floor
             assert (err <= tol * np.abs(want[m, col])).all(), (col, (err / np.maximum(np.abs(want[m, col]), 1e-300)).max())
         for col in (4 + j, 6 + j, 8 + j):
-            assert np.abs(got[m, col] - want[m, col]).max() <= recv_tol_deg, (col, np.abs(got[m, col] - want[m, col]).max())
+            d = np.abs(got[m, col] - want[m, col])
+            assert d.max() <= (5e-3 if noisy else recv_tol_deg) and (d > recv_tol_deg).sum() <= noisy, (col, d.max(), (d > recv_tol_deg).sum())
 
 
 def test_two_ray_selection_oracle_equals_reference():
@@ -142,7 +157,7 @@ def test_two_ray_selection_host_build(hostsim):
     f(n, rx.ctypes.data_as(dp), dist.ctypes.data_as(dp), tx.ctypes.data_as(dp), got.ctypes.data_as(dp), ig.ctypes.data_as(ip),
       ty.ctypes.data_as(ip))
     want, ig_want = InIceOracle().two_rays(rx, dist, tx)
-    check_two_rays(got, ig, want, ig_want, max_flag_mismatch=1)
+    check_two_rays(got, ig, want, ig_want, max_flag_mismatch=0, recv_tol_deg=1e-9)
     assert ((ty >= 1) & (ty <= 4)).all()
     # same depth, zero distance: the straight-line patch (IceRayTracing.cc:3190-3200)
     assert ig[n - 6].tolist() == [1, 0] and got[n - 6, 4] == 90.0 and got[n - 6, 2] == 0.0
@@ -226,25 +241,31 @@ def test_kernel_matches_reference_golden(solver):
     g = golden("inice.npz")
     out, mask = solver.inice_solve(torch.from_numpy(g["z0"]), torch.from_numpy(g["x1"]), torch.from_numpy(g["z1"]))
     got = out.cpu().numpy().T
-    counts = check_inice(got, g["out"], recv_tol_deg=5e-3, max_flag_mismatch=2, flipped=g["z0"] > g["z1"], ra_rtol=5e-8)
+    counts = check_inice(got, g["out"], recv_tol_deg=1e-9, max_flag_mismatch=0, flipped=g["z0"] > g["z1"], noisy_frac=2e-3)
     popc = np.array([bin(int(x)).count("1") for x in mask.cpu().numpy()])
-    assert (popc != counts).sum() <= 2
+    assert np.array_equal(popc, counts)
+    # L and arrival times of the direct and reflected rays: the reference build's bits
+    fr = g["out"][:, 8:12] != -1000
+    for k, b in ((19, 0), (20, 1), (4, 0), (5, 1)):
+        assert np.array_equal(got[fr[:, b], k], g["out"][fr[:, b], k]), k
     out_h, mask_h = solver.inice_solve_host(g["z0"], g["x1"], g["z1"])
     assert np.array_equal(out_h, out.cpu().numpy(), equal_nan=True) and np.array_equal(mask_h, mask.cpu().numpy())
 
 
 @pytest.mark.gpu
-def test_kernel_matches_live_reference_20k(solver):
+def test_kernel_matches_live_reference_100k(solver):
+    """north_star: solution-branch counts bit-exact.  100 000 random pairs against the reference build running on this
+    box's host: ZERO flag differences, every distance-like output of all four branches within 1e-9."""
     import torch
     from oracle.ref import InIceOracle, IceRayReference, reference_available
     rng = np.random.default_rng(2024)
-    n = 20000
+    n = 100000
     z0, z1, x1 = rng.uniform(-1501, -1, n), rng.uniform(-201, -1, n), rng.uniform(1, 3001, n)
     # the unmodified reference build when it travelled with the repo, else the plain-C oracle (bit-equal to it)
     checker = IceRayReference() if reference_available("libiceray_ref.so") else InIceOracle()
     ref = checker.solve_batch(z0, x1, z1)
     out, mask = solver.inice_solve(torch.from_numpy(z0), torch.from_numpy(x1), torch.from_numpy(z1))
-    counts = check_inice(out.cpu().numpy().T, ref, recv_tol_deg=5e-3, max_flag_mismatch=4, flipped=z0 > z1, ra_rtol=5e-8)
+    counts = check_inice(out.cpu().numpy().T, ref, recv_tol_deg=1e-9, max_flag_mismatch=0, flipped=z0 > z1, noisy_frac=2e-3)
     hist = np.bincount(counts, minlength=3) / n
     assert 0.3 < hist[0] < 0.45 and 0.5 < hist[2] < 0.7   # SURVEY.md 8a: 38.7 % / 2.9 % / 58.4 %
 
@@ -259,8 +280,7 @@ def test_kernel_edge_cases(solver):
     g = golden("inice.npz")
     for n in (1, 31, 129):
         o, m = solver.inice_solve(torch.from_numpy(g["z0"][:n]), torch.from_numpy(g["x1"][:n]), torch.from_numpy(g["z1"][:n]))
-        check_inice(o.cpu().numpy().T, g["out"][:n], recv_tol_deg=5e-3, max_flag_mismatch=0, flipped=g["z0"][:n] > g["z1"][:n],
-                    ra_rtol=5e-8)
+        check_inice(o.cpu().numpy().T, g["out"][:n], recv_tol_deg=1e-9, max_flag_mismatch=0, flipped=g["z0"][:n] > g["z1"][:n])
     # symmetric pair: swapping Tx and Rx swaps launch and receive angles (the reference's flip, IceRayTracing.cc:631-740)
     a, _ = solver.inice_solve(torch.tensor([-180.0]), torch.tensor([100.0]), torch.tensor([-5.0]))
     b, _ = solver.inice_solve(torch.tensor([-5.0]), torch.tensor([100.0]), torch.tensor([-180.0]))
@@ -281,7 +301,7 @@ def test_two_ray_selection_kernel(solver):
     rx, dist, tx = _two_ray_cases(20000, 5)
     out, ig, ty = solver.inice_two_rays(torch.from_numpy(rx), torch.from_numpy(dist), torch.from_numpy(tx), want_type=True)
     want, ig_want = InIceOracle().two_rays(rx, dist, tx)
-    check_two_rays(out.cpu().numpy().T, ig.cpu().numpy().T, want, ig_want, max_flag_mismatch=4)
+    check_two_rays(out.cpu().numpy().T, ig.cpu().numpy().T, want, ig_want, max_flag_mismatch=0, recv_tol_deg=1e-9, noisy=6)
     ty = ty.cpu().numpy()
     assert ((ty >= 1) & (ty <= 4)).all()
     # host-buffer entry point: same bits as the device entry point
