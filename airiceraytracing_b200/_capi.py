@@ -28,6 +28,7 @@ EXPORTS = [
     "airice_table_copy_column", "airice_table_column_ptr", "airice_table_copy_row_ranges", "airice_solve_device",
     "airice_solve_multi_device", "airice_solve_host", "airice_lookup_device", "airice_lookup_host", "airice_inice_solve_device",
     "airice_inice_solve_host", "airice_inice_two_rays_device", "airice_inice_two_rays_host", "airice_ray_path_device", "airice_ray_path_host", "airice_fp64_peak_tflops", "airice_sync", "airice_trim",
+    "airice_peer_alloc", "airice_peer_free", "airice_peer_open", "airice_peer_close", "airice_peer_copy",
 ]
 
 _lib = None
@@ -77,6 +78,11 @@ def load():
     lib.airice_fp64_peak_tflops.argtypes = [vp, C.POINTER(d)]
     lib.airice_sync.argtypes = [vp]
     lib.airice_trim.argtypes = [vp]
+    lib.airice_peer_alloc.argtypes = [vp, C.c_size_t, pp, C.c_char_p]
+    lib.airice_peer_free.argtypes = [vp, vp]
+    lib.airice_peer_open.argtypes = [vp, C.c_char_p, pp]
+    lib.airice_peer_close.argtypes = [vp, vp]
+    lib.airice_peer_copy.argtypes = [vp, vp, vp, C.c_size_t, vp]
     _lib = lib
     return lib
 

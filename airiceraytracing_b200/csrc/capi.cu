@@ -940,6 +940,48 @@ int airice_ray_path_host(airice_ctx* c, int64_t n, const double* theta, const do
   return 0;
 }
 
+// ---- peer memory (CUDA IPC): see include/airice_b200.h
+int airice_peer_alloc(airice_ctx* c, size_t bytes, void** d_ptr, unsigned char handle[AIRICE_PEER_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == AIRICE_PEER_HANDLE_BYTES, "handle size");
+  if (!c || !d_ptr || !handle) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  void* p = nullptr;
+  CK(cudaMalloc(&p, bytes ? bytes : 1));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  std::memcpy(handle, &h, sizeof(h));
+  *d_ptr = p;
+  return 0;
+}
+int airice_peer_free(airice_ctx* c, void* d_ptr) {
+  if (!c) return fail(-1, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaFree(d_ptr));
+  return 0;
+}
+int airice_peer_open(airice_ctx* c, const unsigned char handle[AIRICE_PEER_HANDLE_BYTES], void** d_ptr) {
+  if (!c || !d_ptr || !handle) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int airice_peer_close(airice_ctx* c, void* d_ptr) {
+  if (!c) return fail(-1, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaIpcCloseMemHandle(d_ptr));
+  return 0;
+}
+int airice_peer_copy(airice_ctx* c, void* d_dst, const void* d_src, size_t bytes, void* stream) {
+  if (!c) return fail(-1, "null context");
+  if (!bytes) return 0;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+
 int airice_fp64_peak_tflops(airice_ctx* c, double* tflops) {
   if (!c || !tflops) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));

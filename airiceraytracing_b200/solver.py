@@ -109,6 +109,46 @@ class AirIceSolver:
         """Return the context's cached device memory (buffers of closed tables, solve scratch) to the driver."""
         check(self.lib.airice_trim(self.handle))
 
+    # ------------------------------------------------------------------ peer memory (multi-GPU reassembly, dist.PeerGather)
+    def peer_alloc(self, nbytes):
+        """-> (device pointer, 64-byte handle another process on this node can open)"""
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        check(self.lib.airice_peer_alloc(self.handle, int(nbytes), C.byref(p), h))
+        return p.value, h.raw
+
+    def peer_open(self, handle):
+        p = C.c_void_p()
+        check(self.lib.airice_peer_open(self.handle, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def peer_close(self, ptr):
+        check(self.lib.airice_peer_close(self.handle, ptr))
+
+    def peer_free(self, ptr):
+        check(self.lib.airice_peer_free(self.handle, ptr))
+
+    def peer_copy(self, dst, src, nbytes, stream=None):
+        check(self.lib.airice_peer_copy(self.handle, dst, src, int(nbytes),
+                                        _stream_ptr(self.torch_device) if stream is None else stream))
+
+    def wrap_device_memory(self, ptr, shape, dtype):
+        """A torch view of device memory of THIS device that the library allocated (no copy, no ownership)."""
+        typestr = {torch.float64: "<f8", torch.uint8: "|u1", torch.int32: "<i4", torch.float32: "<f4"}[dtype]
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                        "strides": None}
+        return torch.as_tensor(_Mem(), device=self.torch_device)
+
+    def solve_into(self, h, d, depth, ice, units, out_ptrs, ok_ptr, straight=None):
+        """airice_solve_device with raw output pointers (columns anywhere this GPU can store to, peer memory included)."""
+        h = h.to(self.torch_device, torch.float64).contiguous()
+        d = d.to(self.torch_device, torch.float64).contiguous()
+        check(self.lib.airice_solve_device(self.handle, h.numel(), h.data_ptr(), d.data_ptr(),
+                                           straight.data_ptr() if straight is not None else None, depth, ice, units,
+                                           ptr_array(out_ptrs), ok_ptr, None, _stream_ptr(self.torch_device)))
+
     # ------------------------------------------------------------------ kernel 1
     def table_dims(self, depth_m, ice_m, h_top=100000.0, h_step=10.0, th_start=90.1, th_step=0.1, th_stop=180.0):
         nh, nth = C.c_int64(), C.c_int64()

@@ -158,6 +158,22 @@ int airice_ray_path_device(airice_ctx *ctx, int64_t n, const double *d_theta, co
 int airice_ray_path_host(airice_ctx *ctx, int64_t n, const double *theta, const double *h, double depth_m, double ice_m,
                          int64_t max_points, double *x, double *z, int32_t *count);
 
+/* ---- peer memory: multi-GPU reassembly without a collective ("one gather per batch").
+ * One process per GPU; the consumer rank allocates the result block with airice_peer_alloc and hands the 64-byte handle
+ * to the producers (any transport: torch.distributed object broadcast, MPI, a file); a producer maps it with
+ * airice_peer_open and passes pointers INTO it as the output columns of airice_solve_device / airice_lookup_device /
+ * airice_table_build_device / ...: its kernel's stores travel over NVLink straight to their final place in the
+ * consumer's HBM while the kernel computes -- the gather is fused into the compute kernel, no staging, no extra launch.
+ * The reference has no counterpart (single process).  The consumer must order its reads after the producers' kernels
+ * (a barrier on the producers' streams, e.g. an NCCL barrier / event + message).  airice_peer_copy is a plain
+ * asynchronous device-to-device copy between any two such pointers for callers that want the block replicated. */
+#define AIRICE_PEER_HANDLE_BYTES 64
+int airice_peer_alloc(airice_ctx *ctx, size_t bytes, void **d_ptr, unsigned char handle[AIRICE_PEER_HANDLE_BYTES]);
+int airice_peer_free(airice_ctx *ctx, void *d_ptr);
+int airice_peer_open(airice_ctx *ctx, const unsigned char handle[AIRICE_PEER_HANDLE_BYTES], void **d_ptr);
+int airice_peer_close(airice_ctx *ctx, void *d_ptr);
+int airice_peer_copy(airice_ctx *ctx, void *d_dst, const void *d_src, size_t bytes, void *stream);
+
 /* ---- measurement helpers */
 int airice_fp64_peak_tflops(airice_ctx *ctx, double *tflops); /* dependent-free DFMA probe, roofline denominator */
 int airice_sync(airice_ctx *ctx);

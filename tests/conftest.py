@@ -149,19 +149,22 @@ def assert_forward_close(got18, ref18, what=""):
     assert np.array_equal(got18[:, 1], ref18[:, 1]), what + ": Tx heights differ"
 
 
-def assert_solve_close(ok, out9, ok_ref, ref9, pi, what="", max_tie_frac=0.0):
+def assert_solve_close(ok, out9, ok_ref, ref9, pi, what="", max_ties=0):
     """cm/rad layout of GetHorizontalDistanceToIntersectionPoint (MultiRayAirIceRefraction.h:170).
 
-    Flags must be identical.  Numeric outputs are compared where the reference found a solution.  `max_tie_frac`
-    allows that fraction of solves to sit one final bisection cell (<=2e-7 deg) away from the reference: those are
-    the rounding ties of the reference's own loose bisection ('bisection replay')."""
+    Flags must be identical.  Numeric outputs are compared where the reference found a solution.  A "tie" is a solve
+    that sits one final bisection cell (<=2.5e-7 deg) away from the reference because a bisection midpoint fell within
+    rounding distance of the root ('bisection replay'); expected rate ~1e-6 per solve, measured 0 in every
+    seeded set below, so the default allows none.  The census is printed (pytest -s) either way."""
     assert np.array_equal(ok, ok_ref), "%s: %d solution flags differ" % (what, int((ok != ok_ref).sum()))
     m = ok_ref
     if not m.any():
         return
     dang = np.abs(out9[m, 4] - ref9[m, 4]) * 180 / pi
     tie = dang > ATOL_ANGLE_DEG
-    assert tie.mean() <= max_tie_frac, "%s: %d launch angles off by more than 1e-7 deg (max %.3e)" % (
+    print("%s: %d solves, %d ties, max launch-angle difference %.3e deg, bit-equal launch angles %.1f %%" % (
+        what, int(m.sum()), int(tie.sum()), dang.max(), 100.0 * (out9[m, 4] == ref9[m, 4]).mean()))
+    assert tie.sum() <= max_ties, "%s: %d launch angles off by more than 1e-7 deg (max %.3e)" % (
         what, int(tie.sum()), dang.max())
     assert dang.max() <= 2.5e-7, "%s: launch angle off by more than one bisection cell: %.3e deg" % (what, dang.max())
     g = ~tie

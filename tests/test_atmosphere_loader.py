@@ -81,7 +81,7 @@ def test_truncated_table_and_shifted_layers(hostsim, oracle_built, tmp_path):
         d = (h - 1000 + 100) * np.tan((180 - ang) * 3.1415927 / 180)
         ok_r, ref = ob.solve_cm_batch(h * 100, d * 100, -10000.0, 100000.0)
         ok, out, _ = hostsim.solve_cm(h * 100, d * 100, -10000.0, 100000.0)
-        assert_solve_close(ok, out, ok_r, ref, 3.1415927, "shifted layers", max_tie_frac=1e-3)
+        assert_solve_close(ok, out, ok_r, ref, 3.1415927, "shifted layers")
     finally:
         _restore(hostsim)
 

@@ -45,7 +45,7 @@ def test_solves_match_oracle_on_fresh_pairs(hostsim, oracle):
     d = (h - 3000 + 200) * np.tan((180 - ang) * PI_M / 180)
     ok_r, ref = oracle.solve_cm_batch(h * 100, d * 100, -20000.0, 300000.0)
     ok, out, _ = hostsim.solve_cm(h * 100, d * 100, -20000.0, 300000.0)
-    assert_solve_close(ok, out, ok_r, ref, PI_M, "fresh pairs", max_tie_frac=1e-3)
+    assert_solve_close(ok, out, ok_r, ref, PI_M, "fresh pairs")
 
 
 def test_replayed_angle_is_the_bisection_midpoint_not_the_true_root(hostsim, oracle):
@@ -77,7 +77,7 @@ def test_closed_form_replay_in_the_special_zones(hostsim, oracle):
     assert np.array_equal(np.isfinite(ref[:, 4]), np.isfinite(out[:, 4]))
     dang = np.abs(out[fin, 4] - ref[fin, 4]) * 180 / PI_M
     assert (dang > 1e-7).mean() <= 1e-3 and dang.max() <= 2.5e-7
-    assert_solve_close(ok, out, ok_r, ref, PI_M, "special zones", max_tie_frac=1e-3)
+    assert_solve_close(ok, out, ok_r, ref, PI_M, "special zones")
 
 
 def test_first_pass_of_the_two_pass_launch(hostsim):
