@@ -28,6 +28,8 @@ EXPORTS = [
     "airice_table_copy_column", "airice_table_column_ptr", "airice_table_copy_row_ranges", "airice_solve_device",
     "airice_solve_multi_device", "airice_solve_host", "airice_lookup_device", "airice_lookup_host", "airice_inice_solve_device",
     "airice_inice_solve_host", "airice_inice_two_rays_device", "airice_inice_two_rays_host", "airice_ray_path_device", "airice_ray_path_host", "airice_fp64_peak_tflops", "airice_sync", "airice_trim",
+    "airice_table_save", "airice_table_load", "airice_oldtable_create", "airice_oldtable_wrap_host", "airice_oldtable_destroy", "airice_oldtable_info",
+    "airice_oldtable_copy_column", "airice_oldtable_copy_positions", "airice_oldtable_interp_device", "airice_oldtable_interp_host",
     "airice_peer_alloc", "airice_peer_free", "airice_peer_open", "airice_peer_close", "airice_peer_copy",
 ]
 
@@ -78,6 +80,17 @@ def load():
     lib.airice_fp64_peak_tflops.argtypes = [vp, C.POINTER(d)]
     lib.airice_sync.argtypes = [vp]
     lib.airice_trim.argtypes = [vp]
+    lib.airice_table_save.argtypes = [vp, C.c_char_p]
+    lib.airice_table_load.argtypes = [vp, C.c_char_p, pp]
+    lib.airice_oldtable_create.argtypes = [vp, d, d, d, d, d, d, pp]
+    lib.airice_oldtable_wrap_host.argtypes = [vp, d, d, d, d, d, vp, pp]
+    lib.airice_oldtable_destroy.argtypes = [vp]
+    lib.airice_oldtable_destroy.restype = None
+    lib.airice_oldtable_info.argtypes = [vp, C.POINTER(i64)]
+    lib.airice_oldtable_copy_column.argtypes = [vp, i, vp]
+    lib.airice_oldtable_copy_positions.argtypes = [vp, vp, vp]
+    lib.airice_oldtable_interp_device.argtypes = [vp, vp, i64, vp, vp, i, vp, vp]
+    lib.airice_oldtable_interp_host.argtypes = [vp, vp, i64, vp, vp, i, vp]
     lib.airice_peer_alloc.argtypes = [vp, C.c_size_t, pp, C.c_char_p]
     lib.airice_peer_free.argtypes = [vp, vp]
     lib.airice_peer_open.argtypes = [vp, C.c_char_p, pp]

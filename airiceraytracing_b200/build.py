@@ -31,12 +31,15 @@ def build(force=False, verbose_ptxas=False):
 
     core = os.path.join(LIBDIR, "libairice_b200.so")
     core_src = [os.path.join(CSRC, f) for f in ("kernels.cu", "capi.cu", "atmosphere.cc")]
-    inice_src = os.path.join(CSRC, "inice_kernels.cu")
-    inice_obj = os.path.join(LIBDIR, "inice_kernels.o")
-    if force or _newer(core, core_src + [inice_src] + headers):
-        # the in-ice solver replays the reference's iterations and must round like its x86 build: no FMA contraction
-        _run(["nvcc"] + NVCC_FLAGS + extra + ["-fmad=false", "-c", "-o", inice_obj, inice_src])
-        _run(["nvcc"] + NVCC_FLAGS + extra + ["-shared", "-o", core] + core_src + [inice_obj])
+    # translation units that must round like the reference's x86 build (no FMA contraction): the in-ice solver replays
+    # the reference's iterations; the old-table lookup is plain arithmetic on stored doubles
+    nofma = [("inice_kernels.cu", "inice_kernels.o"), ("oldtable_kernels.cu", "oldtable_kernels.o")]
+    nofma_src = [os.path.join(CSRC, a) for a, _ in nofma]
+    nofma_obj = [os.path.join(LIBDIR, b) for _, b in nofma]
+    if force or _newer(core, core_src + nofma_src + headers):
+        for src, obj in zip(nofma_src, nofma_obj):
+            _run(["nvcc"] + NVCC_FLAGS + extra + ["-fmad=false", "-c", "-o", obj, src])
+        _run(["nvcc"] + NVCC_FLAGS + extra + ["-shared", "-o", core] + core_src + nofma_obj)
 
     # source-compatible C++ API (namespace MultiRayAirIceRefraction) on top of the C ABI
     compat = os.path.join(LIBDIR, "libMultiRayAirIceRefraction.so")

@@ -54,8 +54,11 @@ struct airice_ctx {
   double* clamp_tab = nullptr;       // device copy of the clamped-bracket table (medium.clamp_tab points at it)
   // buffers of destroyed tables kept for the next table of the same size (a per-antenna loop creates and destroys 64
   // tables of 384 + 455 MB: cudaMalloc / cudaFree of that size cost more than building the table, and jitter wildly)
-  struct SpareBuf { void* p; size_t bytes; };
+  // events: recorded at release time on every stream that used the table; the next owner's build stream waits on them
+  // (no host synchronisation when a table is destroyed)
+  struct SpareBuf { void* p; size_t bytes; std::vector<cudaEvent_t> events; };
   std::vector<SpareBuf> spare;
+  std::vector<airice_table*> tables;   // live tables; airice_destroy detaches them
   // scratch of the solve kernel's two-pass launch, one per stream that has run a solve (launches on one stream are
   // ordered, so they can share it): a counter in the first 256 bytes, then room for `cap` deferred pair indices
   struct DeferScratch { int32_t* buf = nullptr; int64_t cap = 0; };
@@ -82,6 +85,18 @@ struct airice_ctx {
   }
 };
 
+struct airice_oldtable {
+  airice_ctx* ctx = nullptr;
+  int device = 0;
+  int n_h = 0, n_th = 0;
+  int64_t points = 0;
+  double start_h = 0, stop_h = 0, step_h = 0, start_th = 0, stop_th = 0, step_th = 0;
+  std::vector<double> pos_h, pos_th;     // GridPositionH / GridPositionTh
+  double* block = nullptr;               // 9 columns, then the two position arrays (one allocation)
+  double* d_pos_h = nullptr;
+  double* d_pos_th = nullptr;
+};
+
 struct airice_table {
   airice_ctx* ctx = nullptr;
   bool owns = false;
@@ -96,6 +111,11 @@ struct airice_table {
   int* row_last = nullptr;
   int64_t n_h = 0, n_th = 0, cells = 0;
   double loop_stop_h = 0, h_step = 0;
+  mutable std::vector<cudaStream_t> used;   // streams that ran lookups on this table (besides the build stream 0)
+  void note_stream(cudaStream_t s) const {
+    for (cudaStream_t u : used) if (u == s) return;
+    used.push_back(s);
+  }
   LookupTable view() const {
     LookupTable t;
     t.x = x; t.rec = rec; t.row_h = row_h;
@@ -108,7 +128,14 @@ struct airice_table {
 
 namespace {
 
-// Allocate and fill the lookup layout of a table from its column-major form.
+void drop_spares(airice_ctx* c) {
+  for (auto& b : c->spare) {
+    for (cudaEvent_t ev : b.events) cudaEventDestroy(ev);
+    cudaFree(b.p);                 // cudaFree waits for the device
+  }
+  c->spare.clear();
+}
+
 // table-sized device buffers: reuse a spare of (nearly) the right size, else allocate
 cudaError_t table_alloc(airice_ctx* c, void** p, size_t bytes) {
   // best fit: the column block (384 MB) and the lookup layout (455 MB) of the reference grid fall into each other's
@@ -121,19 +148,20 @@ cudaError_t table_alloc(airice_ctx* c, void** p, size_t bytes) {
   }
   if (best < c->spare.size()) {
     *p = c->spare[best].p;
+    // tables are built on the legacy default stream: it waits for the previous owner's last users
+    for (cudaEvent_t ev : c->spare[best].events) { cudaStreamWaitEvent(nullptr, ev, 0); cudaEventDestroy(ev); }
     c->spare.erase(c->spare.begin() + best);
     return cudaSuccess;
   }
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess && !c->spare.empty()) {      // out of memory: give the spares back and retry
     cudaGetLastError();
-    for (auto& b : c->spare) cudaFree(b.p);
-    c->spare.clear();
+    drop_spares(c);
     e = cudaMalloc(p, bytes);
   }
   return e;
 }
-void table_release(airice_ctx* c, void* p, size_t bytes) {
+void table_release(airice_ctx* c, void* p, size_t bytes, const std::vector<cudaStream_t>& used) {
   if (!p) return;
   // keep freed table buffers for the next tables of that size (cudaMalloc/cudaFree of a 400 MB block cost more than
   // building the table): up to a third of the device's memory, 64 antennas' tables (54 GB) included on a B200;
@@ -145,8 +173,19 @@ void table_release(airice_ctx* c, void* p, size_t bytes) {
     c->spare_cap = (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ? total_b / 3 : ((size_t)2 << 30);
   }
   if (bytes >= ((size_t)1 << 20) && held + bytes <= c->spare_cap && c->spare.size() < 512) {
-    cudaDeviceSynchronize();                        // what cudaFree would have waited for
-    c->spare.push_back({p, bytes});
+    // what cudaFree would have waited for, as events instead of a device-wide synchronisation
+    airice_ctx::SpareBuf b{p, bytes, {}};
+    auto mark = [&](cudaStream_t s) {
+      cudaEvent_t ev;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return false;
+      if (cudaEventRecord(ev, s) != cudaSuccess) { cudaEventDestroy(ev); return false; }
+      b.events.push_back(ev);
+      return true;
+    };
+    bool okm = mark(nullptr);
+    for (cudaStream_t s : used) if (s) okm = mark(s) && okm;
+    if (!okm) { cudaGetLastError(); cudaDeviceSynchronize(); }
+    c->spare.push_back(b);
   } else {
     cudaFree(p);
   }
@@ -301,6 +340,18 @@ int airice_create(const char* atmosphere_path, int variant, int device, airice_c
 void airice_destroy(airice_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  // tables that outlive their context: free their device memory now and leave the handles as empty shells that
+  // airice_table_destroy can still be called on (every other call on them fails with "null table")
+  for (airice_table* t : c->tables) {
+    if (t->owns && t->cols[0]) cudaFree(t->cols[0]);
+    if (t->pack) cudaFree(t->pack);
+    for (auto& col : t->cols) col = nullptr;
+    t->pack = nullptr; t->x = nullptr; t->rec = nullptr; t->row_h = nullptr; t->row_first = t->row_last = nullptr;
+    t->cells = 0; t->n_h = 0;
+    t->ctx = nullptr;
+  }
+  c->tables.clear();
   for (int s = 0; s < airice_ctx::kSlots; s++) {
     if (c->dev[s]) cudaFree(c->dev[s]);
     if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
@@ -312,7 +363,7 @@ void airice_destroy(airice_ctx* c) {
   if (c->inice_cols) cudaFree(c->inice_cols);
   if (c->path_plans) cudaFree(c->path_plans);
   if (c->clamp_tab) cudaFree(c->clamp_tab);
-  for (auto& b : c->spare) cudaFree(b.p);
+  drop_spares(c);
   for (auto& d : c->defer) if (d.second.buf) cudaFree(d.second.buf);
   if (c->fork_ev) cudaEventDestroy(c->fork_ev);
   for (int s = 0; s < airice_ctx::kSlots; s++) if (c->join_ev[s]) cudaEventDestroy(c->join_ev[s]);
@@ -371,6 +422,7 @@ int airice_table_create(airice_ctx* c, double depth_m, double ice_m, double h_to
   if (rc) return fail(rc, err);
   airice_table* t = new airice_table();
   t->ctx = c; t->owns = true;
+  c->tables.push_back(t);
   t->n_h = g.first_skipped_row < g.n_h ? g.first_skipped_row : g.n_h;
   t->n_th = g.n_th; t->cells = t->n_h * t->n_th;
   t->loop_stop_h = g.loop_stop_h; t->h_step = g.h_step;
@@ -415,6 +467,7 @@ int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, 
     airice_table* t = new airice_table();
     out[q] = t;
     t->ctx = c; t->owns = true;
+    c->tables.push_back(t);
     t->n_h = n_h; t->n_th = g.n_th; t->cells = cells;
     t->loop_stop_h = g.loop_stop_h; t->h_step = g.h_step;
     float* block = nullptr;
@@ -465,6 +518,7 @@ int airice_table_wrap(airice_ctx* c, const float* const* d_cols32, int64_t n_h, 
   if (n_h * n_th >= 2147483647LL) return fail(-5, "lookup tables are limited to 2^31-1 cells");
   airice_table* t = new airice_table();
   t->ctx = c; t->owns = false;
+  c->tables.push_back(t);
   for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t->cols[k] = const_cast<float*>(d_cols32[k]);
   t->n_h = n_h; t->n_th = n_th; t->cells = n_h * n_th; t->loop_stop_h = loop_stop_h; t->h_step = h_step;
   int rc = pack_table(t);
@@ -475,33 +529,113 @@ int airice_table_wrap(airice_ctx* c, const float* const* d_cols32, int64_t n_h, 
 
 void airice_table_destroy(airice_table* t) {
   if (!t) return;
-  cudaSetDevice(t->ctx->device);
-  if (t->owns && t->cols[0]) table_release(t->ctx, t->cols[0], t->cols_bytes);
-  if (t->pack) table_release(t->ctx, t->pack, t->pack_bytes);
+  if (t->ctx) {                      // else: the context was destroyed first and took the device memory with it
+    airice_ctx* c = t->ctx;
+    cudaSetDevice(c->device);
+    if (t->owns && t->cols[0]) table_release(c, t->cols[0], t->cols_bytes, t->used);
+    if (t->pack) table_release(c, t->pack, t->pack_bytes, t->used);
+    for (size_t i = 0; i < c->tables.size(); i++)
+      if (c->tables[i] == t) { c->tables.erase(c->tables.begin() + i); break; }
+  }
   delete t;
 }
 
+// ---- table persistence.  File: 64-byte header {"AIRICETB", u32 version = 1, u32 columns = 11, i64 n_h, i64 n_th,
+// f64 loop_stop_h, f64 h_step, u64 FNV-1a of the payload, 8 reserved bytes}, then the 11 float columns in
+// AllTableAllAntData order, column-major, little-endian.
+namespace {
+struct TableFileHeader {
+  char magic[8];
+  uint32_t version, ncols;
+  int64_t n_h, n_th;
+  double loop_stop_h, h_step;
+  uint64_t checksum;
+  uint64_t reserved;
+};
+static_assert(sizeof(TableFileHeader) == 64, "header layout");
+uint64_t fnv1a(const void* p, size_t n) {
+  const unsigned char* b = (const unsigned char*)p;
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+}  // namespace
+
+int airice_table_save(const airice_table* t, const char* path) {
+  if (!t || !t->ctx || !path) return fail(-1, "null argument");
+  CK(cudaSetDevice(t->ctx->device));
+  const size_t n = (size_t)t->cells * AIRICE_TABLE_NCOLS32;
+  std::vector<float> host(n);
+  for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++)
+    CK(cudaMemcpy(host.data() + (size_t)k * t->cells, t->cols[k], sizeof(float) * (size_t)t->cells, cudaMemcpyDeviceToHost));
+  TableFileHeader hd;
+  std::memset(&hd, 0, sizeof(hd));
+  std::memcpy(hd.magic, "AIRICETB", 8);
+  hd.version = 1; hd.ncols = AIRICE_TABLE_NCOLS32; hd.n_h = t->n_h; hd.n_th = t->n_th;
+  hd.loop_stop_h = t->loop_stop_h; hd.h_step = t->h_step;
+  hd.checksum = fnv1a(host.data(), n * sizeof(float));
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return fail(-7, std::string("cannot open for writing: ") + path);
+  const bool okw = std::fwrite(&hd, sizeof(hd), 1, f) == 1 && std::fwrite(host.data(), sizeof(float), n, f) == n;
+  if (std::fclose(f) != 0 || !okw) return fail(-7, std::string("short write: ") + path);
+  return 0;
+}
+
+int airice_table_load(airice_ctx* c, const char* path, airice_table** out) {
+  if (!c || !path || !out) return fail(-1, "null argument");
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return fail(-7, std::string("cannot open: ") + path);
+  TableFileHeader hd;
+  if (std::fread(&hd, sizeof(hd), 1, f) != 1) { std::fclose(f); return fail(-8, "table file: truncated header"); }
+  if (std::memcmp(hd.magic, "AIRICETB", 8) != 0) { std::fclose(f); return fail(-8, "table file: bad magic"); }
+  if (hd.version != 1 || hd.ncols != AIRICE_TABLE_NCOLS32) { std::fclose(f); return fail(-8, "table file: unsupported version / column count"); }
+  if (hd.n_h <= 0 || hd.n_th <= 0 || hd.n_h * hd.n_th >= 2147483647LL) { std::fclose(f); return fail(-8, "table file: bad dimensions"); }
+  const size_t cells = (size_t)(hd.n_h * hd.n_th), n = cells * AIRICE_TABLE_NCOLS32;
+  std::vector<float> host(n);
+  const size_t got = std::fread(host.data(), sizeof(float), n, f);
+  const bool extra = std::fgetc(f) != EOF;
+  std::fclose(f);
+  if (got != n || extra) return fail(-8, "table file: payload size does not match the header");
+  if (fnv1a(host.data(), n * sizeof(float)) != hd.checksum) return fail(-8, "table file: checksum mismatch");
+  CK(cudaSetDevice(c->device));
+  airice_table* t = new airice_table();
+  t->ctx = c; t->owns = true;
+  c->tables.push_back(t);
+  t->n_h = hd.n_h; t->n_th = hd.n_th; t->cells = (int64_t)cells; t->loop_stop_h = hd.loop_stop_h; t->h_step = hd.h_step;
+  float* block = nullptr;
+  t->cols_bytes = sizeof(float) * n;
+  cudaError_t e = table_alloc(c, (void**)&block, t->cols_bytes);
+  if (e != cudaSuccess) { airice_table_destroy(t); return cuda_fail(e, "cudaMalloc(table)"); }
+  for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t->cols[k] = block + (int64_t)k * t->cells;
+  e = cudaMemcpyAsync(block, host.data(), t->cols_bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e != cudaSuccess) { airice_table_destroy(t); return cuda_fail(e, "upload table"); }
+  int rc = pack_table(t);          // synchronises the stream: `host` may go
+  if (rc) { airice_table_destroy(t); return rc; }
+  *out = t;
+  return 0;
+}
+
 int airice_table_info(const airice_table* t, int64_t info[4]) {
-  if (!t) return fail(-1, "null table");
+  if (!t || !t->ctx) return fail(-1, "null table (or its context was destroyed)");
   info[0] = t->n_h; info[1] = t->n_th; info[2] = t->cells; info[3] = AIRICE_TABLE_NCOLS32;
   return 0;
 }
 
 int airice_table_copy_column(const airice_table* t, int col, float* host_out) {
-  if (!t || col < 0 || col >= AIRICE_TABLE_NCOLS32) return fail(-1, "bad table/column");
+  if (!t || !t->ctx || col < 0 || col >= AIRICE_TABLE_NCOLS32) return fail(-1, "bad table/column");
   CK(cudaSetDevice(t->ctx->device));
   CK(cudaMemcpy(host_out, t->cols[col], sizeof(float) * t->cells, cudaMemcpyDeviceToHost));
   return 0;
 }
 
 int airice_table_column_ptr(const airice_table* t, int col, const float** d_ptr) {
-  if (!t || col < 0 || col >= AIRICE_TABLE_NCOLS32) return fail(-1, "bad table/column");
+  if (!t || !t->ctx || col < 0 || col >= AIRICE_TABLE_NCOLS32) return fail(-1, "bad table/column");
   *d_ptr = t->cols[col];
   return 0;
 }
 
 int airice_table_copy_row_ranges(const airice_table* t, int32_t* host_first, int32_t* host_last) {
-  if (!t) return fail(-1, "null table");
+  if (!t || !t->ctx) return fail(-1, "null table");
   CK(cudaSetDevice(t->ctx->device));
   CK(cudaMemcpy(host_first, t->row_first, sizeof(int) * t->n_h, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(host_last, t->row_last, sizeof(int) * t->n_h, cudaMemcpyDeviceToHost));
@@ -674,6 +808,8 @@ int airice_lookup_device(airice_ctx* c, const airice_table* t, int64_t n, const 
   std::memset(&a, 0, sizeof(a));
   a.n = n; a.h_cm = d_h_cm; a.d_cm = d_dist_cm; a.ok = d_ok;
   for (int k = 0; k < AIRICE_LOOKUP_NCOLS; k++) a.out[k] = d_out[k];
+  if (t->ctx != c) return fail(-1, "table belongs to another (or a destroyed) context");
+  t->note_stream((cudaStream_t)stream);
   cudaError_t e = launch_lookup(c->medium, t->view(), a, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_lookup");
   return 0;
@@ -700,6 +836,7 @@ int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const do
     std::memset(&a, 0, sizeof(a));
     a.n = m; a.h_cm = dh; a.d_cm = dh + chunk; a.ok = (uint8_t*)(dh + (2 + nc) * chunk);
     for (int k = 0; k < nc; k++) a.out[k] = dh + (2 + k) * chunk;
+    t->note_stream(s);
     cudaError_t e = launch_lookup(c->medium, t->view(), a, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_lookup");
     for (int k = 0; k < nc; k++)
@@ -876,6 +1013,33 @@ int airice_inice_two_rays_host(airice_ctx* c, int64_t n, const double* rx_depth,
   return 0;
 }
 
+namespace {
+// plans: per-ray plan scratch for this launch, or nullptr = the context's own (grow-only; callers on one stream)
+int ray_path_launch(airice_ctx* c, int64_t n, const double* d_theta, const double* d_h, double depth_m, double ice_m,
+                    int64_t max_points, double* d_x, double* d_z, int32_t* d_count, void* plans, cudaStream_t s) {
+  const int in_ice = depth_m < 0 ? 1 : 0;
+  const AirIcePlan& p = c->plan(ice_m, in_ice ? depth_m : 0.0);
+  PathArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n; a.theta = d_theta; a.h = d_h; a.max_points = max_points; a.x = d_x; a.z = d_z; a.count = d_count;
+  if (!plans) {
+    const size_t need = path_plan_bytes() * (size_t)n;
+    if (c->path_plan_cap < need) {
+      CK(cudaDeviceSynchronize());      // an earlier call on another stream may still read the old scratch
+      if (c->path_plans) cudaFree(c->path_plans);
+      c->path_plans = nullptr; c->path_plan_cap = 0;
+      CK(cudaMalloc(&c->path_plans, need));
+      c->path_plan_cap = need;
+    }
+    plans = c->path_plans;
+  }
+  a.plans = (AirIcePathPlan*)plans;
+  cudaError_t e = launch_ray_path(c->medium, p, a, s);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_ray_path");
+  return 0;
+}
+}  // namespace
+
 int airice_ray_path_device(airice_ctx* c, int64_t n, const double* d_theta, const double* d_h, double depth_m, double ice_m,
                            int64_t max_points, double* d_x, double* d_z, int32_t* d_count, void* stream) {
   if (!c) return fail(-1, "null context");
@@ -883,25 +1047,7 @@ int airice_ray_path_device(airice_ctx* c, int64_t n, const double* d_theta, cons
   if (!d_theta || !d_h || !d_count || (max_points > 0 && (!d_x || !d_z))) return fail(-1, "null argument");
   if (max_points < 0) return fail(-3, "max_points < 0");
   CK(cudaSetDevice(c->device));
-  cudaStream_t s = (cudaStream_t)stream;
-  const int in_ice = depth_m < 0 ? 1 : 0;
-  const AirIcePlan& p = c->plan(ice_m, in_ice ? depth_m : 0.0);
-  PathArgs a;
-  std::memset(&a, 0, sizeof(a));
-  a.n = n; a.theta = d_theta; a.h = d_h; a.max_points = max_points; a.x = d_x; a.z = d_z; a.count = d_count;
-  // plan scratch owned by the context (grow-only; a context serves one call at a time)
-  const size_t need = path_plan_bytes() * (size_t)n;
-  if (c->path_plan_cap < need) {
-    CK(cudaStreamSynchronize(s));
-    if (c->path_plans) cudaFree(c->path_plans);
-    c->path_plans = nullptr; c->path_plan_cap = 0;
-    CK(cudaMalloc(&c->path_plans, need));
-    c->path_plan_cap = need;
-  }
-  a.plans = (AirIcePathPlan*)c->path_plans;
-  cudaError_t e = launch_ray_path(c->medium, p, a, s);
-  if (e != cudaSuccess) return cuda_fail(e, "launch_ray_path");
-  return 0;
+  return ray_path_launch(c, n, d_theta, d_h, depth_m, ice_m, max_points, d_x, d_z, d_count, nullptr, (cudaStream_t)stream);
 }
 
 int airice_ray_path_host(airice_ctx* c, int64_t n, const double* theta, const double* h, double depth_m, double ice_m,
@@ -915,7 +1061,10 @@ int airice_ray_path_host(airice_ctx* c, int64_t n, const double* theta, const do
   int64_t chunk = max_points > 0 ? (int64_t)(16 << 20) / max_points : n;
   if (chunk < 1) chunk = 1;
   if (chunk > n) chunk = n;
-  int rc = ensure_slots(c, (size_t)chunk * (sizeof(double) * (2 + 2 * (size_t)max_points) + sizeof(int32_t)) + 64);
+  // each staging slot carries its own plan scratch: consecutive chunks run on two streams, and the plan kernel of chunk
+  // k+1 must not overwrite the plans the fill kernel of chunk k is still reading
+  const size_t plan_off = ((size_t)chunk * (sizeof(double) * (2 + 2 * (size_t)max_points) + sizeof(int32_t)) + 255) / 256 * 256;
+  int rc = ensure_slots(c, plan_off + path_plan_bytes() * (size_t)chunk + 64);
   if (rc) return rc;
   int slot = 0;
   for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
@@ -925,15 +1074,178 @@ int airice_ray_path_host(airice_ctx* c, int64_t n, const double* theta, const do
     double* dx = dh + 2 * chunk;
     double* dz = dx + chunk * max_points;
     int32_t* dc = (int32_t*)(dz + chunk * max_points);
+    void* plans = (char*)c->dev[slot] + plan_off;
     CK(cudaMemcpyAsync(dh, theta + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(dh + chunk, h + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
-    rc = airice_ray_path_device(c, m, dh, dh + chunk, depth_m, ice_m, max_points, dx, dz, dc, s);
+    rc = ray_path_launch(c, m, dh, dh + chunk, depth_m, ice_m, max_points, dx, dz, dc, plans, s);
     if (rc) return rc;
     if (max_points > 0) {
       CK(cudaMemcpyAsync(x + off * max_points, dx, sizeof(double) * m * max_points, cudaMemcpyDeviceToHost, s));
       CK(cudaMemcpyAsync(z + off * max_points, dz, sizeof(double) * m * max_points, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaMemcpyAsync(count + off, dc, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s));
+  }
+  for (int s = 0; s < airice_ctx::kSlots; s++)
+    if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
+  return 0;
+}
+
+// ---- kernel 6: old solve-per-cell table + inverse-distance lookup (MakeTable / GetInterpolatedValue)
+namespace {
+int oldtable_shape(airice_oldtable* t, double ice_m, double start_th, double stop_th, double step_h, double step_th) {
+  if (!(step_h > 0) || !(step_th > 0) || !(stop_th > start_th)) return fail(-3, "bad old-table grid");
+  t->start_h = ice_m + 1;                       // MultiRayAirIceRefraction.cc:1629-1636
+  t->stop_h = 100000;
+  t->start_th = start_th; t->stop_th = stop_th; t->step_h = step_h; t->step_th = step_th;
+  const double wh = t->stop_h - t->start_h, wt = stop_th - start_th;
+  const double nh = (wh / step_h) + 1, nt = (wt / step_th) + 1;
+  if (!(nh >= 2) || !(nt >= 2) || nh * nt >= 2147483647.0) return fail(-5, "old-table grid needs 2 .. 2^31-1 nodes (the reference indexes them with int)");
+  t->n_h = (int)nh; t->n_th = (int)nt;          // the reference's double -> int truncation
+  t->points = (int64_t)t->n_h * t->n_th;
+  t->pos_h.resize(t->n_h); t->pos_th.resize(t->n_th);
+  for (int ih = 0; ih < t->n_h; ih++) t->pos_h[ih] = (ih == t->n_h - 1) ? t->stop_h : t->start_h + step_h * ih;
+  for (int it = 0; it < t->n_th; it++) t->pos_th[it] = (it == t->n_th - 1) ? stop_th : start_th + step_th * it;
+  return 0;
+}
+int oldtable_alloc(airice_oldtable* t) {
+  const size_t cols_b = sizeof(double) * (size_t)t->points * AIRICE_OLDTABLE_COLS;
+  const size_t pos_b = sizeof(double) * ((size_t)t->n_h + (size_t)t->n_th);
+  CK(cudaMalloc((void**)&t->block, cols_b + pos_b));
+  t->d_pos_h = t->block + (size_t)t->points * AIRICE_OLDTABLE_COLS;
+  t->d_pos_th = t->d_pos_h + t->n_h;
+  CK(cudaMemcpy(t->d_pos_h, t->pos_h.data(), sizeof(double) * t->n_h, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(t->d_pos_th, t->pos_th.data(), sizeof(double) * t->n_th, cudaMemcpyHostToDevice));
+  return 0;
+}
+}  // namespace
+
+int airice_oldtable_create(airice_ctx* c, double ice_m, double depth_m, double start_th, double stop_th, double step_h,
+                           double step_th, airice_oldtable** out) {
+  if (!c || !out) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  airice_oldtable* t = new airice_oldtable();
+  t->ctx = c; t->device = c->device;
+  int rc = oldtable_shape(t, ice_m, start_th, stop_th, step_h, step_th);
+  if (rc == 0) rc = oldtable_alloc(t);
+  if (rc) { airice_oldtable_destroy(t); return rc; }
+  // tan() of the node angles on the host: the distance each node asks for is formed from glibc's tan like the reference's
+  std::vector<double> tn(t->n_th);
+  for (int it = 0; it < t->n_th; it++) tn[it] = tan((180 - t->pos_th[it]) * (c->medium.pi / 180.0));
+  const int64_t chunk = t->points < (4 << 20) ? t->points : (4 << 20);
+  double* scratch = nullptr;     // [tan n_th] then 11 columns of one chunk: h, d, th | X, X_air, t_air, t_ice, launch, T_S, T_P, incident
+  cudaError_t e = cudaMalloc((void**)&scratch, sizeof(double) * ((size_t)t->n_th + 11 * (size_t)chunk));
+  if (e != cudaSuccess) { airice_oldtable_destroy(t); return cuda_fail(e, "cudaMalloc(old table scratch)"); }
+  auto done = [&](int code) { cudaFree(scratch); if (code) airice_oldtable_destroy(t); return code; };
+  e = cudaMemcpy(scratch, tn.data(), sizeof(double) * t->n_th, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return done(cuda_fail(e, "upload tangents"));
+  double* col = scratch + t->n_th;
+  for (int64_t off = 0; off < t->points && rc == 0; off += chunk) {
+    const int64_t m = t->points - off < chunk ? t->points - off : chunk;
+    OldGridArgs g;
+    std::memset(&g, 0, sizeof(g));
+    g.cell0 = off; g.n = m; g.n_th = t->n_th; g.pos_h = t->d_pos_h; g.pos_th = t->d_pos_th; g.col_tan = scratch;
+    g.ice = ice_m; g.depth = depth_m; g.h = col; g.d = col + chunk; g.th = col + 2 * chunk;
+    e = launch_oldgrid_cells(g, nullptr);
+    if (e != cudaSuccess) return done(cuda_fail(e, "launch_oldgrid_cells"));
+    double* cols[AIRICE_SOLVE_NCOLS] = {nullptr};
+    const int want[8] = {0, 1, 3, 4, 5, 7, 8, 11};
+    for (int k = 0; k < 8; k++) cols[want[k]] = col + (3 + k) * chunk;
+    // ok flag not needed (MakeTable applies its own acceptance test); the solver wants a flag buffer: reuse the h column's tail? no -- own bytes
+    rc = airice_solve_device(c, m, g.h, g.d, g.th, depth_m, ice_m, AIRICE_UNITS_M_DEG, cols, nullptr, nullptr, nullptr);
+    if (rc) return done(rc);
+    OldPackArgs pk;
+    std::memset(&pk, 0, sizeof(pk));
+    pk.n = m; pk.h = g.h; pk.d = g.d; pk.x = cols[0]; pk.x_air = cols[1]; pk.t_air = cols[3]; pk.t_ice = cols[4];
+    pk.launch = cols[5]; pk.ts = cols[7]; pk.tp = cols[8]; pk.inc = cols[11]; pk.c = c->medium.c;
+    for (int k = 0; k < AIRICE_OLDTABLE_COLS; k++) pk.col[k] = t->block + (size_t)k * t->points + off;
+    e = launch_oldgrid_pack(pk, nullptr);
+    if (e != cudaSuccess) return done(cuda_fail(e, "launch_oldgrid_pack"));
+  }
+  e = cudaStreamSynchronize(nullptr);
+  if (e != cudaSuccess) return done(cuda_fail(e, "old table"));
+  *out = t;
+  return done(0);
+}
+
+int airice_oldtable_wrap_host(airice_ctx* c, double ice_m, double start_th, double stop_th, double step_h, double step_th,
+                              const double* cols9, airice_oldtable** out) {
+  if (!c || !out || !cols9) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  airice_oldtable* t = new airice_oldtable();
+  t->ctx = c; t->device = c->device;
+  int rc = oldtable_shape(t, ice_m, start_th, stop_th, step_h, step_th);
+  if (rc == 0) rc = oldtable_alloc(t);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpy(t->block, cols9, sizeof(double) * (size_t)t->points * AIRICE_OLDTABLE_COLS, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "upload old table");
+  }
+  if (rc) { airice_oldtable_destroy(t); return rc; }
+  *out = t;
+  return 0;
+}
+
+void airice_oldtable_destroy(airice_oldtable* t) {
+  if (!t) return;
+  if (t->block) { cudaSetDevice(t->device); cudaFree(t->block); }
+  delete t;
+}
+
+int airice_oldtable_info(const airice_oldtable* t, int64_t info[3]) {
+  if (!t || !info) return fail(-1, "null argument");
+  info[0] = t->n_h; info[1] = t->n_th; info[2] = t->points;
+  return 0;
+}
+
+int airice_oldtable_copy_column(const airice_oldtable* t, int col, double* host_out) {
+  if (!t || !host_out || col < 0 || col >= AIRICE_OLDTABLE_COLS) return fail(-1, "bad table/column");
+  CK(cudaSetDevice(t->device));
+  CK(cudaMemcpy(host_out, t->block + (size_t)col * t->points, sizeof(double) * (size_t)t->points, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int airice_oldtable_copy_positions(const airice_oldtable* t, double* host_h, double* host_th) {
+  if (!t || !host_h || !host_th) return fail(-1, "null argument");
+  std::memcpy(host_h, t->pos_h.data(), sizeof(double) * t->n_h);
+  std::memcpy(host_th, t->pos_th.data(), sizeof(double) * t->n_th);
+  return 0;
+}
+
+int airice_oldtable_interp_device(airice_ctx* c, const airice_oldtable* t, int64_t n, const double* d_h, const double* d_th,
+                                  int rt_parameter, double* d_out, void* stream) {
+  if (!c || !t) return fail(-1, "null argument");
+  if (rt_parameter < 0 || rt_parameter >= AIRICE_OLDTABLE_COLS) return fail(-1, "rtParameter out of range (0..8)");
+  if (n == 0) return 0;
+  if (!d_h || !d_th || !d_out) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  OldInterpArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n; a.h = d_h; a.th = d_th; a.z = t->block + (size_t)rt_parameter * t->points; a.pos_h = t->d_pos_h; a.pos_th = t->d_pos_th;
+  a.n_h = t->n_h; a.n_th = t->n_th; a.start_h = t->start_h; a.start_th = t->start_th; a.step_h = t->step_h; a.step_th = t->step_th;
+  a.out = d_out;
+  cudaError_t e = launch_old_interp(a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_old_interp");
+  return 0;
+}
+
+int airice_oldtable_interp_host(airice_ctx* c, const airice_oldtable* t, int64_t n, const double* h, const double* th,
+                                int rt_parameter, double* out) {
+  if (!c || !t) return fail(-1, "null argument");
+  if (n == 0) return 0;
+  if (!h || !th || !out) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int64_t chunk = n < (1 << 20) ? n : (1 << 20);
+  int rc = ensure_slots(c, (size_t)chunk * sizeof(double) * 3 + 64);
+  if (rc) return rc;
+  int slot = 0;
+  for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    double* dh = (double*)c->dev[slot];
+    cudaStream_t s = c->streams[slot];
+    CK(cudaMemcpyAsync(dh, h + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, th + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    rc = airice_oldtable_interp_device(c, t, m, dh, dh + chunk, rt_parameter, dh + 2 * chunk, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out + off, dh + 2 * chunk, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
   }
   for (int s = 0; s < airice_ctx::kSlots; s++)
     if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
@@ -1001,8 +1313,7 @@ int airice_trim(airice_ctx* c) {
   if (!c) return fail(-1, "null context");
   CK(cudaSetDevice(c->device));
   CK(cudaDeviceSynchronize());
-  for (auto& b : c->spare) cudaFree(b.p);
-  c->spare.clear();
+  drop_spares(c);
   for (auto& d : c->defer) if (d.second.buf) cudaFree(d.second.buf);
   c->defer.clear();
   return 0;

@@ -168,6 +168,37 @@ struct PathArgs {
 size_t path_plan_bytes();
 cudaError_t launch_ray_path(const AirIceMedium& m, const AirIcePlan& p, const PathArgs& a, cudaStream_t s);
 
+// ---- kernel 6: the old solve-per-cell table (MakeTable, M.cc:1618-1696) and its inverse-distance lookup
+// (GetInterpolatedValue, M.cc:1700-1794); oldtable_kernels.cu
+struct OldGridArgs {
+  int64_t cell0, n;        // nodes [cell0, cell0 + n) of the grid, node = ih * n_th + ith
+  int n_th;
+  const double* pos_h;     // GridPositionH [n_h] (host-made: start + step * ih, last snapped, M.cc:1646-1655)
+  const double* pos_th;    // GridPositionTh [n_th]
+  const double* col_tan;   // tan((180 - th) * (pi / 180)) per angle node (host libm)
+  double ice, depth;       // m; depth signed as the caller passed it
+  double *h, *d, *th;      // outputs [n]: the solver's inputs (Tx height, distance, StraightAngle)
+};
+cudaError_t launch_oldgrid_cells(const OldGridArgs& a, cudaStream_t s);
+struct OldPackArgs {
+  int64_t n;
+  const double *h, *d;                                          // node height and requested distance
+  const double *x, *x_air, *t_air, *t_ice, *launch, *ts, *tp, *inc;   // kernel 2, M_DEG columns 0, 1, 3, 4, 5, 7, 8, 11
+  double c;                                                     // spedc: optical path = time * c
+  double* col[9];                                               // GridZValue[0..8] at this chunk's first node
+};
+cudaError_t launch_oldgrid_pack(const OldPackArgs& a, cudaStream_t s);
+struct OldInterpArgs {
+  int64_t n;
+  const double *h, *th;    // queries (m, deg)
+  const double* z;         // the GridZValue column asked for
+  const double *pos_h, *pos_th;
+  int n_h, n_th;
+  double start_h, start_th, step_h, step_th;
+  double* out;
+};
+cudaError_t launch_old_interp(const OldInterpArgs& a, cudaStream_t s);
+
 // ---- FP64 FMA peak probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
 cudaError_t fp64_peak_probe(double* tflops_out, int iters, cudaStream_t s);
 

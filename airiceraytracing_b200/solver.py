@@ -2,6 +2,7 @@
 MakeAtmosphere() once, then tables / solves / lookups).  All arrays are torch CUDA tensors (device API) or
 numpy / pinned torch CPU tensors (host API); nothing is computed in Python."""
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -36,6 +37,7 @@ class Table:
 
     def __init__(self, solver, handle, keepalive=None):
         self.solver, self.handle, self._keep = solver, handle, keepalive
+        solver._tables.add(self)          # closed with the solver: a table must not outlive its context
         info = (C.c_int64 * 4)()
         check(solver.lib.airice_table_info(handle, info))
         self.n_h, self.n_th, self.cells = int(info[0]), int(info[1]), int(info[2])
@@ -52,9 +54,65 @@ class Table:
         check(self.solver.lib.airice_table_copy_row_ranges(self.handle, first.ctypes.data, last.ctypes.data))
         return first, last
 
+    def save(self, path):
+        """Write the 11 float columns + grid description to a versioned file (airice_table_save)."""
+        check(self.solver.lib.airice_table_save(self.handle, str(path).encode()))
+
     def close(self):
         if self.handle:
-            self.solver.lib.airice_table_destroy(self.handle)
+            if getattr(self.solver, "handle", None):     # the context is gone: its tables went with it
+                self.solver.lib.airice_table_destroy(self.handle)
+            self.handle = None
+            self.solver._tables.discard(self)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class OldTable:
+    """Device-resident old solve-per-cell grid (GridZValue[0..8]) with batched GetInterpolatedValue."""
+
+    def __init__(self, solver, handle):
+        self.solver, self.handle = solver, handle
+        info = (C.c_int64 * 3)()
+        check(solver.lib.airice_oldtable_info(handle, info))
+        self.n_h, self.n_th, self.points = int(info[0]), int(info[1]), int(info[2])
+
+    def columns(self):
+        out = np.empty((9, self.points), dtype=np.float64)
+        for k in range(9):
+            check(self.solver.lib.airice_oldtable_copy_column(self.handle, k, out[k].ctypes.data))
+        return out
+
+    def positions(self):
+        ph, pt = np.empty(self.n_h), np.empty(self.n_th)
+        check(self.solver.lib.airice_oldtable_copy_positions(self.handle, ph.ctypes.data, pt.ctypes.data))
+        return ph, pt
+
+    def interp(self, h, th, par):
+        s = self.solver
+        h = h.to(s.torch_device, torch.float64).contiguous()
+        th = th.to(s.torch_device, torch.float64).contiguous()
+        out = torch.empty_like(h)
+        check(s.lib.airice_oldtable_interp_device(s.handle, self.handle, h.numel(), h.data_ptr(), th.data_ptr(), int(par),
+                                                  out.data_ptr(), _stream_ptr(s.torch_device)))
+        return out
+
+    def interp_host(self, h, th, par):
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        th = np.ascontiguousarray(th, dtype=np.float64)
+        out = np.empty_like(h)
+        check(self.solver.lib.airice_oldtable_interp_host(self.solver.handle, self.handle, h.size, h.ctypes.data, th.ctypes.data,
+                                                          int(par), out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.handle:
+            if getattr(self.solver, "handle", None):
+                self.solver.lib.airice_oldtable_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -67,6 +125,7 @@ class Table:
 class AirIceSolver:
     def __init__(self, atmosphere="Atmosphere.dat", variant=_capi.VARIANT_MULTIRAY, device=0):
         self.lib = _capi.load()
+        self._tables = weakref.WeakSet()
         if not torch.cuda.is_available():
             raise _capi.AirIceError("no CUDA device visible: airiceraytracing_b200 has no CPU path")
         self.device = int(device)
@@ -78,6 +137,8 @@ class AirIceSolver:
 
     def close(self):
         if getattr(self, "handle", None):
+            for t in list(self._tables):
+                t.close()
             self.lib.airice_destroy(self.handle)
             self.handle = None
 
@@ -206,6 +267,23 @@ class AirIceSolver:
         check(self.lib.airice_table_create_multi(self.handle, n, dep, ice_m, h_top, h_step, th_start, th_step, th_stop,
                                                  C.cast(hs, C.POINTER(C.c_void_p))))
         return [Table(self, C.c_void_p(hs[q])) for q in range(n)]
+
+    def table_load(self, path):
+        h = C.c_void_p()
+        check(self.lib.airice_table_load(self.handle, str(path).encode(), C.byref(h)))
+        return Table(self, h)
+
+    def oldtable_create(self, ice_m, depth_m, start_th=90.05, stop_th=179.95, step_h=25.0, step_th=0.01):
+        """MakeTable (old solve-per-cell grid) on the device; reference defaults = 3880 x 8990 solves."""
+        h = C.c_void_p()
+        check(self.lib.airice_oldtable_create(self.handle, ice_m, depth_m, start_th, stop_th, step_h, step_th, C.byref(h)))
+        return OldTable(self, h)
+
+    def oldtable_wrap(self, cols9, ice_m, start_th, stop_th, step_h, step_th):
+        cols9 = np.ascontiguousarray(cols9, dtype=np.float64)
+        h = C.c_void_p()
+        check(self.lib.airice_oldtable_wrap_host(self.handle, ice_m, start_th, stop_th, step_h, step_th, cols9.ctypes.data, C.byref(h)))
+        return OldTable(self, h)
 
     def table_wrap(self, cols32, n_h, n_th, loop_stop_h, h_step):
         """Wrap an [11, n_h*n_th] float32 device tensor (kept alive by the returned Table)."""

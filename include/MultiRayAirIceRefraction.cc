@@ -34,6 +34,7 @@ struct State {
   std::vector<airice_table *> tables;          // index = order of MakeRayTracingTable calls
   double ice_set[3] = {1.78, -0.43, 0.0132};
   long mtime = -1, size = -1;
+  airice_oldtable *old_table = nullptr;        // device copy of GridZValue (last MakeTable)
 };
 inline State &state() {
   static State s;
@@ -205,6 +206,22 @@ int MakeRayTracingTables(const std::vector<double> &AntennaDepths_cm, double Ice
   return 0;
 }
 
+// Persistence (new): the reference rebuilds every table in every process.
+int SaveRayTracingTable(int AntennaNumber, const std::string &path) {
+  detail::State &s = detail::state();
+  if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size()) return 1;
+  if (airice_table_save(s.tables[AntennaNumber], path.c_str()) != 0) { detail::report("SaveRayTracingTable"); return 1; }
+  return 0;
+}
+int LoadRayTracingTable(const std::string &path) {
+  if (MakeAtmosphere() != 0) return -1;
+  detail::State &s = detail::state();
+  airice_table *t = nullptr;
+  if (airice_table_load(s.ctx, path.c_str(), &t) != 0) { detail::report("LoadRayTracingTable"); return -1; }
+  s.tables.push_back(t);
+  return (int)s.tables.size() - 1;
+}
+
 int GetTableColumn(int AntennaNumber, int col, std::vector<float> &out) {
   detail::State &s = detail::state();
   if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size()) return 1;
@@ -324,59 +341,50 @@ void GetRayTracingSolutions(double RayLaunchAngleInAir, double AirTxHeight, doub
   for (int i = 0; i < AIRICE_TABLE_COLS64; i++) dummy[1 + i] = o[i];
 }
 
-// MultiRayAirIceRefraction.cc:1618-1696: the old solve-per-cell table, one launch of the batched solver over the
-// whole (height x straight-angle) grid.  cm in; nine double columns, -1000 where the solve misses.
+// MultiRayAirIceRefraction.cc:1618-1696: the old solve-per-cell table.  The grid is generated, solved and kept on the GPU
+// (airice_oldtable_create: one launch-angle solve per node in batched launches); the reference's public GridZValue /
+// GridPosition vectors are filled from it so that code reading them keeps working.  cm in; nine double columns, -1000 where
+// the solve misses.
 void MakeTable(double IceLayerHeight, double AntennaDepth) {
   IceLayerHeight = IceLayerHeight / 100;
   AntennaDepth = AntennaDepth / 100;
   std::cout << "making the table now " << AntennaDepth << " " << IceLayerHeight << std::endl;
   if (MakeAtmosphere() != 0) return;
+  detail::State &st = detail::state();
+  if (st.old_table) { airice_oldtable_destroy(st.old_table); st.old_table = nullptr; }
   GridStartH = IceLayerHeight + 1;
   GridStopH = 100000;
   GridWidthH = GridStopH - GridStartH;
   GridWidthTh = GridStopTh - GridStartTh;
-  TotalStepsH_O = (GridWidthH / GridStepSizeH_O) + 1;
-  TotalStepsTh_O = (GridWidthTh / GridStepSizeTh_O) + 1;
-  GridPoints = TotalStepsH_O * TotalStepsTh_O;
-  GridPositionH.resize(TotalStepsH_O);
-  GridPositionTh.resize(TotalStepsTh_O);
-  const long n = (long)TotalStepsH_O * TotalStepsTh_O;
-  std::vector<double> hh(n), dd(n), th(n), out((size_t)n * AIRICE_SOLVE_COLS);
-  std::vector<unsigned char> ok(n);
-  for (int ih = 0; ih < TotalStepsH_O; ih++) {
-    for (int ith = 0; ith < TotalStepsTh_O; ith++) {
-      double h = GridStartH + GridStepSizeH_O * ih;
-      double t = GridStartTh + GridStepSizeTh_O * ith;
-      if (ih == TotalStepsH_O - 1) h = GridStopH;
-      if (ith == TotalStepsTh_O - 1) t = GridStopTh;
-      GridPositionH[ih] = h;
-      GridPositionTh[ith] = t;
-      const long i = (long)ih * TotalStepsTh_O + ith;
-      hh[i] = h; th[i] = t;
-      dd[i] = (h - IceLayerHeight + AntennaDepth) * tan((180 - t) * (pi / 180.0));  // MultiRayAirIceRefraction.cc:1662
-    }
-  }
   for (int c = 0; c < 10; c++) GridZValue[c].clear();
-  if (airice_solve_host(detail::state().ctx, n, hh.data(), dd.data(), th.data(), AntennaDepth, IceLayerHeight,
-                        AIRICE_UNITS_M_DEG_C, out.data(), ok.data()) != 0) {
+  if (airice_oldtable_create(st.ctx, IceLayerHeight, AntennaDepth, GridStartTh, GridStopTh, GridStepSizeH_O, GridStepSizeTh_O,
+                             &st.old_table) != 0) {
     detail::report("MakeTable");
+    st.old_table = nullptr;
     return;
   }
-  for (int c = 0; c < 9; c++) GridZValue[c].resize(n);
-  const double *X = &out[0 * n], *Xair = &out[1 * n], *tair = &out[3 * n], *tice = &out[4 * n], *launch = &out[5 * n];
-  const double *ts = &out[7 * n], *tp = &out[8 * n], *inc = &out[11 * n];
-  for (long i = 0; i < n; i++) {
-    const double d = dd[i];
-    // the reference accepts on the distance test alone here (MultiRayAirIceRefraction.cc:1667), without the X<0 veto
-    const bool accept = (fabs(X[i] - d) / d < 0.01 && d <= 100) || (fabs(X[i] - d) < 1 && d > 100);
-    if (accept) {
-      GridZValue[0][i] = hh[i]; GridZValue[1][i] = X[i]; GridZValue[2][i] = tice[i] * spedc; GridZValue[3][i] = tair[i] * spedc;
-      GridZValue[4][i] = launch[i]; GridZValue[5][i] = Xair[i]; GridZValue[6][i] = ts[i]; GridZValue[7][i] = tp[i];
-      GridZValue[8][i] = inc[i];
-    } else {
-      for (int c = 0; c < 9; c++) GridZValue[c][i] = -1000;
-    }
+  int64_t info[3];
+  airice_oldtable_info(st.old_table, info);
+  TotalStepsH_O = (int)info[0];
+  TotalStepsTh_O = (int)info[1];
+  GridPoints = (int)info[2];
+  GridPositionH.resize(TotalStepsH_O);
+  GridPositionTh.resize(TotalStepsTh_O);
+  airice_oldtable_copy_positions(st.old_table, GridPositionH.data(), GridPositionTh.data());
+  for (int c = 0; c < AIRICE_OLDTABLE_COLS; c++) {
+    GridZValue[c].resize(GridPoints);
+    if (airice_oldtable_copy_column(st.old_table, c, GridZValue[c].data()) != 0) detail::report("MakeTable");
   }
+}
+
+// Batched GetInterpolatedValue on the device-resident grid of the last MakeTable (new, not in the reference): one thread
+// per query, same arithmetic as the scalar function below.  Returns 0 on success.
+int GetInterpolatedValueBatch(long n, const double *hR, const double *thR, int rtParameter, double *out) {
+  detail::State &st = detail::state();
+  if (!st.old_table) { std::cerr << "GetInterpolatedValueBatch: MakeTable has not been called" << std::endl; return -1; }
+  const int rc = airice_oldtable_interp_host(st.ctx, st.old_table, n, hR, thR, rtParameter, out);
+  if (rc != 0) detail::report("GetInterpolatedValueBatch");
+  return rc;
 }
 
 // MultiRayAirIceRefraction.cc:1700-1794: inverse-distance weighting over the 2x2 nodes below/left of the rounded bin,

@@ -67,6 +67,11 @@ void GetRayTracingSolutions(double RayLaunchAngleInAir, double AirTxHeight, doub
                             double dummy[20], bool &InIce);
 void MakeTable(double IceLayerHeight, double AntennaDepth);
 double GetInterpolatedValue(double hR, double thR, int rtParameter);
+// batched form on the GPU-resident grid of the last MakeTable (new): out[i] = GetInterpolatedValue(hR[i], thR[i], rtParameter)
+int GetInterpolatedValueBatch(long n, const double *hR, const double *thR, int rtParameter, double *out);
+// persistence of a forward table (new; the reference rebuilds every table per process): writes / appends table AntennaNumber
+int SaveRayTracingTable(int AntennaNumber, const std::string &path);
+int LoadRayTracingTable(const std::string &path);   // appended like a MakeRayTracingTable call; returns its index or -1
 
 // ---- the medium model as the reference exposes it (MultiRayAirIceRefraction.h:90-119): parameters of the parsed
 // atmosphere held by the GPU context (needs MakeAtmosphere(), i.e. a GPU) and of the mutable ice model.  z in metres.

@@ -80,6 +80,12 @@ void airice_table_destroy(airice_table *t);
 int airice_table_info(const airice_table *t, int64_t info[4]);
 int airice_table_copy_column(const airice_table *t, int col, float *host_out);
 int airice_table_column_ptr(const airice_table *t, int col, const float **d_ptr);
+/* Persistence: the reference keeps AllTableAllAntData in memory only and rebuilds every table per
+ * process (50-90 s each on a CPU).  save writes the 11 float columns with a 64-byte versioned header (dimensions,
+ * loop_stop_h, h_step, checksum); load rebuilds the device table and its lookup layout from such a file -- lookups on the
+ * loaded table return the bits of the original.  Errors: -7 I/O, -8 not a table file / wrong version / damaged. */
+int airice_table_save(const airice_table *t, const char *path);
+int airice_table_load(airice_ctx *ctx, const char *path, airice_table **out);
 /* row trim ranges (FindClosestAirTxHeight's StartBin/EndBin scans, MultiRayAirIceRefraction.cc:1050-1072), per row */
 int airice_table_copy_row_ranges(const airice_table *t, int32_t *host_first, int32_t *host_last);
 
@@ -157,6 +163,32 @@ int airice_ray_path_device(airice_ctx *ctx, int64_t n, const double *d_theta, co
                            int64_t max_points, double *d_x, double *d_z, int32_t *d_count, void *stream);
 int airice_ray_path_host(airice_ctx *ctx, int64_t n, const double *theta, const double *h, double depth_m, double ice_m,
                          int64_t max_points, double *x, double *z, int32_t *count);
+
+/* ---- kernel 6: the old solve-per-cell table = MakeTable (MultiRayAirIceRefraction.cc:1618-1696, .h:193; grid globals
+ * .h:38-54) and its lookup GetInterpolatedValue (MultiRayAirIceRefraction.cc:1700-1794, .h:195), device resident.
+ * Nodes: Tx heights ice_m + 1, + step_h, ... 100000 m (last snapped) x straight-line angles start_th, + step_th, ...
+ * stop_th (last snapped); the reference's defaults are (90.05, 179.95, 25, 0.01) = 3880 x 8990 = 34.9 M launch-angle
+ * solves.  Node counts are the reference's int truncations of width/step + 1.  Nine f64 columns GridZValue[0..8] =
+ * {h, THD, optical path ice, optical path air, launch angle, THD in air, T_S, T_P, incident angle}, -1000 where the solve
+ * misses; node = ih * n_th + ith.  depth_m signed as MakeTable's AntennaDepth (negative = in ice). */
+typedef struct airice_oldtable airice_oldtable;
+#define AIRICE_OLDTABLE_COLS 9
+int airice_oldtable_create(airice_ctx *ctx, double ice_m, double depth_m, double start_th, double stop_th, double step_h,
+                           double step_th, airice_oldtable **out);
+/* Wraps nine HOST columns of a grid made elsewhere (e.g. by the reference) for device lookups. */
+int airice_oldtable_wrap_host(airice_ctx *ctx, double ice_m, double start_th, double stop_th, double step_h, double step_th,
+                              const double *cols9, airice_oldtable **out);
+void airice_oldtable_destroy(airice_oldtable *t);
+/* info[0] = TotalStepsH_O, info[1] = TotalStepsTh_O, info[2] = GridPoints */
+int airice_oldtable_info(const airice_oldtable *t, int64_t info[3]);
+int airice_oldtable_copy_column(const airice_oldtable *t, int col, double *host_out);
+/* GridPositionH [info[0]] and GridPositionTh [info[1]] */
+int airice_oldtable_copy_positions(const airice_oldtable *t, double *host_h, double *host_th);
+/* Batched GetInterpolatedValue(hR, thR, rtParameter): DEVICE arrays in and out, one thread per query. */
+int airice_oldtable_interp_device(airice_ctx *ctx, const airice_oldtable *t, int64_t n, const double *d_h, const double *d_th,
+                                  int rt_parameter, double *d_out, void *stream);
+int airice_oldtable_interp_host(airice_ctx *ctx, const airice_oldtable *t, int64_t n, const double *h, const double *th,
+                                int rt_parameter, double *out);
 
 /* ---- peer memory: multi-GPU reassembly without a collective ("one gather per batch").
  * One process per GPU; the consumer rank allocates the result block with airice_peer_alloc and hands the 64-byte handle

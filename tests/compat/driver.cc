@@ -104,12 +104,38 @@ int main(int argc, char **argv) {
   if (argc > 2) {
     FILE *f = std::fopen(argv[2], "r");
     double qh, qt;
+    std::vector<double> qhs, qts;
     while (f && std::fscanf(f, "%lf %lf", &qh, &qt) == 2) {
+      qhs.push_back(qh); qts.push_back(qt);
       std::printf("old_q");
       for (int p = 0; p < 9; p++) std::printf(" %.17g", MultiRayAirIceRefraction::GetInterpolatedValue(qh, qt, p));
       std::printf("\n");
     }
     if (f) std::fclose(f);
+    // the batched form on the GPU-resident grid: same bits as the scalar host loop above
+    long differ = 0;
+    std::vector<double> o(qhs.size());
+    for (int p = 0; p < 9; p++) {
+      const int rc = MultiRayAirIceRefraction::GetInterpolatedValueBatch((long)qhs.size(), qhs.data(), qts.data(), p, o.data());
+      if (rc != 0) differ += 1000000;
+      for (size_t q = 0; q < qhs.size(); q++) {
+        const double want = MultiRayAirIceRefraction::GetInterpolatedValue(qhs[q], qts[q], p);
+        differ += std::memcmp(&want, &o[q], sizeof(double)) != 0;
+      }
+    }
+    std::printf("old_batch_differ %ld %zu\n", differ, qhs.size());
+  }
+  // persistence: table 0 saved, loaded as a new table, same lookup bits
+  if (argc > 3) {
+    const int rcs = MultiRayAirIceRefraction::SaveRayTracingTable(0, argv[3]);
+    const int idx = MultiRayAirIceRefraction::LoadRayTracingTable(argv[3]);
+    double a[9], b[9];
+    const bool ka = MultiRayAirIceRefraction::GetHorizontalDistanceToIntersectionPoint_Table(
+        AirTxHeight * 100, HorizontalDistance * 100, AntennaDepth * 100, IceLayerHeight * 100, 0, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]);
+    // idx lies beyond AntennaDepths, so the depth remap leaves it alone and the loaded table itself answers
+    const bool kb = idx >= 0 && MultiRayAirIceRefraction::GetHorizontalDistanceToIntersectionPoint_Table(
+        AirTxHeight * 100, HorizontalDistance * 100, AntennaDepth * 100, IceLayerHeight * 100, idx, b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], b[8]);
+    std::printf("persist %d %d %d %d %d\n", rcs, idx, (int)ka, (int)kb, (int)(std::memcmp(a, b, sizeof(a)) == 0));
   }
   return 0;
 }

@@ -105,3 +105,20 @@ def test_kernel_path_matches_oracle_and_cli(solver, oracle):
     assert np.array_equal(ch, count[:4]) and np.array_equal(xh, x[:4, :1000], equal_nan=True) and np.array_equal(zh, z[:4, :1000], equal_nan=True)
     x0, z0, c0 = solver.ray_path(torch.from_numpy(theta), torch.from_numpy(h), -200.0, 3000.0, max_points=0)
     assert x0.shape == (64, 0) and np.array_equal(c0.cpu().numpy(), count)
+
+
+@pytest.mark.gpu
+def test_ray_path_host_multi_chunk_equals_device_path(solver):
+    """airice_ray_path_host cuts a batch into chunks of 16M points that alternate between two streams; every chunk has its
+    own plan scratch (a shared one was overwritten by the next chunk's plan kernel: round-1 advisor finding).  2 600 rays x
+    17 300 points = 45M points = 3 chunks."""
+    import torch
+    rng = np.random.default_rng(12)
+    n, mp_ = 2600, 17300
+    theta = rng.uniform(120.0, 179.0, n)
+    h = rng.uniform(15000.0, 20000.0, n)
+    xd, zd, cd = solver.ray_path(torch.from_numpy(theta), torch.from_numpy(h), -200.0, 3000.0, max_points=mp_)
+    xh, zh, ch = solver.ray_path_host(theta, h, -200.0, 3000.0, mp_)
+    assert np.array_equal(ch, cd.cpu().numpy())
+    assert np.array_equal(xh, xd.cpu().numpy(), equal_nan=True) and np.array_equal(zh, zd.cpu().numpy(), equal_nan=True)
+    assert (ch > 12000).all()
