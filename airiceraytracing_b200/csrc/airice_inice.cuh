@@ -641,26 +641,30 @@ AIRICE_HD int inice_solve(const AirIceInIce& m, double z0_in, double x1, double 
 // RecieveAngle[2], IncidenceAngleInIce[2]; ignore[2] = IgnoreCh (1 = ray present); type[2] = the reference's internal
 // RayType (1 D, 2 R, 3 Ra1, 4 Ra2).  The assignments are a cascade in which later cases overwrite earlier ones; the
 // order below is the reference's.
+// att4 / att_out: optional AttD, AttR, AttRa[0..1] (1 - attenuation of the four candidates) and the AttRay[2] they become;
+// they ride through the same cascade and swap (IceRayTracing.cc:3014-3148)
 AIRICE_HD void inice_pick_two_rays(const AirIceInIce& m, const double* o, double rx_depth, double distance, double tx_depth,
-                                   double* res, int* ignore, int* type) {
+                                   double* res, int* ignore, int* type, const double* att4 = nullptr, double* att_out = nullptr) {
   const double timeD = o[4], timeR = o[5], timeRa0 = o[6], timeRa1 = o[7];
   const double pathD = o[25], pathR = o[26], pathRa0 = o[27], pathRa1 = o[28];
   const double RangD = o[8], RangR = o[9], RangRa0 = o[10], RangRa1 = o[11];
   const double LangD = o[0], LangR = o[1], LangRa0 = o[2], LangRa1 = o[3];
   double T[2] = {timeD, timeR}, P[2] = {pathD, pathR}, Rv[2] = {RangD, RangR}, La[2] = {LangD, LangR};
+  const double AttD = att4 ? att4[0] : 0, AttR = att4 ? att4[1] : 0, AttRa0 = att4 ? att4[2] : 0, AttRa1 = att4 ? att4[3] : 0;
+  double At[2] = {AttD, AttR};
   int ty[2] = {1, 2};
   double inc[2] = {100, o[18]};
   if (RangR == -1000) { inc[0] = 100; inc[1] = 100; }
-#define INICE_SET(slot, t, p, r, l, k) do { T[slot] = t; P[slot] = p; Rv[slot] = r; La[slot] = l; ty[slot] = k; } while (0)
-  if (RangD != -1000) INICE_SET(0, timeD, pathD, RangD, LangD, 1);
-  if (RangR != -1000) INICE_SET(1, timeR, pathR, RangR, LangR, 2);
-  if (RangRa0 != -1000 && RangD != -1000) { INICE_SET(0, timeD, pathD, RangD, LangD, 1); INICE_SET(1, timeRa0, pathRa0, RangRa0, LangRa0, 3); }
-  if (RangRa0 != -1000 && RangR != -1000) { INICE_SET(1, timeR, pathR, RangR, LangR, 2); INICE_SET(0, timeRa0, pathRa0, RangRa0, LangRa0, 3); }
-  if (RangRa1 != -1000 && RangD != -1000) { INICE_SET(0, timeD, pathD, RangD, LangD, 1); INICE_SET(1, timeRa1, pathRa1, RangRa1, LangRa1, 4); }
-  if (RangRa1 != -1000 && RangR != -1000) { INICE_SET(1, timeR, pathR, RangR, LangR, 2); INICE_SET(0, timeRa1, pathRa1, RangRa1, LangRa1, 4); }
-  if (RangRa1 != -1000 && RangRa0 != -1000) { INICE_SET(1, timeRa1, pathRa1, RangRa1, LangRa1, 4); INICE_SET(0, timeRa0, pathRa0, RangRa0, LangRa0, 3); }
-  if (Rv[1] == -1000 && Rv[0] == -1000 && RangRa0 != -1000) INICE_SET(0, timeRa0, pathRa0, RangRa0, LangRa0, 3);
-  if (Rv[1] == -1000 && Rv[0] == -1000 && RangRa1 != -1000) INICE_SET(1, timeRa1, pathRa1, RangRa1, LangRa1, 4);
+#define INICE_SET(slot, t, p, r, l, k, at) do { T[slot] = t; P[slot] = p; Rv[slot] = r; La[slot] = l; ty[slot] = k; At[slot] = at; } while (0)
+  if (RangD != -1000) INICE_SET(0, timeD, pathD, RangD, LangD, 1, AttD);
+  if (RangR != -1000) INICE_SET(1, timeR, pathR, RangR, LangR, 2, AttR);
+  if (RangRa0 != -1000 && RangD != -1000) { INICE_SET(0, timeD, pathD, RangD, LangD, 1, AttD); INICE_SET(1, timeRa0, pathRa0, RangRa0, LangRa0, 3, AttRa0); }
+  if (RangRa0 != -1000 && RangR != -1000) { INICE_SET(1, timeR, pathR, RangR, LangR, 2, AttR); INICE_SET(0, timeRa0, pathRa0, RangRa0, LangRa0, 3, AttRa0); }
+  if (RangRa1 != -1000 && RangD != -1000) { INICE_SET(0, timeD, pathD, RangD, LangD, 1, AttD); INICE_SET(1, timeRa1, pathRa1, RangRa1, LangRa1, 4, AttRa1); }
+  if (RangRa1 != -1000 && RangR != -1000) { INICE_SET(1, timeR, pathR, RangR, LangR, 2, AttR); INICE_SET(0, timeRa1, pathRa1, RangRa1, LangRa1, 4, AttRa1); }
+  if (RangRa1 != -1000 && RangRa0 != -1000) { INICE_SET(1, timeRa1, pathRa1, RangRa1, LangRa1, 4, AttRa1); INICE_SET(0, timeRa0, pathRa0, RangRa0, LangRa0, 3, AttRa0); }
+  if (Rv[1] == -1000 && Rv[0] == -1000 && RangRa0 != -1000) INICE_SET(0, timeRa0, pathRa0, RangRa0, LangRa0, 3, AttRa0);
+  if (Rv[1] == -1000 && Rv[0] == -1000 && RangRa1 != -1000) INICE_SET(1, timeRa1, pathRa1, RangRa1, LangRa1, 4, AttRa1);
 #undef INICE_SET
   int ig[2] = {1, 1};
   if (Rv[0] == -1000) ig[0] = 0;
@@ -671,6 +675,7 @@ AIRICE_HD void inice_pick_two_rays(const AirIceInIce& m, const double* o, double
     d = Rv[0]; Rv[0] = Rv[1]; Rv[1] = d;
     d = T[0]; T[0] = T[1]; T[1] = d;
     d = P[0]; P[0] = P[1]; P[1] = d;
+    d = At[0]; At[0] = At[1]; At[1] = d;
     const int k = ty[0]; ty[0] = ty[1]; ty[1] = k;
   }
   if (rx_depth == tx_depth && T[0] == 0 && P[0] == 0) {     // IceRayTracing.cc:3190-3200
@@ -684,4 +689,5 @@ AIRICE_HD void inice_pick_two_rays(const AirIceInIce& m, const double* o, double
   res[8] = inc[0]; res[9] = inc[1];
   ignore[0] = ig[0]; ignore[1] = ig[1];
   type[0] = ty[0]; type[1] = ty[1];
+  if (att_out) { att_out[0] = At[0]; att_out[1] = At[1]; }
 }

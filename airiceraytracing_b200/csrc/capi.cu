@@ -24,6 +24,10 @@ int cuda_fail(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
   return -100 - (int)e;
 }
+#define NEED_AIR(c)                                                                                              \
+  do {                                                                                                           \
+    if ((c)->no_air) return fail(-9, "this context was created without an atmosphere file: in-ice entry points only"); \
+  } while (0)
 #define CK(call)                                  \
   do {                                            \
     cudaError_t e__ = (call);                     \
@@ -33,6 +37,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 struct airice_ctx {
   int device = 0;
+  bool no_air = false;               // created without an atmosphere file: only the in-ice entry points work
   AirIceMedium medium;
   double n0 = 0;
   int npoints = 0;
@@ -51,6 +56,9 @@ struct airice_ctx {
   size_t inice_bytes[kSlots] = {0, 0};
   double* inice_cols = nullptr;      // 29 columns of one chunk for airice_inice_two_rays_*
   void* path_plans = nullptr;        // per-ray plans of airice_ray_path_*
+  int32_t* quad_stats = nullptr;     // attenuation quadrature: overflow count, largest interval count
+  double* focus_scratch = nullptr;   // airice_inice_focusing_device / airice_inice_table_create intermediates
+  int64_t focus_cap = 0;
   double* clamp_tab = nullptr;       // device copy of the clamped-bracket table (medium.clamp_tab points at it)
   // buffers of destroyed tables kept for the next table of the same size (a per-antenna loop creates and destroys 64
   // tables of 384 + 455 MB: cudaMalloc / cudaFree of that size cost more than building the table, and jitter wildly)
@@ -83,6 +91,17 @@ struct airice_ctx {
     }
     return it->second;
   }
+};
+
+struct airice_inice_table {
+  int device = 0;
+  int n_x = 0, n_z = 0;
+  int64_t points = 0;
+  double step_x = 0, step_z = 0;
+  std::vector<float> pos_x, pos_z;       // GridPositionXb / GridPositionZb (float in the reference)
+  double* block = nullptr;               // 13 columns, then the two float position arrays
+  float* d_pos_x = nullptr;
+  float* d_pos_z = nullptr;
 };
 
 struct airice_oldtable {
@@ -310,7 +329,8 @@ int airice_device_count(void) {
 }
 
 int airice_create(const char* atmosphere_path, int variant, int device, airice_ctx** out) {
-  if (!out || !atmosphere_path) return fail(-1, "null argument");
+  if (!out) return fail(-1, "null argument");
+  const bool ice_only = !atmosphere_path || !atmosphere_path[0];   // in-ice entry points only (no GDAS file needed)
   if (variant != AIRICE_VARIANT_MULTIRAY && variant != AIRICE_VARIANT_PYWRAP) return fail(-1, "unknown variant");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -321,11 +341,20 @@ int airice_create(const char* atmosphere_path, int variant, int device, airice_c
   airice_ctx* c = new airice_ctx();
   c->device = device;
   std::string err;
-  int rc = load_medium(atmosphere_path, variant, &c->medium, &c->n0, &c->npoints, &err);
-  if (rc != 0) { delete c; return fail(rc, err); }
+  if (ice_only) {
+    std::memset(&c->medium, 0, sizeof(c->medium));
+    c->medium.nlayers = 0; c->medium.variant = variant;
+    c->medium.A_ice = 1.78; c->medium.B_ice = -0.43; c->medium.C_ice = 0.0132;
+    c->medium.pi = (variant == AIRICE_VARIANT_PYWRAP) ? 4.0 * atan(1.0) : 3.1415927;
+    c->medium.deg2rad = c->medium.pi / 180.0; c->medium.rad2deg = 180.0 / c->medium.pi; c->medium.c = 299792458.0;
+    c->no_air = true;
+  } else {
+    int rc = load_medium(atmosphere_path, variant, &c->medium, &c->n0, &c->npoints, &err);
+    if (rc != 0) { delete c; return fail(rc, err); }
+  }
   e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaSetDevice"); }
-  {
+  if (!ice_only) {
     std::vector<double> tab(2 * AIRICE_CLAMP_N);
     make_clamp_table(c->medium, tab.data());
     e = cudaMalloc((void**)&c->clamp_tab, sizeof(double) * tab.size());
@@ -362,6 +391,8 @@ void airice_destroy(airice_ctx* c) {
     if (c->inice_scratch[k]) cudaFree(c->inice_scratch[k]);
   if (c->inice_cols) cudaFree(c->inice_cols);
   if (c->path_plans) cudaFree(c->path_plans);
+  if (c->quad_stats) cudaFree(c->quad_stats);
+  if (c->focus_scratch) cudaFree(c->focus_scratch);
   if (c->clamp_tab) cudaFree(c->clamp_tab);
   drop_spares(c);
   for (auto& d : c->defer) if (d.second.buf) cudaFree(d.second.buf);
@@ -403,6 +434,7 @@ int airice_table_build_device(airice_ctx* c, double depth_m, double ice_m, doubl
                               double th_start, double th_step, double th_stop, int64_t row_begin, int64_t row_end,
                               double* const* cols64, float* const* cols32, void* stream) {
   if (!c) return fail(-1, "null context");
+  NEED_AIR(c);
   if (!cols64 && !cols32) return fail(-1, "no output columns");
   CK(cudaSetDevice(c->device));
   TableGrid g; std::string err;
@@ -414,6 +446,7 @@ int airice_table_build_device(airice_ctx* c, double depth_m, double ice_m, doubl
 int airice_table_create(airice_ctx* c, double depth_m, double ice_m, double h_top, double h_step, double th_start,
                         double th_step, double th_stop, airice_table** out) {
   if (!c || !out) return fail(-1, "null argument");
+  NEED_AIR(c);
   // a receiver in the ice: the fused pass of airice_table_create_multi (columns + lookup layout in one kernel, same bits)
   if (depth_m < 0) return airice_table_create_multi(c, 1, &depth_m, ice_m, h_top, h_step, th_start, th_step, th_stop, out);
   CK(cudaSetDevice(c->device));
@@ -442,6 +475,7 @@ int airice_table_create(airice_ctx* c, double depth_m, double ice_m, double h_to
 int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, double ice_m, double h_top, double h_step,
                               double th_start, double th_step, double th_stop, airice_table** out) {
   if (!c || !out || !depths_m || n_ant <= 0) return fail(-1, "null argument");
+  NEED_AIR(c);
   for (int q = 0; q < n_ant; q++)
     if (!(depths_m[q] < 0)) return fail(-6, "airice_table_create_multi: every antenna must sit in the ice (depth < 0); "
                                             "a receiver in air changes the surface height of the air walk");
@@ -645,6 +679,7 @@ int airice_table_copy_row_ranges(const airice_table* t, int32_t* host_first, int
 int airice_forward_device(airice_ctx* c, int64_t n, const double* d_theta, const double* d_h, double depth_m,
                           double ice_m, double* const* cols64, void* stream) {
   if (!c || !cols64) return fail(-1, "null argument");
+  NEED_AIR(c);
   CK(cudaSetDevice(c->device));
   // GetRayTracingSolutions takes the surface height as given (no depth fold); depth>=0 just means "no ice leg"
   const int in_ice = depth_m < 0 ? 1 : 0;
@@ -661,6 +696,7 @@ int airice_forward_device(airice_ctx* c, int64_t n, const double* d_theta, const
 int airice_forward_host(airice_ctx* c, int64_t n, const double* theta, const double* h, double depth_m, double ice_m,
                         double* out) {
   if (!c) return fail(-1, "null context");
+  NEED_AIR(c);
   if (n == 0) return 0;
   if (!theta || !h || !out) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));
@@ -695,6 +731,7 @@ int airice_solve_device(airice_ctx* c, int64_t n, const double* d_h, const doubl
                         double depth, double ice, int units, double* const* d_out, uint8_t* d_ok, int32_t* d_nevals,
                         void* stream) {
   if (!c || !d_out) return fail(-1, "null argument");
+  NEED_AIR(c);
   if (units != AIRICE_UNITS_M_DEG && units != AIRICE_UNITS_CM_RAD) return fail(-1, "unknown units");
   if (n == 0) return 0;
   CK(cudaSetDevice(c->device));
@@ -759,6 +796,7 @@ int airice_solve_multi_device(airice_ctx* c, int64_t n_points, int n_ant, const 
 int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* dist, const double* straight,
                       double depth, double ice, int units, double* out, uint8_t* ok) {
   if (!c) return fail(-1, "null context");
+  NEED_AIR(c);
   if (units != AIRICE_UNITS_M_DEG && units != AIRICE_UNITS_CM_RAD) return fail(-1, "unknown units");
   if (n == 0) return 0;
   if (!h || !dist || !out || !ok) return fail(-1, "null argument");
@@ -929,8 +967,20 @@ namespace {
 constexpr int64_t kRaysChunk = 1 << 20;
 
 // solve + pick for one chunk of DEVICE inputs on stream s; the 29 intermediate columns live in the context
+struct AttSpec { bool on = false; double A0 = 0, frequency = 0; double* att[2] = {nullptr, nullptr}; };
+
+// the context's quadrature statistics: [0] integrals that ran out of interval storage, [1] largest interval count (> 24)
+int quad_stats(airice_ctx* c, int32_t** out) {
+  if (!c->quad_stats) {
+    CK(cudaMalloc((void**)&c->quad_stats, 2 * sizeof(int32_t)));
+    CK(cudaMemset(c->quad_stats, 0, 2 * sizeof(int32_t)));
+  }
+  *out = c->quad_stats;
+  return 0;
+}
+
 int two_rays_chunk(airice_ctx* c, int64_t m, const double* d_rx, const double* d_dist, const double* d_tx, double* const* out10,
-                   int32_t* const* ignore2, int32_t* const* type2, cudaStream_t s) {
+                   int32_t* const* ignore2, int32_t* const* type2, cudaStream_t s, const AttSpec* att = nullptr) {
   if (c->inice_cols_n < m) {
     CK(cudaStreamSynchronize(s));
     if (c->inice_cols) cudaFree(c->inice_cols);
@@ -955,6 +1005,12 @@ int two_rays_chunk(airice_ctx* c, int64_t m, const double* d_rx, const double* d
   for (int k = 0; k < AIRICE_INICE_RAYS_NCOLS; k++) p.out[k] = out10[k];
   p.ignore[0] = ignore2[0]; p.ignore[1] = ignore2[1];
   p.type[0] = type2 ? type2[0] : nullptr; p.type[1] = type2 ? type2[1] : nullptr;
+  if (att && att->on) {
+    p.att[0] = att->att[0]; p.att[1] = att->att[1];
+    p.A0 = att->A0; p.frequency = att->frequency;
+    p.w0 = log(0.0001); p.w2 = log(3.16); p.w = log(att->frequency);     // IceRayTracing.cc:146: libm, like the reference
+    { int rc = quad_stats(c, &p.quad_stats); if (rc) return rc; }
+  }
   e = launch_inice_pick(p, s);
   if (e != cudaSuccess) return cuda_fail(e, "launch_inice_pick");
   return 0;
@@ -1013,6 +1069,346 @@ int airice_inice_two_rays_host(airice_ctx* c, int64_t n, const double* rx_depth,
   return 0;
 }
 
+// ---- attenuation, focusing, in-ice table
+int airice_inice_two_rays_att_device(airice_ctx* c, int64_t n, const double* d_rx_depth, const double* d_distance,
+                                     const double* d_tx_depth, double A0, double frequency_ghz, double* const* d_out,
+                                     double* const* d_att, int32_t* const* d_ignore, int32_t* const* d_type, void* stream) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!d_rx_depth || !d_distance || !d_tx_depth || !d_out || !d_att || !d_att[0] || !d_att[1] || !d_ignore || !d_ignore[0] ||
+      !d_ignore[1])
+    return fail(-1, "null argument");
+  if (!(frequency_ghz > 0)) return fail(-3, "frequency must be positive (GHz)");
+  CK(cudaSetDevice(c->device));
+  for (int64_t off = 0; off < n; off += kRaysChunk) {
+    const int64_t m = (n - off < kRaysChunk) ? (n - off) : kRaysChunk;
+    double* o[AIRICE_INICE_RAYS_NCOLS];
+    for (int k = 0; k < AIRICE_INICE_RAYS_NCOLS; k++) o[k] = d_out[k] ? d_out[k] + off : nullptr;
+    int32_t* ig[2] = {d_ignore[0] + off, d_ignore[1] + off};
+    int32_t* ty[2] = {d_type && d_type[0] ? d_type[0] + off : nullptr, d_type && d_type[1] ? d_type[1] + off : nullptr};
+    AttSpec as;
+    as.on = true; as.A0 = A0; as.frequency = frequency_ghz; as.att[0] = d_att[0] + off; as.att[1] = d_att[1] + off;
+    const int rc = two_rays_chunk(c, m, d_rx_depth + off, d_distance + off, d_tx_depth + off, o, ig, ty, (cudaStream_t)stream, &as);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int airice_inice_two_rays_att_host(airice_ctx* c, int64_t n, const double* rx_depth, const double* distance,
+                                   const double* tx_depth, double A0, double frequency_ghz, double* out, double* att,
+                                   int32_t* ignore) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!rx_depth || !distance || !tx_depth || !out || !att || !ignore) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int nc = AIRICE_INICE_RAYS_NCOLS;
+  const int64_t chunk = n < kRaysChunk ? n : kRaysChunk;
+  int rc = ensure_slots(c, (size_t)chunk * (sizeof(double) * (3 + nc + 2) + 2 * sizeof(int32_t)) + 64);
+  if (rc) return rc;
+  cudaStream_t s = c->streams[0];
+  double* dh = (double*)c->dev[0];
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    CK(cudaMemcpyAsync(dh, rx_depth + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, distance + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + 2 * chunk, tx_depth + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    double* o[nc];
+    for (int k = 0; k < nc; k++) o[k] = dh + (3 + k) * chunk;
+    double* at[2] = {dh + (3 + nc) * chunk, dh + (4 + nc) * chunk};
+    int32_t* ig0 = (int32_t*)(dh + (5 + nc) * chunk);
+    int32_t* ig[2] = {ig0, ig0 + chunk};
+    rc = airice_inice_two_rays_att_device(c, m, dh, dh + chunk, dh + 2 * chunk, A0, frequency_ghz, o, at, ig, nullptr, s);
+    if (rc) return rc;
+    for (int k = 0; k < nc; k++)
+      CK(cudaMemcpyAsync(out + (int64_t)k * n + off, o[k], sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    for (int k = 0; k < 2; k++) {
+      CK(cudaMemcpyAsync(att + (int64_t)k * n + off, at[k], sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(ignore + (int64_t)k * n + off, ig[k], sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int airice_inice_attenuation_device(airice_ctx* c, int64_t n, int kind, double A0, double frequency_ghz, const double* d_z0,
+                                    const double* d_z1, const double* d_zmax, const double* d_L, double* d_out, void* stream) {
+  if (!c) return fail(-1, "null context");
+  if (kind < 0 || kind > 2) return fail(-1, "kind: 0 direct, 1 reflected, 2 refracted");
+  if (n == 0) return 0;
+  if (!d_z0 || !d_z1 || !d_L || !d_out || (kind == 2 && !d_zmax)) return fail(-1, "null argument");
+  if (!(frequency_ghz > 0)) return fail(-3, "frequency must be positive (GHz)");
+  CK(cudaSetDevice(c->device));
+  InIceAttArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n; a.kind = kind; a.z0 = d_z0; a.z1 = d_z1; a.zmax = d_zmax; a.L = d_L; a.out = d_out;
+  a.A = c->medium.A_ice; a.B = c->medium.B_ice; a.C = c->medium.C_ice;
+  a.A0 = A0; a.frequency = frequency_ghz; a.w0 = log(0.0001); a.w2 = log(3.16); a.w = log(frequency_ghz);
+  { int rc = quad_stats(c, &a.quad_stats); if (rc) return rc; }
+  cudaError_t e = launch_inice_attenuation(a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_inice_attenuation");
+  return 0;
+}
+
+int airice_inice_attenuation_host(airice_ctx* c, int64_t n, int kind, double A0, double frequency_ghz, const double* z0,
+                                  const double* z1, const double* zmax, const double* L, double* out) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!z0 || !z1 || !L || !out || (kind == 2 && !zmax)) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int64_t chunk = n < (1 << 20) ? n : (1 << 20);
+  int rc = ensure_slots(c, (size_t)chunk * sizeof(double) * 5 + 64);
+  if (rc) return rc;
+  cudaStream_t s = c->streams[0];
+  double* dh = (double*)c->dev[0];
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    CK(cudaMemcpyAsync(dh, z0 + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, z1 + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    if (kind == 2) CK(cudaMemcpyAsync(dh + 2 * chunk, zmax + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + 3 * chunk, L + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    rc = airice_inice_attenuation_device(c, m, kind, A0, frequency_ghz, dh, dh + chunk, dh + 2 * chunk, dh + 3 * chunk, dh + 4 * chunk, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out + off, dh + 4 * chunk, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int airice_inice_quadrature_stats(airice_ctx* c, int64_t out[2]) {
+  if (!c || !out) return fail(-1, "null argument");
+  out[0] = out[1] = 0;
+  if (!c->quad_stats) return 0;
+  CK(cudaSetDevice(c->device));
+  int32_t h[2];
+  CK(cudaMemcpy(h, c->quad_stats, sizeof(h), cudaMemcpyDeviceToHost));   // synchronises with the kernels that wrote it
+  out[0] = h[0]; out[1] = h[1];
+  return 0;
+}
+
+namespace {
+// scratch of one focusing chunk: [rx - 0.01][10 cols A][10 cols B][ignore A x2, ignore B x2 as int32]
+int focus_scratch(airice_ctx* c, int64_t m, cudaStream_t s) {
+  if (c->focus_cap >= m) return 0;
+  CK(cudaStreamSynchronize(s));
+  if (c->focus_scratch) cudaFree(c->focus_scratch);
+  c->focus_scratch = nullptr; c->focus_cap = 0;
+  CK(cudaMalloc((void**)&c->focus_scratch, sizeof(double) * 23 * (size_t)m));
+  c->focus_cap = m;
+  return 0;
+}
+
+// GetFocusingFactor for m DEVICE triples.  sol_a / ign_a: optional, the caller's own two-ray solution at zR (MakeTable
+// has just computed it: the reference computes it twice); else solved here.
+int focusing_chunk(airice_ctx* c, int64_t m, const double* d_zT, const double* d_xR, const double* d_zR, double* const* out2,
+                   double* const* sol_a_in, cudaStream_t s) {
+  int rc = focus_scratch(c, m, s);
+  if (rc) return rc;
+  const int64_t cap = c->focus_cap;
+  double* base = c->focus_scratch;
+  double* rxb = base;
+  double* A[AIRICE_INICE_RAYS_NCOLS];
+  double* B[AIRICE_INICE_RAYS_NCOLS];
+  for (int k = 0; k < AIRICE_INICE_RAYS_NCOLS; k++) { A[k] = base + (1 + k) * cap; B[k] = base + (11 + k) * cap; }
+  int32_t* ig = (int32_t*)(base + 21 * cap);
+  int32_t* igA[2] = {ig, ig + cap};
+  int32_t* igB[2] = {ig + 2 * cap, ig + 3 * cap};
+  if (!sol_a_in) {
+    rc = two_rays_chunk(c, m, d_zR, d_xR, d_zT, A, igA, nullptr, s);     // GetRayTracingSolutions(zR, xR, zT, ...)
+    if (rc) return rc;
+  }
+  cudaError_t e = launch_inice_shift(m, d_zR, -0.01, rxb, s);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_inice_shift");
+  rc = two_rays_chunk(c, m, rxb, d_xR, d_zT, B, igB, nullptr, s);        // GetRayTracingSolutions(zR - 0.01, xR, zT, ...)
+  if (rc) return rc;
+  InIceFocusArgs f;
+  std::memset(&f, 0, sizeof(f));
+  f.n = m; f.zT = d_zT; f.zR = d_zR;
+  for (int k = 0; k < AIRICE_INICE_RAYS_NCOLS; k++) { f.sol_a[k] = sol_a_in ? sol_a_in[k] : A[k]; f.sol_b[k] = B[k]; }
+  f.A = c->medium.A_ice; f.B = c->medium.B_ice; f.C = c->medium.C_ice;
+  f.out[0] = out2[0]; f.out[1] = out2[1];
+  e = launch_inice_focusing(f, s);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_inice_focusing");
+  return 0;
+}
+}  // namespace
+
+int airice_inice_focusing_device(airice_ctx* c, int64_t n, const double* d_zT, const double* d_xR, const double* d_zR,
+                                 double* const* d_out, void* stream) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!d_zT || !d_xR || !d_zR || !d_out || !d_out[0] || !d_out[1]) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  for (int64_t off = 0; off < n; off += kRaysChunk) {
+    const int64_t m = (n - off < kRaysChunk) ? (n - off) : kRaysChunk;
+    double* o[2] = {d_out[0] + off, d_out[1] + off};
+    const int rc = focusing_chunk(c, m, d_zT + off, d_xR + off, d_zR + off, o, nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int airice_inice_focusing_host(airice_ctx* c, int64_t n, const double* zT, const double* xR, const double* zR, double* out) {
+  if (!c) return fail(-1, "null context");
+  if (n == 0) return 0;
+  if (!zT || !xR || !zR || !out) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int64_t chunk = n < kRaysChunk ? n : kRaysChunk;
+  int rc = ensure_slots(c, (size_t)chunk * sizeof(double) * 5 + 64);
+  if (rc) return rc;
+  cudaStream_t s = c->streams[0];
+  double* dh = (double*)c->dev[0];
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    CK(cudaMemcpyAsync(dh, zT + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, xR + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + 2 * chunk, zR + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    double* o[2] = {dh + 3 * chunk, dh + 4 * chunk};
+    rc = focusing_chunk(c, m, dh, dh + chunk, dh + 2 * chunk, o, nullptr, s);
+    if (rc) return rc;
+    for (int k = 0; k < 2; k++) CK(cudaMemcpyAsync(out + (int64_t)k * n + off, o[k], sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// IceRayTracing::MakeTable (IceRayTracing.cc:2614-2724)
+int airice_inice_table_create(airice_ctx* c, double shower_hit_distance, double shower_depth, double zR, double step_x,
+                              double step_z, double width_x, double width_z, airice_inice_table** out) {
+  if (!c || !out) return fail(-1, "null argument");
+  if (!(step_x > 0) || !(step_z > 0) || !(width_x > 0) || !(width_z > 0)) return fail(-3, "bad in-ice table grid");
+  CK(cudaSetDevice(c->device));
+  airice_inice_table* t = new airice_inice_table();
+  t->device = c->device;
+  t->step_x = step_x; t->step_z = step_z;
+  const double nx = (width_x / step_x) + 1, nz = (width_z / step_z) + 1;      // the reference's double -> int truncation
+  if (!(nx >= 2) || !(nz >= 2) || nx * nz >= 2147483647.0) { delete t; return fail(-5, "in-ice table needs 2 .. 2^31-1 nodes"); }
+  t->n_x = (int)nx; t->n_z = (int)nz;
+  t->points = (int64_t)t->n_x * t->n_z;
+  double start_x = shower_hit_distance - (width_x / 2);
+  if (shower_hit_distance <= width_x / 2) start_x = 0;
+  double start_z = shower_depth - (width_z / 2);
+  const double stop_z = shower_depth + (width_z / 2);
+  if (fabs(shower_depth) <= 10 || stop_z >= 0) start_z = -20;
+  t->pos_x.resize(t->n_x); t->pos_z.resize(t->n_z);
+  for (int ix = 0; ix < t->n_x; ix++) t->pos_x[ix] = (float)(start_x + step_x * ix);    // float, IceRayTracing.hh:29-30
+  for (int iz = 0; iz < t->n_z; iz++) t->pos_z[iz] = (float)(start_z + step_z * iz);
+  const size_t cols_b = sizeof(double) * (size_t)t->points * AIRICE_INICE_TABLE_NCOLS;
+  cudaError_t e = cudaMalloc((void**)&t->block, cols_b + sizeof(float) * ((size_t)t->n_x + t->n_z));
+  if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(in-ice table)"); }
+  t->d_pos_x = (float*)((char*)t->block + cols_b);
+  t->d_pos_z = t->d_pos_x + t->n_x;
+  e = cudaMemcpy(t->d_pos_x, t->pos_x.data(), sizeof(float) * t->n_x, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(t->d_pos_z, t->pos_z.data(), sizeof(float) * t->n_z, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { airice_inice_table_destroy(t); return cuda_fail(e, "upload positions"); }
+  // per chunk: xT, zT, rx | 10 solution columns | 2 attenuation | 2 focusing | 2 ignore (int32 pairs)
+  const int64_t chunk = t->points < kRaysChunk ? t->points : kRaysChunk;
+  double* scratch = nullptr;
+  e = cudaMalloc((void**)&scratch, sizeof(double) * 18 * (size_t)chunk);
+  if (e != cudaSuccess) { airice_inice_table_destroy(t); return cuda_fail(e, "cudaMalloc(in-ice table scratch)"); }
+  auto done = [&](int code) { cudaFree(scratch); if (code) airice_inice_table_destroy(t); return code; };
+  cudaStream_t s = nullptr;
+  for (int64_t off = 0; off < t->points; off += chunk) {
+    const int64_t m = t->points - off < chunk ? t->points - off : chunk;
+    InIceTableNodeArgs g;
+    std::memset(&g, 0, sizeof(g));
+    g.node0 = off; g.n = m; g.n_z = t->n_z; g.start_x = start_x; g.start_z = start_z; g.step_x = step_x; g.step_z = step_z; g.zR = zR;
+    g.xT = scratch; g.zT = scratch + chunk; g.rx = scratch + 2 * chunk;
+    e = launch_inice_table_nodes(g, s);
+    if (e != cudaSuccess) return done(cuda_fail(e, "launch_inice_table_nodes"));
+    double* sol[AIRICE_INICE_RAYS_NCOLS];
+    for (int k = 0; k < AIRICE_INICE_RAYS_NCOLS; k++) sol[k] = scratch + (3 + k) * chunk;
+    double* at[2] = {scratch + 13 * chunk, scratch + 14 * chunk};
+    double* fo[2] = {scratch + 15 * chunk, scratch + 16 * chunk};
+    int32_t* ig0 = (int32_t*)(scratch + 17 * chunk);
+    int32_t* ig[2] = {ig0, ig0 + chunk};
+    // GetRayTracingSolutions(zR, xT, zT, ...) with A0 = 1, frequency = 0.1 GHz (IceRayTracing.cc:2654-2664)
+    int rc = airice_inice_two_rays_att_device(c, m, g.rx, g.xT, g.zT, 1.0, 0.1, sol, at, ig, nullptr, s);
+    if (rc) return done(rc);
+    // GetFocusingFactor(zT, xT, zR): its first solution is the one above
+    rc = focusing_chunk(c, m, g.zT, g.xT, g.rx, fo, sol, s);
+    if (rc) return done(rc);
+    InIceTablePackArgs pk;
+    std::memset(&pk, 0, sizeof(pk));
+    pk.n = m;
+    for (int k = 0; k < AIRICE_INICE_RAYS_NCOLS; k++) pk.sol[k] = sol[k];
+    pk.att[0] = at[0]; pk.att[1] = at[1]; pk.ignore[0] = ig[0]; pk.ignore[1] = ig[1]; pk.focusing[0] = fo[0]; pk.focusing[1] = fo[1];
+    for (int k = 0; k < AIRICE_INICE_TABLE_NCOLS; k++) pk.col[k] = t->block + (size_t)k * t->points + off;
+    e = launch_inice_table_pack(pk, s);
+    if (e != cudaSuccess) return done(cuda_fail(e, "launch_inice_table_pack"));
+  }
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return done(cuda_fail(e, "in-ice table"));
+  *out = t;
+  return done(0);
+}
+
+void airice_inice_table_destroy(airice_inice_table* t) {
+  if (!t) return;
+  if (t->block) { cudaSetDevice(t->device); cudaFree(t->block); }
+  delete t;
+}
+
+int airice_inice_table_info(const airice_inice_table* t, int64_t info[3]) {
+  if (!t || !info) return fail(-1, "null argument");
+  info[0] = t->n_x; info[1] = t->n_z; info[2] = t->points;
+  return 0;
+}
+
+int airice_inice_table_copy_column(const airice_inice_table* t, int col, double* host_out) {
+  if (!t || !host_out || col < 0 || col >= AIRICE_INICE_TABLE_NCOLS) return fail(-1, "bad table/column");
+  CK(cudaSetDevice(t->device));
+  CK(cudaMemcpy(host_out, t->block + (size_t)col * t->points, sizeof(double) * (size_t)t->points, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int airice_inice_table_copy_positions(const airice_inice_table* t, float* host_x, float* host_z) {
+  if (!t || !host_x || !host_z) return fail(-1, "null argument");
+  std::memcpy(host_x, t->pos_x.data(), sizeof(float) * t->n_x);
+  std::memcpy(host_z, t->pos_z.data(), sizeof(float) * t->n_z);
+  return 0;
+}
+
+int airice_inice_table_interp_device(airice_ctx* c, const airice_inice_table* t, int64_t n, const double* d_x, const double* d_z,
+                                     int rt_parameter, double* d_out, void* stream) {
+  if (!c || !t) return fail(-1, "null argument");
+  if (rt_parameter < 0 || rt_parameter >= AIRICE_INICE_TABLE_NCOLS) return fail(-1, "rtParameter out of range (0..12)");
+  if (n == 0) return 0;
+  if (!d_x || !d_z || !d_out) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  InIceTableInterpArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n; a.x = d_x; a.z = d_z; a.pos_x = t->d_pos_x; a.pos_z = t->d_pos_z; a.n_x = t->n_x; a.n_z = t->n_z;
+  a.step_x = t->step_x; a.step_z = t->step_z; a.col = t->block + (size_t)rt_parameter * t->points; a.out = d_out;
+  cudaError_t e = launch_inice_table_interp(a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_inice_table_interp");
+  return 0;
+}
+
+int airice_inice_table_interp_host(airice_ctx* c, const airice_inice_table* t, int64_t n, const double* x, const double* z,
+                                   int rt_parameter, double* out) {
+  if (!c || !t) return fail(-1, "null argument");
+  if (n == 0) return 0;
+  if (!x || !z || !out) return fail(-1, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int64_t chunk = n < (1 << 20) ? n : (1 << 20);
+  int rc = ensure_slots(c, (size_t)chunk * sizeof(double) * 3 + 64);
+  if (rc) return rc;
+  int slot = 0;
+  for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+    const int64_t m = (n - off < chunk) ? (n - off) : chunk;
+    double* dh = (double*)c->dev[slot];
+    cudaStream_t s = c->streams[slot];
+    CK(cudaMemcpyAsync(dh, x + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dh + chunk, z + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    rc = airice_inice_table_interp_device(c, t, m, dh, dh + chunk, rt_parameter, dh + 2 * chunk, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out + off, dh + 2 * chunk, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+  }
+  for (int s = 0; s < airice_ctx::kSlots; s++)
+    if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
+  return 0;
+}
+
 namespace {
 // plans: per-ray plan scratch for this launch, or nullptr = the context's own (grow-only; callers on one stream)
 int ray_path_launch(airice_ctx* c, int64_t n, const double* d_theta, const double* d_h, double depth_m, double ice_m,
@@ -1043,6 +1439,7 @@ int ray_path_launch(airice_ctx* c, int64_t n, const double* d_theta, const doubl
 int airice_ray_path_device(airice_ctx* c, int64_t n, const double* d_theta, const double* d_h, double depth_m, double ice_m,
                            int64_t max_points, double* d_x, double* d_z, int32_t* d_count, void* stream) {
   if (!c) return fail(-1, "null context");
+  NEED_AIR(c);
   if (n == 0) return 0;
   if (!d_theta || !d_h || !d_count || (max_points > 0 && (!d_x || !d_z))) return fail(-1, "null argument");
   if (max_points < 0) return fail(-3, "max_points < 0");
@@ -1053,6 +1450,7 @@ int airice_ray_path_device(airice_ctx* c, int64_t n, const double* d_theta, cons
 int airice_ray_path_host(airice_ctx* c, int64_t n, const double* theta, const double* h, double depth_m, double ice_m,
                          int64_t max_points, double* x, double* z, int32_t* count) {
   if (!c) return fail(-1, "null context");
+  NEED_AIR(c);
   if (n == 0) return 0;
   if (!theta || !h || !count || (max_points > 0 && (!x || !z))) return fail(-1, "null argument");
   if (max_points < 0) return fail(-3, "max_points < 0");
@@ -1122,6 +1520,7 @@ int oldtable_alloc(airice_oldtable* t) {
 int airice_oldtable_create(airice_ctx* c, double ice_m, double depth_m, double start_th, double stop_th, double step_h,
                            double step_th, airice_oldtable** out) {
   if (!c || !out) return fail(-1, "null argument");
+  NEED_AIR(c);
   CK(cudaSetDevice(c->device));
   airice_oldtable* t = new airice_oldtable();
   t->ctx = c; t->device = c->device;

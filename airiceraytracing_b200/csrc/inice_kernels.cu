@@ -7,6 +7,7 @@
 // different branch count.  exp / log / pow are glibc's own algorithms (airice_glibc_math.cuh) for the same reason.
 #include "airice_inice.cuh"
 #include "airice_inice_machine.cuh"
+#include "airice_inice_att.cuh"
 #include "kernels.cuh"
 
 namespace airice {
@@ -204,6 +205,8 @@ __global__ void __launch_bounds__(kThreads) airice_inice_ra_finish_kernel(const 
 }
 
 // the two physical rays of each pair out of the four candidates (elementwise; HBM bound: 29 + 3 columns in, 10 + 4 out)
+template <bool ATT>     // ATT: with the attenuation integrals (a QAGS run per candidate ray: its own instantiation keeps the plain
+                        // selection at its register count)
 __global__ void __launch_bounds__(256) airice_inice_pick_kernel(const InIcePickArgs a) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= a.n) return;
@@ -213,13 +216,98 @@ __global__ void __launch_bounds__(256) airice_inice_pick_kernel(const InIcePickA
   for (int k = 0; k < AIRICE_INICE_NCOLS; k++) o[k] = a.in[k][i];
   double res[AIRICE_INICE_RAYS_NCOLS];
   int ig[2], ty[2];
-  inice_pick_two_rays(m, o, a.rx_depth[i], a.distance[i], a.tx_depth[i], res, ig, ty);
+  if (ATT) {
+    const InIceAttModel am = {a.A0, a.frequency, a.w0, a.w2, a.w};
+    double att4[4], att2[2];
+    int flags = 0, worst = 0;
+    inice_candidate_attenuations(m, am, o, a.rx_depth[i], a.tx_depth[i], att4, flags, worst);
+    inice_pick_two_rays(m, o, a.rx_depth[i], a.distance[i], a.tx_depth[i], res, ig, ty, att4, att2);
+    a.att[0][i] = att2[0]; a.att[1][i] = att2[1];
+    if (a.quad_stats) {
+      if (flags) atomicAdd(a.quad_stats, 1);
+      if (worst > 24) atomicMax(a.quad_stats + 1, worst);
+    }
+  } else {
+    inice_pick_two_rays(m, o, a.rx_depth[i], a.distance[i], a.tx_depth[i], res, ig, ty);
+  }
 #pragma unroll
   for (int k = 0; k < AIRICE_INICE_RAYS_NCOLS; k++)
     if (a.out[k]) a.out[k][i] = res[k];
   a.ignore[0][i] = ig[0]; a.ignore[1][i] = ig[1];
   if (a.type[0]) a.type[0][i] = ty[0];
   if (a.type[1]) a.type[1][i] = ty[1];
+}
+
+__global__ void __launch_bounds__(128) airice_inice_attenuation_kernel(const InIceAttArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= a.n) return;
+  const AirIceInIce m = inice_make_model(a.A, a.B, a.C);
+  const InIceAttModel am = {a.A0, a.frequency, a.w0, a.w2, a.w};
+  int flags = 0, worst = 0;
+  a.out[i] = inice_total_attenuation(m, am, a.kind, a.z0[i], a.z1[i], a.kind == 2 ? a.zmax[i] : 0.0, a.L[i], flags, worst);
+  if (a.quad_stats) {
+    if (flags) atomicAdd(a.quad_stats, 1);
+    if (worst > 24) atomicMax(a.quad_stats + 1, worst);
+  }
+}
+
+__global__ void __launch_bounds__(256) airice_inice_focusing_kernel(const InIceFocusArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.n) return;
+  const AirIceInIce m = inice_make_model(a.A, a.B, a.C);
+  const double path_a[2] = {a.sol_a[2][i], a.sol_a[3][i]}, launch_a[2] = {a.sol_a[4][i], a.sol_a[5][i]};
+  const double recv_a[2] = {a.sol_a[6][i], a.sol_a[7][i]};
+  const double launch_b[2] = {a.sol_b[4][i], a.sol_b[5][i]}, recv_b[2] = {a.sol_b[6][i], a.sol_b[7][i]};
+  double f[2] = {1, 1};                      // the reference's callers pass {1, 1} (IceRayTracing.cc:2666)
+  inice_focusing(m, a.zT[i], a.zR[i], path_a, launch_a, recv_a, launch_b, recv_b, f);
+  a.out[0][i] = f[0]; a.out[1][i] = f[1];
+}
+
+__global__ void __launch_bounds__(256) airice_inice_shift_kernel(int64_t n, const double* in, double shift, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = in[i] + shift;
+}
+
+// grid nodes of IceRayTracing::MakeTable: node = ix * n_z + iz, xT = start_x + step_x * ix, zT = start_z + step_z * iz
+__global__ void __launch_bounds__(256) airice_inice_table_nodes_kernel(const InIceTableNodeArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.n) return;
+  const int64_t node = a.node0 + i;
+  const int ix = (int)(node / a.n_z), iz = (int)(node - (int64_t)ix * a.n_z);
+  a.xT[i] = a.start_x + a.step_x * ix;
+  a.zT[i] = a.start_z + a.step_z * iz;
+  a.rx[i] = a.zR;
+}
+
+// GridZValueb[AntNum][0..12] (IceRayTracing.cc:2680-2715): ray 1 {time, path, launch, receive, attenuation, focusing},
+// ray 2 {same six, incidence angle on the surface}; -1000 where the ray is absent; NaN focusing -> 1
+__global__ void __launch_bounds__(256) airice_inice_table_pack_kernel(const InIceTablePackArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.n) return;
+  double f0 = a.focusing[0][i], f1 = a.focusing[1][i];
+  if (f0 != f0) f0 = 1;
+  if (f1 != f1) f1 = 1;
+  double v[AIRICE_INICE_TABLE_NCOLS];
+  if (a.ignore[0][i] != 0) {
+    v[0] = a.sol[0][i]; v[1] = a.sol[2][i]; v[2] = a.sol[4][i]; v[3] = a.sol[6][i]; v[4] = a.att[0][i]; v[5] = f0;
+  } else {
+    for (int k = 0; k < 6; k++) v[k] = -1000;
+  }
+  if (a.ignore[1][i] != 0) {
+    v[6] = a.sol[1][i]; v[7] = a.sol[3][i]; v[8] = a.sol[5][i]; v[9] = a.sol[7][i]; v[10] = a.att[1][i]; v[11] = f1;
+    const double inc = a.sol[9][i];
+    v[12] = (inc != 100) ? inc : -1000;
+  } else {
+    for (int k = 6; k < 13; k++) v[k] = -1000;
+  }
+#pragma unroll
+  for (int k = 0; k < AIRICE_INICE_TABLE_NCOLS; k++) a.col[k][i] = v[k];
+}
+
+__global__ void __launch_bounds__(256) airice_inice_table_interp_kernel(const InIceTableInterpArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.n) return;
+  a.out[i] = inice_table_interp(a.pos_x, a.pos_z, a.n_x, a.n_z, a.step_x, a.step_z, a.col, a.x[i], a.z[i]);
 }
 
 int ladder_grid() {
@@ -258,6 +346,38 @@ cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_inice_attenuation(const InIceAttArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  if (!a.z0 || !a.z1 || !a.L || !a.out || (a.kind == 2 && !a.zmax) || a.kind < 0 || a.kind > 2) return cudaErrorInvalidValue;
+  airice_inice_attenuation_kernel<<<dim3((unsigned)((a.n + 127) / 128)), 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_inice_focusing(const InIceFocusArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  airice_inice_focusing_kernel<<<dim3((unsigned)((a.n + 255) / 256)), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_inice_shift(int64_t n, const double* in, double shift, double* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  airice_inice_shift_kernel<<<dim3((unsigned)((n + 255) / 256)), 256, 0, s>>>(n, in, shift, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_inice_table_nodes(const InIceTableNodeArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  airice_inice_table_nodes_kernel<<<dim3((unsigned)((a.n + 255) / 256)), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_inice_table_pack(const InIceTablePackArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  airice_inice_table_pack_kernel<<<dim3((unsigned)((a.n + 255) / 256)), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_inice_table_interp(const InIceTableInterpArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  airice_inice_table_interp_kernel<<<dim3((unsigned)((a.n + 255) / 256)), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_inice_pick(const InIcePickArgs& a, cudaStream_t s) {
   if (a.n <= 0) return cudaSuccess;
   const int64_t blocks = (a.n + 255) / 256;
@@ -265,7 +385,8 @@ cudaError_t launch_inice_pick(const InIcePickArgs& a, cudaStream_t s) {
   for (int k = 0; k < AIRICE_INICE_NCOLS; k++)
     if (!a.in[k]) return cudaErrorInvalidValue;
   if (!a.ignore[0] || !a.ignore[1]) return cudaErrorInvalidValue;
-  airice_inice_pick_kernel<<<dim3((unsigned)blocks), 256, 0, s>>>(a);
+  if (a.att[0] && a.att[1]) airice_inice_pick_kernel<true><<<dim3((unsigned)blocks), 256, 0, s>>>(a);
+  else airice_inice_pick_kernel<false><<<dim3((unsigned)blocks), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -151,8 +151,63 @@ struct InIcePickArgs {
   double* out[AIRICE_INICE_RAYS_NCOLS];    // TimeRay[2], PathRay[2], LaunchAngle[2], RecieveAngle[2], IncidenceAngleInIce[2]
   int32_t* ignore[2];                      // IgnoreCh[2]: 1 = ray present
   int32_t* type[2];                        // RayType[2] (1 D, 2 R, 3 Ra1, 4 Ra2); nullptr = skip
+  // attenuation (IceRayTracing.cc:2970-2987): att[0] != nullptr -> AttRay[2] = 1 - integral of A0 / L_att along the ray
+  double* att[2];
+  double A0, frequency, w0, w2, w;         // w0 = log(0.0001), w2 = log(3.16), w = log(frequency): host libm
+  int32_t* quad_stats;                     // [2] device: integrals that ran out of interval storage, largest interval count
 };
 cudaError_t launch_inice_pick(const InIcePickArgs& a, cudaStream_t s);
+
+// ---- kernel 4c: GetTotalAttenuationDirect / Reflected / Refracted (IceRayTracing.cc:203-219) for n rays
+struct InIceAttArgs {
+  int64_t n;
+  int kind;                                // 0 direct, 1 reflected, 2 refracted
+  const double *z0, *z1, *zmax, *L;        // zmax: refracted only
+  double A, B, C, A0, frequency, w0, w2, w;
+  double* out;
+  int32_t* quad_stats;
+};
+cudaError_t launch_inice_attenuation(const InIceAttArgs& a, cudaStream_t s);
+
+// ---- kernel 4d: GetFocusingFactor (IceRayTracing.cc:3218-3293) from the two-ray solutions at zR (a) and zR - 0.01 (b)
+struct InIceFocusArgs {
+  int64_t n;
+  const double *zT, *zR;
+  const double* sol_a[AIRICE_INICE_RAYS_NCOLS];   // kernel 4b columns
+  const double* sol_b[AIRICE_INICE_RAYS_NCOLS];
+  double A, B, C;
+  double* out[2];
+};
+cudaError_t launch_inice_focusing(const InIceFocusArgs& a, cudaStream_t s);
+// rx - 0.01 for the second solution; grid nodes and the 13 columns of IceRayTracing::MakeTable (IceRayTracing.cc:2614-2724)
+cudaError_t launch_inice_shift(int64_t n, const double* in, double shift, double* out, cudaStream_t s);
+struct InIceTableNodeArgs {
+  int64_t node0, n;
+  int n_z;
+  double start_x, start_z, step_x, step_z, zR;
+  double *xT, *zT, *rx;                    // outputs [n]
+};
+cudaError_t launch_inice_table_nodes(const InIceTableNodeArgs& a, cudaStream_t s);
+#define AIRICE_INICE_TABLE_NCOLS 13
+struct InIceTablePackArgs {
+  int64_t n;
+  const double* sol[AIRICE_INICE_RAYS_NCOLS];
+  const double* att[2];
+  const int32_t* ignore[2];
+  const double* focusing[2];
+  double* col[AIRICE_INICE_TABLE_NCOLS];   // at this chunk's first node
+};
+cudaError_t launch_inice_table_pack(const InIceTablePackArgs& a, cudaStream_t s);
+struct InIceTableInterpArgs {
+  int64_t n;
+  const double *x, *z;
+  const float *pos_x, *pos_z;
+  int n_x, n_z;
+  double step_x, step_z;
+  const double* col;
+  double* out;
+};
+cudaError_t launch_inice_table_interp(const InIceTableInterpArgs& a, cudaStream_t s);
 
 // ---- kernel 5: ray-path emission (SingleRayAirIceRefraction.C:226-299), airice_path.cuh
 struct PathArgs {

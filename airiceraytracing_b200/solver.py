@@ -131,7 +131,8 @@ class AirIceSolver:
         self.device = int(device)
         self.torch_device = torch.device("cuda", self.device)
         h = C.c_void_p()
-        check(self.lib.airice_create(str(atmosphere).encode(), int(variant), self.device, C.byref(h)))
+        # atmosphere=None: an ice-only context (in-ice entry points only, no GDAS file needed)
+        check(self.lib.airice_create(str(atmosphere).encode() if atmosphere else None, int(variant), self.device, C.byref(h)))
         self.handle = h
         self.variant = variant
 
@@ -419,6 +420,118 @@ def _inice_two_rays(self, rx_depth, distance, tx_depth, want_type=False):
     return (out, ig, ty) if want_type else (out, ig)
 
 
+def _inice_two_rays_att(self, rx_depth, distance, tx_depth, A0, frequency_ghz):
+    """GetRayTracingSolutions with attenuation -> (out [10, n], att [2, n] = AttRay, ignore [2, n] int32)."""
+    rx = rx_depth.to(self.torch_device, torch.float64).contiguous()
+    ds = distance.to(self.torch_device, torch.float64).contiguous()
+    tx = tx_depth.to(self.torch_device, torch.float64).contiguous()
+    n = rx.numel()
+    out = torch.empty((_capi.INICE_RAYS_COLS, n), dtype=torch.float64, device=self.torch_device)
+    att = torch.empty((2, n), dtype=torch.float64, device=self.torch_device)
+    ig = torch.empty((2, n), dtype=torch.int32, device=self.torch_device)
+    check(self.lib.airice_inice_two_rays_att_device(
+        self.handle, n, rx.data_ptr(), ds.data_ptr(), tx.data_ptr(), float(A0), float(frequency_ghz),
+        ptr_array([out[k].data_ptr() for k in range(_capi.INICE_RAYS_COLS)]), ptr_array([att[0].data_ptr(), att[1].data_ptr()]),
+        ptr_array([ig[0].data_ptr(), ig[1].data_ptr()]), None, _stream_ptr(self.torch_device)))
+    return out, att, ig
+
+
+def _inice_two_rays_att_host(self, rx_depth, distance, tx_depth, A0, frequency_ghz):
+    n = int(rx_depth.shape[0])
+    out = np.empty((_capi.INICE_RAYS_COLS, n), dtype=np.float64)
+    att = np.empty((2, n), dtype=np.float64)
+    ig = np.empty((2, n), dtype=np.int32)
+    check(self.lib.airice_inice_two_rays_att_host(self.handle, n, _host_ptr(rx_depth), _host_ptr(distance), _host_ptr(tx_depth),
+                                                  float(A0), float(frequency_ghz), _host_ptr(out), _host_ptr(att), _host_ptr(ig)))
+    return out, att, ig
+
+
+def _inice_attenuation(self, kind, A0, frequency_ghz, z0, z1, L, zmax=None):
+    """GetTotalAttenuationDirect (kind 0) / Reflected (1) / Refracted (2) on device tensors -> [n]."""
+    z0 = z0.to(self.torch_device, torch.float64).contiguous()
+    z1 = z1.to(self.torch_device, torch.float64).contiguous()
+    L = L.to(self.torch_device, torch.float64).contiguous()
+    zm = zmax.to(self.torch_device, torch.float64).contiguous() if zmax is not None else None
+    out = torch.empty_like(z0)
+    check(self.lib.airice_inice_attenuation_device(self.handle, z0.numel(), int(kind), float(A0), float(frequency_ghz), z0.data_ptr(),
+                                                   z1.data_ptr(), zm.data_ptr() if zm is not None else None, L.data_ptr(),
+                                                   out.data_ptr(), _stream_ptr(self.torch_device)))
+    return out
+
+
+def _inice_focusing(self, zT, xR, zR):
+    """GetFocusingFactor(zT, xR, zR) with the initial {1, 1} -> [2, n]."""
+    zT = zT.to(self.torch_device, torch.float64).contiguous()
+    xR = xR.to(self.torch_device, torch.float64).contiguous()
+    zR = zR.to(self.torch_device, torch.float64).contiguous()
+    out = torch.empty((2, zT.numel()), dtype=torch.float64, device=self.torch_device)
+    check(self.lib.airice_inice_focusing_device(self.handle, zT.numel(), zT.data_ptr(), xR.data_ptr(), zR.data_ptr(),
+                                                ptr_array([out[0].data_ptr(), out[1].data_ptr()]), _stream_ptr(self.torch_device)))
+    return out
+
+
+def _inice_quadrature_stats(self):
+    v = (C.c_int64 * 2)()
+    check(self.lib.airice_inice_quadrature_stats(self.handle, v))
+    return int(v[0]), int(v[1])
+
+
+class InIceTable:
+    """IceRayTracing::MakeTable's grid (13 columns, GridZValueb[AntNum]) on the device, with batched GetInterpolatedValue."""
+
+    def __init__(self, solver, handle):
+        self.solver, self.handle = solver, handle
+        info = (C.c_int64 * 3)()
+        check(solver.lib.airice_inice_table_info(handle, info))
+        self.n_x, self.n_z, self.points = int(info[0]), int(info[1]), int(info[2])
+
+    def columns(self):
+        out = np.empty((13, self.points), dtype=np.float64)
+        for k in range(13):
+            check(self.solver.lib.airice_inice_table_copy_column(self.handle, k, out[k].ctypes.data))
+        return out
+
+    def positions(self):
+        px, pz = np.empty(self.n_x, dtype=np.float32), np.empty(self.n_z, dtype=np.float32)
+        check(self.solver.lib.airice_inice_table_copy_positions(self.handle, px.ctypes.data, pz.ctypes.data))
+        return px, pz
+
+    def interp(self, x, z, par):
+        s = self.solver
+        x = x.to(s.torch_device, torch.float64).contiguous()
+        z = z.to(s.torch_device, torch.float64).contiguous()
+        out = torch.empty_like(x)
+        check(s.lib.airice_inice_table_interp_device(s.handle, self.handle, x.numel(), x.data_ptr(), z.data_ptr(), int(par),
+                                                     out.data_ptr(), _stream_ptr(s.torch_device)))
+        return out
+
+    def interp_host(self, x, z, par):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        out = np.empty_like(x)
+        check(self.solver.lib.airice_inice_table_interp_host(self.solver.handle, self.handle, x.size, x.ctypes.data, z.ctypes.data,
+                                                             int(par), out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.handle:
+            self.solver.lib.airice_inice_table_destroy(self.handle)     # holds no pointer into the context
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _inice_table_create(self, shower_hit_distance, shower_depth, zR, step_x=0.1, step_z=0.1, width_x=40.0, width_z=20.0):
+    h = C.c_void_p()
+    check(self.lib.airice_inice_table_create(self.handle, shower_hit_distance, shower_depth, zR, step_x, step_z, width_x, width_z,
+                                             C.byref(h)))
+    return InIceTable(self, h)
+
+
 def _inice_two_rays_host(self, rx_depth, distance, tx_depth):
     n = int(rx_depth.shape[0])
     out = np.empty((_capi.INICE_RAYS_COLS, n), dtype=np.float64)
@@ -465,6 +578,12 @@ AirIceSolver.inice_solve = _inice_solve
 AirIceSolver.inice_solve_host = _inice_solve_host
 AirIceSolver.inice_two_rays = _inice_two_rays
 AirIceSolver.inice_two_rays_host = _inice_two_rays_host
+AirIceSolver.inice_two_rays_att = _inice_two_rays_att
+AirIceSolver.inice_two_rays_att_host = _inice_two_rays_att_host
+AirIceSolver.inice_attenuation = _inice_attenuation
+AirIceSolver.inice_focusing = _inice_focusing
+AirIceSolver.inice_quadrature_stats = _inice_quadrature_stats
+AirIceSolver.inice_table_create = _inice_table_create
 
 
 def _host_ptr(a):

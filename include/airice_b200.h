@@ -31,6 +31,8 @@ enum { AIRICE_UNITS_M_DEG_C = 0, AIRICE_UNITS_CM_RAD_C = 1 };
 
 /* ---- context: replaces MakeAtmosphere() (MultiRayAirIceRefraction.cc:920-942, .h:157) and
  * AirIceRayTracing::MakeAtmosphere(file) (pythonwrapper/AirIceRayTracing.cc:860-882).  Parses the GDAS file once. */
+/* atmosphere_path NULL or "": an ice-only context (the reference's IceRayTracing namespace needs no atmosphere file);
+ * the air->ice entry points then fail with -9. */
 int airice_create(const char *atmosphere_path, int variant, int device, airice_ctx **out);
 void airice_destroy(airice_ctx *ctx);
 const char *airice_last_error(void);
@@ -149,6 +151,57 @@ int airice_inice_two_rays_device(airice_ctx *ctx, int64_t n, const double *d_rx_
 /* HOST buffers: out[col*n + i] with 10 columns, ignore[k*n + i] with k = 0, 1 */
 int airice_inice_two_rays_host(airice_ctx *ctx, int64_t n, const double *rx_depth, const double *distance,
                                const double *tx_depth, double *out, int32_t *ignore);
+
+/* ---- kernels 4c-4e: attenuation, focusing factor and the in-ice interpolation table.
+ * airice_inice_two_rays_att_*: IceRayTracing::GetRayTracingSolutions WITH its A0 / frequency / AttRay arguments
+ * (IceRayTracing.cc:2907-3210): AttRay[k] = 1 - integral of A0 / L_att(z, f) along ray k (GetTotalAttenuationDirect /
+ * Reflected / Refracted, IceRayTracing.cc:203-219; integrand :165-176 with the AraSim temperature and attenuation-length
+ * model :135-162).  The reference integrates with gsl_integration_qags(epsabs 0, epsrel 1e-7, limit 1000)
+ * (IceRayTracing.cc:179-200); the kernel runs the same QAGS procedure per ray (21-point Gauss-Kronrod, bisection by
+ * largest error, epsilon extrapolation).  frequency in GHz.  att: 2 column pointers (device) / att[k*n + i] (host). */
+int airice_inice_two_rays_att_device(airice_ctx *ctx, int64_t n, const double *d_rx_depth, const double *d_distance,
+                                     const double *d_tx_depth, double A0, double frequency_ghz, double *const *d_out,
+                                     double *const *d_att, int32_t *const *d_ignore, int32_t *const *d_type, void *stream);
+int airice_inice_two_rays_att_host(airice_ctx *ctx, int64_t n, const double *rx_depth, const double *distance,
+                                   const double *tx_depth, double A0, double frequency_ghz, double *out, double *att,
+                                   int32_t *ignore);
+/* GetTotalAttenuationDirect (kind 0) / Reflected (1) / Refracted (2; d_zmax = turning depth) for n rays with Snell
+ * parameter L between depths z0 and z1 (IceRayTracing.cc:203-219). */
+int airice_inice_attenuation_device(airice_ctx *ctx, int64_t n, int kind, double A0, double frequency_ghz,
+                                    const double *d_z0, const double *d_z1, const double *d_zmax, const double *d_L,
+                                    double *d_out, void *stream);
+int airice_inice_attenuation_host(airice_ctx *ctx, int64_t n, int kind, double A0, double frequency_ghz, const double *z0,
+                                  const double *z1, const double *zmax, const double *L, double *out);
+/* out[0] = integrals that would have needed more than the 64 intervals a thread holds (the reference allows 1000; their
+ * result is the running total instead of the extrapolated one), out[1] = largest interval count seen above 24.  Both 0 in
+ * every test; a non-zero out[0] means results that may differ from the reference's. */
+int airice_inice_quadrature_stats(airice_ctx *ctx, int64_t out[2]);
+/* IceRayTracing::GetFocusingFactor(zT, xR, zR, focusing[2]) (IceRayTracing.cc:3218-3293) with the initial {1, 1} its
+ * caller passes: two two-ray solutions (receiver at zR and at zR - 0.01 m) -> sqrt(path / (sin(recv) |dz / dlaunch|) nTx / nRx)
+ * per ray.  out: 2 column pointers (device) / out[k*n + i] (host). */
+int airice_inice_focusing_device(airice_ctx *ctx, int64_t n, const double *d_zT, const double *d_xR, const double *d_zR,
+                                 double *const *d_out, void *stream);
+int airice_inice_focusing_host(airice_ctx *ctx, int64_t n, const double *zT, const double *xR, const double *zR, double *out);
+/* IceRayTracing::MakeTable(ShowerHitDistance, ShowerDepth, zR, AntNum) (IceRayTracing.cc:2614-2724): emitter positions
+ * (xT, zT) on a grid around the shower (reference globals IceRayTracing.hh:33-36: steps 0.1 m, widths 40 m x 20 m =
+ * 401 x 201 nodes), one receiver depth zR; per node the two-ray solution with attenuation (A0 = 1, 0.1 GHz) and the
+ * focusing factors.  13 f64 columns = GridZValueb[AntNum][0..12]: ray 1 {time, path, launch, receive, AttRay, focusing},
+ * ray 2 {the same six, incidence angle on the surface}; -1000 = absent.  node = ix * n_z + iz; positions are float. */
+typedef struct airice_inice_table airice_inice_table;
+#define AIRICE_INICE_TABLE_COLS 13
+int airice_inice_table_create(airice_ctx *ctx, double shower_hit_distance, double shower_depth, double zR, double step_x,
+                              double step_z, double width_x, double width_z, airice_inice_table **out);
+void airice_inice_table_destroy(airice_inice_table *t);
+/* info[0] = TotalStepsX_O, info[1] = TotalStepsZ_O, info[2] = GridPoints */
+int airice_inice_table_info(const airice_inice_table *t, int64_t info[3]);
+int airice_inice_table_copy_column(const airice_inice_table *t, int col, double *host_out);
+int airice_inice_table_copy_positions(const airice_inice_table *t, float *host_x, float *host_z);
+/* IceRayTracing::GetInterpolatedValue(xT, zT, rtParameter, AntNum) (IceRayTracing.cc:2727-2905), batched: bilinear in a
+ * cell whose four nodes exist, inverse-distance weighting over the existing ones otherwise, -1000 outside the grid. */
+int airice_inice_table_interp_device(airice_ctx *ctx, const airice_inice_table *t, int64_t n, const double *d_x,
+                                     const double *d_z, int rt_parameter, double *d_out, void *stream);
+int airice_inice_table_interp_host(airice_ctx *ctx, const airice_inice_table *t, int64_t n, const double *x, const double *z,
+                                   int rt_parameter, double *out);
 
 /* ---- kernel 5: ray-path emission = the RayPathinAirnIce.txt dump of the reference's CLI
  * (SingleRayAirIceRefraction.C:226-299 on the layer walk of :133-152; `./SingleRayAirIceRefraction 200 170 20000 3000`

@@ -454,6 +454,58 @@ class IceRayReference:
         """GetRayTracingSolutions(RxDepth, Distance, TxDepth, ...) -> (out[n,10], IgnoreCh[n,2])"""
         return _two_rays(self.lib.iceref_two_rays_batch, rx_depth, distance, tx_depth)
 
+    # ---- SURVEY.md 8f-4: attenuation (through the stand-in's QAGS), focusing, in-ice table
+    def two_rays_att(self, rx_depth, distance, tx_depth, A0, frequency):
+        """-> (out[n,10], AttRay[n,2], IgnoreCh[n,2])"""
+        rx = np.ascontiguousarray(rx_depth, dtype=np.float64)
+        dist = np.ascontiguousarray(distance, dtype=np.float64)
+        tx = np.ascontiguousarray(tx_depth, dtype=np.float64)
+        out, att, ig = np.zeros((rx.size, 10)), np.zeros((rx.size, 2)), np.zeros((rx.size, 2), dtype=np.int32)
+        f = self.lib.iceref_two_rays_att_batch
+        f.argtypes = [C.c_long, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, c_double_p, c_double_p, C.POINTER(C.c_int)]
+        f(rx.size, _dp(rx), _dp(dist), _dp(tx), A0, frequency, _dp(out), _dp(att), ig.ctypes.data_as(C.POINTER(C.c_int)))
+        return out, att, ig
+
+    def attenuation(self, kind, A0, frequency, z0, z1, zmax, L):
+        f = self.lib.iceref_attenuation
+        f.restype = C.c_double
+        f.argtypes = [C.c_int] + [C.c_double] * 6
+        return f(kind, A0, frequency, z0, z1, zmax, L)
+
+    def focusing(self, zT, xR, zR):
+        zT = np.ascontiguousarray(zT, dtype=np.float64)
+        xR = np.ascontiguousarray(xR, dtype=np.float64)
+        zR = np.ascontiguousarray(zR, dtype=np.float64)
+        out = np.zeros((zT.size, 2))
+        f = self.lib.iceref_focusing_batch
+        f.argtypes = [C.c_long, c_double_p, c_double_p, c_double_p, c_double_p]
+        f(zT.size, _dp(zT), _dp(xR), _dp(zR), _dp(out))
+        return out
+
+    def make_table(self, hit_distance, shower_depth, zR, step_x=0.1, step_z=0.1, width_x=40.0, width_z=20.0, ant=0, n_ant=1):
+        """MakeTable on the given grid -> (columns [13, points], pos_x float32, pos_z float32)"""
+        L = self.lib
+        L.iceref_set_grid.argtypes = [C.c_double] * 4
+        L.iceref_make_table.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.iceref_set_grid(step_x, step_z, width_x, width_z)
+        L.iceref_make_table(n_ant, hit_distance, shower_depth, zR, ant)
+        info = (C.c_long * 3)()
+        L.iceref_table_info(ant, info)
+        cols = np.zeros((13, info[2]))
+        L.iceref_table_column.argtypes = [C.c_int, C.c_int, c_double_p]
+        for k in range(13):
+            L.iceref_table_column(ant, k, _dp(cols[k]))
+        px, pz = np.zeros(info[0], dtype=np.float32), np.zeros(info[1], dtype=np.float32)
+        L.iceref_table_positions.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.iceref_table_positions(ant, px.ctypes.data, pz.ctypes.data)
+        return cols, px, pz
+
+    def interp(self, x, z, par, ant=0):
+        f = self.lib.iceref_interp
+        f.restype = C.c_double
+        f.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+        return np.array([f(float(a), float(b), par, ant) for a, b in zip(x, z)])
+
     def solve_batch(self, z0, x1, z1):
         z0 = np.ascontiguousarray(z0, dtype=np.float64)
         x1 = np.ascontiguousarray(x1, dtype=np.float64)

@@ -9,6 +9,7 @@
 #include "airice_inice.cuh"
 #include "airice_path.cuh"
 #include "airice_inice_machine.cuh"
+#include "airice_inice_att.cuh"
 
 using namespace airice;
 
@@ -148,6 +149,49 @@ void sim_inice_two_rays_batch(long n, const double* rx, const double* dist, cons
     inice_solve(m, tx[i], dist[i], rx[i], o);
     inice_pick_two_rays(m, o, rx[i], dist[i], tx[i], out10 + 10 * i, ignore2 + 2 * i, type2 + 2 * i);
   }
+}
+// the same with the attenuation outputs (QAGS per candidate ray); stats[0] = interval-storage overflows, [1] = most intervals
+void sim_inice_two_rays_att_batch(long n, const double* rx, const double* dist, const double* tx, double A0, double frequency,
+                                  double* out10, double* att2, int* ignore2, int* stats) {
+  const AirIceInIce m = inice_make_model(1.78, -0.43, 0.0132);
+  const InIceAttModel am = {A0, frequency, log(0.0001), log(3.16), log(frequency)};
+  int flags = 0, worst = 0, over = 0;
+  for (long i = 0; i < n; i++) {
+    double o[29], att4[4];
+    int ty[2];
+    inice_solve(m, tx[i], dist[i], rx[i], o);
+    flags = 0;
+    inice_candidate_attenuations(m, am, o, rx[i], tx[i], att4, flags, worst);
+    over += flags != 0;
+    inice_pick_two_rays(m, o, rx[i], dist[i], tx[i], out10 + 10 * i, ignore2 + 2 * i, ty, att4, att2 + 2 * i);
+  }
+  stats[0] = over; stats[1] = worst;
+}
+double sim_inice_attenuation(int kind, double A0, double frequency, double z0, double z1, double zmax, double L) {
+  const AirIceInIce m = inice_make_model(1.78, -0.43, 0.0132);
+  const InIceAttModel am = {A0, frequency, log(0.0001), log(3.16), log(frequency)};
+  int flags = 0, worst = 0;
+  return inice_total_attenuation(m, am, kind, z0, z1, zmax, L, flags, worst);
+}
+// GetFocusingFactor(zT, xR, zR) with the initial {1, 1}
+void sim_inice_focusing_batch(long n, const double* zT, const double* xR, const double* zR, double* out2) {
+  const AirIceInIce m = inice_make_model(1.78, -0.43, 0.0132);
+  for (long i = 0; i < n; i++) {
+    double o[29], a[10], b[10];
+    int ig[2], ty[2];
+    inice_solve(m, zT[i], xR[i], zR[i], o);
+    inice_pick_two_rays(m, o, zR[i], xR[i], zT[i], a, ig, ty);
+    const double zb = zR[i] - 0.01;
+    inice_solve(m, zT[i], xR[i], zb, o);
+    inice_pick_two_rays(m, o, zb, xR[i], zT[i], b, ig, ty);
+    double f[2] = {1, 1};
+    inice_focusing(m, zT[i], zR[i], a + 2, a + 4, a + 6, b + 4, b + 6, f);
+    out2[2 * i] = f[0]; out2[2 * i + 1] = f[1];
+  }
+}
+double sim_inice_table_interp(const float* pos_x, const float* pos_z, int n_x, int n_z, double step_x, double step_z,
+                              const double* col, double x, double z) {
+  return inice_table_interp(pos_x, pos_z, n_x, n_z, step_x, step_z, col, x, z);
 }
 // ray-path polyline through the host build of airice_path.cuh; depth negative in ice; returns the point count
 long sim_ray_path(double theta, double h, double ice, double depth, long max_points, double* x, double* z) {
