@@ -420,8 +420,8 @@ def _inice_two_rays(self, rx_depth, distance, tx_depth, want_type=False):
     return (out, ig, ty) if want_type else (out, ig)
 
 
-def _inice_two_rays_att(self, rx_depth, distance, tx_depth, A0, frequency_ghz):
-    """GetRayTracingSolutions with attenuation -> (out [10, n], att [2, n] = AttRay, ignore [2, n] int32)."""
+def _inice_two_rays_att(self, rx_depth, distance, tx_depth, A0, frequency_ghz, want_type=False):
+    """GetRayTracingSolutions with attenuation -> (out [10, n], att [2, n] = AttRay, ignore [2, n] int32[, type [2, n]])."""
     rx = rx_depth.to(self.torch_device, torch.float64).contiguous()
     ds = distance.to(self.torch_device, torch.float64).contiguous()
     tx = tx_depth.to(self.torch_device, torch.float64).contiguous()
@@ -429,11 +429,13 @@ def _inice_two_rays_att(self, rx_depth, distance, tx_depth, A0, frequency_ghz):
     out = torch.empty((_capi.INICE_RAYS_COLS, n), dtype=torch.float64, device=self.torch_device)
     att = torch.empty((2, n), dtype=torch.float64, device=self.torch_device)
     ig = torch.empty((2, n), dtype=torch.int32, device=self.torch_device)
+    ty = torch.empty((2, n), dtype=torch.int32, device=self.torch_device) if want_type else None
     check(self.lib.airice_inice_two_rays_att_device(
         self.handle, n, rx.data_ptr(), ds.data_ptr(), tx.data_ptr(), float(A0), float(frequency_ghz),
         ptr_array([out[k].data_ptr() for k in range(_capi.INICE_RAYS_COLS)]), ptr_array([att[0].data_ptr(), att[1].data_ptr()]),
-        ptr_array([ig[0].data_ptr(), ig[1].data_ptr()]), None, _stream_ptr(self.torch_device)))
-    return out, att, ig
+        ptr_array([ig[0].data_ptr(), ig[1].data_ptr()]), ptr_array([ty[0].data_ptr(), ty[1].data_ptr()]) if want_type else None,
+        _stream_ptr(self.torch_device)))
+    return (out, att, ig, ty) if want_type else (out, att, ig)
 
 
 def _inice_two_rays_att_host(self, rx_depth, distance, tx_depth, A0, frequency_ghz):
