@@ -128,6 +128,7 @@ struct airice_table {
   float* row_h = nullptr;
   int* row_first = nullptr;
   int* row_last = nullptr;
+  float* rowblk = nullptr;     // per-row search blocks (header + first tree levels of the index halving), kernels.cuh
   int64_t n_h = 0, n_th = 0, cells = 0;
   double loop_stop_h = 0, h_step = 0;
   mutable std::vector<cudaStream_t> used;   // streams that ran lookups on this table (besides the build stream 0)
@@ -140,7 +141,7 @@ struct airice_table {
     t.x = x; t.rec = rec; t.row_h = row_h;
     t.cells = cells; t.n_h = (int)n_h; t.n_th = (int)n_th;
     t.loop_stop_h = loop_stop_h; t.h_step = h_step;
-    t.row_first = row_first; t.row_last = row_last;
+    t.row_first = row_first; t.row_last = row_last; t.rowblk = rowblk;
     return t;
   }
 };
@@ -216,7 +217,8 @@ int pack_alloc(airice_table* t) {
   const size_t x_bytes = (sizeof(float) * (size_t)t->cells + 255) / 256 * 256;
   const size_t rowh_bytes = (sizeof(float) * (size_t)t->n_h + 255) / 256 * 256;
   const size_t range_bytes = (sizeof(int) * (size_t)t->n_h + 255) / 256 * 256;
-  t->pack_bytes = rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes;
+  const size_t blk_bytes = (sizeof(float) * AIRICE_ROWBLK * (size_t)t->n_h + 255) / 256 * 256;
+  t->pack_bytes = rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes + blk_bytes;
   cudaError_t e = table_alloc(t->ctx, &t->pack, t->pack_bytes);
   if (e != cudaSuccess) { t->pack = nullptr; return cuda_fail(e, "cudaMalloc(lookup layout)"); }
   char* base = (char*)t->pack;
@@ -225,13 +227,15 @@ int pack_alloc(airice_table* t) {
   t->row_h = (float*)(base + rec_bytes + x_bytes);
   t->row_first = (int*)(base + rec_bytes + x_bytes + rowh_bytes);
   t->row_last = (int*)(base + rec_bytes + x_bytes + rowh_bytes + range_bytes);
+  t->rowblk = (float*)(base + rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes);
   return 0;
 }
 // ... and fill it from the column-major form.
 int pack_table(airice_table* t) {
   int rc = pack_alloc(t);
   if (rc) return rc;
-  cudaError_t e = launch_pack_table(t->cols, t->cells, (int)t->n_h, (int)t->n_th, t->x, t->rec, t->row_h, t->row_first, t->row_last, nullptr);
+  cudaError_t e = launch_pack_table(t->cols, t->cells, (int)t->n_h, (int)t->n_th, t->x, t->rec, t->row_h, t->row_first, t->row_last,
+                                    t->rowblk, nullptr);
   if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
   if (e != cudaSuccess) return cuda_fail(e, "pack table");
   return 0;
@@ -536,7 +540,8 @@ int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, 
   ma.row_h = (float* const*)(d_blocks + 3 * (size_t)n_ant);
   rc = build_rows(c, g, 0, n_h, nullptr, nullptr, nullptr, &ma);
   for (int q = 0; q < n_ant && rc == 0; q++) {
-    e = launch_row_ranges(out[q]->x, cells, (int)n_h, (int)g.n_th, out[q]->row_first, out[q]->row_last, nullptr);
+    e = launch_row_ranges(out[q]->x, out[q]->row_h, cells, (int)n_h, (int)g.n_th, out[q]->row_first, out[q]->row_last, out[q]->rowblk,
+                          nullptr);
     if (e != cudaSuccess) rc = cuda_fail(e, "row ranges");
   }
   if (rc == 0 && (e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "multi-antenna tables");

@@ -278,6 +278,53 @@ __global__ void airice_pack_kernel(const float* c0, const float* c1, const float
   if (i % n_th == 0) row_h[i / n_th] = c0[i];
 }
 
+// Per-row search blocks (LookupTable::rowblk).  One thread per (row, slot): slots 0..7 header, 8..39 tree of the row's own
+// window, 40..71 tree of the second row's window.  The midpoints FindClosestTHD visits (M.cc:1131-1143) depend only on
+// the window it starts from, which is a per-row constant, so the first levels of its halving are a fixed binary tree per
+// row: 9701 rows x 288 B = 2.8 MB for the reference grid, L2 resident, against eight dependent loads per row scattered
+// over the 35 MB X column.
+__global__ void airice_row_block_kernel(const float* __restrict__ X, const float* __restrict__ row_h, int64_t cells, int n_h, int n_th,
+                                        const int* __restrict__ row_first, const int* __restrict__ row_last, float* rowblk) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n_h * AIRICE_ROWBLK) return;
+  const int row = (int)(t / AIRICE_ROWBLK), slot = (int)(t - (int64_t)row * AIRICE_ROWBLK);
+  const int total = (int)cells - 1;
+  const int s1 = row_first[row], e1 = row_last[row];
+  int s2 = s1 - n_th, e2 = e1 - n_th;
+  if (s2 < 0) s2 = s1 + n_th;
+  if (e2 < 0) e2 = e1 + n_th;
+  auto xat = [&](int i) { return (i >= 0 && i <= total) ? X[i] : 0.f; };
+  auto hat = [&](int i) { const int r = i / n_th; return (i >= 0 && r < n_h) ? row_h[r] : 0.f; };
+  float v = 0.f;
+  if (slot < 8) {
+    switch (slot) {
+      case 0: v = __int_as_float(s1); break;
+      case 1: v = __int_as_float(e1); break;
+      case 2: v = xat(s1); break;
+      case 3: v = xat(s2); break;
+      case 4: v = hat(s1); break;
+      case 5: v = hat(s2); break;
+      case 6: v = hat(row); break;     // column 0 indexed with the ROW index, as the reference writes it (M.cc:1076)
+      default: v = 0.f; break;
+    }
+  } else {
+    const int node = (slot - 8) & 31;
+    int s = (slot < 40) ? s1 : s2, e = (slot < 40) ? e1 : e2;
+    // node = 2^k - 1 + j: level k, path j (most significant bit first)
+    int k = 0;
+    while ((2 << k) - 1 <= node) k++;
+    const int j = node - ((1 << k) - 1);
+    bool reachable = node < 31;
+    for (int lvl = 0; lvl < k && reachable; lvl++) {
+      if (e - s < 3) { reachable = false; break; }
+      const int mid = (s + e) / 2;
+      if ((j >> (k - 1 - lvl)) & 1) s = mid; else e = mid;
+    }
+    if (reachable && e - s >= 3) v = xat((s + e) / 2);
+  }
+  rowblk[t] = v;
+}
+
 // FindClosestTHD (M.cc:1128-1169) = <=8 index halvings while the window is >=3 wide (halve_thd2), then a linear scan
 // (scan_thd).
 __device__ __forceinline__ void load_rec(const float4* __restrict__ rec, int i, double* v) {
@@ -287,14 +334,28 @@ __device__ __forceinline__ void load_rec(const float4* __restrict__ rec, int i, 
 
 // The index halvings of FindClosestTHD for the two rows of a query in lock step: the two chains of dependent loads
 // (eight each, L2 or DRAM latency apiece) overlap instead of running one after the other.
-__device__ __forceinline__ void halve_thd2(const float* __restrict__ X, double d, bool on1, int& s1, int& e1, bool on2, int& s2, int& e2) {
+// The first AIRICE_TREE_LEVELS halvings read the row's tree (one 128-byte line per row, L1 hits after the first), the
+// remaining ones the dense X column inside the window the tree has narrowed down to (1/32 of the row: one or two lines).
+// X[mid] == d leaves the window as it is, and every later halving would revisit the same midpoint: `st` ends the walk.
+__device__ __forceinline__ void halve_thd2(const float* __restrict__ X, const float* __restrict__ tree1, const float* __restrict__ tree2,
+                                           double d, bool on1, int& s1, int& e1, bool on2, int& s2, int& e2) {
+  bool st1 = !on1, st2 = !on2;
+  int j1 = 0, j2 = 0;
+#pragma unroll
+  for (int lvl = 0; lvl < AIRICE_TREE_LEVELS; lvl++) {
+    const bool g1 = !st1 && (e1 - s1 >= 3), g2 = !st2 && (e2 - s2 >= 3);
+    const int m1 = (s1 + e1) / 2, m2 = (s2 + e2) / 2;
+    const float x1 = g1 ? __ldg(tree1 + ((1 << lvl) - 1) + j1) : 0.f, x2 = g2 ? __ldg(tree2 + ((1 << lvl) - 1) + j2) : 0.f;
+    if (g1) { const double v = (double)x1 - d; if (v > 0) { s1 = m1; j1 = 2 * j1 + 1; } else if (v < 0) { e1 = m1; j1 = 2 * j1; } else st1 = true; }
+    if (g2) { const double v = (double)x2 - d; if (v > 0) { s2 = m2; j2 = 2 * j2 + 1; } else if (v < 0) { e2 = m2; j2 = 2 * j2; } else st2 = true; }
+  }
 #pragma unroll 1
-  for (int i = 0; i < 8; i++) {
-    const bool g1 = on1 && (e1 - s1 >= 3), g2 = on2 && (e2 - s2 >= 3);
+  for (int i = AIRICE_TREE_LEVELS; i < 8; i++) {
+    const bool g1 = !st1 && (e1 - s1 >= 3), g2 = !st2 && (e2 - s2 >= 3);
     const int m1 = (s1 + e1) / 2, m2 = (s2 + e2) / 2;
     const float x1 = g1 ? __ldg(X + m1) : 0.f, x2 = g2 ? __ldg(X + m2) : 0.f;
-    if (g1) { const double v = (double)x1 - d; if (v > 0) s1 = m1; if (v < 0) e1 = m1; }
-    if (g2) { const double v = (double)x2 - d; if (v > 0) s2 = m2; if (v < 0) e2 = m2; }
+    if (g1) { const double v = (double)x1 - d; if (v > 0) s1 = m1; else if (v < 0) e1 = m1; else st1 = true; }
+    if (g2) { const double v = (double)x2 - d; if (v > 0) s2 = m2; else if (v < 0) e2 = m2; else st2 = true; }
   }
 }
 // the rest of FindClosestTHD (M.cc:1148-1168) on the halved window
@@ -342,24 +403,30 @@ __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_look
 #pragma unroll
   for (int k = 0; k < 10; k++) PI[k] = 0.0;
   bool ok = true, oor1 = false, oor2 = false;
-  if (h <= maxh && h >= minh && h > 0) {
-    // FindClosestAirTxHeight (M.cc:1033-1126)
-    const int cur = (int)floor((h - t.loop_stop_h) / t.h_step);
-    const int row = t.n_h - cur - 1;
-    const int s1 = __ldg(t.row_first + row), e1 = __ldg(t.row_last + row);
-    const double cv0 = fabs((double)__ldg(t.row_h + row / t.n_th) - h);  // column 0 indexed with the ROW index, as written (M.cc:1076)
+  // FindClosestAirTxHeight (M.cc:1033-1126).  A height in the gap between float(loop_stop_h) and loop_stop_h gives row ==
+  // n_h: the reference reads past its vectors there (undefined); here the query is simply not answered.
+  const int cur = (int)floor((h - t.loop_stop_h) / t.h_step);
+  const int row = t.n_h - cur - 1;
+  if (h <= maxh && h >= minh && h > 0 && row >= 0 && row < t.n_h) {
+    const float* blk = t.rowblk + (int64_t)row * AIRICE_ROWBLK;
+    // the whole 288-byte block is on its way before the first dependent use (9 sectors: header, 2 x 4 tree sectors)
+    const float4 hd0 = __ldg((const float4*)blk), hd1 = __ldg((const float4*)blk + 1);
+#pragma unroll
+    for (int q = 1; q < 9; q++) asm volatile("prefetch.global.L1 [%0];" ::"l"(blk + 8 * q));
+    const int s1 = __float_as_int(hd0.x), e1 = __float_as_int(hd0.y);
+    const double cv0 = fabs((double)hd1.z - h);  // column 0 indexed with the ROW index, as written (M.cc:1076)
     int s2 = s1 - t.n_th, e2 = e1 - t.n_th;
     if (s2 < 0) s2 = s1 + t.n_th;
     if (e2 < 0) e2 = e1 + t.n_th;
     double P1[10], P2[10];
     const bool two = (cv0 != 0 && h > minh && s2 < total);
-    const double h1 = (double)__ldg(t.row_h + s1 / t.n_th);
-    const double h2 = two ? (double)__ldg(t.row_h + s2 / t.n_th) : h1;
+    const double h1 = (double)hd1.x;
+    const double h2 = two ? (double)hd1.y : h1;
     // "out of range": d beyond the row's largest distance (M.cc:1196-1204), else search and interpolate
-    const bool in1 = d <= (double)__ldg(t.x + s1);
-    const bool in2 = two && (d <= (double)__ldg(t.x + s2));
+    const bool in1 = d <= (double)hd0.z;
+    const bool in2 = two && (d <= (double)hd0.w);
     int a1 = s1, b1 = e1, a2 = s2, b2 = e2;
-    halve_thd2(t.x, d, in1, a1, b1, in2, a2, b2);
+    halve_thd2(t.x, blk + 8, blk + 40, d, in1, a1, b1, in2, a2, b2);
     int i1 = 0, i2 = 0, j1 = 0, j2 = 0;
     double c1 = 0.0, c2 = 0.0;
     if (in1) scan_thd(t.x, d, a1, b1, i1, i2, c1);
@@ -478,21 +545,25 @@ cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const Solve
   return cudaGetLastError();
 }
 
-cudaError_t launch_row_ranges(const float* x, int64_t cells, int n_h, int n_th, int* row_first, int* row_last, cudaStream_t s) {
+cudaError_t launch_row_ranges(const float* x, const float* row_h, int64_t cells, int n_h, int n_th, int* row_first, int* row_last,
+                              float* rowblk, cudaStream_t s) {
   airice_row_range_kernel<<<(n_h + 127) / 128, 128, 0, s>>>(x, cells, n_h, n_th, row_first, row_last);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int64_t threads = (int64_t)n_h * AIRICE_ROWBLK;
+  airice_row_block_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(x, row_h, cells, n_h, n_th, row_first, row_last, rowblk);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pack_table(const float* const* c, int64_t cells, int n_h, int n_th, float* x, float4* rec,
-                              float* row_h, int* row_first, int* row_last, cudaStream_t s) {
+                              float* row_h, int* row_first, int* row_last, float* rowblk, cudaStream_t s) {
   const int64_t blocks = (cells + 255) / 256;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
   airice_pack_kernel<<<dim3((unsigned)blocks), 256, 0, s>>>(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10],
                                                            cells, n_th, x, rec, row_h);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  airice_row_range_kernel<<<(n_h + 127) / 128, 128, 0, s>>>(x, cells, n_h, n_th, row_first, row_last);
-  return cudaGetLastError();
+  return launch_row_ranges(x, row_h, cells, n_h, n_th, row_first, row_last, rowblk, s);
 }
 
 // ---- kernel 5: ray paths.  Step 1: one thread per ray plans its segments; step 2: one thread per point.

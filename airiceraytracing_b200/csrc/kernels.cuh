@@ -52,7 +52,8 @@ struct TableMultiArgs {
   float* const* row_h;
 };
 // per-row trim ranges of a packed table (the part of launch_pack_table the fused pass cannot do per cell)
-cudaError_t launch_row_ranges(const float* x, int64_t cells, int n_h, int n_th, int* row_first, int* row_last, cudaStream_t s);
+cudaError_t launch_row_ranges(const float* x, const float* row_h, int64_t cells, int n_h, int n_th, int* row_first, int* row_last,
+                              float* rowblk, cudaStream_t s);
 cudaError_t launch_table_multi(const AirIceMedium& m, const AirIcePlan& p, const TableMultiArgs& a, cudaStream_t s);
 
 // kernel 1b: the same forward tracer on arbitrary (theta, h) cells (batched GetRayTracingSolutions, M.cc:1796-2017);
@@ -106,9 +107,17 @@ struct LookupTable {
   double loop_stop_h, h_step;
   const int* row_first;  // per row: first/last bin with a usable X (trim of M.cc:1050-1072), precomputed
   const int* row_last;
+  // per-row search block, AIRICE_ROWBLK floats (288 B, sector aligned), built once per table: everything a query needs
+  // before it touches the dense X column.  [0..7] header {s1, e1 (int bits), X[s1], X[s2], h(s1), h(s2), col0[row], 0},
+  // [8..39] the first 5 levels of FindClosestTHD's index halving over this row's trimmed window [s1, e1] as a binary tree
+  // in BFS order (node (level k, path j) at 2^k - 1 + j holds X[(s + e) / 2] of the window that path reaches; j appends a
+  // 1 for "s = mid"), [40..71] the same for the second row's window [s2, e2] = the first row's window shifted by one row.
+  const float* rowblk;
 };
+#define AIRICE_ROWBLK 72
+#define AIRICE_TREE_LEVELS 5
 cudaError_t launch_pack_table(const float* const* cols32, int64_t cells, int n_h, int n_th, float* x, float4* rec,
-                              float* row_h, int* row_first, int* row_last, cudaStream_t s);
+                              float* row_h, int* row_first, int* row_last, float* rowblk, cudaStream_t s);
 struct LookupArgs {
   int64_t n;
   const double* h_cm;

@@ -57,20 +57,35 @@ def workload_config(pairs, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def _cpu_worker(args):
     kind, h_cm, d_cm = args
     from oracle.ref import Oracle, Reference
-    impl = Reference(ATMOSPHERE) if kind == "reference" else Oracle(ATMOSPHERE)
+    impl = Reference(ATMOSPHERE, opt="O0") if kind == "reference_O0" else Reference(ATMOSPHERE) if kind == "reference" else Oracle(ATMOSPHERE)
     t0 = time.perf_counter()
     ok, out = impl.solve_cm_batch(h_cm, d_cm, DEPTH_CM, ICE_CM)
     return time.perf_counter() - t0, int(ok.sum())
 
 
-def cpu_reference_rate(h_cm, d_cm, per_core, cores=None):
+def cpu_reference_rate(h_cm, d_cm, per_core, cores=None, opt="O2"):
     """Times the reference CPU path on the first per_core*cores pairs, one forked process per core (the reference is
-    single-threaded with per-process static state).  Returns (solves/s, cores, kind, sample text)."""
+    single-threaded with per-process static state).  Returns (solves/s, cores, kind, sample text).
+    opt="O0": the build with the reference's shipped Makefile flags (no -O)."""
     from oracle.ref import reference_available
     kind = "reference" if reference_available() else "port"
+    if opt == "O0":
+        if not reference_available("libmultiray_ref_O0.so"):
+            return None
+        kind = "reference_O0"
     cores = cores or max(1, min(os.cpu_count() or 1, 64))
     n = min(per_core * cores, h_cm.size)
     per = n // cores
@@ -82,11 +97,11 @@ def cpu_reference_rate(h_cm, d_cm, per_core, cores=None):
         res = pool.map(_cpu_worker, jobs)
         wall = time.perf_counter() - t0
     rate = per * cores / wall
-    sample = "first %d pairs of the same batch, %d per process x %d processes, %s at -O2, stdout muted" % (
+    sample = "first %d pairs of the same batch, %d per process x %d processes, %s at -%s, stdout muted, CPU: %s" % (
         per * cores, per, cores,
         "unmodified reference MultiRayAirIceRefraction.cc (GetHorizontalDistanceToIntersectionPoint) + GSL stand-in"
-        if kind == "reference" else "oracle/airice_oracle.c restatement")
-    return rate, cores, kind, sample, wall, max(r[0] for r in res)
+        if kind.startswith("reference") else "oracle/airice_oracle.c restatement", opt, cpu_model())
+    return rate, cores, "reference" if kind.startswith("reference") else kind, sample, wall, max(r[0] for r in res)
 
 
 def _cpu_inice_worker(seed):
@@ -133,7 +148,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.pairs, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info[1], "kind": info[2], "sample": info[3]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info[1], "kind": info[2], "sample": info[3],
+                             "cpu_model": cpu_model()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "each step = a bounded sample (%d pairs) of the workload, all %d host cores" % (per_core * cores, cores)}
@@ -203,7 +219,9 @@ def algorithmic_flops(solver, h_cm, nev):
     nv = nev.double()
     first = nv.clamp_max(1.0)
     flops = first * (178.0 * (s + 1) + 100.0) + (nv - first) * (142.0 * (s + 1) + 90.0) + (272.0 * (s + 1) + 355.0)
-    return float(flops.sum()), float(nev.double().mean()), float(s.mean())
+    # SURVEY.md 8(d) as written: F_solve = N_eval F_f(s) + F_full(s) -- no extra credit for the evaluation that also returns the slope
+    flops_8d = nv * (142.0 * (s + 1) + 90.0) + (272.0 * (s + 1) + 355.0)
+    return float(flops_8d.sum()), float(nev.double().mean()), float(s.mean()), float(flops.sum())
 
 
 def bind_near_gpu(index):
@@ -323,27 +341,37 @@ def run_ours(args):
     # ---- roofline of the solve kernel (rank 0's batch)
     _, _, nev = solver.solve(h, d, DEPTH_CM, ICE_CM, UNITS_CM_RAD, out=out, ok=ok, nevals=True)
     torch.cuda.synchronize()
-    flops, mean_evals, mean_segs = algorithmic_flops(solver, h, nev)
+    flops, mean_evals, mean_segs, flops_with_slope = algorithmic_flops(solver, h, nev)
     peak_tf = max(solver.fp64_peak_tflops() for _ in range(2))
+    props = torch.cuda.get_device_properties(dev)
+    nominal_tf = props.multi_processor_count * 64 * 2 * 1.965e9 / 1e12     # 64 DFMA / clk / SM at the 1965 MHz boost clock
     achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
-    traffic = None
-    sass_flop = None
-    tpath = os.path.join(ROOT, "profiles", "solve_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            traffic = tj["dram_bytes_per_pair"] * n
-            sass_flop = tj.get("sass_fp64_flop_per_pair")
-        except Exception:
-            traffic = None
+    # what ncu measured for this kernel (profiles/kernel_facts.json, written from this round's `ncu --set full` capture of the
+    # same launch; bench.py cannot run under a profiler): DRAM bytes, executed FP64 flop, FP64-pipe activity
+    facts = {}
+    try:
+        facts = json.load(open(os.path.join(ROOT, "profiles", "kernel_facts.json")))
+    except Exception:
+        facts = {}
+    sf = facts.get("airice_solve_kernel", {})
+    traffic = sf["dram_bytes_per_unit"] * n if "dram_bytes_per_unit" in sf else None
+    sass_flop = sf.get("sass_fp64_flop_per_unit")
     roofline = {"bound": "fp64", "kernel": "airice_solve_kernel", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "traffic_source": sf.get("source"),
+                "accounting": "SURVEY.md 8(d): F_solve = N_eval F_f(s) + F_full(s), F_f = 142 (s+1) + 90, F_full = 272 (s+1) + 355, "
+                              "N_eval = measured FP64 distance evaluations per solve of THIS solver (the reference: 30.2)",
                 "peak_source": "FP64 FMA rate measured live by airice_fp64_peak_tflops (dependent-free DFMA probe); "
                                "MEASURED_PEAKS.json carries no FP64 figure",
+                "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
                 "algorithmic_flop_per_solve": flops / n, "mean_distance_evals_per_solve": mean_evals,
                 "mean_air_segments": mean_segs, "kernel_ms": kernel_ms,
-                "sass_fp64_flop_per_solve": sass_flop,     # executed DADD + DMUL + 2 DFMA per pair, from the ncu capture
+                "frac_with_slope_term": flops_with_slope / (kernel_ms * 1e-3) / 1e12 / peak_tf,   # round 1's accounting, for continuity
+                "sass_fp64_flop_per_solve": sass_flop,     # executed DADD + DMUL + 2 DFMA per pair (ncu)
+                "frac_sass": (sass_flop * n / (kernel_ms * 1e-3) / 1e12 / peak_tf) if sass_flop else None,
+                "fp64_pipe_active_pct": sf.get("fp64_pipe_active_pct"), "issue_active_pct": sf.get("issue_active_pct"),
                 "hbm": {"algorithmic_bytes_per_solve": 89, "achieved_gbs": 89.0 * n / (kernel_ms * 1e-3) / 1e9}}
+    rooflines = [roofline]
 
     # ---- secondary workloads of the same hot path: table build (MakeRayTracingTable) and table lookup
     extras = {}
@@ -374,6 +402,12 @@ def run_ours(args):
         ms = time_ms(lambda: solver.table_build(-200.0, 3000.0, columns64=None, want32=True, out32=o32))
         extras["table_reference_grid"] = {"grid": "%dx%d = %d cells, 11 float columns (reference layout)" % (n_h, n_th, cells),
                                           "ms": ms, "cells_per_s": cells / ms * 1e3, "store_gbs": cells * 44 / ms / 1e6}
+        tf = facts.get("airice_table_kernel", {})
+        rooflines.append({"kernel": "airice_table_kernel<f32> (reference grid, 79 % of rows in the top layer)", "bound": "fp64",
+                          "achieved": cells * 1640.0 / ms / 1e9, "peak": peak_tf, "unit": "TFLOP/s", "frac": cells * 1640.0 / ms / 1e9 / peak_tf,
+                          "accounting": "SURVEY.md 8(d): 1640 flop/cell on 100-km grids", "ms": ms,
+                          "hbm_store_gbs": cells * 44 / ms / 1e6, "hbm_frac": cells * 44 / ms / 1e6 / hbm_peak,
+                          "traffic": tf.get("dram_bytes_per_unit", 0) * cells or None, "traffic_source": tf.get("source")})
         del o32
         # fine grid (BASELINE config 3): 1 m x 0.005 deg from the top of the tabulated data, rows sharded over ranks
         kw = dict(h_top=23141.03, h_step=1.0, th_start=92.0, th_step=0.005, th_stop=180.0)
@@ -390,12 +424,24 @@ def run_ours(args):
                                              "entry index), rows sharded over %d GPU(s)" % (n_h, n_th, total_cells, world),
                                      "ms": ms, "cells_per_s": total_cells / ms * 1e3, "store_gbs_per_gpu": gbs,
                                      "hbm_frac_of_measured_copy_peak": gbs / hbm_peak}
+        rooflines.append({"kernel": "airice_table_kernel<f64> (C3 fine grid from 23.1 km, 12 README columns)", "bound": "fp64",
+                          "achieved": cells * 1370.0 / ms / 1e9, "peak": peak_tf, "unit": "TFLOP/s", "frac": cells * 1370.0 / ms / 1e9 / peak_tf,
+                          "accounting": "SURVEY.md 8(d): 1370 flop/cell on the 23.1-km-top grid; 96 B/cell stored", "ms": ms,
+                          "hbm_store_gbs": gbs, "hbm_frac": gbs / hbm_peak})
         del o64
         T = solver.table_create(-200.0, 3000.0)
         ms = time_ms(lambda: solver.lookup(T, h, d, out=out, ok=ok))
         extras["lookup"] = {"table": "reference grid 9701x900 float", "lookups": n, "ms": ms, "lookups_per_s": world * n / ms * 1e3,
-                            "algorithmic_gbs": n * (16 + 73 + 192) / ms / 1e6,
-                            "layout": "dense THD column for the index search + 48-byte records (4 cells x 48 B gathered per query)", "solved": float(ok.float().mean())}
+                            "algorithmic_gbs": n * 265.0 / ms / 1e6,
+                            "layout": "per-row search block (header + 5 tree levels of the index halving, 288 B, L2 resident), dense THD "
+                                      "column for the last halvings, 48-byte records (4 cells gathered per query)",
+                            "solved": float(ok.float().mean())}
+        lf = facts.get("airice_lookup_kernel", {})
+        rooflines.append({"kernel": "airice_lookup_kernel", "bound": "hbm", "achieved": n * 265.0 / ms / 1e6, "peak": hbm_peak,
+                          "unit": "GB/s", "frac": n * 265.0 / ms / 1e6 / hbm_peak,
+                          "accounting": "SURVEY.md 8(d): 16 B in + 73 B out + 4 cells x 11 columns x 4 B gathered = 265 B/lookup", "ms": ms,
+                          "traffic": lf.get("dram_bytes_per_unit", 0) * n or None, "traffic_source": lf.get("source"),
+                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (torch copy, burst)"})
         T.close()
         # the same C4 batch pre-sorted by straight-line angle (neighbouring lanes then share layer count and
         # iteration counts), and the "CoREAS-like" mix (low sources, short distances)
@@ -495,19 +541,130 @@ def run_ours(args):
                                       "shared_air_table_solutions_per_s": world * n5 * n_ant / ms_shared * 1e3,
                                       "note": "64 reference-grid tables (9701x900) built, packed and freed per pass; "
                                               "shared_air = airice_table_create_multi (one air walk per cell for all 64 "
-                                              "antennas)"}
+                                              "antennas); in these two legs every rank builds all 64 tables and only the "
+                                              "points are sharded"}
+        if world > 1 and n_ant % world == 0:
+            # the table path sharded by ANTENNA instead: a rank builds the tables of its own n_ant / world antennas only
+            # (shared air walk) and looks all 1e6 points up in them; results stay sharded by antenna
+            na = n_ant // world
+            mine = list(range(rank * na, (rank + 1) * na))
+            gq = torch.Generator(device=dev).manual_seed(20260420)            # the same 1e6 points on every rank
+            nq = n5 * world
+            hq = (3001 + (100000 - 3001) * torch.rand(nq, generator=gq, device=dev, dtype=torch.float64)) * 100
+            aq = 90.2 + (179.8 - 90.2) * torch.rand((na, nq), generator=gq, device=dev, dtype=torch.float64)
+            dq = (hq.unsqueeze(0) - ICE_CM - torch.tensor([depths_cm[a] for a in mine], device=dev, dtype=torch.float64).unsqueeze(1)) * \
+                torch.tan((180 - aq) * (PI_M / 180))
+            del aq
+            oq = torch.empty((9, na, nq), dtype=torch.float64, device=dev)
+            kq = torch.empty((na, nq), dtype=torch.uint8, device=dev)
+
+            def by_antenna():
+                Ts = solver.table_create_multi([depths_cm[a] / 100.0 for a in mine], ICE_CM / 100.0)
+                for j in range(na):
+                    solver.lookup(Ts[j], hq, dq[j], out=oq[:, j], ok=kq[j])
+                for Ta in Ts:
+                    Ta.close()
+            barrier()
+            ms_by_ant = max_over_ranks(time_ms(by_antenna, reps=1, warm=1))
+            extras["c5_multi_antenna"]["antenna_sharded_tables_plus_lookups_ms"] = ms_by_ant
+            extras["c5_multi_antenna"]["antenna_sharded_table_solutions_per_s"] = nq * n_ant / ms_by_ant * 1e3
+            extras["c5_multi_antenna"]["antenna_sharded_note"] = "%d tables per rank (shared air walk), all %d points looked up in each" % (na, nq)
+            del hq, dq, oq, kq
         del o5, k5, d5, h5
         if world > 1:
-            # result reassembly: one all-gather of the 9 output columns
-            gathered = torch.empty((world, 9, n), dtype=torch.float64, device=dev)
-            ms = max_over_ranks(time_ms(lambda: dist.all_gather_into_tensor(gathered, out), reps=3, warm=1))
-            extras["gather"] = {"collective": "ncclAllGather of 9 f64 columns x %d pairs per rank" % n, "ms": ms,
-                                "bus_gbs": (world - 1) * 72.0 * n / ms / 1e6}
+            from airiceraytracing_b200.dist import PeerGather, shard_range
+            tok = torch.zeros(1, device=dev)
+
+            def timed_collective(fn, reps=5, warm=2):
+                for _ in range(warm):
+                    fn()
+                best = 1e30
+                for _ in range(reps):
+                    barrier()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); fn(); b.record(); torch.cuda.synchronize()
+                    best = min(best, max_over_ranks(a.elapsed_time(b)))
+                return best
+            # (i) weak scaling WITH the reassembly north_star names: the results of all ranks' shards in one place (rank 0's
+            # HBM).  Every rank's solve kernel stores its shard straight into rank 0's block over NVLink (PeerGather); the
+            # step ends with a barrier-sized all-reduce that orders rank 0's reads after every producer's kernel.
+            # The whole job is then bound by rank 0's NVLink ingress: (world-1) x 73 B x pairs at <= 900 GB/s.
+            ng = n * world
+            gw = torch.Generator(device=dev).manual_seed(20260418)
+            hw = (3001 + (100000 - 3001) * torch.rand(ng, generator=gw, device=dev, dtype=torch.float64)) * 100
+            aw = 90.2 + (179.8 - 90.2) * torch.rand(ng, generator=gw, device=dev, dtype=torch.float64)
+            dw = (hw - ICE_CM - DEPTH_CM) * torch.tan((180 - aw) * (PI_M / 180))
+            del aw
+            pg = PeerGather(solver, 9, ng, dst=0)
+
+            def with_gather():
+                pg.solve(solver, hw, dw, DEPTH_CM, ICE_CM, UNITS_CM_RAD, sync=False)
+                dist.all_reduce(tok)
+            ms_wg = timed_collective(with_gather)
+            bw, ew = shard_range(ng, rank, world)
+            ow = torch.empty((9, ew - bw), dtype=torch.float64, device=dev)
+            kw_ = torch.empty(ew - bw, dtype=torch.uint8, device=dev)
+            gathered = torch.empty((world, 10, ew - bw), dtype=torch.float64, device=dev) if ng % world == 0 else None
+
+            def nccl_path():
+                solver.solve(hw[bw:ew], dw[bw:ew], DEPTH_CM, ICE_CM, UNITS_CM_RAD, out=ow, ok=kw_)
+                packed = torch.cat([ow, kw_.to(torch.float64).unsqueeze(0)], dim=0)
+                dist.all_gather_into_tensor(gathered, packed)
+            ms_nccl = timed_collective(nccl_path, reps=3, warm=1) if gathered is not None else None
+            pg.close()
+            del hw, dw, ow, kw_, gathered
+            ingress_bytes = 73.0 * n * (world - 1)
+            extras["value_with_gather"] = {
+                "value": ng / ms_wg * 1e3, "unit": UNIT, "ms_per_step": ms_wg, "pairs": ng, "scaling": "weak",
+                "mechanism": "peer-memory stores (CUDA IPC over NVLink): each rank's solve kernel writes its 9 columns + flags "
+                             "into rank 0's result block while it computes; no staging, no collective launch",
+                "consumer_ingress_gbs": ingress_bytes / ms_wg / 1e6,
+                "bound": "NVLink ingress of the consumer GPU: (N-1) x 73 B per pair at <= 900 GB/s per direction = at most "
+                         "%.3g solves/s into one GPU, whatever the number of producers" % (900e9 / 73.0 * world / max(world - 1, 1)),
+                "nccl_all_gather_ms_per_step": ms_nccl,
+                "nccl_note": "round 1's path for comparison: solve into a local shard, concatenate, one ncclAllGather"}
+            # (ii) strong scaling: BASELINE config 4 as ONE batch of 1e7 pairs, index-sharded over the ranks, result on rank 0
+            ns = n
+            gs = torch.Generator(device=dev).manual_seed(20260418)
+            hs_ = (3001 + (100000 - 3001) * torch.rand(ns, generator=gs, device=dev, dtype=torch.float64)) * 100
+            as_ = 90.2 + (179.8 - 90.2) * torch.rand(ns, generator=gs, device=dev, dtype=torch.float64)
+            ds_ = (hs_ - ICE_CM - DEPTH_CM) * torch.tan((180 - as_) * (PI_M / 180))
+            del as_
+            bs, es = shard_range(ns, rank, world)
+            os_ = torch.empty((9, es - bs), dtype=torch.float64, device=dev)
+            ks_ = torch.empty(es - bs, dtype=torch.uint8, device=dev)
+            ms_strong = timed_collective(lambda: solver.solve(hs_[bs:es], ds_[bs:es], DEPTH_CM, ICE_CM, UNITS_CM_RAD, out=os_, ok=ks_))
+            pgs = PeerGather(solver, 9, ns, dst=0)
+
+            def strong_gather():
+                pgs.solve(solver, hs_, ds_, DEPTH_CM, ICE_CM, UNITS_CM_RAD, sync=False)
+                dist.all_reduce(tok)
+            ms_strong_g = timed_collective(strong_gather)
+            pgs.close()
+            extras["strong_scaling"] = {"pairs_global": ns, "ms_sharded_no_gather": ms_strong, "solves_per_s_no_gather": ns / ms_strong * 1e3,
+                                        "ms_with_gather_to_rank0": ms_strong_g, "solves_per_s_with_gather": ns / ms_strong_g * 1e3,
+                                        "speedup_vs_one_gpu_kernel": kernel_ms / ms_strong, "speedup_with_gather": kernel_ms / ms_strong_g,
+                                        "note": "C4 = 1e7 pairs in total; a shard of 1e7 / N pairs runs the single-pass kernel"}
+            del hs_, ds_, os_, ks_
+            # (iii) what the box can move to host memory from all GPUs at once: every rank copies 730 MB (one step's results)
+            # device -> pinned host on its own stream, all ranks together
+            pin = torch.empty(73 * n // 8 + 8, dtype=torch.float64).pin_memory()
+            src = torch.empty_like(pin, device=dev)
+            ms_d2h = timed_collective(lambda: pin.copy_(src, non_blocking=True), reps=3, warm=1)
+            extras["e2e_ceiling"] = {"concurrent_pinned_d2h_gbs_all_ranks": world * pin.numel() * 8 / ms_d2h / 1e6,
+                                     "ms_for_one_steps_results": ms_d2h,
+                                     "e2e_frac_of_ceiling": (e2e_value * 73.0 / 1e9) / (world * pin.numel() * 8 / ms_d2h / 1e6),
+                                     "note": "e2e moves 16 B in + 73 B out per pair over PCIe; its D2H share against a plain "
+                                             "concurrent cudaMemcpyAsync of the same bytes from every GPU of the box"}
+            del pin, src
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         rate, cores, kind, sample, wall, _ = cpu_reference_rate(h_np, d_np, 20000)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "wall_s": wall}
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "wall_s": wall, "cpu_model": cpu_model()}
+        o0 = cpu_reference_rate(h_np, d_np, 5000, opt="O0")       # the reference's shipped Makefile has no -O flag
+        if o0:
+            cpu["shipped_flags_O0"] = {"value": o0[0], "unit": UNIT, "cores": o0[1], "sample": o0[3], "wall_s": o0[4]}
         if "inice" in extras:
             extras["inice"]["cpu_baseline"] = cpu_inice_rate(cores)
 
@@ -523,7 +680,7 @@ def run_ours(args):
                 "kernels_per_step": (["airice_solve_kernel<1> (all pairs; lists the 0.6 % that need a slow path)",
                                       "airice_solve_kernel<2> (the listed pairs, dense warps)"] if n >= 6_000_000
                                      else ["airice_solve_kernel<0>"]),
-                "solved_fraction": solved, "roofline": roofline, "cpu_baseline": cpu}
+                "solved_fraction": solved, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu}
         line.update(extras)
         emit(line)
     if world > 1:
