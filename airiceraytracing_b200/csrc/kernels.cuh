@@ -107,11 +107,8 @@ struct LookupTable {
   double loop_stop_h, h_step;
   const int* row_first;  // per row: first/last bin with a usable X (trim of M.cc:1050-1072), precomputed
   const int* row_last;
-  // per-row search block, AIRICE_ROWBLK floats (288 B, sector aligned), built once per table: everything a query needs
-  // before it touches the dense X column.  [0..7] header {s1, e1 (int bits), X[s1], X[s2], h(s1), h(s2), col0[row], 0},
-  // [8..39] the first 5 levels of FindClosestTHD's index halving over this row's trimmed window [s1, e1] as a binary tree
-  // in BFS order (node (level k, path j) at 2^k - 1 + j holds X[(s + e) / 2] of the window that path reaches; j appends a
-  // 1 for "s = mid"), [40..71] the same for the second row's window [s2, e2] = the first row's window shifted by one row.
+  // per-row search blocks, AIRICE_ROWBLK floats each (288 B): header + the 31 pivots of FindClosestTHD's first five
+  // halvings for the row's own window and for the second row's window (airice_row_block_kernel in kernels.cu)
   const float* rowblk;
 };
 #define AIRICE_ROWBLK 72
