@@ -16,6 +16,7 @@
 #include "airice_path.cuh"
 #include "airice_solve.cuh"
 #include <cstdlib>
+#include <cstring>
 
 #include "kernels.cuh"
 
@@ -280,32 +281,10 @@ __global__ void airice_pack_kernel(const float* c0, const float* c1, const float
   if (i % n_th == 0) row_h[i / n_th] = c0[i];
 }
 
-// Per-row search blocks (LookupTable::rowblk), one thread per (row, slot).
-// FindClosestTHD (M.cc:1128-1169) compares the query distance with X at the midpoints of an index halving that starts
-// from the row's trimmed window -- a per-row constant.  So the midpoints of its first five levels are 31 fixed cells per
-// row ("pivots"), and along a row X decreases with the launch angle, so the outcome of every one of those comparisons
-// follows from ONE number: how many pivots are larger than the query.  A block holds, per row: the header
-// {s1, e1 (int bits), X[s1], X[s2], h(s1), h(s2), col0[row], flags}, the 31 pivots of the row's own window in index order
-// [8..38], and the 31 pivots of the second row's window (the first row's, shifted by one row: M.cc:1113-1121) [40..70].
-// flags bit r: the pivots of row r+1 are all reachable (window wide enough for five halvings) and strictly decreasing;
-// a query on a row without it, or that ties with a pivot, takes the literal walk.
-// 9701 rows x 288 B = 2.8 MB for the reference grid: L2 resident.
-__device__ __forceinline__ bool pivot_of(const float* __restrict__ X, int total, int s, int e, int q, float& v) {
-  // in-order position q (0..30) -> level k, path j (most significant decision first); bit 1 = "s = mid"
-  const int t = __ffs(q + 1) - 1;
-  const int k = AIRICE_TREE_LEVELS - 1 - t;
-  const int j = ((q + 1) >> t) >> 1;
-  for (int lvl = 0; lvl < k; lvl++) {
-    if (e - s < 3) return false;
-    const int mid = (s + e) / 2;
-    if ((j >> (k - 1 - lvl)) & 1) s = mid; else e = mid;
-  }
-  if (e - s < 3) return false;
-  const int mid = (s + e) / 2;
-  if (mid < 0 || mid > total) return false;
-  v = X[mid];
-  return true;
-}
+// Per-row header blocks (LookupTable::rowblk), one thread per (row, slot): everything FindClosestAirTxHeight
+// (M.cc:1033-1126) derives per row, in ONE 32-byte sector per row instead of four dependent loads --
+// {s1, e1 (int bits), X[s1], X[s2], h(s1), h(s2), col0[row], 0}: the trimmed window, the largest distance of the row and of
+// the second row (the first row's window shifted by one row, M.cc:1113-1121), and the three heights the query compares with.
 __global__ void airice_row_block_kernel(const float* __restrict__ X, const float* __restrict__ row_h, int64_t cells, int n_h, int n_th,
                                         const int* __restrict__ row_first, const int* __restrict__ row_last, float* rowblk) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -313,66 +292,51 @@ __global__ void airice_row_block_kernel(const float* __restrict__ X, const float
   const int row = (int)(t / AIRICE_ROWBLK), slot = (int)(t - (int64_t)row * AIRICE_ROWBLK);
   const int total = (int)cells - 1;
   const int s1 = row_first[row], e1 = row_last[row];
-  int s2 = s1 - n_th, e2 = e1 - n_th;
+  int s2 = s1 - n_th;
   if (s2 < 0) s2 = s1 + n_th;
-  if (e2 < 0) e2 = e1 + n_th;
   auto xat = [&](int i) { return (i >= 0 && i <= total) ? X[i] : 0.f; };
   auto hat = [&](int i) { const int r = i / n_th; return (i >= 0 && r < n_h) ? row_h[r] : 0.f; };
   float v = 0.f;
-  if (slot < 8) {
-    switch (slot) {
-      case 0: v = __int_as_float(s1); break;
-      case 1: v = __int_as_float(e1); break;
-      case 2: v = xat(s1); break;
-      case 3: v = xat(s2); break;
-      case 4: v = hat(s1); break;
-      case 5: v = hat(s2); break;
-      case 6: v = hat(row); break;     // column 0 indexed with the ROW index, as the reference writes it (M.cc:1076)
-      default: {
-        int flags = 0;
-        for (int r = 0; r < 2; r++) {
-          const int s = r ? s2 : s1, e = r ? e2 : e1;
-          bool good = s >= 0 && e <= total && s <= e;
-          float prev = 0.f;
-          for (int q = 0; q < 31 && good; q++) {
-            float x;
-            if (!pivot_of(X, total, s, e, q, x)) { good = false; break; }
-            if (q > 0 && !(prev > x)) good = false;      // strictly decreasing (NaN fails)
-            prev = x;
-          }
-          if (good) flags |= 1 << r;
-        }
-        v = __int_as_float(flags);
-      }
-    }
-  } else {
-    const int q = (slot - 8) & 31;
-    if (q < 31) {
-      float x;
-      if (pivot_of(X, total, slot < 40 ? s1 : s2, slot < 40 ? e1 : e2, q, x)) v = x;
-    }
+  switch (slot) {
+    case 0: v = __int_as_float(s1); break;
+    case 1: v = __int_as_float(e1); break;
+    case 2: v = xat(s1); break;
+    case 3: v = xat(s2); break;
+    case 4: v = hat(s1); break;
+    case 5: v = hat(s2); break;
+    case 6: v = hat(row); break;     // column 0 indexed with the ROW index, as the reference writes it (M.cc:1076)
+    default: v = 0.f; break;
   }
   rowblk[t] = v;
 }
 
+// Records, inputs and outputs stream through once (419 MB of records for the reference grid, 730 MB of outputs per 1e7
+// queries): read / written with the streaming cache operators so that they do not push the dense X column (35 MB) and the
+// row blocks (2.8 MB), which every query revisits, out of the 126 MB L2.
 __device__ __forceinline__ void load_rec(const float4* __restrict__ rec, int i, double* v) {
-  const float4 a = __ldg(rec + 3 * (int64_t)i), b = __ldg(rec + 3 * (int64_t)i + 1), c = __ldg(rec + 3 * (int64_t)i + 2);
+  const float4 a = __ldcs(rec + 3 * (int64_t)i), b = __ldcs(rec + 3 * (int64_t)i + 1), c = __ldcs(rec + 3 * (int64_t)i + 2);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; v[8] = c.x; v[9] = c.y;
 }
 
-// FindClosestTHD as written (M.cc:1128-1169): <= 8 index halvings while the window is >= 3 wide, then a linear scan.
-// Dependent loads into the dense X column; taken by the queries the rank search below cannot answer (a tie with a table
-// value, a row with NaN holes or too few usable bins, a window wider than kWin after the pivots: grids with > ~1000 angles).
-__device__ __noinline__ void find_thd_literal(const float* __restrict__ X, double d, int s, int e, int levels, int& i1, int& i2, double& cv) {
+// The index halvings of FindClosestTHD (M.cc:1131-1143) for the two rows of a query in lock step: the two chains of
+// dependent loads overlap instead of running one after the other.  X[mid] == d leaves the window as it is and every later
+// halving would revisit the same midpoint: `st` ends the walk.
+// (Measured and rejected in round 2: the first five levels from a per-row tree / from counting 31 per-row pivots and
+// replaying the halvings arithmetically -- same indices, but the extra 128-byte line per row costs more L2 traffic than
+// the upper halvings, whose few midpoints per row stay cache resident: 1.64 / 2.01 ms against 1.52 ms per 1e7 queries.)
+__device__ __forceinline__ void halve_thd2(const float* __restrict__ X, double d, bool on1, int& s1, int& e1, bool on2, int& s2, int& e2) {
+  bool st1 = !on1, st2 = !on2;
 #pragma unroll 1
-  for (int i = 0; i < levels; i++) {
-    if (e - s >= 3) {
-      const int mid = (s + e) / 2;
-      const double v = (double)__ldg(X + mid) - d;
-      if (v > 0) s = mid;
-      if (v < 0) e = mid;
-    }
+  for (int i = 0; i < 8; i++) {
+    const bool g1 = !st1 && (e1 - s1 >= 3), g2 = !st2 && (e2 - s2 >= 3);
+    const int m1 = (s1 + e1) / 2, m2 = (s2 + e2) / 2;
+    const float x1 = g1 ? __ldg(X + m1) : 0.f, x2 = g2 ? __ldg(X + m2) : 0.f;
+    if (g1) { const double v = (double)x1 - d; if (v > 0) s1 = m1; else if (v < 0) e1 = m1; else st1 = true; }
+    if (g2) { const double v = (double)x2 - d; if (v > 0) s2 = m2; else if (v < 0) e2 = m2; else st2 = true; }
   }
+}
+// the rest of FindClosestTHD (M.cc:1148-1168) on the halved window
+__device__ __forceinline__ void scan_thd(const float* __restrict__ X, double d, int s, int e, int& i1, int& i2, double& cv) {
   double minimum = 100000000000.0;
   int index2 = 0;
 #pragma unroll 1
@@ -388,68 +352,6 @@ __device__ __noinline__ void find_thd_literal(const float* __restrict__ X, doubl
   if (minimum > other) minimum = other;
   i1 = index1; i2 = index2; cv = minimum;
 }
-
-constexpr int kWin = 32;    // cells of the dense X column a query reads after the pivots (a row of <= 32 * 31 usable bins)
-
-// The search of one row.  Phase 1: count the pivots above d (31 independent loads of one 128-byte line) and replay the
-// five halvings on that count.  Phase 2: read the whole remaining window (<= kWin cells, independent loads), count again,
-// replay the last halvings and the scan.  Same comparisons, hence the same indices, as the literal walk whenever X is
-// strictly decreasing over the cells involved and none of them equals d; checked on the fly, literal walk otherwise.
-__device__ __forceinline__ void find_thd(const float* __restrict__ X, const float* __restrict__ piv, bool tree_ok, double d, int s, int e,
-                                         int& i1, int& i2, double& cv) {
-  const int s0 = s, e0 = e;
-  bool fast = tree_ok;
-  int c = 0;
-  if (fast) {
-    bool tie = false;
-#pragma unroll
-    for (int q = 0; q < 31; q++) {
-      const double x = (double)__ldg(piv + q);
-      c += (x > d) ? 1 : 0;
-      tie |= (x == d);
-    }
-    fast = !tie;
-  }
-  if (fast) {
-    int j = 0;
-#pragma unroll
-    for (int k = 0; k < AIRICE_TREE_LEVELS; k++) {
-      const int mid = (s + e) / 2;
-      const int pos = ((2 * j + 1) << (AIRICE_TREE_LEVELS - 1 - k)) - 1;
-      if (pos < c) { s = mid; j = 2 * j + 1; } else { e = mid; j = 2 * j; }
-    }
-    fast = (e - s + 1 <= kWin);
-  }
-  if (fast) {
-    int cnt = 0;
-    bool bad = false;
-    double prev = INFINITY;
-#pragma unroll
-    for (int k = 0; k < kWin; k++) {
-      const bool in = s + k <= e;
-      const double x = in ? (double)__ldg(X + s + k) : -INFINITY;
-      cnt += (in && x > d) ? 1 : 0;
-      bad |= in && (!(prev > x) || x == d);
-      prev = in ? x : prev;
-    }
-    const int w = e - s + 1;
-    if (!bad && cnt >= 1 && cnt < w) {
-      const int p = s + cnt - 1;            // last cell above d
-#pragma unroll
-      for (int k = AIRICE_TREE_LEVELS; k < 8; k++) {
-        if (e - s >= 3) {
-          const int mid = (s + e) / 2;
-          if (mid <= p) s = mid; else e = mid;
-        }
-      }
-      // the scan (M.cc:1148-1156) walks s..p on cells above d with shrinking |x - d| and stops on p + 1 <= e
-      i1 = p; i2 = p + 1; cv = 1.0;         // cv is only compared with 0: neither cell equals d
-      return;
-    }
-  }
-  find_thd_literal(X, d, s0, e0, 8, i1, i2, cv);
-}
-
 // ten parameters of one row at distance d from the bracketing records (GetParValues, M.cc:1196-1240)
 __device__ __forceinline__ void row_interp(const LookupTable& t, double d, int i1, int i2, double cv, double* par) {
   if (cv != 0) {
@@ -467,11 +369,10 @@ __device__ __forceinline__ void row_interp(const LookupTable& t, double d, int i
 #ifndef AIRICE_LOOKUP_MINBLOCKS
 #define AIRICE_LOOKUP_MINBLOCKS 4
 #endif
-template <bool LITERAL>   // LITERAL: every query through find_thd_literal (tests compare the two)
 __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_lookup_kernel(const AirIceMedium m, const LookupTable t, const LookupArgs a) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.n) return;
-  const double h = AIRICE_DIV100(a.h_cm[i]), d = AIRICE_DIV100(a.d_cm[i]);  // M.cc:1307-1308
+  const double h = AIRICE_DIV100(__ldcs(a.h_cm + i)), d = AIRICE_DIV100(__ldcs(a.d_cm + i));  // M.cc:1307-1308
   const int total = (int)t.cells - 1;
   // column 0 holds the row's Tx height in every cell: col0[c] == row_h[c / n_th]
   const double maxh = (double)__ldg(t.row_h), minh = (double)__ldg(t.row_h + total / t.n_th);
@@ -486,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_look
   if (h <= maxh && h >= minh && h > 0 && row >= 0 && row < t.n_h) {
     const float* blk = t.rowblk + (int64_t)row * AIRICE_ROWBLK;
     const float4 hd0 = __ldg((const float4*)blk), hd1 = __ldg((const float4*)blk + 1);
-    const int s1 = __float_as_int(hd0.x), e1 = __float_as_int(hd0.y), flags = LITERAL ? 0 : __float_as_int(hd1.w);
+    const int s1 = __float_as_int(hd0.x), e1 = __float_as_int(hd0.y);
     const double cv0 = fabs((double)hd1.z - h);  // column 0 indexed with the ROW index, as written (M.cc:1076)
     int s2 = s1 - t.n_th, e2 = e1 - t.n_th;
     if (s2 < 0) s2 = s1 + t.n_th;
@@ -498,10 +399,12 @@ __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_look
     // "out of range": d beyond the row's largest distance (M.cc:1196-1204), else search and interpolate
     const bool in1 = d <= (double)hd0.z;
     const bool in2 = two && (d <= (double)hd0.w);
+    int a1 = s1, b1 = e1, a2 = s2, b2 = e2;
+    halve_thd2(t.x, d, in1, a1, b1, in2, a2, b2);
     int i1 = 0, i2 = 0, j1 = 0, j2 = 0;
     double c1 = 0.0, c2 = 0.0;
-    if (in1) find_thd(t.x, blk + 8, (flags & 1) != 0, d, s1, e1, i1, i2, c1);
-    if (in2) find_thd(t.x, blk + 40, (flags & 2) != 0, d, s2, e2, j1, j2, c2);
+    if (in1) scan_thd(t.x, d, a1, b1, i1, i2, c1);
+    if (in2) scan_thd(t.x, d, a2, b2, j1, j2, c2);
     if (in1) row_interp(t, d, i1, i2, c1, P1);
     if (in2) row_interp(t, d, j1, j2, c2, P2);
     oor1 = !in1;
@@ -536,10 +439,10 @@ __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_look
   if (o[4] < 0) ok = false;
   if ((fabs(THD - d) / d > 0.01 && d <= 100) || (fabs(THD - d) > 1 && d > 100)) ok = false;
   if (!ok) { o[0] = 0; o[1] = 0; o[4] = 0; o[5] = 0; }
-  a.ok[i] = ok ? 1 : 0;
+  __stcs(a.ok + i, (uint8_t)(ok ? 1 : 0));
 #pragma unroll
   for (int k = 0; k < 9; k++)
-    if (a.out[k]) a.out[k][i] = o[k];
+    if (a.out[k]) __stcs(a.out[k] + i, o[k]);
 }
 
 // ---------------------------------------------------------------------------------------- FP64 peak probe
@@ -676,9 +579,7 @@ cudaError_t launch_lookup(const AirIceMedium& m, const LookupTable& t, const Loo
   if (a.n <= 0) return cudaSuccess;
   const int64_t blocks = (a.n + kThreads - 1) / kThreads;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
-  const bool literal = getenv("AIRICE_LOOKUP_LITERAL") != nullptr;    // test hook: the reference's walk for every query
-  if (literal) airice_lookup_kernel<true><<<dim3((unsigned)blocks), kThreads, 0, s>>>(m, t, a);
-  else airice_lookup_kernel<false><<<dim3((unsigned)blocks), kThreads, 0, s>>>(m, t, a);
+  airice_lookup_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(m, t, a);
   return cudaGetLastError();
 }
 

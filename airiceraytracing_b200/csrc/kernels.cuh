@@ -107,12 +107,10 @@ struct LookupTable {
   double loop_stop_h, h_step;
   const int* row_first;  // per row: first/last bin with a usable X (trim of M.cc:1050-1072), precomputed
   const int* row_last;
-  // per-row search blocks, AIRICE_ROWBLK floats each (288 B): header + the 31 pivots of FindClosestTHD's first five
-  // halvings for the row's own window and for the second row's window (airice_row_block_kernel in kernels.cu)
+  // per-row header, AIRICE_ROWBLK floats (one 32-byte sector): {s1, e1 (int bits), X[s1], X[s2], h(s1), h(s2), col0[row], 0}
   const float* rowblk;
 };
-#define AIRICE_ROWBLK 72
-#define AIRICE_TREE_LEVELS 5
+#define AIRICE_ROWBLK 8
 cudaError_t launch_pack_table(const float* const* cols32, int64_t cells, int n_h, int n_th, float* x, float4* rec,
                               float* row_h, int* row_first, int* row_last, float* rowblk, cudaStream_t s);
 struct LookupArgs {
