@@ -5,8 +5,8 @@ hand-written sm_100a CUDA kernels behind a C ABI (include/airice_b200.h).  This 
 side used by the tests and the benchmark: device memory and streams come from torch, every number comes from
 libairice_b200.so.  There is no CPU fallback.
 """
-from ._capi import (LIB_PATH, UNITS_CM_RAD, UNITS_M_DEG, VARIANT_MULTIRAY, VARIANT_PYWRAP, AirIceError)
+from ._capi import (LIB_PATH, UNITS_CM_RAD, UNITS_M_DEG, VARIANT_CLI, VARIANT_MULTIRAY, VARIANT_PYWRAP, AirIceError)
 from .solver import AirIceSolver, Table, TABLE_COLUMNS64, TABLE_COLUMNS32, SOLVE_COLUMNS_M_DEG, SOLVE_COLUMNS_CM_RAD
 
 __all__ = ["AirIceSolver", "Table", "AirIceError", "LIB_PATH", "UNITS_CM_RAD", "UNITS_M_DEG", "VARIANT_MULTIRAY",
-           "VARIANT_PYWRAP", "TABLE_COLUMNS64", "TABLE_COLUMNS32", "SOLVE_COLUMNS_M_DEG", "SOLVE_COLUMNS_CM_RAD"]
+           "VARIANT_PYWRAP", "VARIANT_CLI", "TABLE_COLUMNS64", "TABLE_COLUMNS32", "SOLVE_COLUMNS_M_DEG", "SOLVE_COLUMNS_CM_RAD"]

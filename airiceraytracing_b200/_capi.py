@@ -19,6 +19,7 @@ UNITS_M_DEG = 0
 UNITS_CM_RAD = 1
 VARIANT_MULTIRAY = 0
 VARIANT_PYWRAP = 1
+VARIANT_CLI = 2
 
 # every symbol include/airice_b200.h declares
 EXPORTS = [

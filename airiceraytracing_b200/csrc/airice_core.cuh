@@ -57,7 +57,8 @@
 // Per-context medium model (one Atmosphere.dat + ice model + which copy of the reference, i.e. which pi).
 struct AirIceMedium {
   int nlayers;                        // MaxLayers (M.cc:142)
-  int variant;                        // 0 = MultiRayAirIceRefraction, 1 = pythonwrapper/AirIceRayTracing
+  int variant;                        // 0 = MultiRayAirIceRefraction, 1 = pythonwrapper/AirIceRayTracing, 2 = the CLIs'
+                                      // RayTracingFunctions copy (Air2IceRayTracing.C: Brent, its own bracket rule)
   double hlo[AIRICE_MAX_LAYERS + 1];  // ATMLAY[k]/100 in metres; hlo[nlayers] closes the top layer
   double B[AIRICE_MAX_LAYERS];        // B_air
   double C[AIRICE_MAX_LAYERS];        // C_air
@@ -128,11 +129,12 @@ struct AirIceRay {   // everything the reference reports for one ray (metres, se
 // F(stop) and F(start) are formed and rounded separately as GetRayHorizontalPath does (M.cc:463).  The solver path
 // carries L unchanged through all layers and into the ice (M.cc:757-771, 894-902).  Used for the rare real
 // evaluations inside the bisection replay, where the SIGN of d - X must agree with the reference's.
-AIRICE_HD double airice_x_exact(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L) {
+AIRICE_HD double airice_x_exact(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
+                                bool with_ice = true) {
   const double L2 = L * L;
   const double sAir = AIRICE_SQRT(1.0 * 1.0 - L2), sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
   const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
-  const int nseg = nair + (p.has_ice ? 1 : 0);
+  const int nseg = nair + ((p.has_ice && with_ice) ? 1 : 0);
   double X = 0.0;
 #pragma unroll 1
   for (int j = 0; j < nseg; j++) {

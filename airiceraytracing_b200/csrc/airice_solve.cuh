@@ -332,6 +332,99 @@ AIRICE_HD double airice_solve_theta_t(const AirIceMedium& m, const AirIcePlan& p
   return root;
 }
 
+// The launch angle the reference's COMMAND-LINE solver returns (Air2IceRayTracing.C:101-137 on RayTracingFunctions.cc):
+// bracket [straight - 16, straight]; a lower end below 90.00 becomes 90.05 and steps up by 0.05 while the ray does not
+// exist there (X_air NaN or <= 0) and lo <= hi - 1; then gsl_root_fsolver_brent on f = d - X(theta) with
+// gsl_root_test_interval(lo, hi, 0, 1e-9) and at most 20 iterations (RayTracingFunctions.cc:256-291).  Brent's iterates
+// depend on the VALUES of f, not only on its sign, so there is nothing to replay: the loop runs literally (GSL's
+// roots/brent.c, ~6 evaluations of X with reference-like rounding), rare non-finite bracket ends included (the solver
+// state then stays zeroed and the "root" is 0, as with the calloc'ed stand-in of the oracle).
+AIRICE_HD double airice_solve_theta_cli(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double d,
+                                        double thR, int& nevals) {
+  nevals = 0;
+  double lo = thR - 16, hi = thR;
+  if (lo < 90.00) {
+    lo = 90.05;
+#pragma unroll 1
+    while (lo > 89.9) {
+      const double xa = (kt >= p.kb) ? airice_x_exact(m, p, kt, h, n_tx, airice_L_of_theta(m, n_tx, lo), false) : 0.0;
+      nevals++;
+      if ((xa == xa && xa > 0) || lo > hi - 1) break;
+      lo = lo + 0.05;
+    }
+  }
+  if (hi < 90.001 && hi > 90.00) hi = 90.05;
+  auto f = [&](double th) { nevals++; return d - airice_x_exact(m, p, kt, h, n_tx, airice_L_of_theta(m, n_tx, th)); };
+  // gsl_root_fsolver_set -> brent_init
+  double a = 0, b = 0, c = 0, dd = 0, e = 0, fa = 0, fb = 0, fc = 0, root = 0;
+  double x_lower = lo, x_upper = hi;
+  if (!(lo > hi)) {                       // gsl_root_fsolver_set refuses lo > hi before calling the type's init
+    root = 0.5 * (lo + hi);
+    const double f_lower = f(lo);
+    bool ok = isfinite(f_lower);
+    double f_upper = 0;
+    if (ok) { f_upper = f(hi); ok = isfinite(f_upper); }
+    if (ok) { a = lo; fa = f_lower; b = hi; fb = f_upper; c = hi; fc = f_upper; dd = hi - lo; e = hi - lo; }
+  } else {
+    root = 0;
+  }
+#pragma unroll 1
+  for (int iter = 0; iter < 20; iter++) {
+    // brent_iterate
+    bool ac_equal = false;
+    if ((fb < 0 && fc < 0) || (fb > 0 && fc > 0)) { ac_equal = true; c = a; fc = fa; dd = b - a; e = b - a; }
+    if (fabs(fc) < fabs(fb)) { ac_equal = true; a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+    const double tol = 0.5 * 2.2204460492503131e-16 * fabs(b);
+    const double mm = 0.5 * (c - b);
+    bool done_step = false;
+    if (fb == 0) { root = b; x_lower = b; x_upper = b; done_step = true; }
+    else if (fabs(mm) <= tol) {
+      root = b;
+      if (b < c) { x_lower = b; x_upper = c; } else { x_lower = c; x_upper = b; }
+      done_step = true;
+    }
+    if (!done_step) {
+      if (fabs(e) < tol || fabs(fa) <= fabs(fb)) { dd = mm; e = mm; }
+      else {
+        double pp, q, r;
+        const double s = fb / fa;
+        if (ac_equal) { pp = 2 * mm * s; q = 1 - s; }
+        else {
+          q = fa / fc; r = fb / fc;
+          pp = s * (2 * mm * q * (q - r) - (b - a) * (r - 1));
+          q = (q - 1) * (r - 1) * (s - 1);
+        }
+        if (pp > 0) q = -q; else pp = -pp;
+        const double lim1 = 3 * mm * q - fabs(tol * q), lim2 = fabs(e * q);
+        if (2 * pp < (lim1 < lim2 ? lim1 : lim2)) { e = dd; dd = pp / q; }
+        else { dd = mm; e = mm; }
+      }
+      a = b; fa = fb;
+      double bn = b;
+      if (fabs(dd) > tol) bn += dd; else bn += (mm > 0 ? +tol : -tol);
+      const double fbn = f(bn);
+      if (isfinite(fbn)) {              // else GSL_EBADFUNC: the iterate returns before storing its state
+        b = bn; fb = fbn;
+        root = b;
+        double cc = c;
+        if ((fb < 0 && fc < 0) || (fb > 0 && fc > 0)) cc = a;
+        if (b < cc) { x_lower = b; x_upper = cc; } else { x_lower = cc; x_upper = b; }
+      } else {
+        // a, fa were local copies in GSL: the stored state keeps the values from before this iterate
+        // (restore what the failed iterate must not have changed)
+        // NB: c/fc/dd/e changes above are local in GSL as well
+        return root;                     // every further iterate repeats the same failure: root stays
+      }
+    }
+    // gsl_root_test_interval(x_lower, x_upper, 0, 1e-9)
+    if (x_lower > x_upper) break;        // GSL_EINVAL != GSL_CONTINUE
+    const double al = fabs(x_lower), au = fabs(x_upper);
+    const double mn = ((x_lower > 0.0 && x_upper > 0.0) || (x_lower < 0.0 && x_upper < 0.0)) ? (al < au ? al : au) : 0.0;
+    if (fabs(x_upper - x_lower) < 0.000000001 * mn) break;
+  }
+  return root;
+}
+
 AIRICE_HD double airice_solve_theta(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx,
                                     double d, double thR, double ta_straight, double& theta_star,
                                     AirIceSolveStat& st) {

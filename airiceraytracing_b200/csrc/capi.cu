@@ -335,7 +335,8 @@ int airice_device_count(void) {
 int airice_create(const char* atmosphere_path, int variant, int device, airice_ctx** out) {
   if (!out) return fail(-1, "null argument");
   const bool ice_only = !atmosphere_path || !atmosphere_path[0];   // in-ice entry points only (no GDAS file needed)
-  if (variant != AIRICE_VARIANT_MULTIRAY && variant != AIRICE_VARIANT_PYWRAP) return fail(-1, "unknown variant");
+  if (variant != AIRICE_VARIANT_MULTIRAY && variant != AIRICE_VARIANT_PYWRAP && variant != AIRICE_VARIANT_CLI)
+    return fail(-1, "unknown variant");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -349,7 +350,7 @@ int airice_create(const char* atmosphere_path, int variant, int device, airice_c
     std::memset(&c->medium, 0, sizeof(c->medium));
     c->medium.nlayers = 0; c->medium.variant = variant;
     c->medium.A_ice = 1.78; c->medium.B_ice = -0.43; c->medium.C_ice = 0.0132;
-    c->medium.pi = (variant == AIRICE_VARIANT_PYWRAP) ? 4.0 * atan(1.0) : 3.1415927;
+    c->medium.pi = (variant == AIRICE_VARIANT_PYWRAP) ? 4.0 * atan(1.0) : 3.1415927;   // (the CLI copy shares M's pi)
     c->medium.deg2rad = c->medium.pi / 180.0; c->medium.rad2deg = 180.0 / c->medium.pi; c->medium.c = 299792458.0;
     c->no_air = true;
   } else {

@@ -168,7 +168,7 @@ constexpr int kSolveThreads = AIRICE_SOLVE_THREADS;
 constexpr int64_t kTwoPassMinPairs = 6000000;
 // One pair, start to finish.  DEFER (first pass of the two-pass launch): a pair that needs a rare slow path is appended
 // to a.defer_list (0.6 % of a random batch) and what is written for it here is overwritten by the second pass.
-template <bool DEFER>
+template <bool DEFER, bool CLI = false>
 __device__ __forceinline__ void solve_one(const AirIceMedium& m, const AirIcePlan& p, const SolveArgs& a, int64_t i) {
   double h = a.h[i], d = a.d[i];
   double ice = a.ice, depth = a.depth;
@@ -187,8 +187,14 @@ __device__ __forceinline__ void solve_one(const AirIceMedium& m, const AirIcePla
   }
   AirIceSolveStat st;
   double th_star;
-  bool hard;
-  const double theta = airice_solve_theta_t<DEFER>(m, p, kt, h, ntx, d, thR, ta, th_star, st, hard);
+  bool hard = false;
+  double theta;
+  if (CLI) {
+    st.n_newton = 0;
+    theta = airice_solve_theta_cli(m, p, kt, h, ntx, d, thR, st.n_replay);
+  } else {
+    theta = airice_solve_theta_t<DEFER>(m, p, kt, h, ntx, d, thR, ta, th_star, st, hard);
+  }
   // a deferred pair is listed and then carries on with its NaN angle (its outputs are overwritten by the second pass,
   // which the stream orders after this one): leaving the kernel here instead measured 5 % slower for the whole launch
   if (DEFER && hard) a.defer_list[atomicAdd(a.defer_count, 1)] = (int32_t)i;
@@ -243,6 +249,13 @@ __global__ void __launch_bounds__(kSolveThreads, AIRICE_SOLVE_MINBLOCKS) airice_
     if (i >= a.n) return;
     solve_one<PASS == 1>(m, p, a, i);
   }
+}
+
+// variant 2 (the command-line solver, Air2IceRayTracing.C): literal Brent iteration per pair, same output tail
+__global__ void __launch_bounds__(kSolveThreads, AIRICE_SOLVE_MINBLOCKS) airice_solve_cli_kernel(const AirIceMedium m, const AirIcePlan p, const SolveArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * kSolveThreads + threadIdx.x;
+  if (i >= a.n) return;
+  solve_one<false, true>(m, p, a, i);
 }
 
 // ---------------------------------------------------------------------------------------- lookup
@@ -503,6 +516,10 @@ cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const Solve
   if (a.n <= 0) return cudaSuccess;
   const int64_t blocks = (a.n + kSolveThreads - 1) / kSolveThreads;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
+  if (m.variant == 2) {
+    airice_solve_cli_kernel<<<dim3((unsigned)blocks), kSolveThreads, 0, s>>>(m, p, a);
+    return cudaGetLastError();
+  }
   // the second pass is latency bound (~60 us whatever the list length) and the first saves ~8 % of the single-pass
   // time: two passes pay off from ~5e6 pairs per launch
   if (!a.defer_count || !a.defer_list || a.n >= 2147483647LL || a.n < kTwoPassMinPairs) {

@@ -20,7 +20,12 @@ typedef struct airice_ctx airice_ctx;
 typedef struct airice_table airice_table;
 
 enum { AIRICE_VARIANT_MULTIRAY = 0, /* MultiRayAirIceRefraction.{h,cc}: pi = 3.1415927 (MultiRayAirIceRefraction.h:29) */
-       AIRICE_VARIANT_PYWRAP = 1    /* pythonwrapper/AirIceRayTracing.{h,cc}: pi = 4*atan(1) (AirIceRayTracing.h:25) */ };
+       AIRICE_VARIANT_PYWRAP = 1,   /* pythonwrapper/AirIceRayTracing.{h,cc}: pi = 4*atan(1) (AirIceRayTracing.h:25) */
+       AIRICE_VARIANT_CLI = 2       /* the command-line solver Air2IceRayTracing.C on RayTracingFunctions.{h,cc}: pi = 3.1415927
+                                     * (RayTracingFunctions.h:26), gsl_root_fsolver_brent with tolerance 1e-9 and at most 20
+                                     * iterations (Air2IceRayTracing.C:137, RayTracingFunctions.cc:259), bracket rule of
+                                     * Air2IceRayTracing.C:101-129 (lo < 90.00 -> 90.05, stepping while lo <= hi - 1).  Affects
+                                     * airice_solve_*; everything else behaves as variant 0. */ };
 enum { AIRICE_UNITS_M_DEG_C = 0, AIRICE_UNITS_CM_RAD_C = 1 };
 
 #define AIRICE_TABLE_COLS64 17

@@ -48,6 +48,23 @@ void sim_forward(double theta, double h, double ice, double depth, int inice, do
   out[11] = theta; out[12] = r.inc_ice_deg; out[13] = r.recv_deg; out[14] = r.trans_s; out[15] = r.trans_p;
   out[16] = r.p_air; out[17] = r.p_ice;
 }
+// the command-line solver (variant 2: Brent, Air2IceRayTracing.C): out[7] = launch angle, X_air, incident angle on ice, L,
+// t_air [ns], X_ice, receive angle, then t_ice [ns] in out[7]; depth negative in ice
+int sim_solve_cli(double h, double d, double ice, double depth, double* out) {
+  AirIcePlan p; make_plan(g_m, ice, depth, &p);
+  const int kt = top_layer(h);
+  const double ntx = 1.0 + g_m.B[kt < 0 ? 0 : kt] * exp(-g_m.C[kt < 0 ? 0 : kt] * h);
+  double ta;
+  const double thR = airice_straight_angle(g_m, h, d, ice, depth, ta);
+  int nev = 0;
+  const double theta = airice_solve_theta_cli(g_m, p, kt, h, ntx, d, thR, nev);
+  const double L = airice_L_of_theta(g_m, ntx, theta);
+  AirIceRay r;
+  airice_ray_full<false>(g_m, p, kt, h, ntx, L, p.has_ice != 0, true, true, r);
+  out[0] = theta; out[1] = r.x_air; out[2] = r.inc_ice_deg; out[3] = L; out[4] = r.t_air * 1e9; out[5] = r.x_ice; out[6] = r.recv_deg;
+  out[7] = r.t_ice * 1e9;
+  return nev;
+}
 // GetHorizontalDistanceToIntersectionPoint layout (cm/rad): out[9]; stats[0..2] = newton evals, replay evals, theta*
 int sim_solve_cm(double h_cm, double d_cm, double depth_cm, double ice_cm, double* out, double* stats) {
   const double h = h_cm / 100, d = d_cm / 100, ice = ice_cm / 100, depth = depth_cm / 100;
