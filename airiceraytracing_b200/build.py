@@ -28,6 +28,7 @@ def build(force=False, verbose_ptxas=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".h"))]
     headers += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
     extra = ["-Xptxas", "-v"] if verbose_ptxas else []
+    extra += os.environ.get("AIRICE_EXTRA_NVCC", "").split()       # development: -D knobs of the kernels (tools/*_probe)
 
     core = os.path.join(LIBDIR, "libairice_b200.so")
     core_src = [os.path.join(CSRC, f) for f in ("kernels.cu", "capi.cu", "atmosphere.cc")]

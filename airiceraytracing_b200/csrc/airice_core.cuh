@@ -38,6 +38,9 @@
 #endif
 
 #define AIRICE_MAX_LAYERS 5
+#ifndef AIRICE_PEEL_TOP
+#define AIRICE_PEEL_TOP 0
+#endif
 #ifndef AIRICE_UNROLL_XFAST
 #define AIRICE_UNROLL_XFAST 1
 #endif
@@ -268,6 +271,19 @@ AIRICE_HD double airice_x_dx(const AirIceMedium& m, const AirIcePlan& p, int kt,
   if (kt >= p.kb) {
     const double sAir = AIRICE_SQRT(1.0 * 1.0 - L2);
     const double yAir = AIRICE_RCP(sAir);
+#if AIRICE_PEEL_TOP
+#pragma unroll 1
+    for (int k = p.kb; k < kt; k++) {
+      double seg, dseg;
+      airice_seg_x_dx<true>(1.0, sAir, yAir, L, L2, p.neg_c[k], p.inv_neg_c[k], p.start_x[k], p.start_n[k], p.stop_x[k], p.stop_n[k], seg, dseg);
+      X -= seg; dX -= dseg;
+    }
+    {
+      double seg, dseg;
+      airice_seg_x_dx<true>(1.0, sAir, yAir, L, L2, p.neg_c[kt], p.inv_neg_c[kt], h, n_tx, p.stop_x[kt], p.stop_n[kt], seg, dseg);
+      X -= seg; dX -= dseg;
+    }
+#else
 #pragma unroll 1
     for (int k = p.kb; k <= kt; k++) {
       const bool top = (k == kt);
@@ -277,6 +293,7 @@ AIRICE_HD double airice_x_dx(const AirIceMedium& m, const AirIcePlan& p, int kt,
       airice_seg_x_dx<true>(1.0, sAir, yAir, L, L2, p.neg_c[k], p.inv_neg_c[k], xt, nt, p.stop_x[k], p.stop_n[k], seg, dseg);
       X -= seg; dX -= dseg;
     }
+#endif
   }
   if (p.has_ice) {
     const double sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
@@ -340,6 +357,18 @@ AIRICE_HD float airice_x_newton_f32(const AirIceMedium& m, const AirIcePlan& p, 
     // bottom-up (see airice_x_fast).  The upper end of a layer and the lower end of the layer above it are the same
     // point to single precision (1e-5 m and 3e-13 in n apart), so each trip evaluates ONE end and keeps it for the next.
     AirIceEndF32 eb = airice_end_f32(sA2, sA, p.f_q_stop[p.kb], p.f_pa_stop[p.kb]);
+#if AIRICE_PEEL_TOP
+#pragma unroll 1
+    for (int k = p.kb; k < kt; k++) {
+      const AirIceEndF32 et = airice_end_f32(sA2, sA, p.f_q_start[k], p.f_pa_start[k]);
+      airice_seg_f32<true>(1.0f, y, L, L2, eb, et, p.f_cdx[k], p.f_inv_neg_c[k], X, dX);
+      eb = et;
+    }
+    {
+      const AirIceEndF32 et = airice_end_f32(sA2, sA, q_tx, dn_tx);
+      airice_seg_f32<true>(1.0f, y, L, L2, eb, et, h_minus_stop_top_cn, p.f_inv_neg_c[kt], X, dX);
+    }
+#else
 #pragma unroll 1
     for (int k = p.kb; k <= kt; k++) {
       const bool top = (k == kt);
@@ -349,6 +378,7 @@ AIRICE_HD float airice_x_newton_f32(const AirIceMedium& m, const AirIcePlan& p, 
       airice_seg_f32<true>(1.0f, y, L, L2, eb, et, cdx, p.f_inv_neg_c[k], X, dX);
       eb = et;
     }
+#endif
   }
   if (p.has_ice) {
     const float Ai = (float)m.A_ice;

@@ -19,6 +19,7 @@ for l in lines[start:end]:
 rows=list(csv.reader(open('/tmp/cub2/src.csv')))
 h=rows[1]; ii=h.index('Instructions Executed'); ti=h.index('Thread Instructions Executed'); si=h.index('# Samples')
 data=rows[2:]
+data=[r for r in data if len(r)>max(ii,ti,si) and r[ii].isdigit()][:len(ins)]   # several launches in the report: the first one
 assert len(data)==len(ins),(len(data),len(ins))
 agg=defaultdict(lambda:[0,0,0])
 for r,(off,cur,txt) in zip(data,ins):
