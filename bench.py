@@ -433,8 +433,8 @@ def run_ours(args):
         ms = time_ms(lambda: solver.lookup(T, h, d, out=out, ok=ok))
         extras["lookup"] = {"table": "reference grid 9701x900 float", "lookups": n, "ms": ms, "lookups_per_s": world * n / ms * 1e3,
                             "algorithmic_gbs": n * 265.0 / ms / 1e6,
-                            "layout": "per-row search block (header + 5 tree levels of the index halving, 288 B, L2 resident), dense THD "
-                                      "column for the last halvings, 48-byte records (4 cells gathered per query)",
+                            "layout": "one 32-byte header sector per row, dense THD column for the index search (L2 resident: records, "
+                                      "inputs and outputs use the streaming cache operators), 48-byte records (4 cells gathered per query)",
                             "solved": float(ok.float().mean())}
         lf = facts.get("airice_lookup_kernel", {})
         rooflines.append({"kernel": "airice_lookup_kernel", "bound": "hbm", "achieved": n * 265.0 / ms / 1e6, "peak": hbm_peak,
