@@ -30,7 +30,7 @@ EXPORTS = [
     "airice_solve_multi_device", "airice_solve_host", "airice_lookup_device", "airice_lookup_host", "airice_inice_solve_device",
     "airice_inice_solve_host", "airice_inice_two_rays_device", "airice_inice_two_rays_host", "airice_ray_path_device", "airice_ray_path_host", "airice_fp64_peak_tflops", "airice_sync", "airice_trim",
     "airice_inice_two_rays_att_device", "airice_inice_two_rays_att_host", "airice_inice_attenuation_device", "airice_inice_attenuation_host",
-    "airice_inice_quadrature_stats", "airice_inice_focusing_device", "airice_inice_focusing_host", "airice_inice_table_create",
+    "airice_inice_quadrature_stats", "airice_inice_ladder_stats", "airice_inice_focusing_device", "airice_inice_focusing_host", "airice_inice_table_create",
     "airice_inice_table_destroy", "airice_inice_table_info", "airice_inice_table_copy_column", "airice_inice_table_copy_positions",
     "airice_inice_table_interp_device", "airice_inice_table_interp_host", "airice_table_save", "airice_table_load", "airice_oldtable_create", "airice_oldtable_wrap_host", "airice_oldtable_destroy", "airice_oldtable_info",
     "airice_oldtable_copy_column", "airice_oldtable_copy_positions", "airice_oldtable_interp_device", "airice_oldtable_interp_host",
@@ -88,6 +88,7 @@ def load():
     lib.airice_inice_two_rays_att_host.argtypes = [vp, i64, vp, vp, vp, d, d, vp, vp, vp]
     lib.airice_inice_attenuation_device.argtypes = [vp, i64, i, d, d, vp, vp, vp, vp, vp, vp]
     lib.airice_inice_attenuation_host.argtypes = [vp, i64, i, d, d, vp, vp, vp, vp, vp]
+    lib.airice_inice_ladder_stats.argtypes = [vp, C.POINTER(i64)]
     lib.airice_inice_quadrature_stats.argtypes = [vp, C.POINTER(i64)]
     lib.airice_inice_focusing_device.argtypes = [vp, i64, vp, vp, vp, pp, vp]
     lib.airice_inice_focusing_host.argtypes = [vp, i64, vp, vp, vp, vp]

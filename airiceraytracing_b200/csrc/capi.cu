@@ -119,10 +119,14 @@ struct airice_oldtable {
 struct airice_table {
   airice_ctx* ctx = nullptr;
   bool owns = false;
-  float* cols[AIRICE_TABLE_NCOLS32] = {nullptr};   // reference layout (column-major), owned or wrapped
+  // reference layout (column-major), owned or wrapped.  Tables built by the fused multi-antenna pass hold the lookup
+  // layout only (a lookup never reads the columns, and writing them is 46 % of the pass's HBM traffic); the columns are
+  // then made from the records on first use (airice_table_copy_column / _column_ptr / _save): same floats.
+  mutable float* cols[AIRICE_TABLE_NCOLS32] = {nullptr};
   // lookup layout, always owned: dense X, 48-byte records, per-row height, per-row trim ranges (one allocation)
   void* pack = nullptr;
-  size_t cols_bytes = 0, pack_bytes = 0;
+  mutable size_t cols_bytes = 0;
+  size_t pack_bytes = 0;
   float* x = nullptr;
   float4* rec = nullptr;
   float* row_h = nullptr;
@@ -209,6 +213,22 @@ void table_release(airice_ctx* c, void* p, size_t bytes, const std::vector<cudaS
   } else {
     cudaFree(p);
   }
+}
+
+// The reference-layout columns of a table that was built in the lookup layout only.
+int ensure_columns(const airice_table* t) {
+  if (t->cols[0]) return 0;
+  if (!t->ctx || !t->rec) return fail(-1, "table has no data");
+  float* block = nullptr;
+  const size_t bytes = sizeof(float) * (size_t)t->cells * AIRICE_TABLE_NCOLS32;
+  cudaError_t e = table_alloc(t->ctx, (void**)&block, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(table columns)");
+  e = launch_unpack_table(t->rec, t->row_h, t->cells, (int)t->n_th, block, t->cells, nullptr);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+  if (e != cudaSuccess) { cudaFree(block); return cuda_fail(e, "unpack table"); }
+  for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t->cols[k] = block + (int64_t)k * t->cells;
+  t->cols_bytes = bytes;
+  return 0;
 }
 
 // Allocate the lookup layout of a table (dense X, 48-byte records, per-row height and trim ranges: one block).
@@ -493,9 +513,8 @@ int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, 
   if (cells >= 2147483647LL) return fail(-5, "lookup tables are limited to 2^31-1 cells (the reference indexes them with int)");
   for (int q = 0; q < n_ant; q++) out[q] = nullptr;
   std::vector<double> ant(2 * (size_t)n_ant);
-  std::vector<float*> blocks((size_t)n_ant);
   double* d_ant = nullptr;
-  void** d_blocks = nullptr;   // [4][n_ant]: column blocks, records, dense X, row heights
+  void** d_blocks = nullptr;   // [3][n_ant]: records, dense X, row heights
   auto cleanup = [&](int code) {
     for (int q = 0; q < n_ant; q++) { if (out[q]) airice_table_destroy(out[q]); out[q] = nullptr; }
     if (d_ant) cudaFree(d_ant);
@@ -509,24 +528,18 @@ int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, 
     c->tables.push_back(t);
     t->n_h = n_h; t->n_th = g.n_th; t->cells = cells;
     t->loop_stop_h = g.loop_stop_h; t->h_step = g.h_step;
-    float* block = nullptr;
-    t->cols_bytes = sizeof(float) * (size_t)cells * AIRICE_TABLE_NCOLS32;
-    cudaError_t e = table_alloc(c, (void**)&block, t->cols_bytes);
-    if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMalloc(table)"));
-    for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++) t->cols[k] = block + (int64_t)k * cells;
-    blocks[q] = block;
     ant[2 * q] = -depths_m[q];                       // the plan's positive depth (make_plan)
     ant[2 * q + 1] = n_ice(c->medium, -depths_m[q]);
   }
-  // the lookup layout of every table is written by the same pass (no separate pack kernel re-reading the columns)
-  std::vector<void*> ptrs(4 * (size_t)n_ant);
+  // the pass writes the lookup layout of every table and nothing else: the reference-layout columns are made from it
+  // on first use (ensure_columns)
+  std::vector<void*> ptrs(3 * (size_t)n_ant);
   for (int q = 0; q < n_ant; q++) {
     rc = pack_alloc(out[q]);
     if (rc) return cleanup(rc);
-    ptrs[q] = blocks[q];
-    ptrs[(size_t)n_ant + q] = out[q]->rec;
-    ptrs[2 * (size_t)n_ant + q] = out[q]->x;
-    ptrs[3 * (size_t)n_ant + q] = out[q]->row_h;
+    ptrs[q] = out[q]->rec;
+    ptrs[(size_t)n_ant + q] = out[q]->x;
+    ptrs[2 * (size_t)n_ant + q] = out[q]->row_h;
   }
   cudaError_t e = cudaMalloc((void**)&d_ant, sizeof(double) * ant.size());
   if (e == cudaSuccess) e = cudaMalloc((void**)&d_blocks, sizeof(void*) * ptrs.size());
@@ -535,10 +548,10 @@ int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, 
   if (e != cudaSuccess) return cleanup(cuda_fail(e, "antenna arrays"));
   TableMultiArgs ma;
   std::memset(&ma, 0, sizeof(ma));
-  ma.n_ant = n_ant; ma.ant = d_ant; ma.blocks = (float* const*)d_blocks; ma.col_stride = cells;
-  ma.rec = (float4* const*)(d_blocks + n_ant);
-  ma.x = (float* const*)(d_blocks + 2 * (size_t)n_ant);
-  ma.row_h = (float* const*)(d_blocks + 3 * (size_t)n_ant);
+  ma.n_ant = n_ant; ma.ant = d_ant; ma.blocks = nullptr; ma.col_stride = cells;
+  ma.rec = (float4* const*)d_blocks;
+  ma.x = (float* const*)(d_blocks + n_ant);
+  ma.row_h = (float* const*)(d_blocks + 2 * (size_t)n_ant);
   rc = build_rows(c, g, 0, n_h, nullptr, nullptr, nullptr, &ma);
   for (int q = 0; q < n_ant && rc == 0; q++) {
     e = launch_row_ranges(out[q]->x, out[q]->row_h, cells, (int)n_h, (int)g.n_th, out[q]->row_first, out[q]->row_last, out[q]->rowblk,
@@ -604,6 +617,7 @@ uint64_t fnv1a(const void* p, size_t n) {
 int airice_table_save(const airice_table* t, const char* path) {
   if (!t || !t->ctx || !path) return fail(-1, "null argument");
   CK(cudaSetDevice(t->ctx->device));
+  if (int rc = ensure_columns(t)) return rc;
   const size_t n = (size_t)t->cells * AIRICE_TABLE_NCOLS32;
   std::vector<float> host(n);
   for (int k = 0; k < AIRICE_TABLE_NCOLS32; k++)
@@ -664,12 +678,15 @@ int airice_table_info(const airice_table* t, int64_t info[4]) {
 int airice_table_copy_column(const airice_table* t, int col, float* host_out) {
   if (!t || !t->ctx || col < 0 || col >= AIRICE_TABLE_NCOLS32) return fail(-1, "bad table/column");
   CK(cudaSetDevice(t->ctx->device));
+  if (int rc = ensure_columns(t)) return rc;
   CK(cudaMemcpy(host_out, t->cols[col], sizeof(float) * t->cells, cudaMemcpyDeviceToHost));
   return 0;
 }
 
 int airice_table_column_ptr(const airice_table* t, int col, const float** d_ptr) {
   if (!t || !t->ctx || col < 0 || col >= AIRICE_TABLE_NCOLS32) return fail(-1, "bad table/column");
+  CK(cudaSetDevice(t->ctx->device));
+  if (int rc = ensure_columns(t)) return rc;
   *d_ptr = t->cols[col];
   return 0;
 }
@@ -1177,6 +1194,19 @@ int airice_inice_attenuation_host(airice_ctx* c, int64_t n, int kind, double A0,
     CK(cudaMemcpyAsync(out + off, dh + 4 * chunk, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
   }
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int airice_inice_ladder_stats(airice_ctx* c, int64_t out[4]) {
+  if (!c || !out) return fail(-1, "null argument");
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if (!c->inice_scratch[0]) return 0;
+  CK(cudaSetDevice(c->device));
+  int32_t h[8];
+  CK(cudaMemcpy(h, c->inice_scratch[0], sizeof(h), cudaMemcpyDeviceToHost));    // synchronises with the kernels that wrote it
+  unsigned long long w[2];
+  std::memcpy(w, h + 4, sizeof(w));
+  out[0] = h[0]; out[1] = h[2]; out[2] = (int64_t)w[0]; out[3] = (int64_t)w[1];
   return 0;
 }
 

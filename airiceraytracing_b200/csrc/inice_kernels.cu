@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kLadderThreads) airice_inice_ladder_kernel(con
   int slot[InIceRaMachine::kMaxReq] = {0, 0, 0, 0, 0};
   int rot = 0;
   double my_x1 = 0.0;
+  unsigned n_eval = 0, n_zstep = 0;      // work done by this lane: fRaa evaluations and turning-depth falsepos steps
   for (;;) {
     if (!has && !exhausted) {
       j = atomicAdd(a.ra_count + 1, 1);
@@ -128,7 +129,16 @@ __global__ void __launch_bounds__(kLadderThreads) airice_inice_ladder_kernel(con
     // The pool takes at most 32 hard requests per trip -- one for every lane, so that the evaluation below is a single
     // fully occupied pass -- packed greedily in lane order from a start lane that rotates; a pair whose requests do
     // not fit any more simply waits for the next trip.
-    if (!__any_sync(full, has)) break;   // no lane holds a pair and the list is used up
+    if (!__any_sync(full, has)) {        // no lane holds a pair and the list is used up
+      // work census of the launch (bench.py turns it into the kernel's algorithmic-work figure): one atomic per warp
+      const unsigned ev = __reduce_add_sync(full, n_eval), zs = __reduce_add_sync(full, n_zstep);
+      if (lane == 0) {
+        unsigned long long* w = (unsigned long long*)(a.ra_count + 4);
+        atomicAdd(w, (unsigned long long)ev);
+        atomicAdd(w + 1, (unsigned long long)zs);
+      }
+      break;
+    }
     rot = (rot + 11) & 31;
     int incl = __shfl_sync(full, nhard, (lane + rot) & 31);      // lane p holds the count of virtual position p
 #pragma unroll
@@ -155,8 +165,9 @@ __global__ void __launch_bounds__(kLadderThreads) airice_inice_ladder_kernel(con
       const double x = pool.x[lane];
       InIceZmaxIter Z;
       Z.init(a.A, a.B, e5000, x);
+      n_eval++;
 #pragma unroll 1
-      while (!Z.step(a.A, a.B, a.C)) {}
+      do { n_zstep++; } while (!Z.step(a.A, a.B, a.C));
       const double zm = Z.root + 1e-7;
       pool.zm[lane] = zm;
       pool.y[lane] = inice_fraa_given_zmax(g, x, zm);
@@ -329,7 +340,7 @@ cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s) {
   const int64_t blocks = (a.n + kThreads - 1) / kThreads;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
   if (!a.ra_list || !a.ra_count || !a.ra_lad || !a.mask || !a.out[20]) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(a.ra_count, 0, 3 * sizeof(int32_t), s);
+  cudaError_t e = cudaMemsetAsync(a.ra_count, 0, 8 * sizeof(int32_t), s);     // 3 list counters, pad, 2 x u64 work census
   if (e != cudaSuccess) return e;
   const int64_t dr_blocks = (a.n + kDrThreads - 1) / kDrThreads;
   airice_inice_dr_kernel<<<dim3((unsigned)dr_blocks), kDrThreads, 0, s>>>(a);

@@ -109,19 +109,21 @@ __global__ void __launch_bounds__(kThreads) airice_table_multi_kernel(const AirI
     const double xb = __ldg(ma.ant + 2 * q), nb = __ldg(ma.ant + 2 * q + 1);
     double xi, ti, gi, recv;
     airice_ice_leg(m, p, it, xb, nb, xi, ti, gi, recv);
-    float* o = ma.blocks[q] + i;   // like c32[k][i] of the single-table kernel: blocks start at the launch's first cell
-    const int64_t st = ma.col_stride;
-    o[0] = f_h;
-    o[st] = (float)(al.x + xi);
-    o[2 * st] = (float)(ti * m.c);
-    o[3 * st] = f_oa;
-    o[4 * st] = f_th;
-    o[5 * st] = f_xa;
-    o[6 * st] = f_ts;
-    o[7 * st] = f_tp;
-    o[8 * st] = f_ga;
-    o[9 * st] = (float)gi;
-    o[10 * st] = (float)recv;
+    if (ma.blocks) {               // the reference-layout columns; omitted when only the lookup layout is wanted
+      float* o = ma.blocks[q] + i;   // like c32[k][i] of the single-table kernel: blocks start at the launch's first cell
+      const int64_t st = ma.col_stride;
+      o[0] = f_h;
+      o[st] = (float)(al.x + xi);
+      o[2 * st] = (float)(ti * m.c);
+      o[3 * st] = f_oa;
+      o[4 * st] = f_th;
+      o[5 * st] = f_xa;
+      o[6 * st] = f_ts;
+      o[7 * st] = f_tp;
+      o[8 * st] = f_ga;
+      o[9 * st] = (float)gi;
+      o[10 * st] = (float)recv;
+    }
     if (ma.rec) {
       const float f_x = (float)(al.x + xi);
       float4* rq = ma.rec[q] + 3 * c;
@@ -292,6 +294,20 @@ __global__ void airice_pack_kernel(const float* c0, const float* c1, const float
   rec[3 * i + 1] = make_float4(c5[i], c6[i], c7[i], c8[i]);
   rec[3 * i + 2] = make_float4(c9[i], c10[i], 0.f, 0.f);
   if (i % n_th == 0) row_h[i / n_th] = c0[i];
+}
+
+// lookup layout -> the reference's column-major float table (AllTableAllAntData order, M.cc:2101-2111): the inverse of
+// airice_pack_kernel, run on demand for tables that were built in the lookup layout only
+__global__ void airice_unpack_kernel(const float4* __restrict__ rec, const float* __restrict__ row_h, int64_t cells, int n_th,
+                                     float* c0, int64_t stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cells) return;
+  const float4 a = rec[3 * i], b = rec[3 * i + 1], c = rec[3 * i + 2];
+  float* o = c0 + i;
+  o[0] = row_h[i / n_th];
+  o[stride] = a.x; o[2 * stride] = a.y; o[3 * stride] = a.z; o[4 * stride] = a.w;
+  o[5 * stride] = b.x; o[6 * stride] = b.y; o[7 * stride] = b.z; o[8 * stride] = b.w;
+  o[9 * stride] = c.x; o[10 * stride] = c.y;
 }
 
 // Per-row header blocks (LookupTable::rowblk), one thread per (row, slot): everything FindClosestAirTxHeight
@@ -543,6 +559,13 @@ cudaError_t launch_row_ranges(const float* x, const float* row_h, int64_t cells,
   if (e != cudaSuccess) return e;
   const int64_t threads = (int64_t)n_h * AIRICE_ROWBLK;
   airice_row_block_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(x, row_h, cells, n_h, n_th, row_first, row_last, rowblk);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_table(const float4* rec, const float* row_h, int64_t cells, int n_th, float* c0, int64_t stride, cudaStream_t s) {
+  const int64_t blocks = (cells + 255) / 256;
+  if (blocks > 2147483647LL) return cudaErrorInvalidValue;
+  airice_unpack_kernel<<<dim3((unsigned)blocks), 256, 0, s>>>(rec, row_h, cells, n_th, c0, stride);
   return cudaGetLastError();
 }
 

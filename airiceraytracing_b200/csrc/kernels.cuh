@@ -43,7 +43,7 @@ struct TableMultiArgs {
   TableArgs base;
   int n_ant;
   const double* ant;       // device [n_ant][2]: receiver depth (positive, m) and n_ice(depth) (host libm)
-  float* const* blocks;    // device [n_ant]: column-major float block of each antenna's table
+  float* const* blocks;    // device [n_ant]: column-major float block of each antenna's table; nullptr = lookup layout only
   int64_t col_stride;      // elements between two columns of a block (= cells of the whole table)
   // lookup layout of each antenna's table written in the same pass (what airice_pack_kernel derives from the columns);
   // device [n_ant] each, all three null = columns only.  Indexed by the GLOBAL cell (base.cell0 + i).
@@ -111,6 +111,7 @@ struct LookupTable {
   const float* rowblk;
 };
 #define AIRICE_ROWBLK 8
+cudaError_t launch_unpack_table(const float4* rec, const float* row_h, int64_t cells, int n_th, float* c0, int64_t stride, cudaStream_t s);
 cudaError_t launch_pack_table(const float* const* cols32, int64_t cells, int n_h, int n_th, float* x, float4* rec,
                               float* row_h, int* row_first, int* row_last, float* rowblk, cudaStream_t s);
 struct LookupArgs {
@@ -136,8 +137,9 @@ struct InIceArgs {
   // length.  Pass 1 (all pairs: direct + reflected) appends to it; pass 2 (persistent lanes stepping the root-search
   // state machine, each taking the next list entry when its own is finished) and pass 3 (times, paths, angles) walk it.
   int32_t* ra_list;   // [n]
-  int32_t* ra_count;  // [3], zeroed by launch_inice: [0] entries at the front of the list (pairs searching for two
-                      // refracted rays), [1] next list position to hand out (pass 2), [2] entries at the back
+  int32_t* ra_count;  // [8], zeroed by launch_inice: [0] entries at the front of the list (pairs searching for two
+                      // refracted rays), [1] next list position to hand out (pass 2), [2] entries at the back; [4..7] =
+                      // two u64: fRaa evaluations and turning-depth falsepos steps pass 2 ran (work census)
   double* ra_lad;     // [6][n] ladder results (L, f(L), z_max of the two candidate roots) per list entry, pass 2 -> pass 3
 };
 cudaError_t launch_inice(const InIceArgs& a, cudaStream_t s);

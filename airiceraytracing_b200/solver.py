@@ -472,6 +472,13 @@ def _inice_focusing(self, zT, xR, zR):
     return out
 
 
+def _inice_ladder_stats(self):
+    """(pairs searching two roots, pairs searching one, fRaa evaluations, turning-depth steps) of the last in-ice solve"""
+    v = (C.c_int64 * 4)()
+    check(self.lib.airice_inice_ladder_stats(self.handle, v))
+    return tuple(int(x) for x in v)
+
+
 def _inice_quadrature_stats(self):
     v = (C.c_int64 * 2)()
     check(self.lib.airice_inice_quadrature_stats(self.handle, v))
@@ -585,6 +592,7 @@ AirIceSolver.inice_two_rays_att_host = _inice_two_rays_att_host
 AirIceSolver.inice_attenuation = _inice_attenuation
 AirIceSolver.inice_focusing = _inice_focusing
 AirIceSolver.inice_quadrature_stats = _inice_quadrature_stats
+AirIceSolver.inice_ladder_stats = _inice_ladder_stats
 AirIceSolver.inice_table_create = _inice_table_create
 
 

@@ -488,6 +488,20 @@ def run_ours(args):
         popc = torch.tensor([bin(i).count("1") for i in range(16)], device=dev)[mk.long()]
         extras["inice"] = {"pairs_per_gpu": ni, "ms": ms, "solves_per_s": world * ni / ms * 1e3,
                            "branch_count_fractions": [float((popc == k).double().mean()) for k in range(3)]}
+        # algorithmic work of the refracted-ray ladder (pass 2, ~80 % of the time), SURVEY 8(d) flop-equivalents: a falsepos
+        # step of the turning-depth search = 2 exp + ~20 arithmetic = 80; an evaluation of fRaa on top of it = 1 exp, 3 log,
+        # 4 sqrt, 2 div, ~30 arithmetic = 300.  Counted by the kernel itself (airice_inice_ladder_stats).
+        two, one, n_ev, n_zs = solver.inice_ladder_stats()
+        work = 80.0 * n_zs + 300.0 * n_ev
+        extras["inice"]["ladder"] = {"pairs_searching_two_roots": two, "pairs_searching_one_root": one,
+                                     "fraa_evaluations": n_ev, "turning_depth_steps": n_zs,
+                                     "fraa_evaluations_per_listed_pair": n_ev / max(two + one, 1),
+                                     "algorithmic_flop_per_pair": work / ni}
+        rooflines.append({"kernel": "airice_inice_ladder_kernel (+ pass 1 and 3 in the denominator)", "bound": "fp64",
+                          "achieved": work / ms / 1e9, "peak": peak_tf, "unit": "TFLOP/s", "frac": work / ms / 1e9 / peak_tf,
+                          "accounting": "80 flop-eq per turning-depth falsepos step + 300 per fRaa evaluation (kernel-counted); the "
+                                        "direct / reflected searches of pass 1 are not credited", "ms": ms,
+                          "lanes_per_instruction": facts.get("airice_inice_ladder_kernel", {}).get("lanes_per_instruction")})
         # the same through the host-buffer C ABI (pinned memory; 24 B in, 233 B out per pair, copies inside the timing)
         pz0, px1, pz1 = z0.cpu().pin_memory(), x1.cpu().pin_memory(), z1.cpu().pin_memory()
         pout = torch.empty((29, ni), dtype=torch.float64).pin_memory()

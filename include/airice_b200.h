@@ -157,6 +157,11 @@ int airice_inice_two_rays_device(airice_ctx *ctx, int64_t n, const double *d_rx_
 int airice_inice_two_rays_host(airice_ctx *ctx, int64_t n, const double *rx_depth, const double *distance,
                                const double *tx_depth, double *out, int32_t *ignore);
 
+/* Work census of the LAST airice_inice_solve_device / two_rays call of the context (its refracted-ray ladder, pass 2):
+ * out[0], out[1] = pairs that searched for two / one refracted root, out[2] = evaluations of the root function fRaa,
+ * out[3] = falsepos steps of the nested turning-depth search.  Diagnostics for the roofline accounting; synchronises. */
+int airice_inice_ladder_stats(airice_ctx *ctx, int64_t out[4]);
+
 /* ---- kernels 4c-4e: attenuation, focusing factor and the in-ice interpolation table.
  * airice_inice_two_rays_att_*: IceRayTracing::GetRayTracingSolutions WITH its A0 / frequency / AttRay arguments
  * (IceRayTracing.cc:2907-3210): AttRay[k] = 1 - integral of A0 / L_att(z, f) along ray k (GetTotalAttenuationDirect /
