@@ -132,7 +132,10 @@ struct airice_table {
   float* row_h = nullptr;
   int* row_first = nullptr;
   int* row_last = nullptr;
-  float* rowblk = nullptr;     // per-row search blocks (header + first tree levels of the index halving), kernels.cuh
+  float* rowblk = nullptr;     // per-row header blocks, kernels.cuh
+  float4* rowpar = nullptr;    // per-row coordinate parameters of the position table
+  uint16_t* lut = nullptr;     // position table: AIRICE_LUT_EDGES u16 per row (nullptr: rows too long for it)
+  int lut_shift = -1;
   int64_t n_h = 0, n_th = 0, cells = 0;
   double loop_stop_h = 0, h_step = 0;
   mutable std::vector<cudaStream_t> used;   // streams that ran lookups on this table (besides the build stream 0)
@@ -146,6 +149,7 @@ struct airice_table {
     t.cells = cells; t.n_h = (int)n_h; t.n_th = (int)n_th;
     t.loop_stop_h = loop_stop_h; t.h_step = h_step;
     t.row_first = row_first; t.row_last = row_last; t.rowblk = rowblk;
+    t.lut = lut_shift >= 0 ? lut : nullptr; t.lut_shift = lut_shift >= 0 ? lut_shift : 0;
     return t;
   }
 };
@@ -238,7 +242,9 @@ int pack_alloc(airice_table* t) {
   const size_t rowh_bytes = (sizeof(float) * (size_t)t->n_h + 255) / 256 * 256;
   const size_t range_bytes = (sizeof(int) * (size_t)t->n_h + 255) / 256 * 256;
   const size_t blk_bytes = (sizeof(float) * AIRICE_ROWBLK * (size_t)t->n_h + 255) / 256 * 256;
-  t->pack_bytes = rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes + blk_bytes;
+  const size_t par_bytes = (sizeof(float4) * (size_t)t->n_h + 255) / 256 * 256;
+  const size_t lut_bytes = (sizeof(uint16_t) * AIRICE_LUT_EDGES * (size_t)t->n_h + 255) / 256 * 256;
+  t->pack_bytes = rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes + blk_bytes + par_bytes + lut_bytes;
   cudaError_t e = table_alloc(t->ctx, &t->pack, t->pack_bytes);
   if (e != cudaSuccess) { t->pack = nullptr; return cuda_fail(e, "cudaMalloc(lookup layout)"); }
   char* base = (char*)t->pack;
@@ -248,6 +254,9 @@ int pack_alloc(airice_table* t) {
   t->row_first = (int*)(base + rec_bytes + x_bytes + rowh_bytes);
   t->row_last = (int*)(base + rec_bytes + x_bytes + rowh_bytes + range_bytes);
   t->rowblk = (float*)(base + rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes);
+  t->rowpar = (float4*)(base + rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes + blk_bytes);
+  t->lut = (uint16_t*)(base + rec_bytes + x_bytes + rowh_bytes + 2 * range_bytes + blk_bytes + par_bytes);
+  t->lut_shift = lut_shift_for(t->n_th);
   return 0;
 }
 // ... and fill it from the column-major form.
@@ -255,7 +264,7 @@ int pack_table(airice_table* t) {
   int rc = pack_alloc(t);
   if (rc) return rc;
   cudaError_t e = launch_pack_table(t->cols, t->cells, (int)t->n_h, (int)t->n_th, t->x, t->rec, t->row_h, t->row_first, t->row_last,
-                                    t->rowblk, nullptr);
+                                    t->rowblk, t->rowpar, t->lut, t->lut_shift, nullptr);
   if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
   if (e != cudaSuccess) return cuda_fail(e, "pack table");
   return 0;
@@ -555,7 +564,7 @@ int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, 
   rc = build_rows(c, g, 0, n_h, nullptr, nullptr, nullptr, &ma);
   for (int q = 0; q < n_ant && rc == 0; q++) {
     e = launch_row_ranges(out[q]->x, out[q]->row_h, cells, (int)n_h, (int)g.n_th, out[q]->row_first, out[q]->row_last, out[q]->rowblk,
-                          nullptr);
+                          out[q]->rowpar, out[q]->lut, out[q]->lut_shift, nullptr);
     if (e != cudaSuccess) rc = cuda_fail(e, "row ranges");
   }
   if (rc == 0 && (e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "multi-antenna tables");
@@ -859,6 +868,13 @@ int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* d
   return 0;
 }
 
+// test hook: AIRICE_LOOKUP_LITERAL=1 makes every lookup run the literal index search (halvings + scan in the dense column)
+// instead of the position table; both must return the same bits (tests/test_gpu_parity.py)
+static int lookup_literal() {
+  const char* v = std::getenv("AIRICE_LOOKUP_LITERAL");
+  return (v && v[0] == '1') ? 1 : 0;
+}
+
 int airice_lookup_device(airice_ctx* c, const airice_table* t, int64_t n, const double* d_h_cm, const double* d_dist_cm,
                          double* const* d_out, uint8_t* d_ok, void* stream) {
   if (!c || !t) return fail(-1, "null argument");
@@ -869,6 +885,7 @@ int airice_lookup_device(airice_ctx* c, const airice_table* t, int64_t n, const 
   std::memset(&a, 0, sizeof(a));
   a.n = n; a.h_cm = d_h_cm; a.d_cm = d_dist_cm; a.ok = d_ok;
   for (int k = 0; k < AIRICE_LOOKUP_NCOLS; k++) a.out[k] = d_out[k];
+  a.literal = lookup_literal();
   if (t->ctx != c) return fail(-1, "table belongs to another (or a destroyed) context");
   t->note_stream((cudaStream_t)stream);
   cudaError_t e = launch_lookup(c->medium, t->view(), a, (cudaStream_t)stream);
@@ -897,6 +914,7 @@ int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const do
     std::memset(&a, 0, sizeof(a));
     a.n = m; a.h_cm = dh; a.d_cm = dh + chunk; a.ok = (uint8_t*)(dh + (2 + nc) * chunk);
     for (int k = 0; k < nc; k++) a.out[k] = dh + (2 + k) * chunk;
+    a.literal = lookup_literal();
     t->note_stream(s);
     cudaError_t e = launch_lookup(c->medium, t->view(), a, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_lookup");

@@ -310,21 +310,90 @@ __global__ void airice_unpack_kernel(const float4* __restrict__ rec, const float
   o[9 * stride] = c.x; o[10 * stride] = c.y;
 }
 
+// ---- position table (LookupTable::lut).  u(X) = X / (X + xm) with xm = the X of the row's middle bin is within a factor
+// two of linear in the launch angle, i.e. in the bin index, over the whole row (X = H tan(incidence) spans 0 .. 4e7 m), so
+// AIRICE_LUT_EDGES samples of the inverse bin(u) and linear interpolation between them hit the bin of FindClosestTHD
+// (M.cc:1128-1193) exactly for 99.3 % of random queries and are one bin off for the rest (measured on reference-grid rows).
+// Query and build evaluate the coordinate with this one function (same float operations, same rounding).
+__device__ __forceinline__ float lut_coord(float x, float xm, float ulo, float scale) { return (x / (x + xm) - ulo) * scale; }
+
+// One warp per PHYSICAL row: is X strictly decreasing and finite over the row's own trimmed window [row_first, row_last]
+// (then "first bin with X <= d" IS the result of the halvings + scan, see fast_row), the coordinate parameters, and the
+// table: entry k = fractional bin at which the coordinate falls through k.  rowpar[row] = {xm, u_lo, scale, ok (int bits)}.
+__global__ void __launch_bounds__(128) airice_row_lut_kernel(const float* __restrict__ X, int n_h, int n_th, const int* __restrict__ row_first,
+                                                             const int* __restrict__ row_last, int shift, float4* rowpar, uint16_t* lut) {
+  const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (r >= n_h) return;
+  const int base = r * n_th;
+  const int s = row_first[r], e = row_last[r];
+  uint16_t* L = lut + (int64_t)r * AIRICE_LUT_EDGES;
+  const int K = AIRICE_LUT_EDGES - 1;
+  bool ok = shift >= 0 && s >= base && e <= base + n_th - 1 && e - s >= 4;
+  if (ok) {
+    bool mono = true;
+    for (int ip = s + 1 + lane; ip <= e; ip += 32) mono = mono && (X[ip] < X[ip - 1]);
+    ok = __all_sync(0xffffffffu, mono);
+  }
+  float xm = 0.f, ulo = 0.f, scale = 0.f;
+  if (ok) {
+    const float xs = X[s], xe = X[e];
+    xm = X[(s + e) / 2];
+    ulo = xe / (xe + xm);
+    const float uhi = xs / (xs + xm);
+    scale = (float)K / (uhi - ulo);
+    ok = (xm > 0.f) && (xs < 3.0e38f) && (xe >= 0.f) && (uhi > ulo) && (scale < 3.0e38f);
+  }
+  for (int k = lane; k <= K; k += 32) L[k] = 0;
+  __syncwarp();
+  if (ok) {
+    const float fs = (float)(1 << shift);
+    for (int ip = s + 1 + lane; ip <= e; ip += 32) {
+      const float fp = lut_coord(X[ip - 1], xm, ulo, scale), fc = lut_coord(X[ip], xm, ulo, scale);   // fp > fc
+      float kf = ceilf(fc);
+      kf = kf < 0.f ? 0.f : kf;
+      for (int k = (int)kf; (float)k < fp && k <= K; k++) {
+        const float pos = (float)(ip - 1 - base) + (fp - (float)k) / (fp - fc);
+        const float q = rintf(pos * fs);
+        L[k] = (uint16_t)(q < 65535.f ? q : 65535.f);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) { L[K] = (uint16_t)((s - base) << shift); L[0] = (uint16_t)((e - base) << shift); }
+  }
+  if (lane == 0) rowpar[r] = make_float4(xm, ulo, scale, __int_as_float(ok ? 1 : 0));
+}
+
 // Per-row header blocks (LookupTable::rowblk), one thread per (row, slot): everything FindClosestAirTxHeight
-// (M.cc:1033-1126) derives per row, in ONE 32-byte sector per row instead of four dependent loads --
-// {s1, e1 (int bits), X[s1], X[s2], h(s1), h(s2), col0[row], 0}: the trimmed window, the largest distance of the row and of
-// the second row (the first row's window shifted by one row, M.cc:1113-1121), and the three heights the query compares with.
+// (M.cc:1033-1126) derives per row, in ONE 64-byte block per row instead of four dependent loads --
+// {s1, e1 (int bits), X[s1], X[s2], h(s1), h(s2), col0[row], flags | coordinate parameters of the row | of the second row}:
+// the trimmed window, the largest distance of the row and of the second row (the first row's window shifted by one row,
+// M.cc:1113-1121), the three heights the query compares with, and what the position table needs for both rows.
 __global__ void airice_row_block_kernel(const float* __restrict__ X, const float* __restrict__ row_h, int64_t cells, int n_h, int n_th,
-                                        const int* __restrict__ row_first, const int* __restrict__ row_last, float* rowblk) {
+                                        const int* __restrict__ row_first, const int* __restrict__ row_last,
+                                        const float4* __restrict__ rowpar, float* rowblk) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)n_h * AIRICE_ROWBLK) return;
   const int row = (int)(t / AIRICE_ROWBLK), slot = (int)(t - (int64_t)row * AIRICE_ROWBLK);
   const int total = (int)cells - 1;
   const int s1 = row_first[row], e1 = row_last[row];
-  int s2 = s1 - n_th;
+  int s2 = s1 - n_th, e2 = e1 - n_th;
   if (s2 < 0) s2 = s1 + n_th;
+  if (e2 < 0) e2 = e1 + n_th;
   auto xat = [&](int i) { return (i >= 0 && i <= total) ? X[i] : 0.f; };
   auto hat = [&](int i) { const int r = i / n_th; return (i >= 0 && r < n_h) ? row_h[r] : 0.f; };
+  // the row the second window lies in, if it lies in one row that can answer it from its table (its own trimmed window
+  // must contain the shifted one: outside it sit unusable cells)
+  const int r2 = (s2 >= 0 && s2 <= total) ? s2 / n_th : -1;
+  const float4 p1 = rowpar[row];
+  float4 p2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool ok1 = __float_as_int(p1.w) != 0, ok2 = false;
+  if (r2 >= 0 && r2 < n_h && e2 >= s2 && e2 <= total && e2 / n_th == r2) {
+    p2 = rowpar[r2];
+    ok2 = __float_as_int(p2.w) != 0 && s2 >= row_first[r2] && e2 <= row_last[r2];
+  }
+  // the window the kernel walks for the first row is [s1, e1] itself; a first record at index -1 is left to the literal code
+  ok1 = ok1 && s1 >= 1;
+  ok2 = ok2 && s2 >= 1;
   float v = 0.f;
   switch (slot) {
     case 0: v = __int_as_float(s1); break;
@@ -334,6 +403,13 @@ __global__ void airice_row_block_kernel(const float* __restrict__ X, const float
     case 4: v = hat(s1); break;
     case 5: v = hat(s2); break;
     case 6: v = hat(row); break;     // column 0 indexed with the ROW index, as the reference writes it (M.cc:1076)
+    case 7: v = __int_as_float((ok1 ? 1 : 0) | (ok2 ? 2 : 0)); break;
+    case 8: v = p1.x; break;
+    case 9: v = p1.y; break;
+    case 10: v = p1.z; break;
+    case 12: v = p2.x; break;
+    case 13: v = p2.y; break;
+    case 14: v = p2.z; break;
     default: v = 0.f; break;
   }
   rowblk[t] = v;
@@ -395,6 +471,74 @@ __device__ __forceinline__ void row_interp(const LookupTable& t, double d, int i
   }
 }
 
+// FindClosestTHD + GetParValues of one row from the position table.  On a window [s, e] over which X is strictly
+// decreasing and finite the literal search (index halvings M.cc:1131-1143, then the scan M.cc:1148-1168) ends at
+// index2 = the first bin of the window with X <= d and index1 = index2 - 1 whatever path the halvings took: they keep
+// X[s] > d (or s at the window start) and X[e] < d (or e at the window end), an exact hit X[mid] == d stops them with mid
+// inside, and the scan walks down the strictly decreasing |X - d| until the first X <= d.  So a PREDICTED bin ip is the
+// literal result iff X[ip] <= d and (X[ip-1] > d or ip == s) -- checked on the X fields of the two records the
+// interpolation reads anyway.  One bin off (0.7 % of queries): the neighbouring record is fetched.  Anything else
+// (two bins off, no bin with X <= d in the window, record -1) returns false and the literal code runs.
+struct RowRecs { float4 a0, a1, a2, b0, b1, b2; };
+__device__ __forceinline__ void load_rec3(const float4* __restrict__ rec, int i, float4& r0, float4& r1, float4& r2) {
+  r0 = __ldcs(rec + 3 * (int64_t)i); r1 = __ldcs(rec + 3 * (int64_t)i + 1); r2 = __ldcs(rec + 3 * (int64_t)i + 2);
+}
+__device__ __forceinline__ bool fast_row(const LookupTable& t, double d, int s, int e, float xm, float ulo, float scale,
+                                         double* par) {
+  const int K = AIRICE_LUT_EDGES - 1;
+  const int r = s / t.n_th, base = r * t.n_th;
+  const float df = (float)d;
+  float kf = lut_coord(df, xm, ulo, scale);
+  kf = kf > 0.f ? kf : 0.f;                      // also NaN -> 0
+  int k = (int)kf;
+  k = k < K - 1 ? k : K - 1;
+  float fr = kf - (float)k;
+  fr = fr < 1.f ? fr : 1.f;
+  const uint16_t* L = t.lut + (int64_t)r * AIRICE_LUT_EDGES;
+  const float l0 = (float)__ldg(L + k), l1 = (float)__ldg(L + k + 1);
+  const float pos = (l0 + (l1 - l0) * fr) * (1.0f / (float)(1 << t.lut_shift));
+  int ip = base + (int)ceilf(pos);
+  ip = ip < s ? s : (ip > e ? e : ip);
+  RowRecs q;
+  load_rec3(t.rec, ip - 1, q.a0, q.a1, q.a2);
+  load_rec3(t.rec, ip, q.b0, q.b1, q.b2);
+  bool found = false;
+#pragma unroll 1
+  for (int tries = 0; tries < 2; tries++) {
+    const double xa = (double)q.a0.x, xb = (double)q.b0.x;
+    if (xb <= d) {
+      if (xa > d || ip == s) { found = true; break; }
+      ip--;                                      // the crossing is one bin earlier (ip > s here)
+      q.b0 = q.a0; q.b1 = q.a1; q.b2 = q.a2;
+      load_rec3(t.rec, ip - 1, q.a0, q.a1, q.a2);
+    } else {
+      if (!(xb > d) || ip >= e) return false;    // NaN, or no bin with X <= d left in the window
+      ip++;
+      q.a0 = q.b0; q.a1 = q.b1; q.a2 = q.b2;
+      load_rec3(t.rec, ip, q.b0, q.b1, q.b2);
+    }
+  }
+  if (!found) {
+    const double xa = (double)q.a0.x, xb = (double)q.b0.x;
+    if (!(xb <= d && (xa > d || ip == s))) return false;
+  }
+  const double y1[10] = {q.a0.x, q.a0.y, q.a0.z, q.a0.w, q.a1.x, q.a1.y, q.a1.z, q.a1.w, q.a2.x, q.a2.y};
+  const double y2[10] = {q.b0.x, q.b0.y, q.b0.z, q.b0.w, q.b1.x, q.b1.y, q.b1.z, q.b1.w, q.b2.x, q.b2.y};
+  // closest value of the scan (M.cc:1170-1176), then GetParValues (M.cc:1205-1235)
+  double cv = fabs(d - y2[0]);
+  const double other = fabs(d - y1[0]);
+  if (cv > other) cv = other;
+  if (cv != 0) {
+    const double w = (d - y1[0]) / (y2[0] - y1[0]);
+#pragma unroll
+    for (int j = 0; j < 10; j++) par[j] = y1[j] + (y2[j] - y1[j]) * w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 10; j++) par[j] = y2[j];
+  }
+  return true;
+}
+
 #ifndef AIRICE_LOOKUP_MINBLOCKS
 #define AIRICE_LOOKUP_MINBLOCKS 4
 #endif
@@ -414,9 +558,10 @@ __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_look
   const int cur = (int)floor((h - t.loop_stop_h) / t.h_step);
   const int row = t.n_h - cur - 1;
   if (h <= maxh && h >= minh && h > 0 && row >= 0 && row < t.n_h) {
-    const float* blk = t.rowblk + (int64_t)row * AIRICE_ROWBLK;
-    const float4 hd0 = __ldg((const float4*)blk), hd1 = __ldg((const float4*)blk + 1);
+    const float4* blk = (const float4*)(t.rowblk + (int64_t)row * AIRICE_ROWBLK);
+    const float4 hd0 = __ldg(blk), hd1 = __ldg(blk + 1), hp1 = __ldg(blk + 2), hp2 = __ldg(blk + 3);
     const int s1 = __float_as_int(hd0.x), e1 = __float_as_int(hd0.y);
+    const int fl = (t.lut && !a.literal) ? __float_as_int(hd1.w) : 0;
     const double cv0 = fabs((double)hd1.z - h);  // column 0 indexed with the ROW index, as written (M.cc:1076)
     int s2 = s1 - t.n_th, e2 = e1 - t.n_th;
     if (s2 < 0) s2 = s1 + t.n_th;
@@ -428,14 +573,21 @@ __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_look
     // "out of range": d beyond the row's largest distance (M.cc:1196-1204), else search and interpolate
     const bool in1 = d <= (double)hd0.z;
     const bool in2 = two && (d <= (double)hd0.w);
-    int a1 = s1, b1 = e1, a2 = s2, b2 = e2;
-    halve_thd2(t.x, d, in1, a1, b1, in2, a2, b2);
-    int i1 = 0, i2 = 0, j1 = 0, j2 = 0;
-    double c1 = 0.0, c2 = 0.0;
-    if (in1) scan_thd(t.x, d, a1, b1, i1, i2, c1);
-    if (in2) scan_thd(t.x, d, a2, b2, j1, j2, c2);
-    if (in1) row_interp(t, d, i1, i2, c1, P1);
-    if (in2) row_interp(t, d, j1, j2, c2, P2);
+    // the common case: both rows from the position table (rowblk -> table -> records: three dependent steps)
+    bool lit1 = in1, lit2 = in2;
+    if (in1 && (fl & 1)) lit1 = !fast_row(t, d, s1, e1, hp1.x, hp1.y, hp1.z, P1);
+    if (in2 && (fl & 2)) lit2 = !fast_row(t, d, s2, e2, hp2.x, hp2.y, hp2.z, P2);
+    if (lit1 || lit2) {
+      // the literal search for the row(s) the table could not answer
+      int a1 = s1, b1 = e1, a2 = s2, b2 = e2;
+      halve_thd2(t.x, d, lit1, a1, b1, lit2, a2, b2);
+      int i1 = 0, i2 = 0, j1 = 0, j2 = 0;
+      double c1 = 0.0, c2 = 0.0;
+      if (lit1) scan_thd(t.x, d, a1, b1, i1, i2, c1);
+      if (lit2) scan_thd(t.x, d, a2, b2, j1, j2, c2);
+      if (lit1) row_interp(t, d, i1, i2, c1, P1);
+      if (lit2) row_interp(t, d, j1, j2, c2, P2);
+    }
     oor1 = !in1;
     oor2 = two ? !in2 : oor1;
     // height interpolation (M.cc:1376-1401)
@@ -552,13 +704,24 @@ cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const Solve
   return cudaGetLastError();
 }
 
+int lut_shift_for(int64_t n_th) {
+  // positions are bins of a row in u16 fixed point: up to 6 fraction bits while n_th << shift stays below 65536
+  if (n_th <= 0 || n_th > 65535) return -1;
+  int sh = 0;
+  while (sh < 6 && (n_th << (sh + 1)) <= 65535) sh++;
+  return sh;
+}
+
 cudaError_t launch_row_ranges(const float* x, const float* row_h, int64_t cells, int n_h, int n_th, int* row_first, int* row_last,
-                              float* rowblk, cudaStream_t s) {
+                              float* rowblk, float4* rowpar, uint16_t* lut, int lut_shift, cudaStream_t s) {
   airice_row_range_kernel<<<(n_h + 127) / 128, 128, 0, s>>>(x, cells, n_h, n_th, row_first, row_last);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  airice_row_lut_kernel<<<(unsigned)(((int64_t)n_h * 32 + 127) / 128), 128, 0, s>>>(x, n_h, n_th, row_first, row_last, lut_shift, rowpar, lut);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
   const int64_t threads = (int64_t)n_h * AIRICE_ROWBLK;
-  airice_row_block_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(x, row_h, cells, n_h, n_th, row_first, row_last, rowblk);
+  airice_row_block_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(x, row_h, cells, n_h, n_th, row_first, row_last, rowpar, rowblk);
   return cudaGetLastError();
 }
 
@@ -570,14 +733,15 @@ cudaError_t launch_unpack_table(const float4* rec, const float* row_h, int64_t c
 }
 
 cudaError_t launch_pack_table(const float* const* c, int64_t cells, int n_h, int n_th, float* x, float4* rec,
-                              float* row_h, int* row_first, int* row_last, float* rowblk, cudaStream_t s) {
+                              float* row_h, int* row_first, int* row_last, float* rowblk, float4* rowpar, uint16_t* lut,
+                              int lut_shift, cudaStream_t s) {
   const int64_t blocks = (cells + 255) / 256;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
   airice_pack_kernel<<<dim3((unsigned)blocks), 256, 0, s>>>(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10],
                                                            cells, n_th, x, rec, row_h);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  return launch_row_ranges(x, row_h, cells, n_h, n_th, row_first, row_last, rowblk, s);
+  return launch_row_ranges(x, row_h, cells, n_h, n_th, row_first, row_last, rowblk, rowpar, lut, lut_shift, s);
 }
 
 // ---- kernel 5: ray paths.  Step 1: one thread per ray plans its segments; step 2: one thread per point.

@@ -53,7 +53,8 @@ struct TableMultiArgs {
 };
 // per-row trim ranges of a packed table (the part of launch_pack_table the fused pass cannot do per cell)
 cudaError_t launch_row_ranges(const float* x, const float* row_h, int64_t cells, int n_h, int n_th, int* row_first, int* row_last,
-                              float* rowblk, cudaStream_t s);
+                              float* rowblk, float4* rowpar, uint16_t* lut, int lut_shift, cudaStream_t s);
+int lut_shift_for(int64_t n_th);   // fraction bits of the position table (-1: rows too long for u16 positions, no table)
 cudaError_t launch_table_multi(const AirIceMedium& m, const AirIcePlan& p, const TableMultiArgs& a, cudaStream_t s);
 
 // kernel 1b: the same forward tracer on arbitrary (theta, h) cells (batched GetRayTracingSolutions, M.cc:1796-2017);
@@ -107,19 +108,31 @@ struct LookupTable {
   double loop_stop_h, h_step;
   const int* row_first;  // per row: first/last bin with a usable X (trim of M.cc:1050-1072), precomputed
   const int* row_last;
-  // per-row header, AIRICE_ROWBLK floats (one 32-byte sector): {s1, e1 (int bits), X[s1], X[s2], h(s1), h(s2), col0[row], 0}
+  // per-row header, AIRICE_ROWBLK floats (one 64-byte block): {s1, e1 (int bits), X[s1], X[s2], h(s1), h(s2), col0[row],
+  // flags (int bits: 1 = the row's window can be answered from the position table, 2 = the second row's) |
+  // xm, u_lo, scale, 0 of the row | the same of the second row}
   const float* rowblk;
+  // per-row position table (round 2): AIRICE_LUT_EDGES u16 per PHYSICAL row.  Entry k is the (fractional, lut_shift
+  // fraction bits) bin of the row at which u(X) = X / (X + xm) falls through u_lo + k / scale; a query's bin of
+  // FindClosestTHD is predicted by linear interpolation between two entries and then VERIFIED on the records it is
+  // going to read anyway (X[i2] <= d < X[i1] on a strictly decreasing window is the literal search's result), so the
+  // eight dependent index halvings and the linear scan in the dense column are the fallback, not the rule.
+  const uint16_t* lut;
+  int lut_shift;
 };
-#define AIRICE_ROWBLK 8
+#define AIRICE_ROWBLK 16
+#define AIRICE_LUT_EDGES 128
 cudaError_t launch_unpack_table(const float4* rec, const float* row_h, int64_t cells, int n_th, float* c0, int64_t stride, cudaStream_t s);
 cudaError_t launch_pack_table(const float* const* cols32, int64_t cells, int n_h, int n_th, float* x, float4* rec,
-                              float* row_h, int* row_first, int* row_last, float* rowblk, cudaStream_t s);
+                              float* row_h, int* row_first, int* row_last, float* rowblk, float4* rowpar, uint16_t* lut,
+                              int lut_shift, cudaStream_t s);
 struct LookupArgs {
   int64_t n;
   const double* h_cm;
   const double* d_cm;
   double* out[AIRICE_LOOKUP_NCOLS];  // same 9 slots as the CM_RAD solve
   uint8_t* ok;                       // solution flag (M.cc:1356-1449)
+  int literal;                       // test hook: 1 = always run the literal index search (AIRICE_LOOKUP_LITERAL=1)
 };
 cudaError_t launch_lookup(const AirIceMedium& m, const LookupTable& t, const LookupArgs& a, cudaStream_t s);
 
