@@ -562,9 +562,17 @@ int airice_table_create_multi(airice_ctx* c, int n_ant, const double* depths_m, 
   ma.x = (float* const*)(d_blocks + n_ant);
   ma.row_h = (float* const*)(d_blocks + 2 * (size_t)n_ant);
   rc = build_rows(c, g, 0, n_h, nullptr, nullptr, nullptr, &ma);
-  for (int q = 0; q < n_ant && rc == 0; q++) {
-    e = launch_row_ranges(out[q]->x, out[q]->row_h, cells, (int)n_h, (int)g.n_th, out[q]->row_first, out[q]->row_last, out[q]->rowblk,
-                          out[q]->rowpar, out[q]->lut, out[q]->lut_shift, nullptr);
+  for (int q0 = 0; q0 < n_ant && rc == 0; q0 += AIRICE_ROWPREP_MAX) {
+    RowPrepBatch b;
+    std::memset(&b, 0, sizeof(b));
+    b.n_tab = (n_ant - q0 < AIRICE_ROWPREP_MAX) ? (n_ant - q0) : AIRICE_ROWPREP_MAX;
+    b.cells = cells; b.n_h = (int)n_h; b.n_th = (int)g.n_th; b.lut_shift = out[q0]->lut_shift;
+    for (int k = 0; k < b.n_tab; k++) {
+      const airice_table* t = out[q0 + k];
+      b.tab[k].x = t->x; b.tab[k].row_h = t->row_h; b.tab[k].row_first = t->row_first; b.tab[k].row_last = t->row_last;
+      b.tab[k].rowblk = t->rowblk; b.tab[k].rowpar = t->rowpar; b.tab[k].lut = t->lut;
+    }
+    e = launch_row_prep(b, nullptr);
     if (e != cudaSuccess) rc = cuda_fail(e, "row ranges");
   }
   if (rc == 0 && (e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "multi-antenna tables");

@@ -83,12 +83,47 @@ __global__ void __launch_bounds__(kThreads) airice_table_kernel(const AirIceMedi
   }
 }
 
-// One thread per cell, all antennas: air walk + surface once, then one ice leg (1 sqrt, 2 log, 1 atan) and 11 float
-// stores per antenna.  Same arithmetic as airice_table_kernel<false, true> per antenna, hence the same bits.
-__global__ void __launch_bounds__(kThreads) airice_table_multi_kernel(const AirIceMedium m, const AirIcePlan p,
-                                                                      const TableMultiArgs ma) {
+// ---- bulk stores (cp.async.bulk, SASS UBLKCP): a CTA's records of one antenna are one contiguous run in global memory
+// (kMultiThreads x 48 B) and its dense-X values another (kMultiThreads x 4 B), so the CTA stages them in shared memory and
+// ONE thread hands each run to the copy engine -- 2 store instructions per CTA and antenna instead of 4 per thread, whole
+// lines written at once (a warp's float4 record stores touch a 1.5 KB span three times, a third of it each).
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#ifndef AIRICE_MULTI_THREADS
+#define AIRICE_MULTI_THREADS 128
+#endif
+#ifndef AIRICE_MULTI_BULK
+#define AIRICE_MULTI_BULK 0
+#endif
+#ifndef AIRICE_MULTI_MINBLOCKS
+#define AIRICE_MULTI_MINBLOCKS 1
+#endif
+#ifndef AIRICE_MULTI_UNROLL
+#define AIRICE_MULTI_UNROLL 1
+#endif
+constexpr int kMultiThreads = AIRICE_MULTI_THREADS;
+
+// One thread per cell, all antennas: air walk + surface once, then one ice leg (1 sqrt, 2 log, 1 atan) per antenna.
+// Same arithmetic as airice_table_kernel<false, true> per antenna, hence the same bits.  Output per antenna: the lookup
+// layout (48-byte record + dense X; bulk stores from a double-buffered staging area when the CTA is full and the runs
+// are 16-byte aligned) and/or the 11 reference-layout columns (plain stores).
+__global__ void __launch_bounds__(kMultiThreads, AIRICE_MULTI_MINBLOCKS) airice_table_multi_kernel(const AirIceMedium m, const AirIcePlan p,
+                                                                           const TableMultiArgs ma) {
+  __shared__ __align__(128) float4 s_rec[2][kMultiThreads * 3];
+  __shared__ __align__(128) float s_x[2][kMultiThreads];
   const TableArgs& a = ma.base;
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int tid = threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.x * kMultiThreads;
+  const int64_t i = i0 + tid;
+  // whole CTA or nothing: the staging path has barriers
+  const bool bulk = AIRICE_MULTI_BULK && ma.rec && !ma.blocks && (i0 + kMultiThreads <= a.ncells) && (((a.cell0 + i0) & 3) == 0);
   if (i >= a.ncells) return;
   const int64_t c = a.cell0 + i;
   const int64_t row = c / a.n_th;
@@ -104,7 +139,8 @@ __global__ void __launch_bounds__(kThreads) airice_table_multi_kernel(const AirI
   const AirIceIceTop it = airice_ice_top(m, p, al.L);
   const float f_h = (float)h, f_th = (float)theta, f_xa = (float)al.x, f_oa = (float)(al.t * m.c), f_ga = (float)al.g;
   const float f_ts = (float)r.trans_s, f_tp = (float)r.trans_p;
-#pragma unroll 1
+  constexpr int kUnrollQ = AIRICE_MULTI_UNROLL;
+#pragma unroll kUnrollQ
   for (int q = 0; q < ma.n_ant; q++) {
     const double xb = __ldg(ma.ant + 2 * q), nb = __ldg(ma.ant + 2 * q + 1);
     double xi, ti, gi, recv;
@@ -126,14 +162,33 @@ __global__ void __launch_bounds__(kThreads) airice_table_multi_kernel(const AirI
     }
     if (ma.rec) {
       const float f_x = (float)(al.x + xi);
-      float4* rq = ma.rec[q] + 3 * c;
-      ma.x[q][c] = f_x;
-      rq[0] = make_float4(f_x, (float)(ti * m.c), f_oa, f_th);
-      rq[1] = make_float4(f_xa, f_ts, f_tp, f_ga);
-      rq[2] = make_float4((float)gi, (float)recv, 0.f, 0.f);
+      const float4 r0 = make_float4(f_x, (float)(ti * m.c), f_oa, f_th);
+      const float4 r1 = make_float4(f_xa, f_ts, f_tp, f_ga);
+      const float4 r2 = make_float4((float)gi, (float)recv, 0.f, 0.f);
+      if (bulk) {
+        // buffer q & 1 was last read by the bulk group of antenna q - 2, which thread 0 saw finished before the barrier
+        // of antenna q - 1
+        const int b = q & 1;
+        float4* sr = &s_rec[b][tid * 3];       // stride 48 B: the eight threads of a quarter-warp cover all 32 banks
+        sr[0] = r0; sr[1] = r1; sr[2] = r2;
+        s_x[b][tid] = f_x;
+        fence_async_smem();
+        if (tid == 0) bulk_wait_read_all();
+        __syncthreads();
+        if (tid == 0) {
+          bulk_store_s2g(ma.rec[q] + 3 * (a.cell0 + i0), &s_rec[b][0], (uint32_t)(sizeof(float4) * 3 * kMultiThreads));
+          bulk_store_s2g(ma.x[q] + (a.cell0 + i0), &s_x[b][0], (uint32_t)(sizeof(float) * kMultiThreads));
+          bulk_commit();
+        }
+      } else {
+        float4* rq = ma.rec[q] + 3 * c;
+        ma.x[q][c] = f_x;
+        rq[0] = r0; rq[1] = r1; rq[2] = r2;
+      }
       if (j == 0) ma.row_h[q][row] = f_h;
     }
   }
+  if (bulk && tid == 0) bulk_wait_read_all();     // the staging area must outlive the copy engine's reads
 }
 
 __global__ void __launch_bounds__(kThreads) airice_forward_kernel(const AirIceMedium m, const AirIcePlan p, const ForwardArgs a) {
@@ -269,8 +324,11 @@ __device__ __forceinline__ bool usable_x(double v) {
 // Per-row trim of FindClosestAirTxHeight (M.cc:1050-1072) done once per table instead of once per query:
 // row_last = highest bin <= row end with a usable X, row_first = lowest bin >= row start with a usable X.
 // The scans run past the row like the reference's do (bounded by the table here).
-__global__ void airice_row_range_kernel(const float* __restrict__ X, int64_t cells, int n_h, int n_th, int* row_first,
-                                        int* row_last) {
+__global__ void airice_row_range_kernel(const RowPrepBatch b) {
+  const RowPrepTab& T = b.tab[blockIdx.y];
+  const float* __restrict__ X = T.x;
+  const int64_t cells = b.cells;
+  const int n_h = b.n_h, n_th = b.n_th;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_h) return;
   const int64_t lo = (int64_t)r * n_th, hi = lo + n_th - 1;
@@ -278,8 +336,8 @@ __global__ void airice_row_range_kernel(const float* __restrict__ X, int64_t cel
   while (s >= 0 && !usable_x((double)X[s])) s--;
   int64_t e = lo;
   while (e < cells && !usable_x((double)X[e])) e++;
-  row_last[r] = (int)s;
-  row_first[r] = (int)e;
+  T.row_last[r] = (int)s;
+  T.row_first[r] = (int)e;
 }
 
 // column-major reference layout -> lookup layout (dense X + 48-byte records + per-row height)
@@ -315,52 +373,67 @@ __global__ void airice_unpack_kernel(const float4* __restrict__ rec, const float
 // AIRICE_LUT_EDGES samples of the inverse bin(u) and linear interpolation between them hit the bin of FindClosestTHD
 // (M.cc:1128-1193) exactly for 99.3 % of random queries and are one bin off for the rest (measured on reference-grid rows).
 // Query and build evaluate the coordinate with this one function (same float operations, same rounding).
-__device__ __forceinline__ float lut_coord(float x, float xm, float ulo, float scale) { return (x / (x + xm) - ulo) * scale; }
+__device__ __forceinline__ float lut_coord(float x, float xm, float ulo, float scale) { return (__fdividef(x, x + xm) - ulo) * scale; }
 
-// One warp per PHYSICAL row: is X strictly decreasing and finite over the row's own trimmed window [row_first, row_last]
+// One CTA per PHYSICAL row: is X strictly decreasing and finite over the row's own trimmed window [row_first, row_last]
 // (then "first bin with X <= d" IS the result of the halvings + scan, see fast_row), the coordinate parameters, and the
 // table: entry k = fractional bin at which the coordinate falls through k.  rowpar[row] = {xm, u_lo, scale, ok (int bits)}.
-__global__ void __launch_bounds__(128) airice_row_lut_kernel(const float* __restrict__ X, int n_h, int n_th, const int* __restrict__ row_first,
-                                                             const int* __restrict__ row_last, int shift, float4* rowpar, uint16_t* lut) {
-  const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (r >= n_h) return;
+constexpr int kLutThreads = 128;
+constexpr int kLutStage = 2048;          // rows up to this many bins are staged in shared memory
+__global__ void __launch_bounds__(kLutThreads) airice_row_lut_kernel(const RowPrepBatch b) {
+  __shared__ float sx[kLutStage];
+  const RowPrepTab& T = b.tab[blockIdx.y];
+  const float* __restrict__ X = T.x;
+  const int n_th = b.n_th, shift = b.lut_shift;
+  const int r = blockIdx.x, tid = threadIdx.x;
   const int base = r * n_th;
-  const int s = row_first[r], e = row_last[r];
-  uint16_t* L = lut + (int64_t)r * AIRICE_LUT_EDGES;
+  // the row itself does not depend on its trim range: both are fetched in one round trip (the kernel is a chain of
+  // dependent cold loads per CTA otherwise: range -> window ends -> bins)
+  const bool staged = n_th <= kLutStage;
+  if (staged)
+    for (int j = tid; j < n_th; j += kLutThreads) sx[j] = X[base + j];
+  const int s = T.row_first[r], e = T.row_last[r];
+  uint16_t* L = T.lut + (int64_t)r * AIRICE_LUT_EDGES;
   const int K = AIRICE_LUT_EDGES - 1;
-  bool ok = shift >= 0 && s >= base && e <= base + n_th - 1 && e - s >= 4;
-  if (ok) {
-    bool mono = true;
-    for (int ip = s + 1 + lane; ip <= e; ip += 32) mono = mono && (X[ip] < X[ip - 1]);
-    ok = __all_sync(0xffffffffu, mono);
-  }
+  for (int k = tid; k <= K; k += kLutThreads) L[k] = 0;
+  __syncthreads();
+  bool ok = shift >= 0 && s >= base && e <= base + n_th - 1 && e - s >= 4;     // uniform over the CTA
+  auto xat = [&](int ip) { return staged ? sx[ip - base] : X[ip]; };            // ip inside the row
   float xm = 0.f, ulo = 0.f, scale = 0.f;
   if (ok) {
-    const float xs = X[s], xe = X[e];
-    xm = X[(s + e) / 2];
-    ulo = xe / (xe + xm);
-    const float uhi = xs / (xs + xm);
+    const float xs = xat(s), xe = xat(e);
+    xm = xat((s + e) / 2);
+    ulo = __fdividef(xe, xe + xm);
+    const float uhi = __fdividef(xs, xs + xm);
     scale = (float)K / (uhi - ulo);
     ok = (xm > 0.f) && (xs < 3.0e38f) && (xe >= 0.f) && (uhi > ulo) && (scale < 3.0e38f);
   }
-  for (int k = lane; k <= K; k += 32) L[k] = 0;
-  __syncwarp();
+  bool mono = true;
   if (ok) {
+    for (int ip = s + 1 + tid; ip <= e; ip += kLutThreads) mono = mono && (xat(ip) < xat(ip - 1));
+    // entry k (0 < k < K): bisect the window for the first bin whose X is at or below the X of coordinate k, then place
+    // the crossing between that bin and the one before it linearly in the coordinate
     const float fs = (float)(1 << shift);
-    for (int ip = s + 1 + lane; ip <= e; ip += 32) {
-      const float fp = lut_coord(X[ip - 1], xm, ulo, scale), fc = lut_coord(X[ip], xm, ulo, scale);   // fp > fc
-      float kf = ceilf(fc);
-      kf = kf < 0.f ? 0.f : kf;
-      for (int k = (int)kf; (float)k < fp && k <= K; k++) {
-        const float pos = (float)(ip - 1 - base) + (fp - (float)k) / (fp - fc);
-        const float q = rintf(pos * fs);
-        L[k] = (uint16_t)(q < 65535.f ? q : 65535.f);
+    for (int k = 1 + tid; k < K; k += kLutThreads) {
+      const float uk = ulo + (float)k / scale;
+      const float xk = __fdividef(uk * xm, 1.0f - uk);
+      int lo = s, hi = e;                              // X[lo] > xk >= X[hi] on a decreasing row
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (xat(mid) > xk) lo = mid; else hi = mid;
       }
+      const float fp = lut_coord(xat(lo), xm, ulo, scale), fc = lut_coord(xat(hi), xm, ulo, scale);
+      float fr = __fdividef(fp - (float)k, fp - fc);
+      fr = fr > 0.f ? (fr < 1.f ? fr : 1.f) : 0.f;     // also NaN -> 0
+      const float q = rintf(((float)(lo - base) + fr) * fs);
+      L[k] = (uint16_t)(q < 65535.f ? q : 65535.f);
     }
-    __syncwarp();
-    if (lane == 0) { L[K] = (uint16_t)((s - base) << shift); L[0] = (uint16_t)((e - base) << shift); }
   }
-  if (lane == 0) rowpar[r] = make_float4(xm, ulo, scale, __int_as_float(ok ? 1 : 0));
+  ok = __syncthreads_and(ok && mono) != 0;
+  if (tid == 0) {
+    if (ok) { L[K] = (uint16_t)((s - base) << shift); L[0] = (uint16_t)((e - base) << shift); }
+    T.rowpar[r] = make_float4(xm, ulo, scale, __int_as_float(ok ? 1 : 0));
+  }
 }
 
 // Per-row header blocks (LookupTable::rowblk), one thread per (row, slot): everything FindClosestAirTxHeight
@@ -368,9 +441,16 @@ __global__ void __launch_bounds__(128) airice_row_lut_kernel(const float* __rest
 // {s1, e1 (int bits), X[s1], X[s2], h(s1), h(s2), col0[row], flags | coordinate parameters of the row | of the second row}:
 // the trimmed window, the largest distance of the row and of the second row (the first row's window shifted by one row,
 // M.cc:1113-1121), the three heights the query compares with, and what the position table needs for both rows.
-__global__ void airice_row_block_kernel(const float* __restrict__ X, const float* __restrict__ row_h, int64_t cells, int n_h, int n_th,
-                                        const int* __restrict__ row_first, const int* __restrict__ row_last,
-                                        const float4* __restrict__ rowpar, float* rowblk) {
+__global__ void airice_row_block_kernel(const RowPrepBatch b) {
+  const RowPrepTab& T = b.tab[blockIdx.y];
+  const float* __restrict__ X = T.x;
+  const float* __restrict__ row_h = T.row_h;
+  const int* __restrict__ row_first = T.row_first;
+  const int* __restrict__ row_last = T.row_last;
+  const float4* __restrict__ rowpar = T.rowpar;
+  float* rowblk = T.rowblk;
+  const int64_t cells = b.cells;
+  const int n_h = b.n_h, n_th = b.n_th;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)n_h * AIRICE_ROWBLK) return;
   const int row = (int)(t / AIRICE_ROWBLK), slot = (int)(t - (int64_t)row * AIRICE_ROWBLK);
@@ -666,9 +746,9 @@ cudaError_t launch_table(const AirIceMedium& m, const AirIcePlan& p, const Table
 
 cudaError_t launch_table_multi(const AirIceMedium& m, const AirIcePlan& p, const TableMultiArgs& a, cudaStream_t s) {
   if (a.base.ncells <= 0 || a.n_ant <= 0) return cudaSuccess;
-  const int64_t blocks = (a.base.ncells + kThreads - 1) / kThreads;
+  const int64_t blocks = (a.base.ncells + kMultiThreads - 1) / kMultiThreads;
   if (blocks > 2147483647LL) return cudaErrorInvalidValue;
-  airice_table_multi_kernel<<<dim3((unsigned)blocks), kThreads, 0, s>>>(m, p, a);
+  airice_table_multi_kernel<<<dim3((unsigned)blocks), kMultiThreads, 0, s>>>(m, p, a);
   return cudaGetLastError();
 }
 
@@ -712,17 +792,29 @@ int lut_shift_for(int64_t n_th) {
   return sh;
 }
 
-cudaError_t launch_row_ranges(const float* x, const float* row_h, int64_t cells, int n_h, int n_th, int* row_first, int* row_last,
-                              float* rowblk, float4* rowpar, uint16_t* lut, int lut_shift, cudaStream_t s) {
-  airice_row_range_kernel<<<(n_h + 127) / 128, 128, 0, s>>>(x, cells, n_h, n_th, row_first, row_last);
+// trim ranges, position tables and header blocks of up to AIRICE_ROWPREP_MAX same-shape tables per launch (grid.y = table)
+cudaError_t launch_row_prep(const RowPrepBatch& b, cudaStream_t s) {
+  if (b.n_tab <= 0) return cudaSuccess;
+  if (b.n_tab > AIRICE_ROWPREP_MAX) return cudaErrorInvalidValue;
+  airice_row_range_kernel<<<dim3((unsigned)((b.n_h + 127) / 128), (unsigned)b.n_tab), 128, 0, s>>>(b);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  airice_row_lut_kernel<<<(unsigned)(((int64_t)n_h * 32 + 127) / 128), 128, 0, s>>>(x, n_h, n_th, row_first, row_last, lut_shift, rowpar, lut);
+  airice_row_lut_kernel<<<dim3((unsigned)b.n_h, (unsigned)b.n_tab), kLutThreads, 0, s>>>(b);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int64_t threads = (int64_t)n_h * AIRICE_ROWBLK;
-  airice_row_block_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(x, row_h, cells, n_h, n_th, row_first, row_last, rowpar, rowblk);
+  const int64_t threads = (int64_t)b.n_h * AIRICE_ROWBLK;
+  airice_row_block_kernel<<<dim3((unsigned)((threads + 255) / 256), (unsigned)b.n_tab), 256, 0, s>>>(b);
   return cudaGetLastError();
+}
+
+cudaError_t launch_row_ranges(const float* x, const float* row_h, int64_t cells, int n_h, int n_th, int* row_first, int* row_last,
+                              float* rowblk, float4* rowpar, uint16_t* lut, int lut_shift, cudaStream_t s) {
+  RowPrepBatch b;
+  std::memset(&b, 0, sizeof(b));
+  b.n_tab = 1; b.cells = cells; b.n_h = n_h; b.n_th = n_th; b.lut_shift = lut_shift;
+  b.tab[0].x = x; b.tab[0].row_h = row_h; b.tab[0].row_first = row_first; b.tab[0].row_last = row_last;
+  b.tab[0].rowblk = rowblk; b.tab[0].rowpar = rowpar; b.tab[0].lut = lut;
+  return launch_row_prep(b, s);
 }
 
 cudaError_t launch_unpack_table(const float4* rec, const float* row_h, int64_t cells, int n_th, float* c0, int64_t stride, cudaStream_t s) {

@@ -51,7 +51,21 @@ struct TableMultiArgs {
   float* const* x;
   float* const* row_h;
 };
-// per-row trim ranges of a packed table (the part of launch_pack_table the fused pass cannot do per cell)
+// per-row products of a packed table (trim ranges, position table, header blocks): what the fused pass cannot do per cell.
+// Same-shape tables are prepared together, grid.y = table.
+#define AIRICE_ROWPREP_MAX 32
+struct RowPrepTab {
+  const float* x; const float* row_h;
+  int* row_first; int* row_last;
+  float* rowblk; float4* rowpar; uint16_t* lut;
+};
+struct RowPrepBatch {
+  int n_tab;
+  int64_t cells;
+  int n_h, n_th, lut_shift;
+  RowPrepTab tab[AIRICE_ROWPREP_MAX];
+};
+cudaError_t launch_row_prep(const RowPrepBatch& b, cudaStream_t s);
 cudaError_t launch_row_ranges(const float* x, const float* row_h, int64_t cells, int n_h, int n_th, int* row_first, int* row_last,
                               float* rowblk, float4* rowpar, uint16_t* lut, int lut_shift, cudaStream_t s);
 int lut_shift_for(int64_t n_th);   // fraction bits of the position table (-1: rows too long for u16 positions, no table)
@@ -121,7 +135,9 @@ struct LookupTable {
   int lut_shift;
 };
 #define AIRICE_ROWBLK 16
+#ifndef AIRICE_LUT_EDGES
 #define AIRICE_LUT_EDGES 128
+#endif
 cudaError_t launch_unpack_table(const float4* rec, const float* row_h, int64_t cells, int n_th, float* c0, int64_t stride, cudaStream_t s);
 cudaError_t launch_pack_table(const float* const* cols32, int64_t cells, int n_h, int n_th, float* x, float4* rec,
                               float* row_h, int* row_first, int* row_last, float* rowblk, float4* rowpar, uint16_t* lut,
