@@ -21,6 +21,15 @@ constexpr int kThreads = 128;
 #ifndef AIRICE_INICE_LADDER_THREADS
 #define AIRICE_INICE_LADDER_THREADS 128
 #endif
+// The search state of a lane's pair (InIceRaMachine, 200 B) lives in shared memory: in registers it made the kernel a
+// 144-register one (3 CTAs of 128 threads per SM, 2.8 warps per scheduler to hide FP64 chains with); in shared memory the
+// kernel fits 4 CTAs at 114 registers without spilling: 26.8 -> 23.0 ms per 2e6 pairs (5 / 6 CTAs spill: 23.3 / 23.7 ms).
+#ifndef AIRICE_INICE_LADDER_MINBLOCKS
+#define AIRICE_INICE_LADDER_MINBLOCKS 4
+#endif
+#ifndef AIRICE_INICE_SMEM_MACHINE
+#define AIRICE_INICE_SMEM_MACHINE 1
+#endif
 constexpr int kDrThreads = AIRICE_INICE_DR_THREADS;
 constexpr int kLadderThreads = AIRICE_INICE_LADDER_THREADS;
 
@@ -75,15 +84,20 @@ struct InIceWarpPool {
   unsigned char owner[kCap];
 };
 
-__global__ void __launch_bounds__(kLadderThreads) airice_inice_ladder_kernel(const InIceArgs a) {
+__global__ void __launch_bounds__(kLadderThreads, AIRICE_INICE_LADDER_MINBLOCKS) airice_inice_ladder_kernel(const InIceArgs a) {
   __shared__ InIceWarpPool pools[kLadderThreads / 32];
+#if AIRICE_INICE_SMEM_MACHINE
+  __shared__ InIceRaMachine machines[kLadderThreads];
+  InIceRaMachine& M = machines[threadIdx.x];
+#else
+  InIceRaMachine M;
+#endif
   InIceWarpPool& pool = pools[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   const AirIceInIce m = inice_model(a);
   const int n_front = a.ra_count[0], count = n_front + a.ra_count[2];
   const double e5000 = INICE_EXP(-a.C * 5000.0);
-  InIceRaMachine M;
   int j = 0;
   bool has = false, exhausted = false;
   M.ph = InIceRaMachine::DONE; M.nq = 0; M.xq = 0;

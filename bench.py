@@ -433,8 +433,9 @@ def run_ours(args):
         ms = time_ms(lambda: solver.lookup(T, h, d, out=out, ok=ok))
         extras["lookup"] = {"table": "reference grid 9701x900 float", "lookups": n, "ms": ms, "lookups_per_s": world * n / ms * 1e3,
                             "algorithmic_gbs": n * 265.0 / ms / 1e6,
-                            "layout": "one 32-byte header sector per row, dense THD column for the index search (L2 resident: records, "
-                                      "inputs and outputs use the streaming cache operators), 48-byte records (4 cells gathered per query)",
+                            "layout": "one 64-byte header block per row, per-row position table (128 u16 samples of bin(u), u = X/(X+X_mid)) "
+                                      "predicting FindClosestTHD's bin, verified on the 48-byte records the interpolation reads (4 cells "
+                                      "gathered per query); the literal halvings + scan in the dense THD column are the fallback",
                             "solved": float(ok.float().mean())}
         lf = facts.get("airice_lookup_kernel", {})
         rooflines.append({"kernel": "airice_lookup_kernel", "bound": "hbm", "achieved": n * 265.0 / ms / 1e6, "peak": hbm_peak,
@@ -547,11 +548,23 @@ def run_ours(args):
                 Ta.close()
         barrier()
         ms_shared = max_over_ranks(time_ms(shared_air_tables_and_lookups, reps=1, warm=1))
+
+        def shared_air_tables_only():
+            for Ta in solver.table_create_multi([x / 100.0 for x in depths_cm], ICE_CM / 100.0):
+                Ta.close()
+        ms_build = max_over_ranks(time_ms(shared_air_tables_only, reps=2, warm=1))
+        cells5 = 9701 * 900
+        rooflines.append({"kernel": "airice_table_multi_kernel + row-prep kernels (64 antennas' reference-grid tables, lookup layout)",
+                          "bound": "hbm", "achieved": n_ant * cells5 * 52.0 / ms_build / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": n_ant * cells5 * 52.0 / ms_build / 1e6 / hbm_peak,
+                          "accounting": "48-byte record + 4-byte dense X stored per cell and antenna; co-limited by FP64 "
+                                        "(one ice leg = 1 sqrt, 2 log, 1 atan per cell and antenna)", "ms": ms_build})
         extras["c5_multi_antenna"] = {"points": n5 * world, "antennas": n_ant, "pairs": n5 * world * n_ant,
                                       "direct_ms": ms_direct, "direct_solves_per_s": world * n5 * n_ant / ms_direct * 1e3,
                                       "tables_plus_lookups_ms": ms_table,
                                       "table_solutions_per_s": world * n5 * n_ant / ms_table * 1e3,
                                       "shared_air_tables_plus_lookups_ms": ms_shared,
+                                      "shared_air_tables_only_ms": ms_build,
                                       "shared_air_table_solutions_per_s": world * n5 * n_ant / ms_shared * 1e3,
                                       "note": "64 reference-grid tables (9701x900) built, packed and freed per pass; "
                                               "shared_air = airice_table_create_multi (one air walk per cell for all 64 "
