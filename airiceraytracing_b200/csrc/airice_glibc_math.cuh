@@ -65,16 +65,40 @@ static inline double airice_g_dbl(unsigned long long u) { double x; memcpy(&x, &
 #define AIRICE_G_TAB(name) name##_h
 #endif
 
+// 64-bit literals cost two moves each in SASS (every coefficient of a polynomial became a UMOV pair: 14 moves next to the
+// 12 FP64 operations of one exp); from __constant__ memory they are constant-bank operands of the DFMA itself.  The rare
+// out-of-range fallbacks are real calls, so that CUDA's exp / pow are not inlined (55 dead instructions) into every use.
+#if defined(__CUDACC__)
+static __constant__ double airice_gk[24] = {
+    0x1.71547652b82fep+7, -0x1.62e42fefa0000p-8, -0x1.cf79abc9e3b3ap-47,                              // 0-2 exp reduction
+    0x1.ffffffffffdbdp-2, 0x1.555555555543cp-3, 0x1.55555cf172b91p-5, 0x1.1111167a4d017p-7,           // 3-6 exp C2..C5
+    0x1.62e42fefa3800p-1, 0x1.ef35793c76730p-45,                                                      // 7-8 ln2 hi, lo
+    0x1.555555551305bp-2, -0x1.fffffffeb4590p-3, 0x1.999b324f10111p-3, -0x1.55575e506c89fp-3,         // 9-12 log A1..A4
+    -0x1.0000000000001p-1,                                                                            // 13 log A0
+    -0x1.5555555555560p-1, 0x1.0000000000006p-1, 0x1.999999959554ep-1, -0x1.555555529a47ap-1,         // 14-17 pow A1..A4
+    -0x1.2495b9b4845e9p+0, 0x1.0002b8b263fc3p+0, 0, 0, 0, 0};                                         // 18-19 pow A5, A6
+static __host__ __device__ __noinline__ double airice_glibc_exp_cold(double x) { return exp(x); }
+static __host__ __device__ __noinline__ double airice_glibc_pow_cold(double x, double y) { return pow(x, y); }
+#else
+static inline double airice_glibc_exp_cold(double x) { return exp(x); }
+static inline double airice_glibc_pow_cold(double x, double y) { return pow(x, y); }
+#endif
+#if defined(__CUDA_ARCH__)
+#define AIRICE_GK(i, lit) airice_gk[i]
+#else
+#define AIRICE_GK(i, lit) (lit)
+#endif
+
 // ---- exp (e_exp.c: exp(x) = 2^(k/128) exp(r), |r| <= ln2/256, degree-5 polynomial, 2^(i/128) = scale (1 + tail))
 // The polynomial tail shared by exp and pow: r is the reduced argument, ki the bits of k + Shift.
 AIRICE_G_FN double airice_glibc_exp_tail(double r, unsigned long long ki) {
   const int idx = 2 * (int)(ki & 127);
   const double tail = AIRICE_G_DBL(AIRICE_G_LD(&AIRICE_G_TAB(airice_glibc_exp_tab)[idx]));
   const unsigned long long sbits = AIRICE_G_LD(&AIRICE_G_TAB(airice_glibc_exp_tab)[idx + 1]) + (ki << 45);
-  const double p23 = AIRICE_G_FMA(0x1.555555555543cp-3, r, 0x1.ffffffffffdbdp-2);   // C2 + r C3
+  const double p23 = AIRICE_G_FMA(AIRICE_GK(4, 0x1.555555555543cp-3), r, AIRICE_GK(3, 0x1.ffffffffffdbdp-2));   // C2 + r C3
   const double tr = AIRICE_G_ADD(r, tail);
   const double r2 = AIRICE_G_MUL(r, r);
-  const double p45 = AIRICE_G_FMA(r, 0x1.1111167a4d017p-7, 0x1.55555cf172b91p-5);   // C4 + r C5
+  const double p45 = AIRICE_G_FMA(r, AIRICE_GK(6, 0x1.1111167a4d017p-7), AIRICE_GK(5, 0x1.55555cf172b91p-5));   // C4 + r C5
   const double t = AIRICE_G_FMA(p23, r2, tr);
   const double r4 = AIRICE_G_MUL(r2, r2);
   const double tmp = AIRICE_G_FMA(p45, r4, t);
@@ -86,12 +110,12 @@ AIRICE_G_FN double airice_glibc_exp(double x) {
   const unsigned abstop = (unsigned)(AIRICE_G_BITS(x) >> 52) & 0x7ff;
   if (abstop - 0x3c9u >= 0x3fu) {
     if (abstop < 0x3c9u) return AIRICE_G_ADD(1.0, x);      // |x| < 2^-54
-    return exp(x);                                          // |x| >= 512, inf, NaN: results no ray produces
+    return airice_glibc_exp_cold(x);                        // |x| >= 512, inf, NaN: results no ray produces
   }
-  const double kd0 = AIRICE_G_FMA(x, 0x1.71547652b82fep+7, 0x1.8p+52);      // x N/ln2 + Shift, fused
+  const double kd0 = AIRICE_G_FMA(x, AIRICE_GK(0, 0x1.71547652b82fep+7), 0x1.8p+52);      // x N/ln2 + Shift, fused
   const unsigned long long ki = AIRICE_G_BITS(kd0);
   const double kd = AIRICE_G_SUB(kd0, 0x1.8p+52);
-  const double r = AIRICE_G_FMA(kd, -0x1.cf79abc9e3b3ap-47, AIRICE_G_FMA(kd, -0x1.62e42fefa0000p-8, x));
+  const double r = AIRICE_G_FMA(kd, AIRICE_GK(2, -0x1.cf79abc9e3b3ap-47), AIRICE_G_FMA(kd, AIRICE_GK(1, -0x1.62e42fefa0000p-8), x));
   return airice_glibc_exp_tail(r, ki);
 }
 
@@ -135,16 +159,16 @@ AIRICE_G_FN double airice_glibc_log(double x) {
   const double invc = AIRICE_G_LD(&AIRICE_G_TAB(airice_glibc_log_tab)[2 * i]);
   const double logc = AIRICE_G_LD(&AIRICE_G_TAB(airice_glibc_log_tab)[2 * i + 1]);
   const double kd = (double)k;
-  const double w = AIRICE_G_FMA(kd, 0x1.62e42fefa3800p-1, logc);
+  const double w = AIRICE_G_FMA(kd, AIRICE_GK(7, 0x1.62e42fefa3800p-1), logc);
   const double r = AIRICE_G_FMA(z, invc, -1.0);
-  const double p12 = AIRICE_G_FMA(r, -0x1.fffffffeb4590p-3, 0x1.555555551305bp-2);    // A1 + r A2
+  const double p12 = AIRICE_G_FMA(r, AIRICE_GK(10, -0x1.fffffffeb4590p-3), AIRICE_GK(9, 0x1.555555551305bp-2));    // A1 + r A2
   const double hi = AIRICE_G_ADD(r, w);
   const double r2 = AIRICE_G_MUL(r, r);
   double lo = AIRICE_G_ADD(AIRICE_G_SUB(w, hi), r);
-  lo = AIRICE_G_FMA(kd, 0x1.ef35793c76730p-45, lo);
+  lo = AIRICE_G_FMA(kd, AIRICE_GK(8, 0x1.ef35793c76730p-45), lo);
   const double r3 = AIRICE_G_MUL(r, r2);
-  const double p34 = AIRICE_G_FMA(r, -0x1.55575e506c89fp-3, 0x1.999b324f10111p-3);    // A3 + r A4
-  lo = AIRICE_G_FMA(r2, -0x1.0000000000001p-1, lo);                                   // + r2 A0
+  const double p34 = AIRICE_G_FMA(r, AIRICE_GK(12, -0x1.55575e506c89fp-3), AIRICE_GK(11, 0x1.999b324f10111p-3));    // A3 + r A4
+  lo = AIRICE_G_FMA(r2, AIRICE_GK(13, -0x1.0000000000001p-1), lo);                                   // + r2 A0
   const double p = AIRICE_G_FMA(p34, r2, p12);
   return AIRICE_G_ADD(AIRICE_G_FMA(r3, p, lo), hi);
 }
@@ -153,7 +177,7 @@ AIRICE_G_FN double airice_glibc_log(double x) {
 AIRICE_G_FN double airice_glibc_pow(double x, double y) {
   const unsigned long long ix = AIRICE_G_BITS(x), iy = AIRICE_G_BITS(y);
   const unsigned topx = (unsigned)(ix >> 52), topy = (unsigned)(iy >> 52) & 0x7ff;
-  if (topx - 1u >= 0x7fdu || topy - 0x3beu >= 0x80u) return pow(x, y);   // x not a positive normal, or |y| tiny/huge
+  if (topx - 1u >= 0x7fdu || topy - 0x3beu >= 0x80u) return airice_glibc_pow_cold(x, y);   // x not a positive normal, or |y| tiny/huge
   const unsigned long long tmp = ix - 0x3fe6955500000000ull;
   const int i = (int)(tmp >> 45) & 127;
   const int k = (int)((long long)tmp >> 52);
@@ -162,19 +186,19 @@ AIRICE_G_FN double airice_glibc_pow(double x, double y) {
   const double invc = AIRICE_G_LD(&AIRICE_G_TAB(airice_glibc_powlog_tab)[3 * i]);
   const double logc = AIRICE_G_LD(&AIRICE_G_TAB(airice_glibc_powlog_tab)[3 * i + 1]);
   const double logctail = AIRICE_G_LD(&AIRICE_G_TAB(airice_glibc_powlog_tab)[3 * i + 2]);
-  const double t1 = AIRICE_G_FMA(kd, 0x1.62e42fefa3800p-1, logc);
-  const double lo1 = AIRICE_G_FMA(kd, 0x1.ef35793c76730p-45, logctail);
+  const double t1 = AIRICE_G_FMA(kd, AIRICE_GK(7, 0x1.62e42fefa3800p-1), logc);
+  const double lo1 = AIRICE_G_FMA(kd, AIRICE_GK(8, 0x1.ef35793c76730p-45), logctail);
   const double r = AIRICE_G_FMA(z, invc, -1.0);
   const double ar = AIRICE_G_MUL(r, -0.5);
-  const double p12 = AIRICE_G_FMA(r, 0x1.0000000000006p-1, -0x1.5555555555560p-1);    // A1 + r A2
-  const double p34 = AIRICE_G_FMA(r, -0x1.555555529a47ap-1, 0x1.999999959554ep-1);    // A3 + r A4
+  const double p12 = AIRICE_G_FMA(r, AIRICE_GK(15, 0x1.0000000000006p-1), AIRICE_GK(14, -0x1.5555555555560p-1));    // A1 + r A2
+  const double p34 = AIRICE_G_FMA(r, AIRICE_GK(17, -0x1.555555529a47ap-1), AIRICE_GK(16, 0x1.999999959554ep-1));    // A3 + r A4
   const double t2 = AIRICE_G_ADD(r, t1);
   const double lo2 = AIRICE_G_ADD(AIRICE_G_SUB(t1, t2), r);
   const double ar2 = AIRICE_G_MUL(r, ar);
   const double ar3 = AIRICE_G_MUL(r, ar2);
   const double lo3 = AIRICE_G_FMA(ar, r, -ar2);
   const double hi = AIRICE_G_ADD(t2, ar2);
-  const double p56 = AIRICE_G_FMA(r, 0x1.0002b8b263fc3p+0, -0x1.2495b9b4845e9p+0);    // A5 + r A6
+  const double p56 = AIRICE_G_FMA(r, AIRICE_GK(19, 0x1.0002b8b263fc3p+0), AIRICE_GK(18, -0x1.2495b9b4845e9p+0));    // A5 + r A6
   const double lo4 = AIRICE_G_ADD(AIRICE_G_SUB(t2, hi), ar2);
   const double p36 = AIRICE_G_FMA(p56, ar2, p34);
   const double p16 = AIRICE_G_FMA(ar2, p36, p12);
@@ -189,13 +213,13 @@ AIRICE_G_FN double airice_glibc_pow(double x, double y) {
   const unsigned abstop = (unsigned)(AIRICE_G_BITS(ehi) >> 52) & 0x7ff;
   if (abstop - 0x3c9u >= 0x3fu) {
     if (abstop < 0x3c9u) return AIRICE_G_ADD(1.0, ehi);    // |y log x| < 2^-54 (sign bias 0: x > 0)
-    return pow(x, y);                                       // overflow / underflow range
+    return airice_glibc_pow_cold(x, y);                     // overflow / underflow range
   }
-  const double kd0 = AIRICE_G_FMA(ehi, 0x1.71547652b82fep+7, 0x1.8p+52);
+  const double kd0 = AIRICE_G_FMA(ehi, AIRICE_GK(0, 0x1.71547652b82fep+7), 0x1.8p+52);
   const unsigned long long ki = AIRICE_G_BITS(kd0);
   const double kde = AIRICE_G_SUB(kd0, 0x1.8p+52);
-  double re = AIRICE_G_FMA(kde, -0x1.62e42fefa0000p-8, ehi);
-  re = AIRICE_G_FMA(kde, -0x1.cf79abc9e3b3ap-47, re);
+  double re = AIRICE_G_FMA(kde, AIRICE_GK(1, -0x1.62e42fefa0000p-8), ehi);
+  re = AIRICE_G_FMA(kde, AIRICE_GK(2, -0x1.cf79abc9e3b3ap-47), re);
   re = AIRICE_G_ADD(elo, re);
   return airice_glibc_exp_tail(re, ki);
 }
