@@ -27,6 +27,14 @@ for _ in range(7):
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
     a.record(); S.lookup(T, dh, dd, out=o2, ok=ok); b.record(); torch.cuda.synchronize(); tl.append(a.elapsed_time(b))
 print(os.path.basename(sys.argv[1]), "lookup 1e7: best %%.3f ms -> %%.3e /s, ok %%.4f checksum %%.10e" %% (min(tl), n / min(tl) * 1e3, ok.float().mean().item(), float(o2[5][ok.bool()].sum())))
+n_h, n_th = S.table_dims(-200.0, 3000.0)
+o32 = torch.empty((11, n_h * n_th), dtype=torch.float32, device="cuda")
+for _ in range(3): S.table_build(-200.0, 3000.0, columns64=None, want32=True, out32=o32)
+torch.cuda.synchronize(); tt = []
+for _ in range(7):
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record(); S.table_build(-200.0, 3000.0, columns64=None, want32=True, out32=o32); b.record(); torch.cuda.synchronize(); tt.append(a.elapsed_time(b))
+print(os.path.basename(sys.argv[1]), "table 9701x900 f32: best %%.4f ms" %% min(tt))
 S.solve(dh, dd, -20000., 300000., UNITS_CM_RAD, out=out, ok=ok)
 print(os.path.basename(sys.argv[1]), "solve 1e7: best %%.3f ms  -> %%.3e solves/s, ok %%.4f, checksum %%.10e" %% (min(ts), n / min(ts) * 1e3, ok.float().mean().item(), float(out[5][ok.bool()].sum())))
 ''' % (ROOT, ROOT)
