@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libairice_b200.so")
+# AIRICE_LIB: development override (tools/*_probe.py time alternative builds of the library)
+LIB_PATH = os.environ.get("AIRICE_LIB") or os.path.join(_HERE, "lib", "libairice_b200.so")
 
 TABLE_COLS64 = 17
 TABLE_COLS32 = 11

@@ -28,6 +28,7 @@
 #include <stdint.h>
 
 #include "airice_math.cuh"
+#include "airice_glibc_math.cuh"
 
 #if defined(__CUDACC__)
 #define AIRICE_HD __host__ __device__ __forceinline__
@@ -39,13 +40,16 @@
 
 #define AIRICE_MAX_LAYERS 5
 #ifndef AIRICE_PEEL_TOP
-#define AIRICE_PEEL_TOP 0
+#define AIRICE_PEEL_TOP 1
 #endif
 #ifndef AIRICE_UNROLL_XFAST
 #define AIRICE_UNROLL_XFAST 1
 #endif
 #ifndef AIRICE_UNROLL_FULL
 #define AIRICE_UNROLL_FULL 1
+#endif
+#ifndef AIRICE_UNROLL_RELAY
+#define AIRICE_UNROLL_RELAY 2
 #endif
 
 // Product rounded on its own (never contracted into an FMA with a following add).  Used where the reference forms
@@ -112,6 +116,17 @@ struct AirIcePlan {
 };
 
 AIRICE_HD double airice_n_air(const AirIceMedium& m, int k, double z) { return 1.0 + m.B[k] * exp(-m.C[k] * z); }
+// n(h) of a transmitter as the reference's x86 build rounds it (Getnz_air, M.cc:258: 1 + B exp(-C h) with the product
+// and the sum rounded separately, exp from glibc): on the device glibc's own exp (airice_glibc_math.cuh, 25 instructions
+// with constant-bank coefficients against 53 for CUDA's) and an unfused product, so that L = n sin(theta) starts from the
+// reference's bits.
+AIRICE_HD double airice_n_tx(const AirIceMedium& m, int k, double h) {
+#if defined(__CUDA_ARCH__)
+  return 1.0 + AIRICE_MUL(m.B[k], airice_glibc_exp(-m.C[k] * h));
+#else
+  return 1.0 + m.B[k] * exp(-m.C[k] * h);
+#endif
+}
 
 // Top layer of a transmitter height for the walk (SkipLayersAbove, M.cc:666-676); -1 = in no layer.
 AIRICE_HD int airice_top_layer(const AirIceMedium& m, double h) {
@@ -256,6 +271,9 @@ AIRICE_HD void airice_seg_x_dx(double A, double sA, double inv_sA, double L, dou
   AIRICE_SQRT_RSQRT(nb * nb - L2, Rb, yb);
   AIRICE_SQRT_RSQRT(nt * nt - L2, Rt, yt);
   const double Tb = (AIR ? nb : A * nb) - L2 + sA * Rb, Tt = (AIR ? nt : A * nt) - L2 + sA * Rt;
+  // 1/T_b only enters the slope, but the 20-bit MUFU seed is NOT enough for it: a slope off by 1e-6 moves the Newton
+  // step by 1e-6 of its length, which for the pairs whose single-precision landing point is 1e-4 deg off exceeds the
+  // replay's guard band (measured: one bisection-cell miss in 128 000 solves, tests/test_gpu_parity.py C5 case)
   const double rTt = AIRICE_RCP(Tt), rTb = AIRICE_RCP(Tb);
   const double dG = Cn * (xb - xt) - AIRICE_LOG(Tb * rTt);
   const double c1 = iC * inv_sA;
@@ -449,7 +467,7 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
     if (RELAY) {
       // forward tracer: top-down, L handed from layer to layer
       double sA = 0.0, inv_sA = 0.0, prevR = 0.0, prevH = 0.0, prevT = 1.0, prevLnT = 0.0;
-      constexpr int kUnrollF = AIRICE_UNROLL_FULL;
+      constexpr int kUnrollF = AIRICE_UNROLL_RELAY;
 #pragma unroll kUnrollF
       for (int k = kt; k >= p.kb; k--) {
         const bool top = (k == kt);

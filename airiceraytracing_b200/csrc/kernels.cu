@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kThreads) airice_forward_kernel(const AirIceMe
   const double h = a.h[i], theta = a.theta[i];
   const int kt = airice_top_layer(m, h);
   const int kc = kt < 0 ? 0 : kt;
-  const double ntx = 1.0 + m.B[kc] * exp(-m.C[kc] * h);
+  const double ntx = airice_n_tx(m, kc, h);
   const double L = airice_L_of_theta(m, ntx, theta);
   AirIceRay r;
   airice_ray_full<true>(m, p, kt, h, ntx, L, a.in_ice != 0, a.c64[11] != nullptr, false, r);
@@ -221,25 +221,32 @@ __global__ void __launch_bounds__(kThreads) airice_forward_kernel(const AirIceMe
 #ifndef AIRICE_SOLVE_MINBLOCKS
 #define AIRICE_SOLVE_MINBLOCKS (1024 / AIRICE_SOLVE_THREADS)
 #endif
+#ifndef AIRICE_SOLVE_CMRAD9
+#define AIRICE_SOLVE_CMRAD9 1
+#endif
 constexpr int kSolveThreads = AIRICE_SOLVE_THREADS;
 constexpr int64_t kTwoPassMinPairs = 6000000;
 // One pair, start to finish.  DEFER (first pass of the two-pass launch): a pair that needs a rare slow path is appended
 // to a.defer_list (0.6 % of a random batch) and what is written for it here is overwritten by the second pass.
-template <bool DEFER, bool CLI = false>
+// CMRAD9 = the CoREAS call as BASELINE config 4 makes it, known at launch time: cm / rad units, all nine outputs and the flag
+// wanted, no caller-supplied straight angle, no evaluation census -- the per-column null tests, the unit branches and the
+// metre / degree tail are then not compiled into the kernel at all.
+template <bool DEFER, bool CLI = false, bool CMRAD9 = false>
 __device__ __forceinline__ void solve_one(const AirIceMedium& m, const AirIcePlan& p, const SolveArgs& a, int64_t i) {
   double h = a.h[i], d = a.d[i];
   double ice = a.ice, depth = a.depth;
-  if (a.units == AIRICE_UNITS_CM_RAD) {  // M.cc:947-950
+  const bool cm = CMRAD9 || a.units == AIRICE_UNITS_CM_RAD;
+  if (cm) {  // M.cc:947-950
     h = AIRICE_DIV100(h); d = AIRICE_DIV100(d); ice = AIRICE_DIV100(ice); depth = AIRICE_DIV100(depth);
   }
   const int kt = airice_top_layer(m, h);
   const int kc = kt < 0 ? 0 : kt;
-  const double ntx = 1.0 + m.B[kc] * exp(-m.C[kc] * h);
+  const double ntx = airice_n_tx(m, kc, h);
   double ta;
   double thR = airice_straight_angle(m, h, d, ice, depth, ta);
-  if (a.straight) {
+  if (!CMRAD9 && a.straight) {
     thR = a.straight[i];
-    if (a.units == AIRICE_UNITS_CM_RAD) thR = thR * m.rad2deg;
+    if (cm) thR = thR * m.rad2deg;
     ta = tan((180 - thR) * m.deg2rad);
   }
   AirIceSolveStat st;
@@ -257,12 +264,25 @@ __device__ __forceinline__ void solve_one(const AirIceMedium& m, const AirIcePla
   if (DEFER && hard) a.defer_list[atomicAdd(a.defer_count, 1)] = (int32_t)i;
   const double L = airice_L_of_theta(m, ntx, theta);
   AirIceRay r;
-  const bool full_rec = (a.units != AIRICE_UNITS_CM_RAD);
+  const bool full_rec = !cm;
   airice_ray_full<false>(m, p, kt, h, ntx, L, p.has_ice != 0, full_rec && a.out[11] != nullptr, full_rec && a.out[12] != nullptr, r);
   const double thd = r.x_ice + r.x_air;
+  if (CMRAD9) {
+    a.ok[i] = airice_check_solution(thd, d) ? 1 : 0;
+    a.out[0][i] = (r.t_ice * m.c) * 100;
+    a.out[1][i] = (r.t_air * m.c) * 100;
+    a.out[2][i] = r.p_ice * 100;
+    a.out[3][i] = r.p_air * 100;
+    a.out[4][i] = theta * (m.pi / 180);
+    a.out[5][i] = r.x_air * 100;
+    a.out[6][i] = r.trans_s;
+    a.out[7][i] = r.trans_p;
+    a.out[8][i] = r.recv_deg * (m.pi / 180);
+    return;
+  }
   if (a.ok) a.ok[i] = airice_check_solution(thd, d) ? 1 : 0;
   if (a.nevals) a.nevals[i] = st.n_newton + st.n_replay;
-  if (a.units == AIRICE_UNITS_CM_RAD) {
+  if (cm) {
     if (a.out[0]) a.out[0][i] = (r.t_ice * m.c) * 100;
     if (a.out[1]) a.out[1][i] = (r.t_air * m.c) * 100;
     if (a.out[2]) a.out[2][i] = r.p_ice * 100;
@@ -295,7 +315,7 @@ __device__ __forceinline__ void solve_one(const AirIceMedium& m, const AirIcePla
 // between the pieces every warp runs (measured: the kernel without them is 10 % faster) -- so pass 1 only lists those
 // pairs and pass 2, a fixed grid striding over the list whose length stays on the device, solves them in dense warps
 // (58 us, latency bound).  1e7 pairs: 1.55 ms in one pass, 1.49 ms in two.
-template <int PASS>
+template <int PASS, bool CMRAD9 = false>
 __global__ void __launch_bounds__(kSolveThreads, AIRICE_SOLVE_MINBLOCKS) airice_solve_kernel(const AirIceMedium m, const AirIcePlan p, const SolveArgs a) {
   if (PASS == 2) {
     const int count = *a.defer_count;
@@ -304,7 +324,7 @@ __global__ void __launch_bounds__(kSolveThreads, AIRICE_SOLVE_MINBLOCKS) airice_
   } else {
     const int64_t i = (int64_t)blockIdx.x * kSolveThreads + threadIdx.x;
     if (i >= a.n) return;
-    solve_one<PASS == 1>(m, p, a, i);
+    solve_one<PASS == 1, false, CMRAD9>(m, p, a, i);
   }
 }
 
@@ -776,7 +796,10 @@ cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const Solve
   }
   cudaError_t e = cudaMemsetAsync(a.defer_count, 0, sizeof(int32_t), s);
   if (e != cudaSuccess) return e;
-  airice_solve_kernel<1><<<dim3((unsigned)blocks), kSolveThreads, 0, s>>>(m, p, a);
+  bool cmrad9 = AIRICE_SOLVE_CMRAD9 && a.units == AIRICE_UNITS_CM_RAD && !a.straight && !a.nevals && a.ok;
+  for (int k = 0; k < 9; k++) cmrad9 = cmrad9 && a.out[k] != nullptr;
+  if (cmrad9) airice_solve_kernel<1, true><<<dim3((unsigned)blocks), kSolveThreads, 0, s>>>(m, p, a);
+  else airice_solve_kernel<1><<<dim3((unsigned)blocks), kSolveThreads, 0, s>>>(m, p, a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int64_t second = blocks < 2 * 148 ? blocks : 2 * 148;     // one wave of 2 CTAs per SM strides over the list
