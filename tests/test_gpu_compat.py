@@ -37,6 +37,10 @@ def driver_output(tmp_path_factory, solver):
             continue
         rec.setdefault(p[0], []).append(vals)
     rec["_stdout"] = out
+    # the same driver with the per-call table builds (MakeRayTracingTable builds in-ice antennas' tables together on first
+    # use by default; AIRICE_EAGER_TABLES=1 builds each one in its own call, as the reference does)
+    rec["_stdout_eager"] = subprocess.run([exe, ATMOSPHERE, qfile, str(tmp / "table0e.airicetb")], capture_output=True, text=True,
+                                          check=True, env=dict(os.environ, AIRICE_EAGER_TABLES="1")).stdout
     return rec
 
 
@@ -105,6 +109,14 @@ def test_driver_tables_and_lookup(driver_output, oracle):
         assert np.allclose(g, r, rtol=3e-7, atol=0)
         t.free()
     assert driver_output["table0"][0] == driver_output["table2"][0]
+
+
+def test_driver_deferred_table_builds_change_nothing(driver_output):
+    """MakeRayTracingTable collects the in-ice antennas and builds their tables in one shared-air pass on first use; every
+    number the driver prints (lookups, table columns compared against the batch build, persistence round trip) must be
+    the one the per-call builds give."""
+    assert driver_output["_stdout"] == driver_output["_stdout_eager"]
+    assert "table0 1" in driver_output["_stdout"]
 
 
 def test_driver_batch_tables_equal_per_antenna_tables(driver_output):
