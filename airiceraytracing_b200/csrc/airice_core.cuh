@@ -174,50 +174,6 @@ AIRICE_HD double airice_x_exact(const AirIceMedium& m, const AirIcePlan& p, int 
   return X;
 }
 
-// X(L) and the analytic dX/dL.  The kernels no longer call this (the solver iterates on airice_x_fast after the FP32
-// pre-iteration airice_x_newton_f32); it stays as the FP64 statement of the derivative that the single-precision
-// version is checked against by the host-side unit tests.  Only the converged root matters here (it is re-derived to ~1e-13 deg by the
-// iteration itself and the reported numbers come from airice_ray_full), so this version is arranged for throughput:
-// one log per segment (ln T_stop - ln T_start = ln(T_stop/T_start)), host-precomputed 1/C', 1/R from the sqrt's own
-// refined seed.  dG/dL = L (sA+R)^2 / (T sA R) follows from dT/dL = -L (sA+R)^2/(sA R).
-AIRICE_HD double airice_x_newton(const AirIceMedium& m, const AirIcePlan& p, int kt, double h, double n_tx, double L,
-                                 double& dXdL) {
-  const double L2 = L * L;
-  // X must be good to ~1e-13 relative (the root inherits its error), so 1/sA is a full-precision reciprocal; the
-  // per-end 1/R below only enters the derivative and the Hermite slopes, where ~1e-12 is ample.
-  const double sAir = AIRICE_SQRT(1.0 * 1.0 - L2), sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
-  const double yAir = AIRICE_RCP(sAir), yIce = AIRICE_RCP(sIce);
-  const int nair = (kt >= p.kb) ? (kt - p.kb + 1) : 0;
-  const int nseg = nair + (p.has_ice ? 1 : 0);
-  double X = 0.0, dX = 0.0;
-#pragma unroll 1
-  for (int j = 0; j < nseg; j++) {
-    const bool air = j < nair;
-    const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
-    const double A = air ? 1.0 : m.A_ice;
-    const double sA = air ? sAir : sIce;
-    const double inv_sA = air ? yAir : yIce;
-    const bool top = (j == 0) && air;
-    const double xt = top ? h : p.start_x[k];
-    const double nt = top ? n_tx : p.start_n[k];
-    const double xb = p.stop_x[k], nb = p.stop_n[k];
-    double Rb, yb, Rt, yt;
-    AIRICE_SQRT_RSQRT(nb * nb - L2, Rb, yb);
-    AIRICE_SQRT_RSQRT(nt * nt - L2, Rt, yt);
-    const double Tb = A * nb - L2 + sA * Rb, Tt = A * nt - L2 + sA * Rt;
-    const double rTt = AIRICE_RCP(Tt);
-    const double dG = p.neg_c[k] * (xb - xt) - AIRICE_LOG(Tb * rTt);
-    const double c1 = p.inv_neg_c[k] * inv_sA;           // 1/(C' sA)
-    const double seg = (L * c1) * dG;
-    const double qb = (sA + Rb) * (sA + Rb) * (AIRICE_RCP(Tb) * yb), qt = (sA + Rt) * (sA + Rt) * (rTt * yt);
-    const double dseg = c1 * (A * A * inv_sA * inv_sA * dG + L2 * inv_sA * (qb - qt));
-    X += air ? -seg : seg;
-    dX += air ? -dseg : dseg;
-  }
-  dXdL = dX;
-  return X;
-}
-
 // One segment of X(L): (L / (C' sA)) (C' (xb - xt) - ln(T_b / T_t)).  AIR fixes A = 1 at compile time (the products
 // A n are then exact copies of n, so the values are those of the generic form).
 template <bool AIR>
@@ -229,7 +185,7 @@ AIRICE_HD double airice_seg_x(double A, double sA, double inv_sA, double L, doub
   return (L * (iC * inv_sA)) * dG;
 }
 
-// X(L) only, FP64, arranged like airice_x_newton but without derivative terms: the work horse of the solver's
+// X(L) only, FP64, arranged like airice_x_dx below but without derivative terms: the work horse of the solver's
 // chord iteration (the slope comes from the FP32 pre-iteration or from a secant).  The air layers run BOTTOM-UP:
 // every lane of a warp starts at the surface layer kb (uniform), so the per-layer plan values are warp-uniform
 // constant-bank reads (top-down, lanes whose transmitters sit in different layers read different slots in the same

@@ -37,15 +37,24 @@ AIRICE_HD void airice_path_F_factor(double A, double C, double L, double& pre, d
   sA = sqrt(A * A - L * L);
   pre = (L / C) * (1.0 / sA);
 }
+// exp / log per point: glibc's own algorithms on the device (airice_glibc_math.cuh: the reference's libm, and with their
+// coefficients in the constant bank about half the instructions of CUDA's versions); one exp, one log, one sqrt per point
+#if defined(__CUDA_ARCH__)
+#define AIRICE_PATH_EXP(x) airice_glibc_exp(x)
+#define AIRICE_PATH_LOG(x) airice_glibc_log(x)
+#else
+#define AIRICE_PATH_EXP(x) exp(x)
+#define AIRICE_PATH_LOG(x) log(x)
+#endif
 AIRICE_HD double airice_path_F_air(const AirIceMedium& m, int k, double L, double pre, double sA, double height) {
   const double C = m.C[k], x = -height;
-  const double n = 1.0 + m.B[k] * exp(-m.C[k] * fabs(x));
-  return pre * (C * x - log(1.0 * n - L * L + sA * sqrt(n * n - L * L)));
+  const double n = 1.0 + m.B[k] * AIRICE_PATH_EXP(-m.C[k] * fabs(x));
+  return pre * (C * x - AIRICE_PATH_LOG(1.0 * n - L * L + sA * sqrt(n * n - L * L)));
 }
 AIRICE_HD double airice_path_F_ice(const AirIceMedium& m, double L, double pre, double sA, double i) {
   const double A = m.A_ice, C = m.C_ice;
-  const double n = A + m.B_ice * exp(-C * fabs(i));
-  return pre * (C * i - log(A * n - L * L + sA * sqrt(n * n - L * L)));
+  const double n = A + m.B_ice * AIRICE_PATH_EXP(-C * fabs(i));
+  return pre * (C * i - AIRICE_PATH_LOG(A * n - L * L + sA * sqrt(n * n - L * L)));
 }
 
 // number of loop trips of "for (i = start; i > stop - 1; i = i - 1)": the k >= 0 with start - k > stop - 1

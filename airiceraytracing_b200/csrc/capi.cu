@@ -74,12 +74,18 @@ struct airice_ctx {
   size_t spare_cap = 0;              // bytes of freed table buffers the context may hold (set on first release)
   size_t path_plan_cap = 0;
   int64_t inice_cols_n = 0;
+  // per-row transmitter data (height, n(h), top layer) of the grids tables were built on lately: a caller that alternates
+  // between a few grids (row shards of one grid, two receiver depths in air) neither re-uploads nor synchronises
   struct RowCache {
     double key[7] = {0, 0, 0, 0, 0, 0, 0};
     int64_t r0 = -1, r1 = -1;
     double* d_rows = nullptr;
     int* d_kt = nullptr;
-  } rows;
+    uint64_t used = 0;          // value of row_clock at the last use
+  };
+  static constexpr int kRowCaches = 4;
+  RowCache rows[kRowCaches];
+  uint64_t row_clock = 0;
 
   const AirIcePlan& plan(double ice_m, double depth_m) {
     auto key = std::make_pair(ice_m, depth_m);
@@ -293,14 +299,22 @@ int build_rows(airice_ctx* ctx, const TableGrid& g, int64_t r0, int64_t r1, doub
   if (r1 == r0) return 0;
   const int64_t nr = r1 - r0;
   const double key[7] = {g.h_top, g.h_step, g.loop_stop_h, (double)g.n_h, ctx->medium.B[0], ctx->medium.C[0], (double)ctx->medium.nlayers};
-  airice_ctx::RowCache& rc = ctx->rows;
-  if (!(rc.d_rows && rc.r0 == r0 && rc.r1 == r1 && std::memcmp(rc.key, key, sizeof(key)) == 0)) {
+  airice_ctx::RowCache* hit = nullptr;
+  airice_ctx::RowCache* victim = &ctx->rows[0];
+  for (airice_ctx::RowCache& q : ctx->rows) {
+    if (q.d_rows && q.r0 == r0 && q.r1 == r1 && std::memcmp(q.key, key, sizeof(key)) == 0) hit = &q;
+    if (q.used < victim->used) victim = &q;      // empty slots have used == 0
+  }
+  if (!hit) {
+    airice_ctx::RowCache& rc = *victim;
     std::vector<double> h, ntx;
     std::vector<int> kt;
     grid_rows(ctx->medium, g, r0, r1, &h, &ntx, &kt);
-    CK(cudaStreamSynchronize(s));  // a previous launch on this stream may still read the old arrays
-    if (rc.d_rows) cudaFree(rc.d_rows);
-    if (rc.d_kt) cudaFree(rc.d_kt);
+    if (rc.d_rows) {
+      CK(cudaDeviceSynchronize());  // launches on any stream may still read the evicted arrays
+      cudaFree(rc.d_rows);
+      if (rc.d_kt) cudaFree(rc.d_kt);
+    }
     rc.d_rows = nullptr; rc.d_kt = nullptr; rc.r0 = rc.r1 = -1;
     CK(cudaMalloc((void**)&rc.d_rows, sizeof(double) * 2 * nr));
     CK(cudaMalloc((void**)&rc.d_kt, sizeof(int) * nr));
@@ -309,7 +323,10 @@ int build_rows(airice_ctx* ctx, const TableGrid& g, int64_t r0, int64_t r1, doub
     CK(cudaMemcpy(rc.d_kt, kt.data(), sizeof(int) * nr, cudaMemcpyHostToDevice));
     std::memcpy(rc.key, key, sizeof(key));
     rc.r0 = r0; rc.r1 = r1;
+    hit = &rc;
   }
+  airice_ctx::RowCache& rc = *hit;
+  rc.used = ++ctx->row_clock;
   double* d_rows = rc.d_rows;
   int* d_kt = rc.d_kt;
   TableArgs a;
@@ -419,8 +436,10 @@ void airice_destroy(airice_ctx* c) {
     if (c->dev[s]) cudaFree(c->dev[s]);
     if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
   }
-  if (c->rows.d_rows) cudaFree(c->rows.d_rows);
-  if (c->rows.d_kt) cudaFree(c->rows.d_kt);
+  for (airice_ctx::RowCache& q : c->rows) {
+    if (q.d_rows) cudaFree(q.d_rows);
+    if (q.d_kt) cudaFree(q.d_kt);
+  }
   for (int k = 0; k < airice_ctx::kSlots; k++)
     if (c->inice_scratch[k]) cudaFree(c->inice_scratch[k]);
   if (c->inice_cols) cudaFree(c->inice_cols);

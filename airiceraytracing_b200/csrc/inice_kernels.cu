@@ -38,7 +38,10 @@ __device__ __forceinline__ AirIceInIce inice_model(const InIceArgs& a) {
 }
 
 // pass 1: direct + reflected ray for every pair; all 29 columns written (refracted ones as absent)
-__global__ void __launch_bounds__(kDrThreads) airice_inice_dr_kernel(const InIceArgs a) {
+#ifndef AIRICE_INICE_DR_MINBLOCKS
+#define AIRICE_INICE_DR_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(kDrThreads, AIRICE_INICE_DR_MINBLOCKS) airice_inice_dr_kernel(const InIceArgs a) {
   const int64_t i = (int64_t)blockIdx.x * kDrThreads + threadIdx.x;
   if (i >= a.n) return;
   const AirIceInIce m = inice_model(a);

@@ -111,7 +111,7 @@ void sim_forward_batch(long n, const double* th, const double* h, double ice, do
 // d/dL check: returns X and analytic dX/dL
 double sim_x_total(double h, double ice, double depth, double L, double* dXdL) {
   AirIcePlan p; make_plan(g_m, ice, depth, &p);
-  return airice_x_newton(g_m, p, top_layer(h), h, n_air(g_m, h), L, *dXdL);
+  return airice_x_dx(g_m, p, top_layer(h), h, n_air(g_m, h), L, *dXdL);
 }
 // in-ice solver: IceRayTracing::IceRayTracing(0,z0,x1,z1) layout, out[29] per pair; returns nothing
 void sim_inice_batch(long n, const double* z0, const double* x1, const double* z1, double* out, int* mask) {
