@@ -130,10 +130,12 @@ AIRICE_HD double airice_n_tx(const AirIceMedium& m, int k, double h) {
 
 // Top layer of a transmitter height for the walk (SkipLayersAbove, M.cc:666-676); -1 = in no layer.
 AIRICE_HD int airice_top_layer(const AirIceMedium& m, double h) {
-  int kt = -1;
+  // the k with hlo[k] <= h < hlo[k+1] (half-open, ">=" on the lower edge): the layer edges ascend, so inside
+  // [hlo[0], hlo[nlayers]) that k is the number of interior edges at or below h
+  if (!(h >= m.hlo[0] && h < m.hlo[m.nlayers])) return -1;
+  int kt = 0;
 #pragma unroll
-  for (int k = 0; k < AIRICE_MAX_LAYERS; k++)
-    if (k < m.nlayers && h >= m.hlo[k] && h < m.hlo[k + 1]) kt = k;
+  for (int k = 1; k < AIRICE_MAX_LAYERS; k++) kt += (k < m.nlayers && h >= m.hlo[k]) ? 1 : 0;
   return kt;
 }
 
