@@ -261,7 +261,16 @@ __device__ __forceinline__ void solve_one(const AirIceMedium& m, const AirIcePla
   }
   // a deferred pair is listed and then carries on with its NaN angle (its outputs are overwritten by the second pass,
   // which the stream orders after this one): leaving the kernel here instead measured 5 % slower for the whole launch
-  if (DEFER && hard) a.defer_list[atomicAdd(a.defer_count, 1)] = (int32_t)i;
+  if (DEFER && hard) {
+    // one atomic per warp, aggregated by hand: the compiler's own aggregation of a per-lane atomicAdd is ~45 instructions
+    // in every warp that has a hard pair (1 in 6), 1.1 % of the kernel's issue slots
+    const unsigned act = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(act) - 1;
+    int base = 0;
+    if (lane == leader) asm volatile("atom.global.add.s32 %0, [%1], %2;" : "=r"(base) : "l"(a.defer_count), "r"(__popc(act)) : "memory");
+    base = __shfl_sync(act, base, leader);
+    a.defer_list[base + __popc(act & ((1u << lane) - 1))] = (int32_t)i;
+  }
   const double L = airice_L_of_theta(m, ntx, theta);
   AirIceRay r;
   const bool full_rec = !cm;
