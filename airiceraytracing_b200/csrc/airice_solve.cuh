@@ -439,7 +439,7 @@ AIRICE_HD double airice_straight_angle(const AirIceMedium& m, double h, double d
                                        double& ta) {
   const double den = (depth_signed < 0) ? (h - ice - depth_signed) : (h - (ice + depth_signed));
   ta = d / den;
-  return 180 - (AIRICE_ATAN_Q(ta, 1.0) * (180.0 / m.pi));
+  return 180 - (AIRICE_ATAN_Q(ta, 1.0) * m.rad2deg);
 }
 
 // Solution flag of M.cc:974-983.

@@ -282,11 +282,11 @@ __device__ __forceinline__ void solve_one(const AirIceMedium& m, const AirIcePla
     a.out[1][i] = (r.t_air * m.c) * 100;
     a.out[2][i] = r.p_ice * 100;
     a.out[3][i] = r.p_air * 100;
-    a.out[4][i] = theta * (m.pi / 180);
+    a.out[4][i] = theta * m.deg2rad;
     a.out[5][i] = r.x_air * 100;
     a.out[6][i] = r.trans_s;
     a.out[7][i] = r.trans_p;
-    a.out[8][i] = r.recv_deg * (m.pi / 180);
+    a.out[8][i] = r.recv_deg * m.deg2rad;
     return;
   }
   if (a.ok) a.ok[i] = airice_check_solution(thd, d) ? 1 : 0;
@@ -296,11 +296,11 @@ __device__ __forceinline__ void solve_one(const AirIceMedium& m, const AirIcePla
     if (a.out[1]) a.out[1][i] = (r.t_air * m.c) * 100;
     if (a.out[2]) a.out[2][i] = r.p_ice * 100;
     if (a.out[3]) a.out[3][i] = r.p_air * 100;
-    if (a.out[4]) a.out[4][i] = theta * (m.pi / 180);
+    if (a.out[4]) a.out[4][i] = theta * m.deg2rad;
     if (a.out[5]) a.out[5][i] = r.x_air * 100;
     if (a.out[6]) a.out[6][i] = r.trans_s;
     if (a.out[7]) a.out[7][i] = r.trans_p;
-    if (a.out[8]) a.out[8][i] = r.recv_deg * (m.pi / 180);
+    if (a.out[8]) a.out[8][i] = r.recv_deg * m.deg2rad;
   } else {
     if (a.out[0]) a.out[0][i] = thd;
     if (a.out[1]) a.out[1][i] = r.x_air;
@@ -717,8 +717,8 @@ __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_look
   const double THD = PI[0];
   double o[9];
   o[0] = PI[1] * 100; o[1] = PI[2] * 100; o[2] = PI[8] * 100; o[3] = PI[7] * 100;
-  o[4] = PI[3] * (m.pi / 180); o[5] = PI[4] * 100; o[6] = PI[5]; o[7] = PI[6];
-  o[8] = PI[9] * (m.pi / 180);
+  o[4] = PI[3] * m.deg2rad; o[5] = PI[4] * 100; o[6] = PI[5]; o[7] = PI[6];
+  o[8] = PI[9] * m.deg2rad;
   // validity (M.cc:1417-1456).  When exactly one row is out of range the reference re-solves directly with
   // mis-scaled arguments (M.cc:1419) but THD stays 0, so the distance check below always fails: the result of that
   // solve is unobservable through the flag and is not reproduced.
