@@ -233,7 +233,7 @@ AIRICE_HD void airice_seg_x_dx(double A, double sA, double inv_sA, double L, dou
   // step by 1e-6 of its length, which for the pairs whose single-precision landing point is 1e-4 deg off exceeds the
   // replay's guard band (measured: one bisection-cell miss in 128 000 solves, tests/test_gpu_parity.py C5 case)
   const double rTt = AIRICE_RCP(Tt), rTb = AIRICE_RCP(Tb);
-  const double dG = Cn * (xb - xt) - AIRICE_LOG(Tb * rTt);
+  const double dG = Cn * (xb - xt) - AIRICE_LOG_POS(Tb * rTt);
   const double c1 = iC * inv_sA;
   seg = (L * c1) * dG;
   const double qb = (sA + Rb) * (sA + Rb) * (rTb * yb), qt = (sA + Rt) * (sA + Rt) * (rTt * yt);
@@ -484,7 +484,7 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
         double Rt, yt;
         AIRICE_SQRT_RSQRT(Dt, Rt, yt);
         const double Tt = nt - L2 + sA * Rt;
-        const double lnTt = AIRICE_LOG(Tt), Ht = AIRICE_LOG(nt + Rt);
+        const double lnTt = AIRICE_LOG_POS(Tt), Ht = AIRICE_LOG_POS(nt + Rt);
         double Rb, lnTb, Hb;
         if (k > p.kb && pR > 1.0e-3) {
           const double dR = p.ho_dn2[k] * (0.5 * pY);
@@ -493,8 +493,8 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
           Hb = pH + (p.ho_dn[k] + dR) * AIRICE_RCP_APPROX(pN + pR);
         } else {
           Rb = AIRICE_SQRT(Db);
-          lnTb = AIRICE_LOG(nb - L2 + sA * Rb);
-          Hb = AIRICE_LOG(nb + Rb);
+          lnTb = AIRICE_LOG_POS(nb - L2 + sA * Rb);
+          Hb = AIRICE_LOG_POS(nb + Rb);
         }
         pR = Rt; pY = yt; pT = Tt; pLnT = lnTt; pH = Ht; pN = nt;
         double xs, ts, gs;
