@@ -168,7 +168,7 @@ AIRICE_HD double airice_x_exact(const AirIceMedium& m, const AirIcePlan& p, int 
     const double nt = top ? n_tx : p.start_n[k];
     const double xb = p.stop_x[k], nb = p.stop_n[k];
     const double Rb = AIRICE_SQRT(nb * nb - L2), Rt = AIRICE_SQRT(nt * nt - L2);
-    const double Gb = Cn * xb - AIRICE_LOG(A * nb - L2 + sA * Rb), Gt = Cn * xt - AIRICE_LOG(A * nt - L2 + sA * Rt);
+    const double Gb = Cn * xb - AIRICE_LOG_POS(A * nb - L2 + sA * Rb), Gt = Cn * xt - AIRICE_LOG_POS(A * nt - L2 + sA * Rt);
     const double mult = AIRICE_DIV(L, Cn) * AIRICE_RCP(sA);
     const double seg = AIRICE_MUL(mult, Gb) - AIRICE_MUL(mult, Gt);
     X += air ? -seg : seg;
@@ -183,7 +183,7 @@ AIRICE_HD double airice_seg_x(double A, double sA, double inv_sA, double L, doub
                               double nt, double xb, double nb) {
   const double Rb = AIRICE_SQRT(nb * nb - L2), Rt = AIRICE_SQRT(nt * nt - L2);
   const double Tb = (AIR ? nb : A * nb) - L2 + sA * Rb, Tt = (AIR ? nt : A * nt) - L2 + sA * Rt;
-  const double dG = Cn * (xb - xt) - AIRICE_LOG(Tb * AIRICE_RCP(Tt));
+  const double dG = Cn * (xb - xt) - AIRICE_LOG_POS(Tb * AIRICE_RCP(Tt));
   return (L * (iC * inv_sA)) * dG;
 }
 
@@ -439,7 +439,7 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
         const double Db = nb * nb - L2, Dt = nt * nt - L2;
         const double Rb = AIRICE_SQRT(Db);
         const double Tb = nb - L2 + sA * Rb;
-        const double lnTb = AIRICE_LOG(Tb), Hb = AIRICE_LOG(nb + Rb);
+        const double lnTb = AIRICE_LOG_POS(Tb), Hb = AIRICE_LOG_POS(nb + Rb);
         double Rt, lnTt, Ht;
         if (!top) {
           // Snell hand-over at an interior boundary: L' = L rho with rho = n'/n, i.e. the direction L/n is kept, so
@@ -452,8 +452,8 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
           lnTt = prevLnT + (u - 0.5 * u * u);
         } else {
           Rt = AIRICE_SQRT(Dt);
-          lnTt = AIRICE_LOG(nt - L2 + sA * Rt);
-          Ht = AIRICE_LOG(nt + Rt);
+          lnTt = AIRICE_LOG_POS(nt - L2 + sA * Rt);
+          Ht = AIRICE_LOG_POS(nt + Rt);
         }
         prevR = Rb; prevH = Hb; prevT = Tb; prevLnT = lnTb;
         double xs, ts, gs;
@@ -519,7 +519,7 @@ AIRICE_HD AirIceIceTop airice_ice_top(const AirIceMedium& m, const AirIcePlan& p
   o.sA = AIRICE_SQRT(A * A - o.L2); o.inv_sA = AIRICE_RCP(o.sA);
   o.Dt = nt * nt - o.L2;
   o.Rt = AIRICE_SQRT(o.Dt);
-  o.lnTt = AIRICE_LOG(A * nt - o.L2 + o.sA * o.Rt); o.Ht = AIRICE_LOG(nt + o.Rt);
+  o.lnTt = AIRICE_LOG_POS(A * nt - o.L2 + o.sA * o.Rt); o.Ht = AIRICE_LOG_POS(nt + o.Rt);
   return o;
 }
 // ice leg from the surface to depth xb (n(xb) = nb): GetIcePropagationPar (M.cc:807-869)
@@ -530,7 +530,7 @@ AIRICE_HD void airice_ice_leg(const AirIceMedium& m, const AirIcePlan& p, const 
   const double Cn = p.neg_c[k], iC = p.inv_neg_c[k];
   const double Db = nb * nb - o.L2;
   const double Rb = AIRICE_SQRT(Db);
-  const double lnTb = AIRICE_LOG(A * nb - o.L2 + o.sA * Rb), Hb = AIRICE_LOG(nb + Rb);
+  const double lnTb = AIRICE_LOG_POS(A * nb - o.L2 + o.sA * Rb), Hb = AIRICE_LOG_POS(nb + Rb);
   airice_seg_sums<false>(A, o.inv_sA, (o.L * iC) * o.inv_sA, m.c * Cn, Cn, iC, p.start_x[k], xb, o.Dt, Db, o.Rt, Rb, o.lnTt,
                          lnTb, o.Ht, Hb, xi, ti, gi);
   // receive angle asin(L / n(depth)) (M.cc:824 / 583-589) as atan(L / sqrt(n^2 - L^2)): the square root is Rb
