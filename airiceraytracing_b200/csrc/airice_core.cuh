@@ -226,8 +226,8 @@ template <bool AIR>
 AIRICE_HD void airice_seg_x_dx(double A, double sA, double inv_sA, double L, double L2, double Cn, double iC, double xt,
                                double nt, double xb, double nb, double& seg, double& dseg) {
   double Rb, yb, Rt, yt;
-  AIRICE_SQRT_RSQRT(nb * nb - L2, Rb, yb);
-  AIRICE_SQRT_RSQRT(nt * nt - L2, Rt, yt);
+  AIRICE_SQRT_RSQRT_NZ(nb * nb - L2, Rb, yb);
+  AIRICE_SQRT_RSQRT_NZ(nt * nt - L2, Rt, yt);
   const double Tb = (AIR ? nb : A * nb) - L2 + sA * Rb, Tt = (AIR ? nt : A * nt) - L2 + sA * Rt;
   // 1/T_b only enters the slope, but the 20-bit MUFU seed is NOT enough for it: a slope off by 1e-6 moves the Newton
   // step by 1e-6 of its length, which for the pairs whose single-precision landing point is 1e-4 deg off exceeds the
