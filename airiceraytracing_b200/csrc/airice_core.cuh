@@ -245,7 +245,7 @@ AIRICE_HD double airice_x_dx(const AirIceMedium& m, const AirIcePlan& p, int kt,
   const double L2 = L * L;
   double X = 0.0, dX = 0.0;
   if (kt >= p.kb) {
-    const double sAir = AIRICE_SQRT(1.0 * 1.0 - L2);
+    const double sAir = AIRICE_SQRT_NZ(1.0 * 1.0 - L2);
     const double yAir = AIRICE_RCP(sAir);
 #if AIRICE_PEEL_TOP
 #pragma unroll 1
@@ -272,7 +272,7 @@ AIRICE_HD double airice_x_dx(const AirIceMedium& m, const AirIcePlan& p, int kt,
 #endif
   }
   if (p.has_ice) {
-    const double sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
+    const double sIce = AIRICE_SQRT_NZ(m.A_ice * m.A_ice - L2);
     const double yIce = AIRICE_RCP(sIce);
     const int k = AIRICE_ICE_SLOT;
     double seg, dseg;
@@ -466,7 +466,7 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
       // tail of a solve: one L throughout, so the order of the layers is free; bottom-up keeps the per-layer plan
       // reads warp-uniform (see airice_x_fast)
       const double L2 = Lk * Lk;
-      const double sA = AIRICE_SQRT(1.0 * 1.0 - L2), inv_sA = AIRICE_RCP(sA);
+      const double sA = AIRICE_SQRT_NZ(1.0 * 1.0 - L2), inv_sA = AIRICE_RCP(sA);
       constexpr int kUnrollF = AIRICE_UNROLL_FULL;
       // The lower end of layer k and the upper end of layer k-1 are 1e-5 m and ~4e-13 in n apart (M.cc:715), so
       // R, ln T and H at the lower end follow from the upper end below it to first order in the host-made
@@ -482,7 +482,7 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
         const double xb = p.stop_x[k], nb = p.stop_n[k];
         const double Db = nb * nb - L2, Dt = nt * nt - L2;
         double Rt, yt;
-        AIRICE_SQRT_RSQRT(Dt, Rt, yt);
+        AIRICE_SQRT_RSQRT_NZ(Dt, Rt, yt);
         const double Tt = nt - L2 + sA * Rt;
         const double lnTt = AIRICE_LOG_POS(Tt), Ht = AIRICE_LOG_POS(nt + Rt);
         double Rb, lnTb, Hb;
@@ -492,7 +492,7 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
           lnTb = pLnT + (p.ho_dn[k] + sA * dR) * AIRICE_RCP_APPROX(pT);
           Hb = pH + (p.ho_dn[k] + dR) * AIRICE_RCP_APPROX(pN + pR);
         } else {
-          Rb = AIRICE_SQRT(Db);
+          Rb = AIRICE_SQRT_NZ(Db);
           lnTb = AIRICE_LOG_POS(nb - L2 + sA * Rb);
           Hb = AIRICE_LOG_POS(nb + Rb);
         }
