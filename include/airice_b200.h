@@ -124,7 +124,9 @@ int airice_solve_host(airice_ctx *ctx, int64_t n, const double *h, const double 
 
 /* ---- kernel 3: table lookup = GetHorizontalDistanceToIntersectionPoint_Table
  * (MultiRayAirIceRefraction.cc:1305-1462, .h:189) with FindClosestAirTxHeight / FindClosestTHD / GetParValues
- * (MultiRayAirIceRefraction.cc:1033-1302).  cm/rad in and out, 9 columns as for CM_RAD solves. */
+ * (MultiRayAirIceRefraction.cc:1033-1302).  cm/rad in and out, 9 columns as for CM_RAD solves.  The bin FindClosestTHD's
+ * index halvings + scan end on is predicted from a per-row position table and verified on the records the interpolation
+ * reads (same indices, same bits); AIRICE_LOOKUP_LITERAL=1 in the environment forces the literal search (test hook). */
 int airice_lookup_device(airice_ctx *ctx, const airice_table *t, int64_t n, const double *d_h_cm,
                          const double *d_dist_cm, double *const *d_out, uint8_t *d_ok, void *stream);
 int airice_lookup_host(airice_ctx *ctx, const airice_table *t, int64_t n, const double *h_cm, const double *dist_cm,
