@@ -90,29 +90,30 @@ struct AirIceMedium {
 // Per-(ice height, receiver depth) plan: every ray-independent number of the layer walk, computed on
 // the host with the same libm the reference uses.  Slot AIRICE_MAX_LAYERS of the per-segment arrays is the ice leg.
 #define AIRICE_ICE_SLOT AIRICE_MAX_LAYERS
+// One segment (air layer k, or the ice leg in slot AIRICE_ICE_SLOT).  The values a loop trip reads together sit together
+// and 16-byte aligned, so that a trip's plan reads are 128-bit constant-bank loads (as separate arrays every value was
+// its own LDC: 9.5 % of the solve kernel's instructions).
+struct alignas(16) AirIceSeg {
+  double neg_c, inv_neg_c;    // C' = -C of the segment's medium, and 1/C'
+  double stop_x, stop_n;      // lower end: ice_h for k==kb else hlo[k] (M.cc:722-728); ice leg: depth
+  double start_x, start_n;    // upper end when entered from above: hlo[k+1]-1e-5 (M.cc:715); ice leg: 0
+  // solver path (one L throughout): n_stop[k] - n_start[k-1] and n_stop[k]^2 - n_start[k-1]^2 across the lower boundary
+  // of layer k (~4e-13; 0 for k <= kb): first-order hand-over of R, ln T, H in airice_ray_air<false>
+  double ho_dn, ho_dn2;
+  double relay, ln_relay;     // n_start[k]/n_stop[k+1]: Snell hand-over of the table path (M.cc:1871), and its log (~3e-13)
+  // single-precision companions for the FP32 pre-iteration of the solver (host-computed in double, then rounded):
+  // q = n^2 - A^2 and pa = A (n - A) at both ends of a segment keep the small differences (n-1 ~ 3e-4 in air) exact,
+  // so that R^2 = q + sA^2 and T = pa + sA (sA + R) stay accurate in float even for grazing rays.
+  float f_q_stop, f_pa_stop, f_q_start, f_pa_start;
+  float f_cdx, f_inv_neg_c;   // C' (x_stop - x_start) of a full segment, (float)(1/C')
+  float pad_[2];
+};
 struct AirIcePlan {
   int kb;          // layer that contains the ice surface (= SkipLayersBelow, M.cc:680-690)
   int has_ice;     // receiver below the surface (depth != 0), M.cc:901
   double ice_h;    // ice-surface height after the depth>=0 fold (M.cc:1472-1476)
   double depth;    // receiver depth, positive, 0 when the receiver sits in air
-  double neg_c[AIRICE_MAX_LAYERS + 1];    // C' = -C of the segment's medium
-  double inv_neg_c[AIRICE_MAX_LAYERS + 1];  // 1/C' (Newton phase only)
-  double stop_x[AIRICE_MAX_LAYERS + 1];   // lower end: ice_h for k==kb else hlo[k] (M.cc:722-728); ice leg: depth
-  double stop_n[AIRICE_MAX_LAYERS + 1];
-  double start_x[AIRICE_MAX_LAYERS + 1];  // upper end when entered from above: hlo[k+1]-1e-5 (M.cc:715); ice leg: 0
-  double start_n[AIRICE_MAX_LAYERS + 1];
-  double relay[AIRICE_MAX_LAYERS + 1];    // n_start[k]/n_stop[k+1]: Snell hand-over of the table path (M.cc:1871)
-  double ln_relay[AIRICE_MAX_LAYERS + 1]; // log(relay[k]) (~3e-13): the hand-over of ln(n+R) across the boundary
-  // solver path (one L throughout): n_stop[k] - n_start[k-1] and n_stop[k]^2 - n_start[k-1]^2 across the lower boundary
-  // of layer k (~4e-13; 0 for k <= kb): first-order hand-over of R, ln T, H in airice_ray_air<false>
-  double ho_dn[AIRICE_MAX_LAYERS + 1], ho_dn2[AIRICE_MAX_LAYERS + 1];
-  // single-precision companions for the FP32 pre-iteration of the solver (host-computed in double, then rounded):
-  // q = n^2 - A^2 and pa = A (n - A) at both ends of a segment keep the small differences (n-1 ~ 3e-4 in air) exact,
-  // so that R^2 = q + sA^2 and T = pa + sA (sA + R) stay accurate in float even for grazing rays.
-  float f_q_stop[AIRICE_MAX_LAYERS + 1], f_pa_stop[AIRICE_MAX_LAYERS + 1];
-  float f_q_start[AIRICE_MAX_LAYERS + 1], f_pa_start[AIRICE_MAX_LAYERS + 1];
-  float f_cdx[AIRICE_MAX_LAYERS + 1];       // C' (x_stop - x_start) of a full segment
-  float f_inv_neg_c[AIRICE_MAX_LAYERS + 1];
+  AirIceSeg seg[AIRICE_MAX_LAYERS + 1];
 };
 
 AIRICE_HD double airice_n_air(const AirIceMedium& m, int k, double z) { return 1.0 + m.B[k] * exp(-m.C[k] * z); }
@@ -162,11 +163,11 @@ AIRICE_HD double airice_x_exact(const AirIceMedium& m, const AirIcePlan& p, int 
     const int k = air ? (kt - j) : AIRICE_ICE_SLOT;
     const double A = air ? 1.0 : m.A_ice;
     const double sA = air ? sAir : sIce;
-    const double Cn = p.neg_c[k];
+    const double Cn = p.seg[k].neg_c;
     const bool top = (j == 0) && air;
-    const double xt = top ? h : p.start_x[k];
-    const double nt = top ? n_tx : p.start_n[k];
-    const double xb = p.stop_x[k], nb = p.stop_n[k];
+    const double xt = top ? h : p.seg[k].start_x;
+    const double nt = top ? n_tx : p.seg[k].start_n;
+    const double xb = p.seg[k].stop_x, nb = p.seg[k].stop_n;
     const double Rb = AIRICE_SQRT(nb * nb - L2), Rt = AIRICE_SQRT(nt * nt - L2);
     const double Gb = Cn * xb - AIRICE_LOG_POS(A * nb - L2 + sA * Rb), Gt = Cn * xt - AIRICE_LOG_POS(A * nt - L2 + sA * Rt);
     const double mult = AIRICE_DIV(L, Cn) * AIRICE_RCP(sA);
@@ -202,17 +203,17 @@ AIRICE_HD double airice_x_fast(const AirIceMedium& m, const AirIcePlan& p, int k
 #pragma unroll 1
     for (int k = p.kb; k <= kt; k++) {
       const bool top = (k == kt);
-      const double xt = top ? h : p.start_x[k];
-      const double nt = top ? n_tx : p.start_n[k];
-      X -= airice_seg_x<true>(1.0, sAir, yAir, L, L2, p.neg_c[k], p.inv_neg_c[k], xt, nt, p.stop_x[k], p.stop_n[k]);
+      const double xt = top ? h : p.seg[k].start_x;
+      const double nt = top ? n_tx : p.seg[k].start_n;
+      X -= airice_seg_x<true>(1.0, sAir, yAir, L, L2, p.seg[k].neg_c, p.seg[k].inv_neg_c, xt, nt, p.seg[k].stop_x, p.seg[k].stop_n);
     }
   }
   if (p.has_ice) {
     const double sIce = AIRICE_SQRT(m.A_ice * m.A_ice - L2);
     const double yIce = AIRICE_RCP(sIce);
     const int k = AIRICE_ICE_SLOT;
-    X += airice_seg_x<false>(m.A_ice, sIce, yIce, L, L2, p.neg_c[k], p.inv_neg_c[k], p.start_x[k], p.start_n[k],
-                             p.stop_x[k], p.stop_n[k]);
+    X += airice_seg_x<false>(m.A_ice, sIce, yIce, L, L2, p.seg[k].neg_c, p.seg[k].inv_neg_c, p.seg[k].start_x, p.seg[k].start_n,
+                             p.seg[k].stop_x, p.seg[k].stop_n);
   }
   return X;
 }
@@ -251,22 +252,22 @@ AIRICE_HD double airice_x_dx(const AirIceMedium& m, const AirIcePlan& p, int kt,
 #pragma unroll 1
     for (int k = p.kb; k < kt; k++) {
       double seg, dseg;
-      airice_seg_x_dx<true>(1.0, sAir, yAir, L, L2, p.neg_c[k], p.inv_neg_c[k], p.start_x[k], p.start_n[k], p.stop_x[k], p.stop_n[k], seg, dseg);
+      airice_seg_x_dx<true>(1.0, sAir, yAir, L, L2, p.seg[k].neg_c, p.seg[k].inv_neg_c, p.seg[k].start_x, p.seg[k].start_n, p.seg[k].stop_x, p.seg[k].stop_n, seg, dseg);
       X -= seg; dX -= dseg;
     }
     {
       double seg, dseg;
-      airice_seg_x_dx<true>(1.0, sAir, yAir, L, L2, p.neg_c[kt], p.inv_neg_c[kt], h, n_tx, p.stop_x[kt], p.stop_n[kt], seg, dseg);
+      airice_seg_x_dx<true>(1.0, sAir, yAir, L, L2, p.seg[kt].neg_c, p.seg[kt].inv_neg_c, h, n_tx, p.seg[kt].stop_x, p.seg[kt].stop_n, seg, dseg);
       X -= seg; dX -= dseg;
     }
 #else
 #pragma unroll 1
     for (int k = p.kb; k <= kt; k++) {
       const bool top = (k == kt);
-      const double xt = top ? h : p.start_x[k];
-      const double nt = top ? n_tx : p.start_n[k];
+      const double xt = top ? h : p.seg[k].start_x;
+      const double nt = top ? n_tx : p.seg[k].start_n;
       double seg, dseg;
-      airice_seg_x_dx<true>(1.0, sAir, yAir, L, L2, p.neg_c[k], p.inv_neg_c[k], xt, nt, p.stop_x[k], p.stop_n[k], seg, dseg);
+      airice_seg_x_dx<true>(1.0, sAir, yAir, L, L2, p.seg[k].neg_c, p.seg[k].inv_neg_c, xt, nt, p.seg[k].stop_x, p.seg[k].stop_n, seg, dseg);
       X -= seg; dX -= dseg;
     }
 #endif
@@ -276,8 +277,8 @@ AIRICE_HD double airice_x_dx(const AirIceMedium& m, const AirIcePlan& p, int kt,
     const double yIce = AIRICE_RCP(sIce);
     const int k = AIRICE_ICE_SLOT;
     double seg, dseg;
-    airice_seg_x_dx<false>(m.A_ice, sIce, yIce, L, L2, p.neg_c[k], p.inv_neg_c[k], p.start_x[k], p.start_n[k], p.stop_x[k],
-                           p.stop_n[k], seg, dseg);
+    airice_seg_x_dx<false>(m.A_ice, sIce, yIce, L, L2, p.seg[k].neg_c, p.seg[k].inv_neg_c, p.seg[k].start_x, p.seg[k].start_n, p.seg[k].stop_x,
+                           p.seg[k].stop_n, seg, dseg);
     X += seg; dX += dseg;
   }
   dXdL = dX;
@@ -341,26 +342,26 @@ AIRICE_HD float airice_x_newton_f32(const AirIceMedium& m, const AirIcePlan& p, 
     const float y = AIRICE_F_RSQRT(sA2), sA = sA2 * y;
     // bottom-up (see airice_x_fast).  The upper end of a layer and the lower end of the layer above it are the same
     // point to single precision (1e-5 m and 3e-13 in n apart), so each trip evaluates ONE end and keeps it for the next.
-    AirIceEndF32 eb = airice_end_f32(sA2, sA, p.f_q_stop[p.kb], p.f_pa_stop[p.kb]);
+    AirIceEndF32 eb = airice_end_f32(sA2, sA, p.seg[p.kb].f_q_stop, p.seg[p.kb].f_pa_stop);
 #if AIRICE_PEEL_TOP
 #pragma unroll 1
     for (int k = p.kb; k < kt; k++) {
-      const AirIceEndF32 et = airice_end_f32(sA2, sA, p.f_q_start[k], p.f_pa_start[k]);
-      airice_seg_f32<true>(1.0f, y, L, L2, eb, et, p.f_cdx[k], p.f_inv_neg_c[k], X, dX);
+      const AirIceEndF32 et = airice_end_f32(sA2, sA, p.seg[k].f_q_start, p.seg[k].f_pa_start);
+      airice_seg_f32<true>(1.0f, y, L, L2, eb, et, p.seg[k].f_cdx, p.seg[k].f_inv_neg_c, X, dX);
       eb = et;
     }
     {
       const AirIceEndF32 et = airice_end_f32(sA2, sA, q_tx, dn_tx);
-      airice_seg_f32<true>(1.0f, y, L, L2, eb, et, h_minus_stop_top_cn, p.f_inv_neg_c[kt], X, dX);
+      airice_seg_f32<true>(1.0f, y, L, L2, eb, et, h_minus_stop_top_cn, p.seg[kt].f_inv_neg_c, X, dX);
     }
 #else
 #pragma unroll 1
     for (int k = p.kb; k <= kt; k++) {
       const bool top = (k == kt);
-      const float qt = top ? q_tx : p.f_q_start[k], pat = top ? dn_tx : p.f_pa_start[k];
-      const float cdx = top ? h_minus_stop_top_cn : p.f_cdx[k];
+      const float qt = top ? q_tx : p.seg[k].f_q_start, pat = top ? dn_tx : p.seg[k].f_pa_start;
+      const float cdx = top ? h_minus_stop_top_cn : p.seg[k].f_cdx;
       const AirIceEndF32 et = airice_end_f32(sA2, sA, qt, pat);
-      airice_seg_f32<true>(1.0f, y, L, L2, eb, et, cdx, p.f_inv_neg_c[k], X, dX);
+      airice_seg_f32<true>(1.0f, y, L, L2, eb, et, cdx, p.seg[k].f_inv_neg_c, X, dX);
       eb = et;
     }
 #endif
@@ -370,9 +371,9 @@ AIRICE_HD float airice_x_newton_f32(const AirIceMedium& m, const AirIcePlan& p, 
     const float sA2 = Ai * Ai - L2;
     const float y = AIRICE_F_RSQRT(sA2), sA = sA2 * y;
     const int k = AIRICE_ICE_SLOT;
-    const AirIceEndF32 eb = airice_end_f32(sA2, sA, p.f_q_stop[k], p.f_pa_stop[k]);
-    const AirIceEndF32 et = airice_end_f32(sA2, sA, p.f_q_start[k], p.f_pa_start[k]);
-    airice_seg_f32<false>(Ai, y, L, L2, eb, et, p.f_cdx[k], p.f_inv_neg_c[k], X, dX);
+    const AirIceEndF32 eb = airice_end_f32(sA2, sA, p.seg[k].f_q_stop, p.seg[k].f_pa_stop);
+    const AirIceEndF32 et = airice_end_f32(sA2, sA, p.seg[k].f_q_start, p.seg[k].f_pa_start);
+    airice_seg_f32<false>(Ai, y, L, L2, eb, et, p.seg[k].f_cdx, p.seg[k].f_inv_neg_c, X, dX);
   }
   dXdt = dX * n_tx * w2 * w;   // dL/dt = n_tx / (1+t^2)^{3/2}
   return X;
@@ -400,8 +401,8 @@ AIRICE_HD void airice_ray_surface(const AirIceMedium& m, const AirIcePlan& p, in
                                   bool want_refr, AirIceRay& r) {
   // incidence on the ice surface: receive angle of the bottom air segment, asin(L/n(surface)) (M.cc:760, 583-589).
   // NB: with RELAY the ice leg re-derives L as n_air(surface) sin(incidence) (M.cc:1913, 565-589), which is Lk again.
-  const double n1 = p.stop_n[p.kb < AIRICE_MAX_LAYERS ? p.kb : 0];
-  const double n2 = p.start_n[AIRICE_ICE_SLOT];  // n_ice(0)
+  const double n1 = p.seg[p.kb < AIRICE_MAX_LAYERS ? p.kb : 0].stop_n;
+  const double n2 = p.seg[AIRICE_ICE_SLOT].start_n;  // n_ice(0)
   const double Lsurf = Lk;
   const double si = AIRICE_DIV(Lsurf, n1);
   // asin(L / n1) = atan(L / sqrt(n1^2 - L^2)) when the ray crossed the air (Rsurf is that square root)
@@ -438,13 +439,13 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
 #pragma unroll kUnrollF
       for (int k = kt; k >= p.kb; k--) {
         const bool top = (k == kt);
-        if (!top) Lk = Lk * p.relay[k];
+        if (!top) Lk = Lk * p.seg[k].relay;
         const double L2 = Lk * Lk;
         sA = AIRICE_SQRT(1.0 * 1.0 - L2); inv_sA = AIRICE_RCP(sA);   // changes with every relayed L
-        const double Cn = p.neg_c[k], iC = p.inv_neg_c[k];
-        const double xt = top ? h : p.start_x[k];
-        const double nt = top ? n_tx : p.start_n[k];
-        const double xb = p.stop_x[k], nb = p.stop_n[k];
+        const double Cn = p.seg[k].neg_c, iC = p.seg[k].inv_neg_c;
+        const double xt = top ? h : p.seg[k].start_x;
+        const double nt = top ? n_tx : p.seg[k].start_n;
+        const double xb = p.seg[k].stop_x, nb = p.seg[k].stop_n;
         const double Db = nb * nb - L2, Dt = nt * nt - L2;
         const double Rb = AIRICE_SQRT(Db);
         const double Tb = nb - L2 + sA * Rb;
@@ -455,8 +456,8 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
           // R' = sqrt(n'^2 - L'^2) = rho R and ln(n' + R') = ln(n + R) + ln(rho) hold exactly; T' = n' - L'^2 + sA' R'
           // differs from the T of the layer above by ~3e-13 relative, so ln T' = ln T + log1p((T' - T)/T) needs the
           // quotient to 3-4 digits only.  Saves one sqrt and two logs per interior boundary (6 of the 20 logs of a cell).
-          Rt = p.relay[k] * prevR;
-          Ht = prevH + p.ln_relay[k];
+          Rt = p.seg[k].relay * prevR;
+          Ht = prevH + p.seg[k].ln_relay;
           const double u = ((nt - L2 + sA * Rt) - prevT) * AIRICE_RCP_APPROX(prevT);
           lnTt = prevLnT + (u - 0.5 * u * u);
         } else {
@@ -485,10 +486,10 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
 #pragma unroll kUnrollF
       for (int k = p.kb; k <= kt; k++) {
         const bool top = (k == kt);
-        const double Cn = p.neg_c[k], iC = p.inv_neg_c[k];
-        const double xt = top ? h : p.start_x[k];
-        const double nt = top ? n_tx : p.start_n[k];
-        const double xb = p.stop_x[k], nb = p.stop_n[k];
+        const double Cn = p.seg[k].neg_c, iC = p.seg[k].inv_neg_c;
+        const double xt = top ? h : p.seg[k].start_x;
+        const double nt = top ? n_tx : p.seg[k].start_n;
+        const double xb = p.seg[k].stop_x, nb = p.seg[k].stop_n;
         const double Db = nb * nb - L2, Dt = nt * nt - L2;
         double Rt, yt;
         AIRICE_SQRT_RSQRT_NZ(Dt, Rt, yt);
@@ -496,10 +497,10 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
         const double lnTt = AIRICE_LOG_POS(Tt), Ht = AIRICE_LOG_POS(nt + Rt);
         double Rb, lnTb, Hb;
         if (k > p.kb && pR > 1.0e-3) {
-          const double dR = p.ho_dn2[k] * (0.5 * pY);
+          const double dR = p.seg[k].ho_dn2 * (0.5 * pY);
           Rb = pR + dR;
-          lnTb = pLnT + (p.ho_dn[k] + sA * dR) * AIRICE_RCP_APPROX(pT);
-          Hb = pH + (p.ho_dn[k] + dR) * AIRICE_RCP_APPROX(pN + pR);
+          lnTb = pLnT + (p.seg[k].ho_dn + sA * dR) * AIRICE_RCP_APPROX(pT);
+          Hb = pH + (p.seg[k].ho_dn + dR) * AIRICE_RCP_APPROX(pN + pR);
         } else {
           Rb = AIRICE_SQRT_NZ(Db);
           lnTb = AIRICE_LOG_POS(nb - L2 + sA * Rb);
@@ -522,7 +523,7 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
 // upper end of the ice leg (z = 0): everything that does not depend on the receiver depth
 AIRICE_HD AirIceIceTop airice_ice_top(const AirIceMedium& m, const AirIcePlan& p, double Lk) {
   const int k = AIRICE_ICE_SLOT;
-  const double A = m.A_ice, nt = p.start_n[k];
+  const double A = m.A_ice, nt = p.seg[k].start_n;
   AirIceIceTop o;
   o.L = Lk; o.L2 = Lk * Lk;
   o.sA = AIRICE_SQRT(A * A - o.L2); o.inv_sA = AIRICE_RCP(o.sA);
@@ -536,11 +537,11 @@ AIRICE_HD void airice_ice_leg(const AirIceMedium& m, const AirIcePlan& p, const 
                               double& xi, double& ti, double& gi, double& recv_deg) {
   const int k = AIRICE_ICE_SLOT;
   const double A = m.A_ice;
-  const double Cn = p.neg_c[k], iC = p.inv_neg_c[k];
+  const double Cn = p.seg[k].neg_c, iC = p.seg[k].inv_neg_c;
   const double Db = nb * nb - o.L2;
   const double Rb = AIRICE_SQRT(Db);
   const double lnTb = AIRICE_LOG_POS(A * nb - o.L2 + o.sA * Rb), Hb = AIRICE_LOG_POS(nb + Rb);
-  airice_seg_sums<false>(A, o.inv_sA, (o.L * iC) * o.inv_sA, m.c * Cn, Cn, iC, p.start_x[k], xb, o.Dt, Db, o.Rt, Rb, o.lnTt,
+  airice_seg_sums<false>(A, o.inv_sA, (o.L * iC) * o.inv_sA, m.c * Cn, Cn, iC, p.seg[k].start_x, xb, o.Dt, Db, o.Rt, Rb, o.lnTt,
                          lnTb, o.Ht, Hb, xi, ti, gi);
   // receive angle asin(L / n(depth)) (M.cc:824 / 583-589) as atan(L / sqrt(n^2 - L^2)): the square root is Rb
   recv_deg = AIRICE_ATAN_Q(o.L, Rb) * m.rad2deg;
@@ -555,7 +556,7 @@ AIRICE_HD void airice_ray_full(const AirIceMedium& m, const AirIcePlan& p, int k
   r.recv_deg = 0.0;
   if (in_ice) {
     const AirIceIceTop it = airice_ice_top(m, p, al.L);
-    airice_ice_leg(m, p, it, p.stop_x[AIRICE_ICE_SLOT], p.stop_n[AIRICE_ICE_SLOT], r.x_ice, r.t_ice, r.p_ice, r.recv_deg);
+    airice_ice_leg(m, p, it, p.seg[AIRICE_ICE_SLOT].stop_x, p.seg[AIRICE_ICE_SLOT].stop_n, r.x_ice, r.t_ice, r.p_ice, r.recv_deg);
   }
   airice_ray_surface(m, p, kt, al.L, al.Rsurf, want_inc, want_refr, r);
 }

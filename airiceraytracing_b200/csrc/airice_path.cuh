@@ -88,7 +88,7 @@ AIRICE_HD int airice_path_plan(const AirIceMedium& m, const AirIcePlan& p, doubl
   double last_x = 0.0;
   int total = 0, s = 0;
   for (int k = kt; k >= p.kb; k--, s++) {
-    const double start = (k == kt) ? h : p.start_x[k], stop = p.stop_x[k];
+    const double start = (k == kt) ? h : p.seg[k].start_x, stop = p.seg[k].stop_x;
     const int trips = airice_path_trips(start, stop);
     if (trips < 0 || total > 2000000000 - trips) return -1;
     pl.start[s] = start; pl.stop[s] = stop; pl.x0[s] = last_x; pl.layer[s] = k;

@@ -147,7 +147,7 @@ AIRICE_HD double airice_solve_theta_t(const AirIceMedium& m, const AirIcePlan& p
     if (kt >= p.kb) {
       const int kc = kt < 0 ? 0 : kt;
       const float dn_tx = (float)(n_tx - 1.0);
-      const float cdx_top = (float)(p.neg_c[kc] * (p.stop_x[kc] - h));
+      const float cdx_top = (float)(p.seg[kc].neg_c * (p.seg[kc].stop_x - h));
       const float df = (float)d, capf = (float)t_cap;
       float tf = (float)t, sf = 0.0f;
       float t_a = 0.0f, s_a = 0.0f, t_b = 0.0f;   // the two evaluation points and the first slope: curvature estimate

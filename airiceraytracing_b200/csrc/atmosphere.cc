@@ -206,39 +206,39 @@ void make_plan(const AirIceMedium& m, double ice_h, double depth_signed, AirIceP
     if (ice_h >= m.hlo[k] && ice_h < m.hlo[k + 1]) { p.kb = k; break; }
   }
   for (int k = 0; k <= AIRICE_MAX_LAYERS; k++) {
-    p.neg_c[k] = -1; p.inv_neg_c[k] = -1; p.stop_x[k] = 0; p.stop_n[k] = 1; p.start_x[k] = 0; p.start_n[k] = 1; p.relay[k] = 1; p.ln_relay[k] = 0;
+    p.seg[k].neg_c = -1; p.seg[k].inv_neg_c = -1; p.seg[k].stop_x = 0; p.seg[k].stop_n = 1; p.seg[k].start_x = 0; p.seg[k].start_n = 1; p.seg[k].relay = 1; p.seg[k].ln_relay = 0;
   }
-  for (int k = 0; k < m.nlayers; k++) { p.neg_c[k] = -m.C[k]; p.inv_neg_c[k] = 1.0 / p.neg_c[k]; }
+  for (int k = 0; k < m.nlayers; k++) { p.seg[k].neg_c = -m.C[k]; p.seg[k].inv_neg_c = 1.0 / p.seg[k].neg_c; }
   for (int k = p.kb; k < m.nlayers; k++) {
-    p.stop_x[k] = (k == p.kb) ? ice_h : m.hlo[k];
-    p.stop_n[k] = n_air(m, p.stop_x[k]);
-    p.start_x[k] = m.hlo[k + 1] - 0.00001;
-    p.start_n[k] = n_air(m, p.start_x[k]);
+    p.seg[k].stop_x = (k == p.kb) ? ice_h : m.hlo[k];
+    p.seg[k].stop_n = n_air(m, p.seg[k].stop_x);
+    p.seg[k].start_x = m.hlo[k + 1] - 0.00001;
+    p.seg[k].start_n = n_air(m, p.seg[k].start_x);
   }
   for (int k = p.kb; k + 1 < m.nlayers; k++) {
-    p.relay[k] = p.start_n[k] / p.stop_n[k + 1];
-    p.ln_relay[k] = std::log(p.relay[k]);
+    p.seg[k].relay = p.seg[k].start_n / p.seg[k + 1].stop_n;
+    p.seg[k].ln_relay = std::log(p.seg[k].relay);
   }
-  for (int k = 0; k <= AIRICE_MAX_LAYERS; k++) { p.ho_dn[k] = 0; p.ho_dn2[k] = 0; }
+  for (int k = 0; k <= AIRICE_MAX_LAYERS; k++) { p.seg[k].ho_dn = 0; p.seg[k].ho_dn2 = 0; }
   for (int k = p.kb + 1; k < m.nlayers; k++) {
-    p.ho_dn[k] = p.stop_n[k] - p.start_n[k - 1];
-    p.ho_dn2[k] = (p.stop_n[k] - p.start_n[k - 1]) * (p.stop_n[k] + p.start_n[k - 1]);
+    p.seg[k].ho_dn = p.seg[k].stop_n - p.seg[k - 1].start_n;
+    p.seg[k].ho_dn2 = (p.seg[k].stop_n - p.seg[k - 1].start_n) * (p.seg[k].stop_n + p.seg[k - 1].start_n);
   }
   // ice leg: surface (x=0) down to the receiver (x=depth), GetIcePropagationPar (M.cc:807-869)
-  p.neg_c[AIRICE_ICE_SLOT] = -m.C_ice;
-  p.inv_neg_c[AIRICE_ICE_SLOT] = 1.0 / p.neg_c[AIRICE_ICE_SLOT];
-  p.start_x[AIRICE_ICE_SLOT] = 0.0;
-  p.start_n[AIRICE_ICE_SLOT] = n_ice(m, 0.0);
-  p.stop_x[AIRICE_ICE_SLOT] = p.depth;
-  p.stop_n[AIRICE_ICE_SLOT] = n_ice(m, p.depth);
+  p.seg[AIRICE_ICE_SLOT].neg_c = -m.C_ice;
+  p.seg[AIRICE_ICE_SLOT].inv_neg_c = 1.0 / p.seg[AIRICE_ICE_SLOT].neg_c;
+  p.seg[AIRICE_ICE_SLOT].start_x = 0.0;
+  p.seg[AIRICE_ICE_SLOT].start_n = n_ice(m, 0.0);
+  p.seg[AIRICE_ICE_SLOT].stop_x = p.depth;
+  p.seg[AIRICE_ICE_SLOT].stop_n = n_ice(m, p.depth);
   for (int k = 0; k <= AIRICE_MAX_LAYERS; k++) {
     const double A = (k == AIRICE_ICE_SLOT) ? m.A_ice : 1.0;
-    p.f_q_stop[k] = (float)((p.stop_n[k] - A) * (p.stop_n[k] + A));
-    p.f_pa_stop[k] = (float)(A * (p.stop_n[k] - A));
-    p.f_q_start[k] = (float)((p.start_n[k] - A) * (p.start_n[k] + A));
-    p.f_pa_start[k] = (float)(A * (p.start_n[k] - A));
-    p.f_cdx[k] = (float)(p.neg_c[k] * (p.stop_x[k] - p.start_x[k]));
-    p.f_inv_neg_c[k] = (float)p.inv_neg_c[k];
+    p.seg[k].f_q_stop = (float)((p.seg[k].stop_n - A) * (p.seg[k].stop_n + A));
+    p.seg[k].f_pa_stop = (float)(A * (p.seg[k].stop_n - A));
+    p.seg[k].f_q_start = (float)((p.seg[k].start_n - A) * (p.seg[k].start_n + A));
+    p.seg[k].f_pa_start = (float)(A * (p.seg[k].start_n - A));
+    p.seg[k].f_cdx = (float)(p.seg[k].neg_c * (p.seg[k].stop_x - p.seg[k].start_x));
+    p.seg[k].f_inv_neg_c = (float)p.seg[k].inv_neg_c;
   }
   *plan = p;
 }
