@@ -194,42 +194,42 @@ struct InIceZmaxIter {
   // register set on every path (ncu: 230 instructions per step, 36 of them FP64 arithmetic).  fl and fu are finite and,
   // on the main path, non-zero, so "opposite signs" is one comparison of two predicates.
   AIRICE_HD bool step(double A, double B, double C) {
-    bool stuck = false;
-    if (fl == 0.0 || fu == 0.0) {                    // exact zero at a bracket end: GSL's early exits (rare)
-      if (fl == 0.0) { root = xl; xr = xl; }
-      else { root = xr; xl = xr; }
-    } else {
-      const double oxl = xl, oxr = xr, ofl = fl, ofu = fu;
-      const double x_lin = oxr - (ofu * (oxl - oxr) / (ofl - ofu));
-      const double xb = 0.5 * (oxl + oxr);
-      const double f_lin = A + B * INICE_EXP(-C * x_lin) - L;
-      const double fb = A + B * INICE_EXP(-C * xb) - L;
-      // f not finite at the regula-falsi point (exp overflow for L far below the physical range): GSL returns before
-      // touching its state, so this and all the remaining iterations up to the 100th change nothing
-      if (!isfinite(f_lin)) stuck = true;
-      else if (f_lin == 0.0) { root = x_lin; xl = x_lin; xr = x_lin; }
-      else {
-        const bool pos = ofl > 0.0;
-        const bool opp = pos != (f_lin > 0.0);
-        const double w = opp ? x_lin - oxl : oxr - x_lin;
-        double nxl = opp ? oxl : x_lin, nfl = opp ? ofl : f_lin;
-        double nxr = opp ? x_lin : oxr, nfu = opp ? f_lin : ofu;
-        double nroot = x_lin;
-        if (!(w < 0.5 * (oxr - oxl)) && isfinite(fb)) {
-          const bool oppb = pos ? (fb < 0.0) : (fb > 0.0);
-          const double ra = 0.5 * (oxl + xb), rb = 0.5 * (xb + oxr);
-          nroot = oppb ? (x_lin > xb ? ra : x_lin) : (x_lin < xb ? rb : x_lin);
-          nxr = oppb ? xb : nxr; nfu = oppb ? fb : nfu;
-          nxl = oppb ? nxl : xb; nfl = oppb ? nfl : fb;
-        }
-        xl = nxl; xr = nxr; fl = nfl; fu = nfu; root = nroot;
-      }
+    // Every rare case ends the search in this very step (a zero at a bracket end or at the regula-falsi point collapses the
+    // bracket, which passes the interval test below; a non-finite f leaves the state as it is, and nothing would ever
+    // change it): they return at once, so the loop around this function carries no second copy of the state for them.
+    if (fl == 0.0 || fu == 0.0) {                    // GSL's early exits
+      root = (fl == 0.0) ? xl : xr;
+      xl = root; xr = root;
+      return true;
     }
+    const double oxl = xl, oxr = xr, ofl = fl, ofu = fu;
+    const double x_lin = oxr - (ofu * (oxl - oxr) / (ofl - ofu));
+    const double xb = 0.5 * (oxl + oxr);
+    const double f_lin = A + B * INICE_EXP(-C * x_lin) - L;
+    const double fb = A + B * INICE_EXP(-C * xb) - L;
+    // f not finite at the regula-falsi point (exp overflow for L far below the physical range): GSL returns before
+    // touching its state, so this and all the remaining iterations up to the 100th change nothing
+    if (!isfinite(f_lin)) return true;
+    if (f_lin == 0.0) { root = x_lin; xl = x_lin; xr = x_lin; return true; }
+    const bool pos = ofl > 0.0;
+    const bool opp = pos != (f_lin > 0.0);
+    const double w = opp ? x_lin - oxl : oxr - x_lin;
+    double nxl = opp ? oxl : x_lin, nfl = opp ? ofl : f_lin;
+    double nxr = opp ? x_lin : oxr, nfu = opp ? f_lin : ofu;
+    double nroot = x_lin;
+    if (!(w < 0.5 * (oxr - oxl)) && isfinite(fb)) {
+      const bool oppb = pos ? (fb < 0.0) : (fb > 0.0);
+      const double ra = 0.5 * (oxl + xb), rb = 0.5 * (xb + oxr);
+      nroot = oppb ? (x_lin > xb ? ra : x_lin) : (x_lin < xb ? rb : x_lin);
+      nxr = oppb ? xb : nxr; nfu = oppb ? fb : nfu;
+      nxl = oppb ? nxl : xb; nfl = oppb ? nfl : fb;
+    }
+    xl = nxl; xr = nxr; fl = nfl; fu = nfu; root = nroot;
     if (xl > xr) return true;  // GSL_EINVAL != GSL_CONTINUE
     const double al = fabs(xl), au = fabs(xr);
     const double mn = ((xl > 0.0 && xr > 0.0) || (xl < 0.0 && xr < 0.0)) ? (al < au ? al : au) : 0.0;
     if (fabs(xr - xl) < 1e-6 + 1e-6 * mn) return true;
-    return stuck || ++iter >= 100;
+    return ++iter >= 100;
   }
 };
 AIRICE_HD double inice_zmax(double A, double B, double C, double L) {
