@@ -226,9 +226,10 @@ struct InIceZmaxIter {
     }
     xl = nxl; xr = nxr; fl = nfl; fu = nfu; root = nroot;
     if (xl > xr) return true;  // GSL_EINVAL != GSL_CONTINUE
-    const double al = fabs(xl), au = fabs(xr);
-    const double mn = ((xl > 0.0 && xr > 0.0) || (xl < 0.0 && xr < 0.0)) ? (al < au ? al : au) : 0.0;
-    if (fabs(xr - xl) < 1e-6 + 1e-6 * mn) return true;
+    // gsl_root_test_interval: min(|xl|, |xr|) when both have one sign, else 0 -- with xl <= xr from here on that is xl when
+    // xl > 0, -xr when xr < 0, else 0; and |xr - xl| = xr - xl
+    const double mn = xl > 0.0 ? xl : (xr < 0.0 ? -xr : 0.0);
+    if (xr - xl < 1e-6 + 1e-6 * mn) return true;
     return ++iter >= 100;
   }
 };
