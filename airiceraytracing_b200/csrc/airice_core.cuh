@@ -441,13 +441,13 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
         const bool top = (k == kt);
         if (!top) Lk = Lk * p.seg[k].relay;
         const double L2 = Lk * Lk;
-        sA = AIRICE_SQRT(1.0 * 1.0 - L2); inv_sA = AIRICE_RCP(sA);   // changes with every relayed L
+        sA = AIRICE_SQRT_NZ(1.0 * 1.0 - L2); inv_sA = AIRICE_RCP(sA);   // changes with every relayed L
         const double Cn = p.seg[k].neg_c, iC = p.seg[k].inv_neg_c;
         const double xt = top ? h : p.seg[k].start_x;
         const double nt = top ? n_tx : p.seg[k].start_n;
         const double xb = p.seg[k].stop_x, nb = p.seg[k].stop_n;
         const double Db = nb * nb - L2, Dt = nt * nt - L2;
-        const double Rb = AIRICE_SQRT(Db);
+        const double Rb = AIRICE_SQRT_NZ(Db);
         const double Tb = nb - L2 + sA * Rb;
         const double lnTb = AIRICE_LOG_POS(Tb), Hb = AIRICE_LOG_POS(nb + Rb);
         double Rt, lnTt, Ht;
@@ -461,7 +461,7 @@ AIRICE_HD AirIceAirLeg airice_ray_air(const AirIceMedium& m, const AirIcePlan& p
           const double u = ((nt - L2 + sA * Rt) - prevT) * AIRICE_RCP_APPROX(prevT);
           lnTt = prevLnT + (u - 0.5 * u * u);
         } else {
-          Rt = AIRICE_SQRT(Dt);
+          Rt = AIRICE_SQRT_NZ(Dt);
           lnTt = AIRICE_LOG_POS(nt - L2 + sA * Rt);
           Ht = AIRICE_LOG_POS(nt + Rt);
         }
