@@ -137,5 +137,23 @@ int main(int argc, char **argv) {
         AirTxHeight * 100, HorizontalDistance * 100, AntennaDepth * 100, IceLayerHeight * 100, idx, b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], b[8]);
     std::printf("persist %d %d %d %d %d\n", rcs, idx, (int)ka, (int)kb, (int)(std::memcmp(a, b, sizeof(a)) == 0));
   }
+  // tables asked for under one ice model, used after the model changed back (and an antenna in air in between): the
+  // deferred build must use the model of the time of the MakeRayTracingTable call, like the per-call build does
+  {
+    MultiRayAirIceRefraction::A_ice = 1.775;
+    MultiRayAirIceRefraction::MakeRayTracingTable(-120.0 * 100, IceLayerHeight * 100, 0);   // in ice: collected
+    MultiRayAirIceRefraction::MakeRayTracingTable(50.0 * 100, IceLayerHeight * 100, 0);     // in air: built at once
+    MultiRayAirIceRefraction::MakeRayTracingTable(-60.0 * 100, IceLayerHeight * 100, 0);    // in ice: collected
+    MultiRayAirIceRefraction::A_ice = 1.78;
+    std::vector<float> c;
+    double sum[3] = {0, 0, 0};
+    int rcs[3];
+    const int first = (int)AntennaTableAlreadyMade.size() + 3 + (argc > 3 ? 1 : 0);   // tables 0,1 + batch 2..4 (+ loaded)
+    for (int k = 0; k < 3; k++) {
+      rcs[k] = MultiRayAirIceRefraction::GetTableColumn(first + k, 2, c);               // optical path in ice
+      for (float v : c) if (v == v) sum[k] += v;
+    }
+    std::printf("icemodel_tables %d %d %d %.17g %.17g %.17g\n", rcs[0], rcs[1], rcs[2], sum[0], sum[1], sum[2]);
+  }
   return 0;
 }

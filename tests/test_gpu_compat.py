@@ -117,6 +117,9 @@ def test_driver_deferred_table_builds_change_nothing(driver_output):
     the one the per-call builds give."""
     assert driver_output["_stdout"] == driver_output["_stdout_eager"]
     assert "table0 1" in driver_output["_stdout"]
+    # tables requested under A_ice = 1.775 and read after the model went back to 1.78, an antenna in air between them
+    rc0, rc1, rc2, s0, s1, s2 = driver_output["icemodel_tables"][0]
+    assert (rc0, rc1, rc2) == (0, 0, 0) and s0 > 0 and s2 > 0 and s1 == 0      # receiver in air: no optical path in ice
 
 
 def test_driver_batch_tables_equal_per_antenna_tables(driver_output):
