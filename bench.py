@@ -684,6 +684,17 @@ def run_ours(args):
                                      "note": "e2e moves 16 B in + 73 B out per pair over PCIe; its D2H share against a plain "
                                              "concurrent cudaMemcpyAsync of the same bytes from every GPU of the box"}
             del pin, src
+        else:
+            # one GPU: the same ceiling -- one step's results (730 MB) device -> pinned host in one plain copy
+            pin = torch.empty(73 * n // 8 + 8, dtype=torch.float64).pin_memory()
+            src = torch.empty_like(pin, device=dev)
+            ms_d2h = time_ms(lambda: pin.copy_(src, non_blocking=True), reps=3, warm=1)
+            extras["e2e_ceiling"] = {"concurrent_pinned_d2h_gbs_all_ranks": pin.numel() * 8 / ms_d2h / 1e6,
+                                     "ms_for_one_steps_results": ms_d2h,
+                                     "e2e_frac_of_ceiling": (e2e_value * 73.0 / 1e9) / (pin.numel() * 8 / ms_d2h / 1e6),
+                                     "note": "e2e moves 16 B in + 73 B out per pair over PCIe; its D2H share against one plain "
+                                             "cudaMemcpyAsync of the same bytes to pinned host memory"}
+            del pin, src
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
