@@ -886,8 +886,9 @@ int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* d
     attach_defer_scratch(c, s, &a);
     cudaError_t e = launch_solve(c->medium, p, a, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_solve");
-    for (int k = 0; k < nc; k++)
-      CK(cudaMemcpyAsync(out + (int64_t)k * n + off, a.out[k], sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    // the nc columns of the chunk in ONE strided copy (device pitch = chunk, host pitch = n) instead of nc copies
+    CK(cudaMemcpy2DAsync(out + off, sizeof(double) * (size_t)n, a.out[0], sizeof(double) * (size_t)chunk, sizeof(double) * (size_t)m,
+                         (size_t)nc, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ok + off, a.ok, (size_t)m, cudaMemcpyDeviceToHost, s));
   }
   for (int s = 0; s < airice_ctx::kSlots; s++)
@@ -945,8 +946,9 @@ int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const do
     t->note_stream(s);
     cudaError_t e = launch_lookup(c->medium, t->view(), a, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_lookup");
-    for (int k = 0; k < nc; k++)
-      CK(cudaMemcpyAsync(out + (int64_t)k * n + off, a.out[k], sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    // the nc columns of the chunk in ONE strided copy (device pitch = chunk, host pitch = n) instead of nc copies
+    CK(cudaMemcpy2DAsync(out + off, sizeof(double) * (size_t)n, a.out[0], sizeof(double) * (size_t)chunk, sizeof(double) * (size_t)m,
+                         (size_t)nc, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ok + off, a.ok, (size_t)m, cudaMemcpyDeviceToHost, s));
   }
   for (int s = 0; s < airice_ctx::kSlots; s++)
