@@ -712,7 +712,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 73 * n,
-                        "api": "airice_solve_host (C ABI, pinned host buffers, 1M-pair chunks on 2 streams)",
+                        "api": "airice_solve_host (C ABI, pinned host buffers, 512K-pair chunks on 2 streams)",
                         "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_matches, "host_binding": numa},
                 "gpu_launches": (2 if n >= 6_000_000 else 1) * args.steps,
                 "kernels_per_step": (["airice_solve_kernel<1> (all pairs; lists the 0.6 % that need a slow path)",
