@@ -1,16 +1,22 @@
 // kernels.cu -- the hand-written sm_100a kernels of the air->ice hot path.
 //
 //   airice_table_kernel        one thread per table cell; FP64-pipe bound (~1.7 kflop per 104..180 B written)
-//   airice_table_multi_kernel  the tables of several antennas in one pass (shared air walk) + their lookup layout;
-//                              HBM-write bound (96 B per cell and antenna)
-//   airice_solve_kernel<P>     one thread per Tx->Rx pair (2 single-precision iterations, 1 FP64 evaluation with slope,
+//   airice_table_multi_kernel  the tables of several antennas in one pass (shared air walk), written in the lookup layout
+//                              (52 B per cell and antenna); co-limited by HBM stores and the ice leg's FP64 work
+//   airice_row_range / row_lut / row_block kernels
+//                              per-row products of a packed table (trim ranges, position table, header blocks), batched
+//                              over same-shape tables (grid.y = table)
+//   airice_solve_kernel<P, C>  one thread per Tx->Rx pair (2 single-precision iterations, 1 FP64 evaluation with slope,
 //                              closed-form bisection replay, 1 full ray); issue/latency bound; P = 0 single pass,
-//                              P = 1 / 2 the two-pass launch that solves the rare slow-path pairs in dense warps
-//   airice_lookup_kernel       one thread per query; L2/HBM-latency bound gathers
+//                              P = 1 / 2 the two-pass launch that solves the rare slow-path pairs in dense warps;
+//                              C = the CoREAS-call instantiation (cm / rad, all nine outputs)
+//   airice_lookup_kernel       one thread per query; bin predicted from the row's position table and verified on the
+//                              records; random-sector HBM bound
+//   airice_path_plan / path_fill kernels   ray polylines (one thread per ray, then one per point)
 //
-// No tensor cores (nothing here is a contraction), no shared memory (there is no inter-thread reuse: the only
-// shared data is the ~0.7 KB medium/plan, which lives in the kernel-parameter constant bank), grids sized in
-// whole waves of 148 SMs by the launch wrappers.
+// No tensor cores (nothing here is a contraction).  Shared memory only where threads share data: a row in the position-
+// table kernel, the optional cp.async.bulk staging of the multi-antenna pass.  The ~1 KB medium / plan lives in the
+// kernel-parameter constant bank; grids are sized in whole waves of 148 SMs by the launch wrappers.
 #include <math_constants.h>
 
 #include "airice_path.cuh"
