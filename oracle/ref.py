@@ -405,6 +405,18 @@ class PyWrapReference:
         self.lib.pyref_air2ice(h, d, ice, depth, thR, _dp(out))
         return out
 
+    def set_constant_air(self, on, ice=3000.0):
+        """UseConstantRefractiveIndex / A_const / A_air as TraceIceToAir.C:27-29 would set them (commented out there)."""
+        self.lib.pyref_set_constant_air.argtypes = [C.c_int, C.c_double]
+        self.lib.pyref_set_constant_air(int(on), float(ice))
+
+    def rootfn3(self, h, d, ice, depth, thetas):
+        self.lib.pyref_rootfn3.argtypes = [C.c_double] * 4 + [c_double_p, c_double_p]
+        th = np.ascontiguousarray(thetas, dtype=np.float64)
+        out = np.zeros(3)
+        self.lib.pyref_rootfn3(h, d, ice, depth, _dp(th), _dp(out))
+        return out
+
 
 class InIceOracle:
     """Our plain-C restatement of the in-ice solver (oracle/inice_oracle.c)."""

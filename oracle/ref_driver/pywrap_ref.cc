@@ -27,6 +27,28 @@ int pyref_solution(double h, double d, double depth, double ice, double *out) {
                                                     out[6], out[7]);
   return ok ? 1 : 0;
 }
+// The python-wrapper copy's constant-refractive-index air option, switched on the way the commented-out lines of
+// TraceIceToAir.C:27-29 do it (A_const = n_air(ice surface), flag, A_air = A_const); on = 0 restores the defaults.
+// root_fn[3] receives MinimizeforLaunchAngle at the lower bracket end the option fixes (startanglelim = 90,
+// AirIceRayTracing.cc:986-988) and at two interior angles, for the caller's (h, d, ice, depth > 0).
+void pyref_set_constant_air(int on, double ice) {
+  namespace P = AirIceRayTracing;
+  if (on) {
+    P::UseConstantRefractiveIndex = false;
+    P::A_air = 1.00;
+    P::A_const = P::Getnz_air(ice);
+    P::UseConstantRefractiveIndex = true;
+    P::A_air = P::A_const;
+  } else {
+    P::UseConstantRefractiveIndex = false;
+    P::A_air = 1.00;
+    P::A_const = 1.00;
+  }
+}
+void pyref_rootfn3(double h, double d, double ice, double depth, const double *theta, double *root_fn) {
+  struct AirIceRayTracing::MinforLAng_params p = {h, ice, depth, d};
+  for (int i = 0; i < 3; i++) root_fn[i] = AirIceRayTracing::MinimizeforLaunchAngle(theta[i], &p);
+}
 void pyref_constants(double *out) {
   namespace P = AirIceRayTracing;
   out[0] = P::MaxLayers;
