@@ -604,7 +604,8 @@ int airice_table_wrap(airice_ctx* c, const float* const* d_cols32, int64_t n_h, 
                       double h_step, airice_table** out) {
   if (!c || !out || !d_cols32) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));
-  if (n_h * n_th >= 2147483647LL) return fail(-5, "lookup tables are limited to 2^31-1 cells");
+  if (n_h <= 0 || n_th <= 0) return fail(-5, "table dimensions must be positive");
+  if (n_h >= 2147483647LL || n_th >= 2147483647LL || n_h * n_th >= 2147483647LL) return fail(-5, "lookup tables are limited to 2^31-1 cells");
   airice_table* t = new airice_table();
   t->ctx = c; t->owns = false;
   c->tables.push_back(t);
@@ -679,7 +680,11 @@ int airice_table_load(airice_ctx* c, const char* path, airice_table** out) {
   if (std::fread(&hd, sizeof(hd), 1, f) != 1) { std::fclose(f); return fail(-8, "table file: truncated header"); }
   if (std::memcmp(hd.magic, "AIRICETB", 8) != 0) { std::fclose(f); return fail(-8, "table file: bad magic"); }
   if (hd.version != 1 || hd.ncols != AIRICE_TABLE_NCOLS32) { std::fclose(f); return fail(-8, "table file: unsupported version / column count"); }
-  if (hd.n_h <= 0 || hd.n_th <= 0 || hd.n_h * hd.n_th >= 2147483647LL) { std::fclose(f); return fail(-8, "table file: bad dimensions"); }
+  // each factor bounded first: the product of two untrusted 64-bit values must not overflow before it is tested
+  if (hd.n_h <= 0 || hd.n_th <= 0 || hd.n_h >= 2147483647LL || hd.n_th >= 2147483647LL || hd.n_h * hd.n_th >= 2147483647LL) {
+    std::fclose(f);
+    return fail(-8, "table file: bad dimensions");
+  }
   const size_t cells = (size_t)(hd.n_h * hd.n_th), n = cells * AIRICE_TABLE_NCOLS32;
   std::vector<float> host(n);
   const size_t got = std::fread(host.data(), sizeof(float), n, f);

@@ -598,25 +598,32 @@ struct RowRecs { float4 a0, a1, a2, b0, b1, b2; };
 __device__ __forceinline__ void load_rec3(const float4* __restrict__ rec, int i, float4& r0, float4& r1, float4& r2) {
   r0 = __ldcs(rec + 3 * (int64_t)i); r1 = __ldcs(rec + 3 * (int64_t)i + 1); r2 = __ldcs(rec + 3 * (int64_t)i + 2);
 }
-__device__ __forceinline__ bool fast_row(const LookupTable& t, double d, int s, int e, float xm, float ulo, float scale,
-                                         double* par) {
+// The fast path runs in three steps so that the two rows of a query travel through memory TOGETHER: (1) lut_pick: the
+// two position-table entries of a row, (2) lut_bin + load_rec3: the predicted bin and its two records, (3) fast_finish:
+// verification on the records' X fields and the interpolation.  Written as one function per row, the second row's table
+// entries were only requested after the first row's records had arrived and been verified (the verification loop is a
+// branch the loads cannot be hoisted over): header -> table 1 -> records 1 -> table 2 -> records 2, five dependent round
+// trips of a latency-bound kernel where three do.
+struct RowPick { const uint16_t* L; int k, base; float fr; };
+__device__ __forceinline__ void lut_pick(const LookupTable& t, double d, int s, float xm, float ulo, float scale, RowPick& p) {
   const int K = AIRICE_LUT_EDGES - 1;
-  const int r = s / t.n_th, base = r * t.n_th;
-  const float df = (float)d;
-  float kf = lut_coord(df, xm, ulo, scale);
+  const int r = s / t.n_th;
+  p.base = r * t.n_th;
+  float kf = lut_coord((float)d, xm, ulo, scale);
   kf = kf > 0.f ? kf : 0.f;                      // also NaN -> 0
   int k = (int)kf;
   k = k < K - 1 ? k : K - 1;
-  float fr = kf - (float)k;
-  fr = fr < 1.f ? fr : 1.f;
-  const uint16_t* L = t.lut + (int64_t)r * AIRICE_LUT_EDGES;
-  const float l0 = (float)__ldg(L + k), l1 = (float)__ldg(L + k + 1);
-  const float pos = (l0 + (l1 - l0) * fr) * (1.0f / (float)(1 << t.lut_shift));
-  int ip = base + (int)ceilf(pos);
-  ip = ip < s ? s : (ip > e ? e : ip);
-  RowRecs q;
-  load_rec3(t.rec, ip - 1, q.a0, q.a1, q.a2);
-  load_rec3(t.rec, ip, q.b0, q.b1, q.b2);
+  const float fr = kf - (float)k;
+  p.fr = fr < 1.f ? fr : 1.f;
+  p.k = k;
+  p.L = t.lut + (int64_t)r * AIRICE_LUT_EDGES;
+}
+__device__ __forceinline__ int lut_bin(const LookupTable& t, const RowPick& p, float l0, float l1, int s, int e) {
+  const float pos = (l0 + (l1 - l0) * p.fr) * (1.0f / (float)(1 << t.lut_shift));
+  const int ip = p.base + (int)ceilf(pos);
+  return ip < s ? s : (ip > e ? e : ip);
+}
+__device__ __forceinline__ bool fast_finish(const LookupTable& t, double d, int s, int e, int ip, RowRecs& q, double* par) {
   bool found = false;
 #pragma unroll 1
   for (int tries = 0; tries < 2; tries++) {
@@ -625,7 +632,7 @@ __device__ __forceinline__ bool fast_row(const LookupTable& t, double d, int s, 
       if (xa > d || ip == s) { found = true; break; }
       ip--;                                      // the crossing is one bin earlier (ip > s here)
       q.b0 = q.a0; q.b1 = q.a1; q.b2 = q.a2;
-      load_rec3(t.rec, ip - 1, q.a0, q.a1, q.a2);
+      load_rec3(t.rec, ip > 0 ? ip - 1 : 0, q.a0, q.a1, q.a2);   // record s - 1 is only looked at, never used, when ip == s
     } else {
       if (!(xb > d) || ip >= e) return false;    // NaN, or no bin with X <= d left in the window
       ip++;
@@ -690,8 +697,25 @@ __global__ void __launch_bounds__(kThreads, AIRICE_LOOKUP_MINBLOCKS) airice_look
     const bool in2 = two && (d <= (double)hd0.w);
     // the common case: both rows from the position table (rowblk -> table -> records: three dependent steps)
     bool lit1 = in1, lit2 = in2;
-    if (in1 && (fl & 1)) lit1 = !fast_row(t, d, s1, e1, hp1.x, hp1.y, hp1.z, P1);
-    if (in2 && (fl & 2)) lit2 = !fast_row(t, d, s2, e2, hp2.x, hp2.y, hp2.z, P2);
+    const bool f1 = in1 && (fl & 1), f2 = in2 && (fl & 2);
+    if (f1 || f2) {
+      // a row that does not take the fast path mirrors the one that does: same addresses (no extra sectors), result unused
+      const int sa = f1 ? s1 : s2, ea = f1 ? e1 : e2, sb = f2 ? s2 : s1, eb = f2 ? e2 : e1;
+      const float4 ha = f1 ? hp1 : hp2, hb = f2 ? hp2 : hp1;
+      RowPick pa, pb;
+      lut_pick(t, d, sa, ha.x, ha.y, ha.z, pa);
+      lut_pick(t, d, sb, hb.x, hb.y, hb.z, pb);
+      const float la0 = (float)__ldg(pa.L + pa.k), la1 = (float)__ldg(pa.L + pa.k + 1);
+      const float lb0 = (float)__ldg(pb.L + pb.k), lb1 = (float)__ldg(pb.L + pb.k + 1);
+      const int ipa = lut_bin(t, pa, la0, la1, sa, ea), ipb = lut_bin(t, pb, lb0, lb1, sb, eb);
+      RowRecs qa, qb;
+      load_rec3(t.rec, ipa > 0 ? ipa - 1 : 0, qa.a0, qa.a1, qa.a2);   // bin 0 of the table has no predecessor (see fast_finish)
+      load_rec3(t.rec, ipa, qa.b0, qa.b1, qa.b2);
+      load_rec3(t.rec, ipb > 0 ? ipb - 1 : 0, qb.a0, qb.a1, qb.a2);
+      load_rec3(t.rec, ipb, qb.b0, qb.b1, qb.b2);
+      if (f1) lit1 = !fast_finish(t, d, sa, ea, ipa, qa, P1);
+      if (f2) lit2 = !fast_finish(t, d, sb, eb, ipb, qb, P2);
+    }
     if (lit1 || lit2) {
       // the literal search for the row(s) the table could not answer
       int a1 = s1, b1 = e1, a2 = s2, b2 = e2;
