@@ -63,14 +63,14 @@ def main():
         "ncu_ms": [k1["gpu__time_duration.sum"], k2["gpu__time_duration.sum"]], "unit": "pair",
         "source": "profiles/r02f_solve1e7_metrics.txt: ncu --set full --clock-control none of tools/ncu_target.py solve 1e7 "
                   "(airice_solve_kernel<1> + <2>, one launch each); algorithmic 89 B/pair"}
-    lk = launches(os.path.join(P, "r02f_lookup1e7_metrics.txt"))[0]
+    lk = launches(os.path.join(P, "r02g_lookup1e7_metrics.txt"))[0]
     facts["airice_lookup_kernel"] = {
         "dram_bytes_per_unit": dram(lk) / n, "dram_read_bytes_per_unit": lk["dram__bytes_read.sum"] / n,
         "dram_throughput_pct": lk["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"],
         "l2_hit_pct": lk["lts__t_sector_hit_rate.pct"], "issue_active_pct": lk["smsp__issue_active.avg.pct_of_peak_sustained_active"],
         "long_scoreboard_per_issue": lk["smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"],
         "ncu_ms": lk["gpu__time_duration.sum"], "unit": "lookup",
-        "source": "profiles/r02f_lookup1e7_metrics.txt: ncu --set full of 1e7 lookups on the reference-grid table; algorithmic 265 B/lookup"}
+        "source": "profiles/r02g_lookup1e7_metrics.txt: ncu --set full of 1e7 lookups on the reference-grid table; algorithmic 265 B/lookup"}
     al = launches(os.path.join(P, "r02f_all_metrics.txt"))
     tb = [l for l in al if "airice_table_kernel<1, 0>" in l["name"]]
     big = max(tb, key=lambda l: l["gpu__time_duration.sum"])
