@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(kThreads) airice_forward_kernel(const AirIceMe
 #define AIRICE_SOLVE_CMRAD9 1
 #endif
 constexpr int kSolveThreads = AIRICE_SOLVE_THREADS;
+constexpr int kPass2Threads = 128;          // second pass of the two-pass launch (launch_solve)
 constexpr int64_t kTwoPassMinPairs = 6000000;
 // One pair, start to finish.  DEFER (first pass of the two-pass launch): a pair that needs a rare slow path is appended
 // to a.defer_list (0.6 % of a random batch) and what is written for it here is overwritten by the second pass.
@@ -334,7 +335,7 @@ template <int PASS, bool CMRAD9 = false>
 __global__ void __launch_bounds__(kSolveThreads, AIRICE_SOLVE_MINBLOCKS) airice_solve_kernel(const AirIceMedium m, const AirIcePlan p, const SolveArgs a) {
   if (PASS == 2) {
     const int count = *a.defer_count;
-    for (int j = blockIdx.x * kSolveThreads + threadIdx.x; j < count; j += gridDim.x * kSolveThreads)
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x)
       solve_one<false>(m, p, a, (int64_t)a.defer_list[j]);
   } else {
     const int64_t i = (int64_t)blockIdx.x * kSolveThreads + threadIdx.x;
@@ -841,8 +842,10 @@ cudaError_t launch_solve(const AirIceMedium& m, const AirIcePlan& p, const Solve
   else airice_solve_kernel<1><<<dim3((unsigned)blocks), kSolveThreads, 0, s>>>(m, p, a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int64_t second = blocks < 2 * 148 ? blocks : 2 * 148;     // one wave of 2 CTAs per SM strides over the list
-  airice_solve_kernel<2><<<dim3((unsigned)second), kSolveThreads, 0, s>>>(m, p, a);
+  // the second pass is bound by the length of a warp's instruction stream, not by throughput: 128-thread CTAs, eight per
+  // SM, spread the ~1900 warps of a 1e7-pair launch over every SM (as one wave of 2 x 148 CTAs of 512 threads the listed
+  // pairs filled the first ~118 CTAs only: 1.263 -> 1.257 ms per 1e7 pairs)
+  airice_solve_kernel<2><<<dim3((unsigned)(8 * sm_count())), kPass2Threads, 0, s>>>(m, p, a);   // strides over the list
   return cudaGetLastError();
 }
 
