@@ -857,13 +857,17 @@ int airice_solve_multi_device(airice_ctx* c, int64_t n_points, int n_ant, const 
 // Host-buffer path: the batch is cut into chunks that alternate between two streams, each with its own device
 // staging slot.  Copies go directly from/to the caller's buffers (no extra host memcpy); with pinned caller memory
 // the H2D of chunk k+1, the kernel of chunk k and the D2H of chunk k-1 run concurrently.
-int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* dist, const double* straight,
-                      double depth, double ice, int units, double* out, uint8_t* ok) {
+}  // extern "C"
+namespace {
+// Host-buffer solve.  Either `out` (a dense [nc][n] block, every column wanted) or `cols` (nc host pointers, NULL = the
+// caller does not use that column: it is neither stored by the kernel nor copied back) is given; `ok` may be NULL with `cols`.
+int solve_host_impl(airice_ctx* c, int64_t n, const double* h, const double* dist, const double* straight, double depth,
+                    double ice, int units, double* out, double* const* cols, uint8_t* ok) {
   if (!c) return fail(-1, "null context");
   NEED_AIR(c);
   if (units != AIRICE_UNITS_M_DEG && units != AIRICE_UNITS_CM_RAD) return fail(-1, "unknown units");
   if (n == 0) return 0;
-  if (!h || !dist || !out || !ok) return fail(-1, "null argument");
+  if (!h || !dist || (!out && !cols) || (out && !ok)) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));
   const int nc = units == AIRICE_UNITS_CM_RAD ? AIRICE_SOLVE_COLS_CM_RAD : AIRICE_SOLVE_COLS;
   // pairs per pipeline chunk (H2D -> kernel -> D2H on alternating streams).  The first chunk's upload and kernel are the
@@ -885,8 +889,8 @@ int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* d
     SolveArgs a;
     std::memset(&a, 0, sizeof(a));
     a.n = m; a.h = dh; a.d = dh + chunk; a.ice = ice; a.depth = depth; a.units = units;
-    for (int k = 0; k < nc; k++) a.out[k] = dh + (2 + k) * chunk;
-    a.ok = (uint8_t*)(dh + (3 + nc) * chunk);
+    for (int k = 0; k < nc; k++) a.out[k] = (out || cols[k]) ? dh + (2 + k) * chunk : nullptr;
+    a.ok = ok ? (uint8_t*)(dh + (3 + nc) * chunk) : nullptr;
     if (straight) {
       double* ds = dh + (2 + nc) * chunk;
       CK(cudaMemcpyAsync(ds, straight + off, sizeof(double) * m, cudaMemcpyHostToDevice, s));
@@ -895,18 +899,35 @@ int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* d
     attach_defer_scratch(c, s, &a);
     cudaError_t e = launch_solve(c->medium, p, a, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_solve");
-    // the nc columns of the chunk in ONE strided copy (device pitch = chunk, host pitch = n) instead of nc copies
-    CK(cudaMemcpy2DAsync(out + off, sizeof(double) * (size_t)n, a.out[0], sizeof(double) * (size_t)chunk, sizeof(double) * (size_t)m,
-                         (size_t)nc, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(ok + off, a.ok, (size_t)m, cudaMemcpyDeviceToHost, s));
+    if (out) {
+      // the nc columns of the chunk in ONE strided copy (device pitch = chunk, host pitch = n) instead of nc copies
+      CK(cudaMemcpy2DAsync(out + off, sizeof(double) * (size_t)n, a.out[0], sizeof(double) * (size_t)chunk, sizeof(double) * (size_t)m,
+                           (size_t)nc, cudaMemcpyDeviceToHost, s));
+    } else {
+      for (int k = 0; k < nc; k++)
+        if (cols[k]) CK(cudaMemcpyAsync(cols[k] + off, a.out[k], sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, s));
+    }
+    if (ok) CK(cudaMemcpyAsync(ok + off, a.ok, (size_t)m, cudaMemcpyDeviceToHost, s));
   }
   for (int s = 0; s < airice_ctx::kSlots; s++)
     if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
   return 0;
 }
+}  // namespace
+extern "C" {
 
-// test hook: AIRICE_LOOKUP_LITERAL=1 makes every lookup run the literal index search (halvings + scan in the dense column)
-// instead of the position table; both must return the same bits (tests/test_gpu_parity.py)
+int airice_solve_host(airice_ctx* c, int64_t n, const double* h, const double* dist, const double* straight,
+                      double depth, double ice, int units, double* out, uint8_t* ok) {
+  if (n != 0 && !out) return fail(-1, "null argument");
+  return solve_host_impl(c, n, h, dist, straight, depth, ice, units, out, nullptr, ok);
+}
+
+int airice_solve_host_columns(airice_ctx* c, int64_t n, const double* h, const double* dist, const double* straight,
+                              double depth, double ice, int units, double* const* cols, uint8_t* ok) {
+  if (n != 0 && !cols) return fail(-1, "null argument");
+  return solve_host_impl(c, n, h, dist, straight, depth, ice, units, nullptr, cols, ok);
+}
+
 static int lookup_literal() {
   const char* v = std::getenv("AIRICE_LOOKUP_LITERAL");
   return (v && v[0] == '1') ? 1 : 0;

@@ -31,22 +31,27 @@ extern "C" {
 int Py_TraceIceToAirBatch(double AntennaDepth, double IceLayerHeight, long n, const double *AirTxHeight,
                           const double *HorizontalDistance, double *out) {
   if (!ensure_ctx()) return 1;
-  double *cols = (double *)std::malloc(sizeof(double) * AIRICE_SOLVE_COLS * (size_t)(n > 0 ? n : 1));
-  unsigned char *ok = (unsigned char *)std::malloc((size_t)(n > 0 ? n : 1));
-  int rc = airice_solve_host(g_ctx, n, AirTxHeight, HorizontalDistance, nullptr, AntennaDepth, IceLayerHeight,
-                             AIRICE_UNITS_M_DEG_C, cols, ok);
+  // the six of the thirteen metre/degree values TraceIceToAir.C:31-68 reads: only these cross the PCIe link
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  double *cols = (double *)std::malloc(sizeof(double) * 6 * nn);
+  unsigned char *ok = (unsigned char *)std::malloc(nn);
+  double *x_air = cols, *theta = cols + nn, *recv = cols + 2 * nn, *p_air = cols + 3 * nn, *p_ice = cols + 4 * nn,
+         *refr = cols + 5 * nn;
+  double *want[AIRICE_SOLVE_COLS] = {nullptr};
+  want[1] = x_air; want[5] = theta; want[6] = recv; want[9] = p_air; want[10] = p_ice; want[12] = refr;
+  int rc = airice_solve_host_columns(g_ctx, n, AirTxHeight, HorizontalDistance, nullptr, AntennaDepth, IceLayerHeight,
+                                     AIRICE_UNITS_M_DEG_C, want, ok);
   if (rc == 0) {
     for (long i = 0; i < n; i++) {
       double *o = out + 10 * i;
       if (ok[i]) {
-        const double launch_air = cols[5 * n + i], received_ice = cols[6 * n + i];
         o[0] = AirTxHeight[i]; o[1] = HorizontalDistance[i];
-        o[2] = cols[10 * n + i];        // geometricalPathLengthInIce
-        o[3] = cols[9 * n + i];         // geometricalPathLengthInAir
-        o[4] = received_ice;            // "launchAngle" after std::swap (TraceIceToAir.C:33)
-        o[5] = 180 - launch_air;        // "receivedAngle" = 180 - air launch angle (TraceIceToAir.C:34)
-        o[6] = cols[1 * n + i];         // horidist2interpnt = X_air
-        o[7] = cols[12 * n + i];        // AngleOfIncidenceOnIce = refracted angle below the surface (AirIceRayTracing.cc:1081)
+        o[2] = p_ice[i];                // geometricalPathLengthInIce
+        o[3] = p_air[i];                // geometricalPathLengthInAir
+        o[4] = recv[i];                 // "launchAngle" after std::swap (TraceIceToAir.C:33)
+        o[5] = 180 - theta[i];          // "receivedAngle" = 180 - air launch angle (TraceIceToAir.C:34)
+        o[6] = x_air[i];                // horidist2interpnt = X_air
+        o[7] = refr[i];                 // AngleOfIncidenceOnIce = refracted angle below the surface (AirIceRayTracing.cc:1081)
         o[8] = 0; o[9] = 0;
       } else {
         for (int k = 0; k < 10; k++) o[k] = -1000;

@@ -343,6 +343,25 @@ class AirIceSolver:
                                          _host_ptr(out), _host_ptr(ok)))
         return out, ok
 
+    def solve_host_columns(self, h, d, depth, ice, units=_capi.UNITS_CM_RAD, columns=(), want_ok=True, ok=None):
+        """Host-buffer solve that brings back only the listed output columns (and the flag): the host path is PCIe-bound,
+        so unused columns are not stored by the kernel and do not cross the link.  Returns ({column index: array}, ok)."""
+        n = int(h.shape[0])
+        nc = _capi.SOLVE_COLS_CM_RAD if units == _capi.UNITS_CM_RAD else _capi.SOLVE_COLS
+        # `columns`: column indices, or {index: preallocated float64 host array / pinned tensor of n elements}
+        if isinstance(columns, dict):
+            cols = {int(k): v for k, v in columns.items()}
+        else:
+            cols = {int(k): np.empty(n, dtype=np.float64) for k in columns}
+        if any(k < 0 or k >= nc for k in cols):
+            raise ValueError("column index out of range for these units")
+        if ok is None and want_ok:
+            ok = np.empty(n, dtype=np.uint8)
+        check(self.lib.airice_solve_host_columns(self.handle, n, _host_ptr(h), _host_ptr(d), None, depth, ice, units,
+                                                 ptr_array([_host_ptr(cols[k]) if k in cols else None for k in range(nc)]),
+                                                 _host_ptr(ok) if ok is not None else None))
+        return cols, ok
+
     # ------------------------------------------------------------------ kernel 3
     def lookup(self, table, h_cm, d_cm, out=None, ok=None):
         h_cm = h_cm.to(self.torch_device, torch.float64).contiguous()

@@ -121,6 +121,13 @@ int airice_solve_multi_device(airice_ctx *ctx, int64_t n_points, int n_ant, cons
 /* Same through HOST buffers: out is a dense SoA block out[col*n + i] with 9 (CM_RAD) or 13 (M_DEG) columns. */
 int airice_solve_host(airice_ctx *ctx, int64_t n, const double *h, const double *dist, const double *straight,
                       double depth, double ice, int units, double *out, uint8_t *ok);
+/* The same with one HOST pointer per output column (9 for CM_RAD, 13 for M_DEG, in the column order above): a NULL column
+ * is neither stored by the kernel nor copied back, and `ok` may be NULL.  The host path is bound by the PCIe link
+ * (73 B of results per pair when every column travels), so a caller that reads a subset -- TraceIceToAir.C:31-68 uses
+ * 6 of the 13 metre/degree values of Air2IceRayTracing (AirIceRayTracing.cc:1066-1084) -- gets its answers that much
+ * sooner. */
+int airice_solve_host_columns(airice_ctx *ctx, int64_t n, const double *h, const double *dist, const double *straight,
+                              double depth, double ice, int units, double *const *cols, uint8_t *ok);
 
 /* ---- kernel 3: table lookup = GetHorizontalDistanceToIntersectionPoint_Table
  * (MultiRayAirIceRefraction.cc:1305-1462, .h:189) with FindClosestAirTxHeight / FindClosestTHD / GetParValues
