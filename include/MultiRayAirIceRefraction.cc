@@ -284,6 +284,23 @@ int GetHorizontalDistanceToIntersectionPointBatch(long n, const double *SrcHeigh
   return rc;
 }
 
+int GetHorizontalDistanceToIntersectionPointBatch(long n, const double *SrcHeightASL, const double *HorizontalDistanceToRx,
+                                                  double RxDepthBelowIceBoundary, double IceLayerHeight,
+                                                  double *opticalPathLengthInIce, double *opticalPathLengthInAir,
+                                                  double *geometricalPathLengthInIce, double *geometricalPathLengthInAir,
+                                                  double *launchAngle, double *horizontalDistanceToIntersectionPoint,
+                                                  double *transmissionCoefficientS, double *transmissionCoefficientP,
+                                                  double *RecievedAngleInIce, unsigned char *ok) {
+  if (!detail::ensure_ctx()) return 1;
+  double *const cols[AIRICE_SOLVE_COLS_CM_RAD] = {opticalPathLengthInIce, opticalPathLengthInAir, geometricalPathLengthInIce,
+                                                  geometricalPathLengthInAir, launchAngle, horizontalDistanceToIntersectionPoint,
+                                                  transmissionCoefficientS, transmissionCoefficientP, RecievedAngleInIce};
+  int rc = airice_solve_host_columns(detail::state().ctx, n, SrcHeightASL, HorizontalDistanceToRx, nullptr,
+                                     RxDepthBelowIceBoundary, IceLayerHeight, AIRICE_UNITS_CM_RAD_C, cols, ok);
+  if (rc != 0) detail::report("GetHorizontalDistanceToIntersectionPointBatch");
+  return rc;
+}
+
 // MultiRayAirIceRefraction.cc:945-989
 bool GetHorizontalDistanceToIntersectionPoint(double SrcHeightASL, double HorizontalDistanceToRx,
                                               double RxDepthBelowIceBoundary, double IceLayerHeight,

@@ -92,6 +92,15 @@ double Trans_P(double thetai, double IceLayerHeight);
 int GetHorizontalDistanceToIntersectionPointBatch(long n, const double *SrcHeightASL, const double *HorizontalDistanceToRx,
                                                   double RxDepthBelowIceBoundary, double IceLayerHeight, double *out,
                                                   unsigned char *ok);
+// The same with one array per by-reference argument of the scalar call; a NULL array (or NULL ok) is an output the
+// caller does not read: it is neither computed into a column nor copied back over PCIe, which is what bounds the call.
+int GetHorizontalDistanceToIntersectionPointBatch(long n, const double *SrcHeightASL, const double *HorizontalDistanceToRx,
+                                                  double RxDepthBelowIceBoundary, double IceLayerHeight,
+                                                  double *opticalPathLengthInIce, double *opticalPathLengthInAir,
+                                                  double *geometricalPathLengthInIce, double *geometricalPathLengthInAir,
+                                                  double *launchAngle, double *horizontalDistanceToIntersectionPoint,
+                                                  double *transmissionCoefficientS, double *transmissionCoefficientP,
+                                                  double *RecievedAngleInIce, unsigned char *ok);
 int GetHorizontalDistanceToIntersectionPoint_TableBatch(long n, const double *SrcHeightASL,
                                                         const double *HorizontalDistanceToRx,
                                                         double RxDepthBelowIceBoundary, double IceLayerHeight,

@@ -41,6 +41,16 @@ int main(int argc, char **argv) {
       AirTxHeight * 100, HorizontalDistance * 100, AntennaDepth * 100, IceLayerHeight * 100, oi, oa, gi, ga, la, hx, ts, tp, ra);
   std::printf("direct %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", (int)ok, oi, oa, gi, ga, la, hx, ts, tp, ra);
 
+  {
+    // per-argument batch form: only the launch angle, the distance to the intersection point and the flag are asked for
+    const double hs[2] = {AirTxHeight * 100, 20000.0 * 100}, ds[2] = {HorizontalDistance * 100, 3000.0 * 100};
+    double bl[2] = {0, 0}, bx[2] = {0, 0};
+    unsigned char bk[2] = {0, 0};
+    const int rc = MultiRayAirIceRefraction::GetHorizontalDistanceToIntersectionPointBatch(
+        2, hs, ds, AntennaDepth * 100, IceLayerHeight * 100, nullptr, nullptr, nullptr, nullptr, bl, bx, nullptr, nullptr, nullptr, bk);
+    std::printf("direct_cols %d %d %.17g %.17g %d %.17g %.17g\n", rc, (int)bk[0], bl[0], bx[0], (int)bk[1], bl[1], bx[1]);
+  }
+
   double dummy[20];
   bool inice = true;
   MultiRayAirIceRefraction::GetRayTracingSolutions(170, 20000, 3000, -200, dummy, inice);

@@ -73,6 +73,16 @@ def test_driver_direct_solve_and_forward(driver_output, oracle):
     assert driver_output["direct_A1775"][0][1] != d[1]
 
 
+def test_driver_per_argument_batch_equals_scalar_call(driver_output):
+    """GetHorizontalDistanceToIntersectionPointBatch with NULL for the outputs the caller does not read: the columns that
+    were asked for carry the scalar call's bits."""
+    c = driver_output["direct_cols"][0]
+    d = driver_output["direct"][0]
+    assert c[0] == 0 and c[1] == d[0] == 1
+    assert c[2] == d[5] and c[3] == d[6]          # launch angle, distance to the intersection point
+    assert c[4] == 1 and 1.5 < c[5] < 3.2 and c[6] > 0
+
+
 def test_driver_medium_accessors_and_fresnel(driver_output, oracle):
     """GetB_air/GetC_air/Getnz_air/Getnz_ice and Refl/Trans_S/P of the source-compatible API against the oracle's medium."""
     med = np.array(driver_output["medium"])
