@@ -28,7 +28,7 @@ EXPORTS = [
     "airice_set_ice_model", "airice_table_dims", "airice_table_build_device", "airice_forward_device",
     "airice_forward_host", "airice_table_create", "airice_table_create_multi", "airice_table_wrap", "airice_table_destroy", "airice_table_info",
     "airice_table_copy_column", "airice_table_column_ptr", "airice_table_copy_row_ranges", "airice_solve_device",
-    "airice_solve_multi_device", "airice_solve_host", "airice_solve_host_columns", "airice_lookup_device", "airice_lookup_host", "airice_inice_solve_device",
+    "airice_solve_multi_device", "airice_solve_host", "airice_solve_host_columns", "airice_lookup_device", "airice_lookup_host", "airice_lookup_host_columns", "airice_inice_solve_device",
     "airice_inice_solve_host", "airice_inice_two_rays_device", "airice_inice_two_rays_host", "airice_ray_path_device", "airice_ray_path_host", "airice_fp64_peak_tflops", "airice_sync", "airice_trim",
     "airice_inice_two_rays_att_device", "airice_inice_two_rays_att_host", "airice_inice_attenuation_device", "airice_inice_attenuation_host",
     "airice_inice_quadrature_stats", "airice_inice_ladder_stats", "airice_inice_focusing_device", "airice_inice_focusing_host", "airice_inice_table_create",
@@ -77,6 +77,7 @@ def load():
     lib.airice_forward_host.argtypes = [vp, i64, vp, vp, d, d, vp]
     lib.airice_lookup_device.argtypes = [vp, vp, i64, vp, vp, pp, vp, vp]
     lib.airice_lookup_host.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.airice_lookup_host_columns.argtypes = [vp, vp, i64, vp, vp, pp, vp]
     lib.airice_inice_solve_device.argtypes = [vp, i64, vp, vp, vp, pp, vp, vp]
     lib.airice_inice_solve_host.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     lib.airice_inice_two_rays_device.argtypes = [vp, i64, vp, vp, vp, pp, pp, pp, vp]

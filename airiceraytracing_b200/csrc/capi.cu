@@ -951,11 +951,15 @@ int airice_lookup_device(airice_ctx* c, const airice_table* t, int64_t n, const 
   return 0;
 }
 
-int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const double* h_cm, const double* dist_cm,
-                       double* out, uint8_t* ok) {
+}  // extern "C"
+namespace {
+// Host-buffer lookup: `out` (dense [9][n] block) or `cols` (9 host pointers, NULL = not wanted: not stored, not copied
+// back; `ok` may then be NULL too).
+int lookup_host_impl(airice_ctx* c, const airice_table* t, int64_t n, const double* h_cm, const double* dist_cm, double* out,
+                     double* const* cols, uint8_t* ok) {
   if (!c || !t) return fail(-1, "null argument");
   if (n == 0) return 0;
-  if (!h_cm || !dist_cm || !out || !ok) return fail(-1, "null argument");
+  if (!h_cm || !dist_cm || (!out && !cols) || (out && !ok)) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));
   const int nc = AIRICE_LOOKUP_NCOLS;
   const int64_t chunk = n < (1 << 20) ? (n > 0 ? n : 1) : (1 << 20);
@@ -971,19 +975,38 @@ int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const do
     LookupArgs a;
     std::memset(&a, 0, sizeof(a));
     a.n = m; a.h_cm = dh; a.d_cm = dh + chunk; a.ok = (uint8_t*)(dh + (2 + nc) * chunk);
-    for (int k = 0; k < nc; k++) a.out[k] = dh + (2 + k) * chunk;
+    for (int k = 0; k < nc; k++) a.out[k] = (out || cols[k]) ? dh + (2 + k) * chunk : nullptr;
     a.literal = lookup_literal();
     t->note_stream(s);
     cudaError_t e = launch_lookup(c->medium, t->view(), a, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_lookup");
-    // the nc columns of the chunk in ONE strided copy (device pitch = chunk, host pitch = n) instead of nc copies
-    CK(cudaMemcpy2DAsync(out + off, sizeof(double) * (size_t)n, a.out[0], sizeof(double) * (size_t)chunk, sizeof(double) * (size_t)m,
-                         (size_t)nc, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(ok + off, a.ok, (size_t)m, cudaMemcpyDeviceToHost, s));
+    if (out) {
+      // the nc columns of the chunk in ONE strided copy (device pitch = chunk, host pitch = n) instead of nc copies
+      CK(cudaMemcpy2DAsync(out + off, sizeof(double) * (size_t)n, a.out[0], sizeof(double) * (size_t)chunk, sizeof(double) * (size_t)m,
+                           (size_t)nc, cudaMemcpyDeviceToHost, s));
+    } else {
+      for (int k = 0; k < nc; k++)
+        if (cols[k]) CK(cudaMemcpyAsync(cols[k] + off, a.out[k], sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, s));
+    }
+    if (ok) CK(cudaMemcpyAsync(ok + off, a.ok, (size_t)m, cudaMemcpyDeviceToHost, s));
   }
   for (int s = 0; s < airice_ctx::kSlots; s++)
     if (c->streams[s]) CK(cudaStreamSynchronize(c->streams[s]));
   return 0;
+}
+}  // namespace
+extern "C" {
+
+int airice_lookup_host(airice_ctx* c, const airice_table* t, int64_t n, const double* h_cm, const double* dist_cm,
+                       double* out, uint8_t* ok) {
+  if (n != 0 && !out) return fail(-1, "null argument");
+  return lookup_host_impl(c, t, n, h_cm, dist_cm, out, nullptr, ok);
+}
+
+int airice_lookup_host_columns(airice_ctx* c, const airice_table* t, int64_t n, const double* h_cm, const double* dist_cm,
+                               double* const* cols, uint8_t* ok) {
+  if (n != 0 && !cols) return fail(-1, "null argument");
+  return lookup_host_impl(c, t, n, h_cm, dist_cm, nullptr, cols, ok);
 }
 
 namespace {

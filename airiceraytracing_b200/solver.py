@@ -386,6 +386,22 @@ class AirIceSolver:
                                           _host_ptr(ok)))
         return out, ok
 
+    def lookup_host_columns(self, table, h_cm, d_cm, columns=(), want_ok=True, ok=None):
+        """Host-buffer lookup that brings back only the listed columns (see solve_host_columns)."""
+        n = int(h_cm.shape[0])
+        if isinstance(columns, dict):
+            cols = {int(k): v for k, v in columns.items()}
+        else:
+            cols = {int(k): np.empty(n, dtype=np.float64) for k in columns}
+        if any(k < 0 or k >= _capi.LOOKUP_COLS for k in cols):
+            raise ValueError("column index out of range")
+        if ok is None and want_ok:
+            ok = np.empty(n, dtype=np.uint8)
+        check(self.lib.airice_lookup_host_columns(self.handle, table.handle, n, _host_ptr(h_cm), _host_ptr(d_cm),
+                                                  ptr_array([_host_ptr(cols[k]) if k in cols else None for k in range(_capi.LOOKUP_COLS)]),
+                                                  _host_ptr(ok) if ok is not None else None))
+        return cols, ok
+
 
 INICE_COLUMNS = ["launch_d", "launch_r", "launch_ra1", "launch_ra2", "t_d", "t_r", "t_ra1", "t_ra2", "recv_d", "recv_r",
                  "recv_ra1", "recv_ra2", "t_r_1", "t_r_2", "t_ra1_1", "t_ra1_2", "t_ra2_1", "t_ra2_2", "incidence",

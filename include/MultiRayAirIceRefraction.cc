@@ -321,25 +321,54 @@ bool GetHorizontalDistanceToIntersectionPoint(double SrcHeightASL, double Horizo
   return ok != 0;
 }
 
-int GetHorizontalDistanceToIntersectionPoint_TableBatch(long n, const double *SrcHeightASL,
-                                                        const double *HorizontalDistanceToRx,
-                                                        double RxDepthBelowIceBoundary, double IceLayerHeight,
-                                                        int AntennaNumber, double *out, unsigned char *ok) {
-  (void)RxDepthBelowIceBoundary; (void)IceLayerHeight;
-  detail::State &s = detail::state();
-  if (!detail::ensure_ctx()) return 1;
-  // antenna -> table remap by depth equality (MultiRayAirIceRefraction.cc:1348-1352)
+namespace detail {
+// antenna -> table remap by depth equality (MultiRayAirIceRefraction.cc:1348-1352), pending builds flushed; nullptr = no table
+inline airice_table *table_of_antenna(int AntennaNumber) {
+  State &s = state();
   for (size_t j = 0; j < AntennaTableAlreadyMade.size(); j++) {
     if (AntennaNumber < (int)AntennaDepths.size() && AntennaTableAlreadyMade[j] < (int)AntennaDepths.size() &&
         AntennaDepths[AntennaNumber] == AntennaDepths[AntennaTableAlreadyMade[j]])
       AntennaNumber = (int)j;
   }
-  if (!s.pending.empty()) detail::flush_pending();
+  if (!s.pending.empty()) flush_pending();
   if (AntennaNumber < 0 || AntennaNumber >= (int)s.tables.size() || !s.tables[AntennaNumber]) {
     std::cerr << "MultiRayAirIceRefraction (B200): no table for antenna " << AntennaNumber << std::endl;
-    return 1;
+    return nullptr;
   }
-  int rc = airice_lookup_host(s.ctx, s.tables[AntennaNumber], n, SrcHeightASL, HorizontalDistanceToRx, out, ok);
+  return s.tables[AntennaNumber];
+}
+}  // namespace detail
+
+int GetHorizontalDistanceToIntersectionPoint_TableBatch(long n, const double *SrcHeightASL,
+                                                        const double *HorizontalDistanceToRx,
+                                                        double RxDepthBelowIceBoundary, double IceLayerHeight,
+                                                        int AntennaNumber, double *out, unsigned char *ok) {
+  (void)RxDepthBelowIceBoundary; (void)IceLayerHeight;
+  if (!detail::ensure_ctx()) return 1;
+  airice_table *t = detail::table_of_antenna(AntennaNumber);
+  if (!t) return 1;
+  int rc = airice_lookup_host(detail::state().ctx, t, n, SrcHeightASL, HorizontalDistanceToRx, out, ok);
+  if (rc != 0) detail::report("GetHorizontalDistanceToIntersectionPoint_TableBatch");
+  return rc;
+}
+
+int GetHorizontalDistanceToIntersectionPoint_TableBatch(long n, const double *SrcHeightASL,
+                                                        const double *HorizontalDistanceToRx,
+                                                        double RxDepthBelowIceBoundary, double IceLayerHeight,
+                                                        int AntennaNumber, double *opticalPathLengthInIce,
+                                                        double *opticalPathLengthInAir, double *geometricalPathLengthInIce,
+                                                        double *geometricalPathLengthInAir, double *launchAngle,
+                                                        double *horizontalDistanceToIntersectionPoint,
+                                                        double *transmissionCoefficientS, double *transmissionCoefficientP,
+                                                        double *RecievedAngleInIce, unsigned char *ok) {
+  (void)RxDepthBelowIceBoundary; (void)IceLayerHeight;
+  if (!detail::ensure_ctx()) return 1;
+  airice_table *t = detail::table_of_antenna(AntennaNumber);
+  if (!t) return 1;
+  double *const cols[AIRICE_LOOKUP_COLS] = {opticalPathLengthInIce, opticalPathLengthInAir, geometricalPathLengthInIce,
+                                             geometricalPathLengthInAir, launchAngle, horizontalDistanceToIntersectionPoint,
+                                             transmissionCoefficientS, transmissionCoefficientP, RecievedAngleInIce};
+  int rc = airice_lookup_host_columns(detail::state().ctx, t, n, SrcHeightASL, HorizontalDistanceToRx, cols, ok);
   if (rc != 0) detail::report("GetHorizontalDistanceToIntersectionPoint_TableBatch");
   return rc;
 }

@@ -105,6 +105,15 @@ int GetHorizontalDistanceToIntersectionPoint_TableBatch(long n, const double *Sr
                                                         const double *HorizontalDistanceToRx,
                                                         double RxDepthBelowIceBoundary, double IceLayerHeight,
                                                         int AntennaNumber, double *out, unsigned char *ok);
+int GetHorizontalDistanceToIntersectionPoint_TableBatch(long n, const double *SrcHeightASL,
+                                                        const double *HorizontalDistanceToRx,
+                                                        double RxDepthBelowIceBoundary, double IceLayerHeight,
+                                                        int AntennaNumber, double *opticalPathLengthInIce,
+                                                        double *opticalPathLengthInAir, double *geometricalPathLengthInIce,
+                                                        double *geometricalPathLengthInAir, double *launchAngle,
+                                                        double *horizontalDistanceToIntersectionPoint,
+                                                        double *transmissionCoefficientS, double *transmissionCoefficientP,
+                                                        double *RecievedAngleInIce, unsigned char *ok);
 // copies column `col` (0..10, reference AllTableAllAntData order) of antenna table `AntennaNumber` to the host
 int GetTableColumn(int AntennaNumber, int col, std::vector<float> &out);
 

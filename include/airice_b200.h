@@ -138,6 +138,10 @@ int airice_lookup_device(airice_ctx *ctx, const airice_table *t, int64_t n, cons
                          const double *d_dist_cm, double *const *d_out, uint8_t *d_ok, void *stream);
 int airice_lookup_host(airice_ctx *ctx, const airice_table *t, int64_t n, const double *h_cm, const double *dist_cm,
                        double *out, uint8_t *ok);
+/* The same with one HOST pointer per output column (NULL = not wanted: neither stored nor copied back; ok may be NULL),
+ * like airice_solve_host_columns. */
+int airice_lookup_host_columns(airice_ctx *ctx, const airice_table *t, int64_t n, const double *h_cm,
+                               const double *dist_cm, double *const *cols, uint8_t *ok);
 
 /* ---- kernel 4: in-ice solver = IceRayTracing::IceRayTracing(0, z0, x1, z1) (IceRayTracing.cc:1745-1919; direct,
  * reflected and up to two refracted rays by GetDirectRayPar :626, GetReflectedRayPar :745, GetRefractedRayPar :923).

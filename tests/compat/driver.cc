@@ -51,6 +51,16 @@ int main(int argc, char **argv) {
     std::printf("direct_cols %d %d %.17g %.17g %d %.17g %.17g\n", rc, (int)bk[0], bl[0], bx[0], (int)bk[1], bl[1], bx[1]);
   }
 
+  {
+    // the table lookup in the per-argument batch form, antenna 1: launch angle + flag only
+    const double hs[1] = {AirTxHeight * 100}, ds[1] = {HorizontalDistance * 100};
+    double bl[1] = {0};
+    unsigned char bk[1] = {0};
+    const int rc = MultiRayAirIceRefraction::GetHorizontalDistanceToIntersectionPoint_TableBatch(
+        1, hs, ds, AntennaDepths[1], IceLayerHeight * 100, 1, nullptr, nullptr, nullptr, nullptr, bl, nullptr, nullptr, nullptr, nullptr, bk);
+    std::printf("table_cols %d %d %.17g\n", rc, (int)bk[0], bl[0]);
+  }
+
   double dummy[20];
   bool inice = true;
   MultiRayAirIceRefraction::GetRayTracingSolutions(170, 20000, 3000, -200, dummy, inice);

@@ -83,6 +83,12 @@ def test_driver_per_argument_batch_equals_scalar_call(driver_output):
     assert c[4] == 1 and 1.5 < c[5] < 3.2 and c[6] > 0
 
 
+def test_driver_per_argument_table_batch_equals_scalar_call(driver_output):
+    c = driver_output["table_cols"][0]
+    t1 = driver_output["table1"][0]
+    assert c[0] == 0 and c[1] == t1[0] and c[2] == t1[5]
+
+
 def test_driver_medium_accessors_and_fresnel(driver_output, oracle):
     """GetB_air/GetC_air/Getnz_air/Getnz_ice and Refl/Trans_S/P of the source-compatible API against the oracle's medium."""
     med = np.array(driver_output["medium"])
