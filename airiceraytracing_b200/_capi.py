@@ -35,6 +35,7 @@ EXPORTS = [
     "airice_inice_table_destroy", "airice_inice_table_info", "airice_inice_table_copy_column", "airice_inice_table_copy_positions",
     "airice_inice_table_interp_device", "airice_inice_table_interp_host", "airice_table_save", "airice_table_load", "airice_oldtable_create", "airice_oldtable_wrap_host", "airice_oldtable_destroy", "airice_oldtable_info",
     "airice_oldtable_copy_column", "airice_oldtable_copy_positions", "airice_oldtable_interp_device", "airice_oldtable_interp_host",
+    "airice_host_register", "airice_host_unregister", "airice_host_alloc", "airice_host_free",
     "airice_peer_alloc", "airice_peer_free", "airice_peer_open", "airice_peer_close", "airice_peer_copy",
 ]
 
@@ -114,6 +115,10 @@ def load():
     lib.airice_oldtable_copy_positions.argtypes = [vp, vp, vp]
     lib.airice_oldtable_interp_device.argtypes = [vp, vp, i64, vp, vp, i, vp, vp]
     lib.airice_oldtable_interp_host.argtypes = [vp, vp, i64, vp, vp, i, vp]
+    lib.airice_host_register.argtypes = [vp, C.c_size_t]
+    lib.airice_host_unregister.argtypes = [vp]
+    lib.airice_host_alloc.argtypes = [C.c_size_t, pp]
+    lib.airice_host_free.argtypes = [vp]
     lib.airice_peer_alloc.argtypes = [vp, C.c_size_t, pp, C.c_char_p]
     lib.airice_peer_free.argtypes = [vp, vp]
     lib.airice_peer_open.argtypes = [vp, C.c_char_p, pp]

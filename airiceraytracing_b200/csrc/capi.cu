@@ -22,6 +22,9 @@ int fail(int code, const std::string& msg) {
 }
 int cuda_fail(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  // the runtime also remembers a failed call as its "last error", which the next launch's cudaGetLastError() check would
+  // report as its own (e.g. a refused airice_host_register followed by a solve): it has been reported here, forget it
+  cudaGetLastError();
   return -100 - (int)e;
 }
 #define NEED_AIR(c)                                                                                              \
@@ -1834,6 +1837,29 @@ int airice_fp64_peak_tflops(airice_ctx* c, double* tflops) {
   CK(cudaSetDevice(c->device));
   cudaError_t e = fp64_peak_probe(tflops, 4096, nullptr);
   if (e != cudaSuccess) return cuda_fail(e, "fp64_peak_probe");
+  return 0;
+}
+
+// ---- page-locked host buffers for the host entry points
+int airice_host_register(void* p, size_t bytes) {
+  if (!p || bytes == 0) return fail(-1, "null argument");
+  CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int airice_host_unregister(void* p) {
+  if (!p) return fail(-1, "null argument");
+  CK(cudaHostUnregister(p));
+  return 0;
+}
+int airice_host_alloc(size_t bytes, void** p) {
+  if (!p || bytes == 0) return fail(-1, "null argument");
+  *p = nullptr;
+  CK(cudaHostAlloc(p, bytes, cudaHostAllocPortable));
+  return 0;
+}
+int airice_host_free(void* p) {
+  if (!p) return 0;
+  CK(cudaFreeHost(p));
   return 0;
 }
 

@@ -274,6 +274,17 @@ int GetTableColumn(int AntennaNumber, int col, std::vector<float> &out) {
   return airice_table_copy_column(s.tables[AntennaNumber], col, out.data());
 }
 
+int PinHostBuffer(void *p, size_t bytes) {
+  int rc = airice_host_register(p, bytes);
+  if (rc != 0) detail::report("PinHostBuffer");
+  return rc;
+}
+int UnpinHostBuffer(void *p) {
+  int rc = airice_host_unregister(p);
+  if (rc != 0) detail::report("UnpinHostBuffer");
+  return rc;
+}
+
 int GetHorizontalDistanceToIntersectionPointBatch(long n, const double *SrcHeightASL, const double *HorizontalDistanceToRx,
                                                   double RxDepthBelowIceBoundary, double IceLayerHeight, double *out,
                                                   unsigned char *ok) {

@@ -114,6 +114,10 @@ int GetHorizontalDistanceToIntersectionPoint_TableBatch(long n, const double *Sr
                                                         double *horizontalDistanceToIntersectionPoint,
                                                         double *transmissionCoefficientS, double *transmissionCoefficientP,
                                                         double *RecievedAngleInIce, unsigned char *ok);
+// page-locks / releases a buffer the caller passes to the *Batch functions again and again (cudaHostRegister): the batch
+// calls then run at the PCIe rate instead of staging every copy through the driver
+int PinHostBuffer(void *p, size_t bytes);
+int UnpinHostBuffer(void *p);
 // copies column `col` (0..10, reference AllTableAllAntData order) of antenna table `AntennaNumber` to the host
 int GetTableColumn(int AntennaNumber, int col, std::vector<float> &out);
 

@@ -282,6 +282,17 @@ int airice_peer_open(airice_ctx *ctx, const unsigned char handle[AIRICE_PEER_HAN
 int airice_peer_close(airice_ctx *ctx, void *d_ptr);
 int airice_peer_copy(airice_ctx *ctx, void *d_dst, const void *d_src, size_t bytes, void *stream);
 
+/* ---- page-locked host memory.  The host entry points (airice_*_host*) copy straight from / to the caller's buffers; with
+ * pageable memory every copy is staged through the driver and blocks the calling thread, with page-locked memory the
+ * upload of chunk k+1, the kernel of chunk k and the download of chunk k-1 overlap and the call runs at the PCIe rate.
+ * A C or C++ caller without the CUDA toolkit (CoREAS including MultiRayAirIceRefraction.cc) page-locks the buffers it
+ * reuses with airice_host_register (cudaHostRegister) or takes them from airice_host_alloc (cudaHostAlloc).  The
+ * reference has no counterpart: its arguments are scalars (MultiRayAirIceRefraction.h:186-189). */
+int airice_host_register(void *p, size_t bytes);
+int airice_host_unregister(void *p);
+int airice_host_alloc(size_t bytes, void **p);
+int airice_host_free(void *p);
+
 /* ---- measurement helpers */
 int airice_fp64_peak_tflops(airice_ctx *ctx, double *tflops); /* dependent-free DFMA probe, roofline denominator */
 int airice_sync(airice_ctx *ctx);
