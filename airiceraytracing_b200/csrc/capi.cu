@@ -52,6 +52,12 @@ struct airice_ctx {
   cudaEvent_t fork_ev = nullptr, join_ev[kSlots] = {nullptr, nullptr};   // airice_solve_multi_device's fork/join
   void* dev[kSlots] = {nullptr, nullptr};
   size_t slot_bytes = 0;
+  // scalar and small calls of the host API (the reference's scalar functions are batch-of-1 calls): one page-locked,
+  // device-mapped block that the kernel reads its inputs from and writes its results to directly -- one launch and one
+  // synchronisation per call instead of four copy calls around the launch
+  static const int kSmall = 64;
+  void* zc_host = nullptr;
+  void* zc_dev = nullptr;
   // per-row transmitter data (height, n(h), top layer) of the last table grid built: uploaded once, reused by
   // every rebuild of the same rows (MakeRayTracingTable is called once per antenna depth on the same grid)
   // in-ice solver scratch: compaction list + counter (+ private mask / L_R columns when the caller passes none)
@@ -294,6 +300,19 @@ int ensure_slots(airice_ctx* c, size_t bytes) {
   return 0;
 }
 
+int ensure_mapped(airice_ctx* c) {
+  if (c->zc_host) return 0;
+  const size_t bytes = (size_t)airice_ctx::kSmall * (sizeof(double) * (3 + AIRICE_SOLVE_COLS) + 8);
+  CK(cudaHostAlloc(&c->zc_host, bytes, cudaHostAllocMapped));
+  cudaError_t e = cudaHostGetDevicePointer(&c->zc_dev, c->zc_host, 0);
+  if (e != cudaSuccess) { cudaFreeHost(c->zc_host); c->zc_host = nullptr; return cuda_fail(e, "cudaHostGetDevicePointer"); }
+  return 0;
+}
+bool mapped_small_calls() {
+  static const bool on = std::getenv("AIRICE_NO_MAPPED") == nullptr;   // test hook: the chunked copy path for every size
+  return on;
+}
+
 // Upload per-row transmitter data for rows [r0,r1) and launch kernel 1 on them.
 int build_rows(airice_ctx* ctx, const TableGrid& g, int64_t r0, int64_t r1, double* const* cols64, float* const* cols32,
                cudaStream_t s, TableMultiArgs* multi = nullptr) {
@@ -446,6 +465,7 @@ void airice_destroy(airice_ctx* c) {
   for (int k = 0; k < airice_ctx::kSlots; k++)
     if (c->inice_scratch[k]) cudaFree(c->inice_scratch[k]);
   if (c->inice_cols) cudaFree(c->inice_cols);
+  if (c->zc_host) cudaFreeHost(c->zc_host);
   if (c->path_plans) cudaFree(c->path_plans);
   if (c->quad_stats) cudaFree(c->quad_stats);
   if (c->focus_scratch) cudaFree(c->focus_scratch);
@@ -873,6 +893,34 @@ int solve_host_impl(airice_ctx* c, int64_t n, const double* h, const double* dis
   if (!h || !dist || (!out && !cols) || (out && !ok)) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));
   const int nc = units == AIRICE_UNITS_CM_RAD ? AIRICE_SOLVE_COLS_CM_RAD : AIRICE_SOLVE_COLS;
+  if (n <= airice_ctx::kSmall && mapped_small_calls()) {
+    if (int rc = ensure_slots(c, 256)) return rc;      // makes the streams
+    if (int rc = ensure_mapped(c)) return rc;
+    const int cap = airice_ctx::kSmall;
+    double* hh = (double*)c->zc_host;
+    double* dd = (double*)c->zc_dev;
+    std::memcpy(hh, h, sizeof(double) * n);
+    std::memcpy(hh + cap, dist, sizeof(double) * n);
+    if (straight) std::memcpy(hh + 2 * cap, straight, sizeof(double) * n);
+    const double sc1 = (units == AIRICE_UNITS_CM_RAD) ? 100.0 : 1.0;
+    const AirIcePlan& p1 = c->plan(ice / sc1, depth / sc1);
+    SolveArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = n; a.h = dd; a.d = dd + cap; a.ice = ice; a.depth = depth; a.units = units;
+    if (straight) a.straight = dd + 2 * cap;
+    for (int k = 0; k < nc; k++) a.out[k] = (out || cols[k]) ? dd + (3 + k) * cap : nullptr;
+    a.ok = ok ? (uint8_t*)(dd + (3 + AIRICE_SOLVE_COLS) * cap) : nullptr;
+    cudaStream_t s = c->streams[0];
+    cudaError_t e = launch_solve(c->medium, p1, a, s);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_solve");
+    CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < nc; k++) {
+      double* dst = out ? out + (size_t)k * n : cols[k];
+      if (dst) std::memcpy(dst, hh + (3 + k) * cap, sizeof(double) * n);
+    }
+    if (ok) std::memcpy(ok, (const uint8_t*)(hh + (3 + AIRICE_SOLVE_COLS) * cap), (size_t)n);
+    return 0;
+  }
   // pairs per pipeline chunk (H2D -> kernel -> D2H on alternating streams).  The first chunk's upload and kernel are the
   // only part the D2H link waits for: measured 14.0 / 13.8 / 13.7 / 13.6 ms per 1e7 pairs with 2M / 1M / 512K / 256K
   // pairs per chunk; AIRICE_HOST_CHUNK overrides
@@ -965,6 +1013,31 @@ int lookup_host_impl(airice_ctx* c, const airice_table* t, int64_t n, const doub
   if (!h_cm || !dist_cm || (!out && !cols) || (out && !ok)) return fail(-1, "null argument");
   CK(cudaSetDevice(c->device));
   const int nc = AIRICE_LOOKUP_NCOLS;
+  if (n <= airice_ctx::kSmall && mapped_small_calls()) {
+    if (int rc = ensure_slots(c, 256)) return rc;      // makes the streams
+    if (int rc = ensure_mapped(c)) return rc;
+    const int cap = airice_ctx::kSmall;
+    double* hh = (double*)c->zc_host;
+    double* dd = (double*)c->zc_dev;
+    std::memcpy(hh, h_cm, sizeof(double) * n);
+    std::memcpy(hh + cap, dist_cm, sizeof(double) * n);
+    LookupArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = n; a.h_cm = dd; a.d_cm = dd + cap; a.ok = (uint8_t*)(dd + (2 + nc) * cap);
+    for (int k = 0; k < nc; k++) a.out[k] = (out || cols[k]) ? dd + (2 + k) * cap : nullptr;
+    a.literal = lookup_literal();
+    cudaStream_t s = c->streams[0];
+    t->note_stream(s);
+    cudaError_t e = launch_lookup(c->medium, t->view(), a, s);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_lookup");
+    CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < nc; k++) {
+      double* dst = out ? out + (size_t)k * n : cols[k];
+      if (dst) std::memcpy(dst, hh + (2 + k) * cap, sizeof(double) * n);
+    }
+    if (ok) std::memcpy(ok, (const uint8_t*)(hh + (2 + nc) * cap), (size_t)n);
+    return 0;
+  }
   const int64_t chunk = n < (1 << 20) ? (n > 0 ? n : 1) : (1 << 20);
   int rc = ensure_slots(c, (size_t)chunk * (sizeof(double) * (2 + nc) + 1) + 64);
   if (rc) return rc;
