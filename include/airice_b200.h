@@ -282,6 +282,11 @@ int airice_peer_open(airice_ctx *ctx, const unsigned char handle[AIRICE_PEER_HAN
 int airice_peer_close(airice_ctx *ctx, void *d_ptr);
 int airice_peer_copy(airice_ctx *ctx, void *d_dst, const void *d_src, size_t bytes, void *stream);
 
+/* Host calls of up to 64 pairs or queries (airice_solve_host*, airice_lookup_host*: the reference's scalar functions are
+ * batch-of-1 calls) do not issue copies at all: the kernel reads its inputs from and writes its results to a page-locked,
+ * device-mapped block of the context -- one launch and one synchronisation per call.  AIRICE_NO_MAPPED=1 in the environment
+ * keeps the chunked copy path for every size (test hook). */
+
 /* ---- page-locked host memory.  The host entry points (airice_*_host*) copy straight from / to the caller's buffers; with
  * pageable memory every copy is staged through the driver and blocks the calling thread, with page-locked memory the
  * upload of chunk k+1, the kernel of chunk k and the download of chunk k-1 overlap and the call runs at the PCIe rate.
